@@ -1,0 +1,211 @@
+/*
+ * chr3d.h — C ABI of libchr3d.so, the B200-native replacement for the CNS `dgsa.inp`
+ * distance-geometry simulated-annealing run that chromosome3D.pl drives.
+ *
+ * Citation shorthand:  C3D:N = /root/reference/chromosome3D.pl line N
+ *                      SP:N  = /root/reference/spearman_IF_pdb.pl line N
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; caller allocates every output buffer.
+ *   - every call returns 0 on success, <0 on error; chr3d_last_error() gives the text
+ *     (thread local).  The library never exits/aborts and never falls back to a CPU path:
+ *     without a usable CUDA device every compute entry point returns CHR3D_ERR_NO_DEVICE.
+ *   - bead / residue indices are 0-based in the ABI (the text writers print them 1-based,
+ *     as C3D:198 does).
+ *   - distances in Angstrom, energies in kcal/mol, time in ps, temperature in K.
+ */
+#ifndef CHR3D_H
+#define CHR3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHR3D_OK              0
+#define CHR3D_ERR_ARG        -1
+#define CHR3D_ERR_NO_DEVICE  -2
+#define CHR3D_ERR_CUDA       -3
+#define CHR3D_ERR_CAPACITY   -4
+#define CHR3D_ERR_IO         -5
+#define CHR3D_ERR_SIZE       -6
+
+/* ------------------------------------------------------------------------------------------
+ * Physics / protocol parameters.  Defaults = the literals chromosome3D.pl interpolates into
+ * dgsa.inp (C3D:65-74, 1078-1126, 1395-1426) plus the bead-level restatement of the CNS
+ * NOE soft-square / bond / repel terms.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct chr3d_sa_params {
+    /* NOE soft-square term (class defaults of CNS `readdata`, C3D:1407) */
+    double  noe_scale;      /* md.cool.noe = md.pow.noe = $con_wt = 10      C3D:66,1111,1120 */
+    double  noe_sqconst;    /* sqconstant 1                                                  */
+    double  noe_rswitch;    /* rswitch 1.0 A                                                 */
+    double  noe_asymptote;  /* asymptote 2.0 (slope of the linear tail)                      */
+    int32_t noe_low_soft;   /* 0: square-well below the lower bound, 1: soft on both sides   */
+    int32_t vdw_min_sep;    /* repel acts on |i-j| >= this (2: bonded neighbours excluded)    */
+    /* bead bond term (stand-in for the peptide backbone between consecutive CA atoms)      */
+    double  bond_k;         /* 1000 kcal/mol/A^2                                             */
+    double  bond_r0;        /* 3.8 A                                                         */
+    /* repel term  E = w_vdw * max(0,(s*rmin)^2 - r^2)^2      rexp=2 irexp=2 rcon=1  C3D:1398 */
+    double  vdw_rmin;       /* 4.73 A                                                        */
+    /* dynamics */
+    double  mass;           /* do (mass=100) (all)                                  C3D:1416 */
+    double  fbeta;          /* do (fbeta=10) (all), 1/ps                            C3D:1415 */
+    double  maxwell_temp;   /* maxwell(0.5)                                   C3D:1646-1648 */
+    double  hot_temp;       /* md.hot.temp 2000                                     C3D:1093 */
+    int32_t hot_step;       /* md.hot.step 1000                                     C3D:1095 */
+    int32_t cool_step;      /* md.cool.step 1000                                    C3D:1097 */
+    double  hot_dt;         /* md.hot.ss 0.003 ps                                   C3D:1099 */
+    double  cool_dt;        /* md.cool.ss 0.005 ps                                  C3D:1101 */
+    double  cool_vdw_init;  /* 0.003                                                C3D:1103 */
+    double  cool_vdw_finl;  /* 4.0                                                  C3D:1105 */
+    double  cool_rad_init;  /* $rep1 1.0                                         C3D:70,1107 */
+    double  cool_rad_finl;  /* $rep2 0.85                                        C3D:68,1109 */
+    double  cool_tmpstp;    /* 25 K                                                 C3D:1117 */
+    int32_t pow_step;       /* $mini 15000                                       C3D:71,1124 */
+    int32_t pow_cycl;       /* 10                                                   C3D:1126 */
+    int32_t premin_step;    /* minimize lbfgs nstep=100 (run twice)           C3D:1640,1642 */
+    int32_t images;         /* 2: both mirror images are annealed, lower energy kept C3D:1605 */
+    /* L-BFGS (CNS's own constants are not published in the reference tree: ours, documented) */
+    int32_t lbfgs_m;        /* history length, <= CHR3D_LBFGS_MAX_M                          */
+    int32_t lbfgs_max_ls;   /* max Armijo halvings per iteration                             */
+    double  lbfgs_c1;       /* Armijo constant                                               */
+    double  lbfgs_gtol;     /* stop when rms gradient component < gtol                       */
+    double  pow_drop;       /* drop=10.0 expected first-step energy decrease       C3D:1802 */
+    uint64_t seed;          /* md.seed 82364                                        C3D:980 */
+} chr3d_sa_params;
+
+#define CHR3D_LBFGS_MAX_M 8
+
+/* One instruction of the annealing "stage program" (the bead-level restatement of the
+ * protocol body of dgsa.inp, C3D:1573-1829).  Built by chr3d_build_program().            */
+enum {
+    CHR3D_OP_INIT     = 1,  /* x = x0 with x-coordinate * flag (image +1/-1), v = 0  C3D:1606-1609 */
+    CHR3D_OP_MINIMIZE = 2,  /* L-BFGS, nstep iterations max                  C3D:1640,1642,1802 */
+    CHR3D_OP_MAXWELL  = 3,  /* v ~ Maxwell(temp)                                   C3D:1646-1648 */
+    CHR3D_OP_DYNAMICS = 4,  /* nstep Verlet steps, dt, bath temp; flag = coupling  C3D:1650-1700,1766 */
+    CHR3D_OP_SAVE     = 5,  /* store x,v,E (image 1)                               C3D:1701-1708 */
+    CHR3D_OP_PICK     = 6,  /* keep the lower-energy of current / saved            C3D:1711-1727 */
+    CHR3D_OP_CENTER   = 7,  /* translate geometric centre to origin                C3D:1805-1816 */
+    CHR3D_OP_ENERGY   = 8   /* evaluate energy with this stage's weights (report)  C3D:1818     */
+};
+enum { CHR3D_COUPLE_TCOUP = 1, CHR3D_COUPLE_VSCALE = 2 };
+
+typedef struct chr3d_stage {
+    int32_t op;
+    int32_t nstep;
+    int32_t flag;
+    int32_t pad_;
+    double  dt;       /* ps */
+    double  temp;     /* K */
+    double  w_noe;    /* `weights *` factor x NOE scale                                    */
+    double  w_bond;   /* `weights *` factor x bond_k                                       */
+    double  w_vdw;    /* vdw weight x rcon                                                 */
+    double  repel;    /* nbonds repel= (radius scale s)                                    */
+    double  drop;     /* minimize drop=                                                    */
+} chr3d_stage;
+
+/* energies reported per model, the four terms get_cns_energy() knows (C3D:604-606) */
+enum { CHR3D_E_OVERALL = 0, CHR3D_E_BON = 1, CHR3D_E_VDW = 2, CHR3D_E_NOE = 3, CHR3D_E_COUNT = 4 };
+
+/* One (matrix, alpha) job = one chromosome3D.pl invocation's worth of models (C3D:254-289). */
+typedef struct chr3d_job {
+    /* either an IF matrix (targets derived on the device, C3D:110-206) ...               */
+    const double*  IF;        /* L*L row-major, or NULL                                    */
+    int32_t        L;         /* beads (calc_len_IF, C3D:164)                              */
+    int32_t        min_sep;   /* $SEPARATION 5 (C3D:20,195)                                */
+    double         alpha;     /* -a (C3D:32)                                               */
+    double         K;         /* -k (C3D:31)                                               */
+    /* ... or an explicit restraint table (rows of contact.tbl, C3D:360), used when IF==NULL */
+    const int32_t* ri;
+    const int32_t* rj;
+    const double*  rd;
+    int64_t        nr;
+    /* ensemble */
+    int32_t        n_models;  /* -m (C3D:33) */
+    int32_t        pad_;
+    uint64_t       seed;      /* 0 = use params->seed */
+    const double*  x0;        /* optional start coordinates n_models*L*3; NULL = seeded random coil */
+} chr3d_job;
+
+typedef struct chr3d_result {
+    double*  xyz;          /* n_models*L*3 final coordinates (centred)                     */
+    double*  energies;     /* n_models*CHR3D_E_COUNT                                       */
+    int64_t* force_evals;  /* n_models: energy+force evaluations performed                 */
+    int32_t* hand;         /* n_models: +1/-1 image kept (C3D:1717-1721)                   */
+    int32_t* satisfied;    /* n_models: count_satisfied_tbl_rows numerator (C3D:464-473)   */
+    double*  sum_dev;      /* n_models: sum_noe_dev (C3D:592-599), unrounded               */
+    int64_t  n_restraints; /* rows of the restraint table (out)                            */
+    double   device_ms;    /* kernel time of the run (out)                                 */
+} chr3d_result;
+
+/* ---------------------------------- lifecycle ------------------------------------------- */
+const char* chr3d_version(void);
+const char* chr3d_last_error(void);
+int  chr3d_device_count(void);
+int  chr3d_init(int device);          /* bind this host thread/process to a CUDA device   */
+int  chr3d_shutdown(void);
+
+void chr3d_default_params(chr3d_sa_params* p);
+/* Writes the stage program for `p`; returns the number of stages (or <0).  cap==0: size query. */
+int  chr3d_build_program(const chr3d_sa_params* p, chr3d_stage* out, int cap);
+
+/* ------------------------- (1) IF -> restraints  C3D:110-206, 340-362 -------------------- */
+/* IF2dist_new: tenths[i*L+j] = the `%.1f` text of D as an integer number of tenths
+ * (-10 for the "-1.0" cells).  n_patched (optional) = cells whose decimal rounding could not
+ * be certified from the device result and were re-derived on the host with libm pow.       */
+int chr3d_if_to_dist(const double* IF, int32_t L, double alpha, double K,
+                     int64_t* tenths, int64_t* n_patched);
+/* dist2rr + carr2tbl: rows in the string-sorted key order of C3D:203.  cap==0: size query. */
+int chr3d_if_to_restraints(const double* IF, int32_t L, double alpha, double K, int32_t min_sep,
+                           int32_t* out_i, int32_t* out_j, double* out_d,
+                           int64_t cap, int64_t* out_n);
+int chr3d_write_dist(const char* path, const int64_t* tenths, int32_t L);          /* <ID>.dist  C3D:156-161 */
+int chr3d_write_rr  (const char* path, const int32_t* ri, const int32_t* rj,
+                     const double* rd, int64_t n);                                 /* <ID>.rr    C3D:203-205 */
+int chr3d_write_tbl (const char* path, const int32_t* ri, const int32_t* rj,
+                     const double* rd, int64_t n);                                 /* contact.tbl C3D:360    */
+
+/* ----------------- (2) energy + forces on fixed coordinates (CNS `energy`) --------------- */
+/* xyz: n_models*N*3.  energies: n_models*4.  forces: n_models*N*3 (= -dE/dx), may be NULL. */
+int chr3d_energy_forces(const double* xyz, int32_t n_models, int32_t N,
+                        const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr,
+                        const chr3d_sa_params* p, const chr3d_stage* weights,
+                        double* energies, double* forces);
+
+/* ------------------- (3) the SA run: replaces build_models() C3D:254-289 ----------------- */
+/* Host-buffer call (the e2e path): upload, anneal every model of every job, download.     */
+int chr3d_run_ensemble(const chr3d_job* jobs, int32_t njobs, const chr3d_sa_params* p,
+                       const chr3d_stage* program, int32_t nstages, chr3d_result* results);
+
+/* Device-resident variant: create uploads and derives targets, run only launches kernels on
+ * `stream` (a cudaStream_t, may be NULL), fetch downloads.                                 */
+typedef struct chr3d_ensemble chr3d_ensemble;
+int chr3d_ensemble_create(const chr3d_job* jobs, int32_t njobs, const chr3d_sa_params* p,
+                          const chr3d_stage* program, int32_t nstages, chr3d_ensemble** out);
+int chr3d_ensemble_run(chr3d_ensemble* e, void* stream);
+int chr3d_ensemble_fetch(chr3d_ensemble* e, chr3d_result* results);
+int chr3d_ensemble_info(const chr3d_ensemble* e, int32_t* cluster_size, int32_t* threads,
+                        int32_t* n_launches, int64_t* restraint_rows_total);
+int chr3d_ensemble_destroy(chr3d_ensemble* e);
+
+/* --------------- (4) ranking, violation statistics, PDB  C3D:447-600, 769-880 ------------ */
+/* xyz are rounded to the 3-decimal PDB text first (C3D:727 works on the text fields).     */
+int chr3d_assess(const double* xyz, int32_t n_models, int32_t N,
+                 const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr,
+                 int32_t* satisfied, double* sum_dev);
+/* order[k] = model index of rank k (ascending int(noe), ties by model index; C3D:617,802,823) */
+int chr3d_rank_models(const double* energies, int32_t n_models, int32_t* order);
+/* CNS-style trial structure <ID>_k.pdb: REMARK energies + one CA ATOM per bead + END      */
+int chr3d_write_pdb(const char* path, const double* xyz, int32_t N, const double* energies4,
+                    const char* resnames /* N*3 chars or NULL -> REFSEQUENCE */, int32_t with_conect);
+
+/* --------------------------- (5) Spearman  SP:32-71 -------------------------------------- */
+int chr3d_spearman(const double* IF, int32_t L, const double* xyz, int32_t n_models,
+                   int32_t range, double* rho);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHR3D_H */
