@@ -25,7 +25,7 @@ class SaParams(C.Structure):
         ("cool_vdw_finl", C.c_double), ("cool_rad_init", C.c_double), ("cool_rad_finl", C.c_double),
         ("cool_tmpstp", C.c_double), ("pow_step", C.c_int32), ("pow_cycl", C.c_int32),
         ("premin_step", C.c_int32), ("images", C.c_int32), ("lbfgs_m", C.c_int32),
-        ("lbfgs_max_ls", C.c_int32), ("lbfgs_c1", C.c_double), ("lbfgs_gtol", C.c_double),
+        ("lbfgs_max_ls", C.c_int32), ("lbfgs_c1", C.c_double), ("lbfgs_gtol", C.c_double), ("lbfgs_ftol", C.c_double),
         ("pow_drop", C.c_double), ("seed", C.c_uint64),
     ]
 

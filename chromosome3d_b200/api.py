@@ -1,0 +1,313 @@
+"""Host-side mirror of the reference's interface for the DGSA hot path, over the C ABI.
+
+Everything numerical happens in libchr3d.so (hand-written CUDA for sm_100a).  This module only
+marshals numpy buffers through ctypes, the same way the Perl front end does through its XS/FFI
+shim.  There is no CPU fallback: without the built library or without a GPU
+every compute call raises Chr3dError.
+
+Reference functions mirrored (names follow chromosome3D.pl):
+    calc_len_IF / IF2dist_new / dist2rr / carr2tbl      C3D:110-206, 340-362
+    build_models (the CNS dgsa.inp run)                 C3D:254-289, protocol C3D:1573-1829
+    assess_dgsa + count_satisfied_tbl_rows + sum_noe_dev C3D:447-600, 769-829
+    spearman_IF_pdb.pl                                   SP:32-71
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchr3d.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+class Chr3dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libchr3d error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libchr3d.so (built in-tree by `make -C chromosome3d_b200/csrc` / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Chr3dError(abi.ERR_NO_DEVICE, "libchr3d.so is not built (run __graft_entry__.build()); there is no CPU path")
+        L = C.CDLL(LIB_PATH)
+        L.chr3d_version.restype = C.c_char_p
+        L.chr3d_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise Chr3dError(rc, lib().chr3d_last_error().decode(errors="replace"))
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def version():
+    return lib().chr3d_version().decode()
+
+
+def device_count():
+    return lib().chr3d_device_count()
+
+
+def init(device=0):
+    _check(lib().chr3d_init(device))
+
+
+def fp32_peak(reps=3):
+    v = C.c_double(0)
+    _check(lib().chr3d_fp32_peak(reps, C.byref(v)))
+    return v.value
+
+
+def default_params():
+    p = abi.SaParams()
+    lib().chr3d_default_params(C.byref(p))
+    return p
+
+
+def build_program(p):
+    """The dgsa.inp protocol body as a stage program (C3D:1573-1829)."""
+    n = lib().chr3d_build_program(C.byref(p), None, 0)
+    if n < 0:
+        _check(n)
+    arr = (abi.Stage * n)()
+    lib().chr3d_build_program(C.byref(p), arr, n)
+    return arr
+
+
+# ---------------------------------------------------------------------------------- restraints
+def calc_len_IF(path):
+    """C3D:164-179: L = number of tokens on the first row."""
+    with open(path, "r", newline="") as fh:
+        for line in fh:
+            toks = line.split()
+            if toks:
+                return len(toks)
+    raise ValueError("empty IF matrix %s" % path)
+
+
+def IF2dist_new(IF, alpha, K=11.0):
+    """C3D:110-162.  Returns (tenths int64 (L,L), n_patched): the `%.1f` text of the .dist file."""
+    IF = np.ascontiguousarray(IF, dtype=np.float64)
+    L = IF.shape[0]
+    t = np.zeros((L, L), dtype=np.int64)
+    npatch = C.c_int64(0)
+    _check(lib().chr3d_if_to_dist(_d(IF), L, C.c_double(alpha), C.c_double(K), t.ctypes.data_as(_lp), C.byref(npatch)))
+    return t, npatch.value
+
+
+def if_to_restraints(IF, alpha, K=11.0, min_sep=5):
+    """dist2rr + carr2tbl (C3D:181-206, 340-362): (ri, rj, rd) in the string-sorted row order."""
+    IF = np.ascontiguousarray(IF, dtype=np.float64)
+    L = IF.shape[0]
+    n = C.c_int64(0)
+    _check(lib().chr3d_if_to_restraints(_d(IF), L, C.c_double(alpha), C.c_double(K), min_sep, None, None, None,
+                                        C.c_int64(0), C.byref(n)))
+    cap = max(n.value, 1)
+    ri = np.zeros(cap, dtype=np.int32)
+    rj = np.zeros(cap, dtype=np.int32)
+    rd = np.zeros(cap, dtype=np.float64)
+    if n.value:
+        _check(lib().chr3d_if_to_restraints(_d(IF), L, C.c_double(alpha), C.c_double(K), min_sep, _i(ri), _i(rj), _d(rd),
+                                            C.c_int64(cap), C.byref(n)))
+    return ri[:n.value], rj[:n.value], rd[:n.value]
+
+
+def write_dist(path, tenths):
+    tenths = np.ascontiguousarray(tenths, dtype=np.int64)
+    _check(lib().chr3d_write_dist(path.encode(), tenths.ctypes.data_as(_lp), tenths.shape[0]))
+
+
+def write_rr(path, ri, rj, rd):
+    ri, rj, rd = _list(ri, rj, rd)
+    _check(lib().chr3d_write_rr(path.encode(), _i(ri), _i(rj), _d(rd), C.c_int64(len(ri))))
+
+
+def carr2tbl(path, ri, rj, rd):
+    ri, rj, rd = _list(ri, rj, rd)
+    _check(lib().chr3d_write_tbl(path.encode(), _i(ri), _i(rj), _d(rd), C.c_int64(len(ri))))
+
+
+def _list(ri, rj, rd):
+    return (np.ascontiguousarray(ri, dtype=np.int32), np.ascontiguousarray(rj, dtype=np.int32),
+            np.ascontiguousarray(rd, dtype=np.float64))
+
+
+# ---------------------------------------------------------------------------------- energy
+def energy_forces(xyz, ri, rj, rd, p, weights, want_forces=True):
+    """CNS `energy` at fixed coordinates: (energies (m,4) [overall,bon,vdw,noe], forces (m,N,3))."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    if xyz.ndim == 2:
+        xyz = xyz[None]
+    m, N, _ = xyz.shape
+    ri, rj, rd = _list(ri, rj, rd)
+    e = np.zeros((m, 4))
+    f = np.zeros_like(xyz) if want_forces else None
+    _check(lib().chr3d_energy_forces(_d(xyz), m, N, _i(ri), _i(rj), _d(rd), C.c_int64(len(ri)), C.byref(p),
+                                     C.byref(weights), _d(e), _d(f) if want_forces else None))
+    return e, f
+
+
+# ---------------------------------------------------------------------------------- SA run
+class Job:
+    """One (matrix, alpha) ensemble = one chromosome3D.pl invocation (C3D:28-35)."""
+
+    def __init__(self, IF=None, alpha=0.5, K=11.0, min_sep=5, n_models=20, seed=0, restraints=None, N=None, x0=None):
+        self.IF = None if IF is None else np.ascontiguousarray(IF, dtype=np.float64)
+        self.alpha, self.K, self.min_sep, self.n_models, self.seed = float(alpha), float(K), int(min_sep), int(n_models), int(seed)
+        self.restraints = None if restraints is None else _list(*restraints)
+        self.N = int(self.IF.shape[0] if self.IF is not None else N)
+        self.x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).reshape(self.n_models, self.N, 3)
+
+    def c_struct(self):
+        j = abi.Job()
+        j.L, j.min_sep, j.alpha, j.K = self.N, self.min_sep, self.alpha, self.K
+        j.n_models, j.seed = self.n_models, self.seed
+        if self.IF is not None:
+            j.IF = _d(self.IF)
+        elif self.restraints is not None:
+            ri, rj, rd = self.restraints
+            j.ri, j.rj, j.rd, j.nr = _i(ri), _i(rj), _d(rd), len(ri)
+        if self.x0 is not None:
+            j.x0 = _d(self.x0)
+        return j
+
+
+class JobResult:
+    def __init__(self, job):
+        m, N = job.n_models, job.N
+        self.xyz = np.zeros((m, N, 3))
+        self.energies = np.zeros((m, 4))
+        self.force_evals = np.zeros(m, dtype=np.int64)
+        self.hand = np.zeros(m, dtype=np.int32)
+        self.satisfied = np.zeros(m, dtype=np.int32)
+        self.sum_dev = np.zeros(m)
+        self.n_restraints = 0
+        self.device_ms = 0.0
+
+    def c_struct(self):
+        r = abi.Result()
+        r.xyz, r.energies = _d(self.xyz), _d(self.energies)
+        r.force_evals = self.force_evals.ctypes.data_as(_lp)
+        r.hand, r.satisfied, r.sum_dev = _i(self.hand), _i(self.satisfied), _d(self.sum_dev)
+        return r
+
+
+def _job_arrays(jobs):
+    arr = (abi.Job * len(jobs))()
+    for k, j in enumerate(jobs):
+        arr[k] = j.c_struct()
+    return arr
+
+
+def _collect(results, carr):
+    for r, c in zip(results, carr):
+        r.n_restraints, r.device_ms = c.n_restraints, c.device_ms
+    return results
+
+
+def build_models(jobs, p=None, program=None):
+    """The CNS dgsa run of build_models() (C3D:254-289) for a list of jobs, host buffers in and out."""
+    p = p or default_params()
+    program = program if program is not None else build_program(p)
+    jarr = _job_arrays(jobs)
+    results = [JobResult(j) for j in jobs]
+    rarr = (abi.Result * len(jobs))(*[r.c_struct() for r in results])
+    _check(lib().chr3d_run_ensemble(jarr, len(jobs), C.byref(p), program, len(program), rarr))
+    return _collect(results, rarr)
+
+
+class Ensemble:
+    """Device-resident variant: create() uploads and derives targets, run() only launches kernels."""
+
+    def __init__(self, jobs, p=None, program=None):
+        self.jobs = jobs
+        self.p = p or default_params()
+        self.program = program if program is not None else build_program(self.p)
+        self._h = C.c_void_p()
+        jarr = _job_arrays(jobs)
+        _check(lib().chr3d_ensemble_create(jarr, len(jobs), C.byref(self.p), self.program, len(self.program), C.byref(self._h)))
+
+    def run(self, stream=None):
+        _check(lib().chr3d_ensemble_run(self._h, C.c_void_p(stream or 0)))
+
+    def fetch(self):
+        results = [JobResult(j) for j in self.jobs]
+        rarr = (abi.Result * len(self.jobs))(*[r.c_struct() for r in results])
+        _check(lib().chr3d_ensemble_fetch(self._h, rarr))
+        return _collect(results, rarr)
+
+    def info(self):
+        c, t, n = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        rows = C.c_int64(0)
+        _check(lib().chr3d_ensemble_info(self._h, C.byref(c), C.byref(t), C.byref(n), C.byref(rows)))
+        return dict(cluster=c.value, threads=t.value, launches=n.value, restraint_rows=rows.value)
+
+    def close(self):
+        if self._h:
+            lib().chr3d_ensemble_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------- assessment
+def count_satisfied_and_sum_dev(xyz, ri, rj, rd):
+    """count_satisfied_tbl_rows numerator (C3D:464-473) and sum_noe_dev (C3D:592-599) per model."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    if xyz.ndim == 2:
+        xyz = xyz[None]
+    m, N, _ = xyz.shape
+    ri, rj, rd = _list(ri, rj, rd)
+    sat = np.zeros(m, dtype=np.int32)
+    dev = np.zeros(m)
+    _check(lib().chr3d_assess(_d(xyz), m, N, _i(ri), _i(rj), _d(rd), C.c_int64(len(ri)), _i(sat), _d(dev)))
+    return sat, dev
+
+
+def rank_models(energies):
+    energies = np.ascontiguousarray(energies, dtype=np.float64)
+    order = np.zeros(energies.shape[0], dtype=np.int32)
+    _check(lib().chr3d_rank_models(_d(energies), energies.shape[0], _i(order)))
+    return order
+
+
+def write_pdb(path, xyz, energies=None, resnames=None, with_conect=False):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    e = None if energies is None else np.ascontiguousarray(energies, dtype=np.float64)
+    rn = None if resnames is None else "".join(resnames).encode()
+    _check(lib().chr3d_write_pdb(path.encode(), _d(xyz), xyz.shape[0], _d(e) if e is not None else None, rn,
+                                 1 if with_conect else 0))
+
+
+def spearman_IF_pdb(IF, xyz, rng=3):
+    """SP:32-71: Spearman rho (unrounded fp64) per model; the script prints '%.3f' of it."""
+    IF = np.ascontiguousarray(IF, dtype=np.float64)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    if xyz.ndim == 2:
+        xyz = xyz[None]
+    rho = np.zeros(xyz.shape[0])
+    _check(lib().chr3d_spearman(_d(IF), IF.shape[0], _d(xyz), xyz.shape[0], rng, _d(rho)))
+    return rho

@@ -1,0 +1,114 @@
+// common.h — shared host-side helpers of libchr3d.so (error text, CUDA checks, device structs)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/chr3d.h"
+
+#define CHR3D_API extern "C" __attribute__((visibility("default")))
+
+// AKMA unit system of CNS/X-PLOR
+#define CHR3D_TIMFAC 0.04888821
+#define CHR3D_KBOLTZ 1.987191e-3
+
+namespace chr3d {
+
+void set_error(const char* fmt, ...);
+int  require_device();                 // 0 or CHR3D_ERR_NO_DEVICE, sets the error text
+
+#define CHR3D_CUDA(call)                                                                         \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            chr3d::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return CHR3D_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+// RAII device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// ---- device-side views of the physics parameters / stage program (fp32 compute) -------------
+struct DevParams {
+    float C, rsw, casym, a, b;     // NOE soft-square constants
+    float lo_clamp;                // -rsw if the low side is soft, -inf otherwise
+    float r0;                      // bond length
+    float mass, inv_mass;
+    float fbeta;                   // 1/ps
+    float kboltz;
+    int   m, max_ls;
+    float c1, gtol, ftol;
+    int   general_noe;             // b != 0: use the exact piecewise formula
+};
+struct DevStage {
+    int   op, nstep, flag, pad_;
+    float dt_akma, dt_ps, temp, w_noe, w_bond, w_vdw, R2, drop;
+};
+
+void make_dev_params(const chr3d_sa_params& p, DevParams& d);
+void make_dev_stage(const chr3d_sa_params& p, const chr3d_stage& s, DevStage& d);
+
+// pitch (floats) of the dense target matrix
+static inline int target_pitch(int N) { return (N + 31) & ~31; }
+
+// ---- restraints.cu ---------------------------------------------------------------------------
+// Derives, on the device, the `%.1f` tenths of D = K/(IF^alpha/mean) for every cell (d_tenths, L*L
+// int64) and a certification flag count.  d_IF: L*L doubles on the device.
+// flagged_host: indices of cells whose decimal rounding is not certified (empty when more than
+// CHR3D_MAX_FLAGGED cells are flagged: the caller then re-derives every cell).
+#define CHR3D_MAX_FLAGGED 4096
+int dev_if_to_tenths(const double* d_IF, int L, double alpha, double K, long long* d_tenths,
+                     long long* n_uncertain_host, std::vector<long long>* flagged_host, cudaStream_t s);
+// Dense fp32 target matrix [N][pitch] from tenths: d>0 restraint, -1 none, -2 none + no repel.
+int dev_tenths_to_targets(const long long* d_tenths, int L, int min_sep, int vdw_min_sep, float* d_T,
+                          cudaStream_t s);
+int dev_list_to_targets(const int32_t* d_ri, const int32_t* d_rj, const double* d_rd, long long nr, int N,
+                        int vdw_min_sep, float* d_T, cudaStream_t s);
+// Lexicographically ordered restraint list (C3D:203) from tenths; d_count receives the row count.
+int dev_tenths_to_list(const long long* d_tenths, int L, int min_sep, int32_t* d_ri, int32_t* d_rj,
+                       double* d_rd, long long cap, long long* n_host, cudaStream_t s);
+
+// ---- sa_ensemble.cu --------------------------------------------------------------------------
+struct TrajDesc {
+    const float* T;        // dense targets [N][pitch]
+    const float* x0;       // N*3 start coordinates
+    float*  x_out;         // N*3
+    float*  f_out;         // N*3 or nullptr (forces of the last evaluation)
+    float*  scratch;       // 6*N floats (SAVE slot)
+    double* e_out;         // 4
+    long long* nevals_out; // 1
+    int*    hand_out;      // 1
+    int     N, pitch, model, pad_;
+    unsigned long long seed;
+};
+struct SaLaunchCfg { int cluster; int threads; int stage_targets; size_t smem; };
+int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg);
+int sa_launch(const TrajDesc* d_traj, int n_traj, int Nmax, const DevParams& P, const DevStage* d_prog, int nstages,
+              const SaLaunchCfg& cfg, cudaStream_t s);
+int dev_random_coil(float* d_x0, int N, int n_models, int first_model, double step, unsigned long long seed,
+                    cudaStream_t s);
+
+// ---- assess.cu -------------------------------------------------------------------------------
+int dev_assess(const double* d_xyz, int n_models, int N, const int32_t* d_ri, const int32_t* d_rj,
+               const double* d_rd, long long nr, int32_t* d_sat, double* d_dev, cudaStream_t s);
+int dev_spearman(const double* d_IF, int L, const double* d_xyz, int n_models, int range, double* rho_host,
+                 cudaStream_t s);
+
+}  // namespace chr3d

@@ -72,6 +72,7 @@ typedef struct chr3d_sa_params {
     int32_t lbfgs_max_ls;   /* max Armijo halvings per iteration                             */
     double  lbfgs_c1;       /* Armijo constant                                               */
     double  lbfgs_gtol;     /* stop when rms gradient component < gtol                       */
+    double  lbfgs_ftol;     /* stop when a quasi-Newton step lowers E by <= ftol*max(|E|,1)  */
     double  pow_drop;       /* drop=10.0 expected first-step energy decrease       C3D:1802 */
     uint64_t seed;          /* md.seed 82364                                        C3D:980 */
 } chr3d_sa_params;
@@ -150,6 +151,10 @@ int  chr3d_shutdown(void);
 void chr3d_default_params(chr3d_sa_params* p);
 /* Writes the stage program for `p`; returns the number of stages (or <0).  cap==0: size query. */
 int  chr3d_build_program(const chr3d_sa_params* p, chr3d_stage* out, int cap);
+
+/* Measurement aid: FP32 FMA throughput of the device in TFLOP/s (roofline denominator of the
+ * FP32-bound small-N kernel).                                                              */
+int chr3d_fp32_peak(int reps, double* tflops);
 
 /* ------------------------- (1) IF -> restraints  C3D:110-206, 340-362 -------------------- */
 /* IF2dist_new: tenths[i*L+j] = the `%.1f` text of D as an integer number of tenths
