@@ -2,6 +2,8 @@
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 #include <algorithm>
 #include <map>
 #include <memory>
@@ -17,6 +19,13 @@ void set_error(const char* fmt, ...) {
     g_err = buf;
 }
 static int g_device = -1;
+// CHR3D_TRACE=1: host-side phase timings on stderr (development aid)
+struct Trace {
+    bool on; double t0; const char* what;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    explicit Trace(const char* w) : what(w) { static int en = getenv("CHR3D_TRACE") ? 1 : 0; on = en; if (on) t0 = now(); }
+    void lap(const char* tag) { if (on) { cudaDeviceSynchronize(); double t = now(); fprintf(stderr, "[chr3d] %s/%s %.3f ms\n", what, tag, 1e3 * (t - t0)); t0 = t; } }
+};
 int require_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -313,6 +322,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
                            int nstages, bool want_forces, std::vector<DevBuf<float>>* fbufs, chr3d_ensemble** out) {
     if (!jobs || njobs < 1 || !p || !program || nstages < 1 || !out) { set_error("ensemble_create: bad arguments"); return CHR3D_ERR_ARG; }
     if (int rc = require_device()) return rc;
+    Trace tr("create");
     std::unique_ptr<chr3d_ensemble> e(new chr3d_ensemble());
     make_dev_params(*p, e->P);
     e->nstages = nstages;
@@ -332,6 +342,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         if (jb.IF) {
             DevBuf<double> dIF; DevBuf<long long> dT;
             if (int rc = if_to_tenths_certified(jb.IF, N, jb.alpha, jb.K, dIF, dT, nullptr, 0)) return rc;
+            tr.lap("tenths");
             if (int rc = dev_tenths_to_targets(dT.p, N, jb.min_sep, p->vdw_min_sep, jd->T.p, 0)) return rc;
             long long n = 0;
             if (int rc = dev_tenths_to_list(dT.p, N, jb.min_sep, nullptr, nullptr, nullptr, 0, &n, 0)) return rc;
@@ -344,6 +355,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             if (int rc = upload_list(*jd, jb.ri, jb.rj, jb.rd, jb.nr, 0)) return rc;
             if (int rc = dev_list_to_targets(jd->ri.p, jd->rj.p, jd->rd.p, jb.nr, N, p->vdw_min_sep, jd->T.p, 0)) return rc;
         }
+        tr.lap("targets+list");
         e->rows_total += jd->nr * jb.n_models;
         const size_t nx = (size_t)jb.n_models * N * 3;
         CHR3D_CUDA(jd->x0.alloc(nx)); CHR3D_CUDA(jd->xout.alloc(nx)); CHR3D_CUDA(jd->scratch.alloc(2 * nx));
@@ -358,6 +370,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             if (int rc = dev_random_coil(jd->x0.p, N, jb.n_models, 0, p->bond_r0, jd->seed, 0)) return rc;
         }
         if (want_forces) CHR3D_CUDA((*fbufs)[jn].alloc(nx));
+        tr.lap("alloc+coil");
         if (int rc = sa_choose_config(N, jb.n_models, e->P.m, &jd->cfg)) return rc;
         jd->traj0 = (int)tds.size();
         for (int m = 0; m < jb.n_models; m++) {
@@ -387,6 +400,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
     CHR3D_CUDA(cudaMemcpy(e->traj.p, tds.data(), sizeof(TrajDesc) * tds.size(), cudaMemcpyHostToDevice));
     CHR3D_CUDA(cudaEventCreate(&e->ev0)); CHR3D_CUDA(cudaEventCreate(&e->ev1));
     CHR3D_CUDA(cudaDeviceSynchronize());
+    tr.lap("finish");
     *out = e.release();
     return 0;
 }
@@ -412,7 +426,9 @@ CHR3D_API int chr3d_ensemble_run(chr3d_ensemble* e, void* stream) {
 
 CHR3D_API int chr3d_ensemble_fetch(chr3d_ensemble* e, chr3d_result* results) {
     if (!e || !results) { set_error("chr3d_ensemble_fetch: bad arguments"); return CHR3D_ERR_ARG; }
+    Trace tr("fetch");
     CHR3D_CUDA(cudaDeviceSynchronize());
+    tr.lap("wait_kernels");
     float ms = 0.f;
     if (e->ran) CHR3D_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     for (size_t jn = 0; jn < e->jobs.size(); jn++) {
@@ -430,6 +446,7 @@ CHR3D_API int chr3d_ensemble_fetch(chr3d_ensemble* e, chr3d_result* results) {
         if (r.force_evals) CHR3D_CUDA(cudaMemcpy(r.force_evals, jd.nev.p, sizeof(long long) * jd.n_models, cudaMemcpyDeviceToHost));
         if (r.hand) CHR3D_CUDA(cudaMemcpy(r.hand, jd.hand.p, sizeof(int32_t) * jd.n_models, cudaMemcpyDeviceToHost));
         r.n_restraints = jd.nr; r.device_ms = ms;
+        tr.lap("assess+d2h");
     }
     return 0;
 }
@@ -448,9 +465,12 @@ CHR3D_API int chr3d_run_ensemble(const chr3d_job* jobs, int32_t njobs, const chr
                                  const chr3d_stage* program, int32_t nstages, chr3d_result* results) {
     chr3d_ensemble* e = nullptr;
     if (int rc = chr3d_ensemble_create(jobs, njobs, p, program, nstages, &e)) return rc;
+    Trace tr("run_ensemble");
     int rc = chr3d_ensemble_run(e, nullptr);
     if (!rc) rc = chr3d_ensemble_fetch(e, results);
+    tr.lap("run+fetch");
     chr3d_ensemble_destroy(e);
+    tr.lap("destroy");
     return rc;
 }
 

@@ -11,6 +11,7 @@
 // fp64 operations the Perl itself performs on those values, in the same order.
 #include <cub/cub.cuh>
 #include "common.h"
+#include "seqsum.cuh"
 
 namespace chr3d {
 
@@ -108,7 +109,7 @@ int dev_assess(const double* d_xyz, int n_models, int N, const int32_t* d_ri, co
     dim3 grid((unsigned)((nr + 255) / 256), n_models);
     assess_terms_kernel<<<grid, 256, 0, s>>>(mx.p, n_models, N, d_ri, d_rj, d_rd, nr, d_sat, dense ? terms.p : nullptr, dense ? nullptr : terms.p);
     CHR3D_CUDA(cudaGetLastError());
-    if (dense) seq_rows_sum_kernel<<<(n_models + 31) / 32, 32, 0, s>>>(terms.p, per_model, n_models, d_dev);
+    if (dense) seq_sum_staged_kernel<<<n_models, 256, 0, s>>>(terms.p, per_model, d_dev);
     else block_sum_kernel<<<n_models, 256, 0, s>>>(terms.p, per_model, d_dev);
     CHR3D_CUDA(cudaGetLastError());
     CHR3D_CUDA(cudaStreamSynchronize(s));
@@ -126,6 +127,7 @@ __device__ __forceinline__ unsigned long long order_key(double v) {
 // pair index -> (h, i) for the list of ordered pairs with |i-h| >= range in row-major order
 __device__ __forceinline__ void pair_at(long long L, long long range, long long h, long long c, long long* i) {
     // row h keeps columns [0, h-range] and [h+range, L-1]
+    if (range <= 0) { *i = c; return; }
     long long left = h - range + 1; if (left < 0) left = 0;
     *i = c < left ? c : (h + range + (c - left));
 }
@@ -136,7 +138,7 @@ __global__ void row_offsets_kernel(int L, int range, long long* offs) {
         offs[h] = s;
         long long left = h - range + 1; if (left < 0) left = 0;
         long long right = (long long)L - (h + range); if (right < 0) right = 0;
-        s += left + right;
+        s += range <= 0 ? (long long)L : left + right;
     }
     offs[L] = s;
 }

@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 #include "common.h"
+#include "seqsum.cuh"
 
 namespace chr3d {
 
@@ -108,11 +109,11 @@ int dev_if_to_tenths(const double* d_IF, int L, double alpha, double K, long lon
     pow_kernel<<<blocks, 256, 0, s>>>(d_IF, P.p, n, alpha);
     CHR3D_CUDA(cudaGetLastError());
     if (L <= SEQ_SUM_MAX_L) {
-        seq_sum_kernel<<<1, 32, 0, s>>>(P.p, n, sum.p);
+        seq_sum_staged_kernel<<<1, 256, 0, s>>>(P.p, n, sum.p);
     } else {
         CHR3D_CUDA(rows.alloc((size_t)L));
         row_sum_kernel<<<(L + 127) / 128, 128, 0, s>>>(P.p, L, rows.p);
-        seq_sum_kernel<<<1, 32, 0, s>>>(rows.p, L, sum.p);
+        seq_sum_staged_kernel<<<1, 256, 0, s>>>(rows.p, L, sum.p);
     }
     CHR3D_CUDA(cudaGetLastError());
     double total = 0.0;
