@@ -311,3 +311,76 @@ def spearman_IF_pdb(IF, xyz, rng=3):
     rho = np.zeros(xyz.shape[0])
     _check(lib().chr3d_spearman(_d(IF), IF.shape[0], _d(xyz), xyz.shape[0], rng, _d(rho)))
     return rho
+
+
+# ---------------------------------------------------------------------------------- one large structure
+def nccl_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the caller broadcasts it, e.g. over torch.distributed)."""
+    buf = (C.c_ubyte * 128)()
+    _check(lib().chr3d_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def synthetic_if(N, seed):
+    """Synthetic IF matrix of SURVEY 8(d), generated on the device (same definition as datasets.synthetic_if)."""
+    out = np.zeros((N, N))
+    _check(lib().chr3d_synthetic_if(N, C.c_uint64(seed), _d(out)))
+    return out
+
+
+class Single:
+    """One structure of thousands of beads (the large-N engine), optionally one rank of a row-block
+    (tile-range) partition over the GPUs of a node.  Same dgsa.inp protocol (C3D:1573-1829)."""
+
+    def __init__(self, IF=None, N=None, alpha=0.5, K=11.0, min_sep=5, synth_seed=0, x0=None, seed=0, p=None, program=None,
+                 rank=0, world=1, nccl_id=None):
+        self.IF = None if IF is None else np.ascontiguousarray(IF, dtype=np.float64)
+        self.N = int(self.IF.shape[0] if self.IF is not None else N)
+        self.p = p or default_params()
+        self.program = program if program is not None else build_program(self.p)
+        self.x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).reshape(self.N, 3)
+        self._h = C.c_void_p()
+        idbuf = None
+        if nccl_id is not None:
+            idbuf = (C.c_ubyte * 128).from_buffer_copy(bytes(nccl_id))
+        _check(lib().chr3d_single_create(_d(self.IF) if self.IF is not None else None, self.N, C.c_double(alpha), C.c_double(K),
+                                         int(min_sep), C.c_uint64(synth_seed), _d(self.x0) if self.x0 is not None else None,
+                                         C.c_uint64(seed), C.byref(self.p), self.program, len(self.program), int(rank), int(world),
+                                         idbuf, C.byref(self._h)))
+
+    def run(self, stream=None):
+        _check(lib().chr3d_single_run(self._h, C.c_void_p(stream or 0)))
+
+    def eval_bench(self, reps=20, want_energy=True, stream=None):
+        """(tile_ms, eval_ms): device time of the pair-tile kernel alone / of a whole force evaluation."""
+        a, b = C.c_double(0), C.c_double(0)
+        _check(lib().chr3d_single_eval_bench(self._h, C.c_void_p(stream or 0), int(reps), 1 if want_energy else 0, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fetch(self):
+        xyz = np.zeros((self.N, 3))
+        f = np.zeros((self.N, 3))
+        e = np.zeros(4)
+        nev, nl, npairs = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        hand = C.c_int32(0)
+        ms = C.c_double(0)
+        _check(lib().chr3d_single_fetch(self._h, _d(xyz), _d(e), _d(f), C.byref(nev), C.byref(hand), C.byref(ms), C.byref(nl), C.byref(npairs)))
+        return dict(xyz=xyz, forces=f, energies=e, force_evals=nev.value, hand=hand.value, device_ms=ms.value, launches=nl.value,
+                    restraint_rows=npairs.value)
+
+    def info(self):
+        nt, mine, tb = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        ctas = C.c_int32(0)
+        _check(lib().chr3d_single_info(self._h, C.byref(nt), C.byref(mine), C.byref(ctas), C.byref(tb)))
+        return dict(n_tiles=nt.value, tiles_this_rank=mine.value, ctas=ctas.value, target_bytes=tb.value)
+
+    def close(self):
+        if self._h:
+            lib().chr3d_single_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

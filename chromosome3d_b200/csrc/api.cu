@@ -95,8 +95,8 @@ static int patch_cells(const double* IF, int L, double alpha, double K, long lon
     return 0;
 }
 // IF (host) -> tenths on the device, certified
-static int if_to_tenths_certified(const double* IF, int L, double alpha, double K, DevBuf<double>& dIF,
-                                  DevBuf<long long>& dT, long long* n_patched, cudaStream_t s) {
+int if_to_tenths_certified(const double* IF, int L, double alpha, double K, DevBuf<double>& dIF,
+                           DevBuf<long long>& dT, long long* n_patched, cudaStream_t s) {
     const size_t n = (size_t)L * L;
     CHR3D_CUDA(dIF.alloc(n)); CHR3D_CUDA(dT.alloc(n));
     CHR3D_CUDA(cudaMemcpyAsync(dIF.p, IF, sizeof(double) * n, cudaMemcpyHostToDevice, s));

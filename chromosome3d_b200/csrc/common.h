@@ -85,6 +85,13 @@ int dev_list_to_targets(const int32_t* d_ri, const int32_t* d_rj, const double* 
 int dev_tenths_to_list(const long long* d_tenths, int L, int min_sep, int32_t* d_ri, int32_t* d_rj,
                        double* d_rd, long long cap, long long* n_host, cudaStream_t s);
 
+// ---- api.cu ----------------------------------------------------------------------------------
+// IF (host) -> `%.1f` tenths on the device with certified decimal rounding (bit-exact with the Perl)
+int if_to_tenths_certified(const double* IF, int L, double alpha, double K, DevBuf<double>& dIF,
+                           DevBuf<long long>& dT, long long* n_patched, cudaStream_t s);
+// largest L for which the single-structure engine derives its targets through the certified table
+#define CHR3D_EXACT_TABLE_MAX_L 4096
+
 // ---- sa_ensemble.cu --------------------------------------------------------------------------
 struct TrajDesc {
     const float* T;        // dense targets [N][pitch]

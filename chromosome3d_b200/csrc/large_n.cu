@@ -1,0 +1,1040 @@
+// large_n.cu — the large-N hot path: one structure of thousands of beads per GPU (or per rank).
+//
+// Replaces the same CNS dgsa.inp run (C3D:254-289, protocol C3D:1573-1829) for chromosomes far
+// beyond the reference's 663-bead cap (C3D:93-94): synthetic 50 kb (N=4,985) and 10 kb (N=24,925)
+// resolutions of BASELINE.json.
+//
+// Data layout in HBM
+//   * targets: upper triangle of the dense target matrix in 128x128 fp32 tiles, tile-packed in
+//     row-major tile order (I <= J), each tile one contiguous 64 KB block -> one TMA bulk copy
+//     (cp.async.bulk, SASS UBLKCP) per tile.  4 B per unordered pair: the algorithmic minimum.
+//     Sentinels: -1 no restraint, -2 no restraint and no repel (|i-j| < vdw_min_sep, lower part of
+//     diagonal tiles, padding).
+//   * coordinates / forces / L-BFGS vectors: float4 arrays of N.
+// Force evaluation = ln_tile_kernel (persistent CTAs, contiguous tile ranges, double-buffered TMA,
+// symmetric tile evaluation: every unordered pair is evaluated once and its force goes to both beads)
+//   - a warp owns 8 rows of the tile, a lane 4 columns: 32 pairs per thread per tile in registers;
+//   - row forces stay in registers while consecutive tiles share the tile row, column forces are
+//     reduced across the 16 warps through shared memory once per tile;
+//   - partial forces are written per tile / per row segment and summed in a fixed order by
+//     ln_reduce_kernel: no atomics, bit-reproducible.
+// Multi-GPU: rank g owns a contiguous range of the tile list (and only that part of the targets);
+// after the local reduction forces (+ energies) are summed with one NCCL all-reduce per force
+// evaluation over NVLink and every rank integrates all N beads redundantly, so no coordinate
+// exchange is needed (N*16 B per evaluation either way).
+// MD and L-BFGS run as small vector kernels with all decisions taken on the device (no host
+// round trip per step); the host only polls a `done` flag every few dozen evaluations.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <memory>
+#include <vector>
+#include "common.h"
+#ifdef CHR3D_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace chr3d {
+
+#define LN_TB 128
+#define LN_THREADS 512
+#define LN_TILE_FLOATS (LN_TB * LN_TB)
+#define LN_MAXB (2 * CHR3D_LBFGS_MAX_M + 1)
+#define LN_KMAX 64
+
+struct LnTerms { float wnC, wnC2m, lo, rsw, wv, wv4, R2; };
+
+// one symmetric pair: accumulates the force on i (fi) and on j (fj) and, if WANT_E, the energies.
+// r^2 carries a 1e-12 floor folded into the FMA chain (coincident beads), as the oracle's max(r^2, 1e-12).
+template <bool WANT_E, bool LOW_SOFT>
+__device__ __forceinline__ void pair_sym(const LnTerms& t, float xi, float yi, float zi, float xj, float yj, float zj, float d,
+                                         float& fix, float& fiy, float& fiz, float& fjx, float& fjy, float& fjz, float& en, float& ev) {
+    const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
+    const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, 1e-12f)));
+    const float rinv = rsqrtf(r2);
+    const float delta = fmaf(r2, rinv, -d);                    // r - d
+    float h = fminf(delta, t.rsw);
+    if (LOW_SOFT) h = fmaxf(h, t.lo);
+    const bool has = d > 0.f;
+    float tr = fmaxf(t.R2 - r2, 0.f);
+    tr = d > -1.5f ? tr : 0.f;
+    const float w2h = (has ? t.wnC2m : 0.f) * h;               // -2 w C h
+    if (WANT_E) {
+        en = fmaf(-0.5f * w2h, 2.f * delta - h, en);           // w C h (2 delta - h)
+        ev = fmaf(t.wv * tr, tr, ev);
+    }
+    const float coef = fmaf(t.wv4, tr, w2h * rinv);            // 4 w_vdw t - (dE_noe/dr)/r
+    fix = fmaf(coef, dx, fix); fiy = fmaf(coef, dy, fiy); fiz = fmaf(coef, dz, fiz);
+    fjx = fmaf(-coef, dx, fjx); fjy = fmaf(-coef, dy, fjy); fjz = fmaf(-coef, dz, fjz);
+}
+
+__host__ __device__ inline long long tile_index(long long I, long long J, long long nT) { return I * nT - I * (I - 1) / 2 + (J - I); }
+__device__ inline void tile_coords(long long t, long long nT, int& I, int& J) {
+    // largest I with I*nT - I(I-1)/2 <= t
+    double a = (double)(2 * nT + 1);
+    long long i = (long long)floor((a - sqrt(a * a - 8.0 * (double)t)) * 0.5);
+    if (i < 0) i = 0;
+    while (i > 0 && tile_index(i, i, nT) > t) i--;
+    while (tile_index(i + 1, i + 1, nT) <= t) i++;
+    I = (int)i; J = (int)(i + (t - tile_index(i, i, nT)));
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    }
+}
+
+struct LnTileArgs {
+    const float* Dt;          // tile-packed targets of this rank: tiles [t0, t1)
+    long long t0, t1, nT;
+    int N;
+    const float4* x;
+    float* colpart;           // [(t - t0)][3][128]
+    float4* rowpart;          // [cta][maxseg][128]
+    int* seg_I;               // [cta][maxseg] tile row of each segment (-1 unused)
+    double* epart;            // [cta][2]
+    int maxseg;
+    LnTerms terms;
+};
+
+// dynamic smem: 2 x 64 KB tile buffers + 2 x colp[3][16][128] + 2 mbarriers
+#define LN_SMEM (2 * LN_TILE_FLOATS * 4 + 2 * 3 * 16 * LN_TB * 4 + 64)
+
+template <bool WANT_E, bool LOW_SOFT>
+__global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* dbuf = (float*)smem;
+    float* colp = (float*)(smem + 2 * LN_TILE_FLOATS * 4);
+    uint64_t* bar = (uint64_t*)(smem + 2 * LN_TILE_FLOATS * 4 + 2 * 3 * 16 * LN_TB * 4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long ntl = a.t1 - a.t0;
+    const long long c0 = a.t0 + (ntl * blockIdx.x) / gridDim.x, c1 = a.t0 + (ntl * (blockIdx.x + 1)) / gridDim.x;
+    int* segI = a.seg_I + (size_t)blockIdx.x * a.maxseg;
+    for (int s = tid; s < a.maxseg; s += LN_THREADS) segI[s] = -1;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long t, int stage) {      // one elected thread: 64 KB bulk copy of tile t
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar[stage])), "r"(LN_TILE_FLOATS * 4) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(a.Dt + (size_t)(t - a.t0) * LN_TILE_FLOATS),
+                       "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])) : "memory");
+    };
+    if (tid == 0) { if (c0 < c1) issue(c0, 0); if (c0 + 1 < c1) issue(c0 + 1, 1); }
+
+    int I = 0, J = 0;
+    if (c0 < c1) tile_coords(c0, a.nT, I, J);
+    int curI = -1, seg = -1;
+    float xi[8], yi[8], zi[8], fix[8], fiy[8], fiz[8];
+    float en = 0.f, ev = 0.f; double den = 0.0, dev = 0.0;
+    uint32_t phase[2] = {0, 0};
+    const LnTerms tm = a.terms;
+
+    auto flush_rows = [&]() {
+        // reduce the 8 row accumulators over the 32 lanes (columns) of this warp
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            float vx = fix[r], vy = fiy[r], vz = fiz[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { vx += __shfl_xor_sync(0xffffffffu, vx, o); vy += __shfl_xor_sync(0xffffffffu, vy, o); vz += __shfl_xor_sync(0xffffffffu, vz, o); }
+            if (lane == r) a.rowpart[((size_t)blockIdx.x * a.maxseg + seg) * LN_TB + warp * 8 + r] = make_float4(vx, vy, vz, 0.f);
+        }
+        den += (double)en; dev += (double)ev; en = 0.f; ev = 0.f;
+    };
+
+    for (long long t = c0; t < c1; t++) {
+        const int stage = (int)((t - c0) & 1);
+        if (I != curI) {
+            if (curI >= 0) flush_rows();
+            curI = I; seg++;
+            if (tid == 0) segI[seg] = I;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                int i = I * LN_TB + warp * 8 + r; if (i >= a.N) i = a.N - 1;
+                float4 p = a.x[i]; xi[r] = p.x; yi[r] = p.y; zi[r] = p.z; fix[r] = fiy[r] = fiz[r] = 0.f;
+            }
+        }
+        float xj[4], yj[4], zj[4], fjx[4] = {0.f, 0.f, 0.f, 0.f}, fjy[4] = {0.f, 0.f, 0.f, 0.f}, fjz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int j = J * LN_TB + lane * 4 + c; if (j >= a.N) j = a.N - 1;
+            float4 p = a.x[j]; xj[c] = p.x; yj[c] = p.y; zj[c] = p.z;
+        }
+        mbar_wait(&bar[stage], phase[stage]); phase[stage] ^= 1;
+        const float* D = dbuf + (size_t)stage * LN_TILE_FLOATS + (size_t)(warp * 8) * LN_TB + lane * 4;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const float4 d4 = *reinterpret_cast<const float4*>(D + r * LN_TB);
+            pair_sym<WANT_E, LOW_SOFT>(tm, xi[r], yi[r], zi[r], xj[0], yj[0], zj[0], d4.x, fix[r], fiy[r], fiz[r], fjx[0], fjy[0], fjz[0], en, ev);
+            pair_sym<WANT_E, LOW_SOFT>(tm, xi[r], yi[r], zi[r], xj[1], yj[1], zj[1], d4.y, fix[r], fiy[r], fiz[r], fjx[1], fjy[1], fjz[1], en, ev);
+            pair_sym<WANT_E, LOW_SOFT>(tm, xi[r], yi[r], zi[r], xj[2], yj[2], zj[2], d4.z, fix[r], fiy[r], fiz[r], fjx[2], fjy[2], fjz[2], en, ev);
+            pair_sym<WANT_E, LOW_SOFT>(tm, xi[r], yi[r], zi[r], xj[3], yj[3], zj[3], d4.w, fix[r], fiy[r], fiz[r], fjx[3], fjy[3], fjz[3], en, ev);
+        }
+        // column partials: [comp][warp][128], this lane's 4 consecutive columns
+        float* cp = colp + (size_t)stage * 3 * 16 * LN_TB;
+        *reinterpret_cast<float4*>(cp + (0 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
+        *reinterpret_cast<float4*>(cp + (1 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
+        *reinterpret_cast<float4*>(cp + (2 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
+        __syncthreads();                 // tile buffer `stage` is free, column partials are complete
+        if (tid == 0 && t + 2 < c1) issue(t + 2, stage);
+        if (tid < 3 * LN_TB) {
+            const int comp = tid / LN_TB, col = tid % LN_TB;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; w++) s += cp[(comp * 16 + w) * LN_TB + col];
+            a.colpart[((size_t)(t - a.t0) * 3 + comp) * LN_TB + col] = s;
+        }
+        J++; if (J == (int)a.nT) { I++; J = I; }
+    }
+    if (curI >= 0) flush_rows();
+    // block energy
+    __shared__ double esh[2][16];
+    for (int o = 16; o > 0; o >>= 1) { den += __shfl_xor_sync(0xffffffffu, den, o); dev += __shfl_xor_sync(0xffffffffu, dev, o); }
+    if (lane == 0) { esh[0][warp] = den; esh[1][warp] = dev; }
+    __syncthreads();
+    if (tid == 0) {
+        double s0 = 0, s1 = 0;
+        for (int w = 0; w < 16; w++) { s0 += esh[0][w]; s1 += esh[1][w]; }
+        a.epart[blockIdx.x * 2] = s0; a.epart[blockIdx.x * 2 + 1] = s1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-order reduction of the partial forces; rank 0 adds the bond term
+// ------------------------------------------------------------------------------------------------
+struct LnReduceArgs {
+    const float* colpart; const float4* rowpart; const int* seg_I; const double* epart;
+    long long t0, t1, nT; int N, ncta, maxseg, add_bond;
+    const float4* x; float4* f;         // f has N + 1 entries; entry N is unused padding
+    double* escal;                       // [3] e_noe, e_vdw, e_bond of this rank
+    float w_bond, r0;
+};
+__global__ void __launch_bounds__(LN_TB) ln_reduce_kernel(LnReduceArgs a) {
+    const int B = blockIdx.x, tid = threadIdx.x, i = B * LN_TB + tid;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    for (int I = 0; I <= B; I++) {                       // tiles (I, B): column partials
+        long long t = tile_index(I, B, a.nT);
+        if (t < a.t0 || t >= a.t1) continue;
+        const float* cp = a.colpart + (size_t)(t - a.t0) * 3 * LN_TB;
+        fx += cp[tid]; fy += cp[LN_TB + tid]; fz += cp[2 * LN_TB + tid];
+    }
+    for (int c = 0; c < a.ncta; c++)                      // row segments with tile row B
+        for (int s = 0; s < a.maxseg; s++) {
+            int sI = a.seg_I[(size_t)c * a.maxseg + s];
+            if (sI < 0) break;
+            if (sI != B) continue;
+            float4 v = a.rowpart[((size_t)c * a.maxseg + s) * LN_TB + tid];
+            fx += v.x; fy += v.y; fz += v.z;
+        }
+    float eb = 0.f;
+    if (a.add_bond && i < a.N) {
+        const float4 xi = a.x[i];
+        for (int s = -1; s <= 1; s += 2) {
+            int nb = i + s; if (nb < 0 || nb >= a.N) continue;
+            const float4 xn = a.x[nb];
+            float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
+            float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f), rinv = rsqrtf(r2), r = r2 * rinv, u = r - a.r0;
+            float g = 2.f * a.w_bond * u * rinv;
+            fx -= g * dx; fy -= g * dy; fz -= g * dz;
+            if (s == 1) eb = a.w_bond * u * u;
+        }
+    }
+    if (i < a.N) a.f[i] = make_float4(fx, fy, fz, 0.f);
+    // bond energy: block sum -> atomic-free two-level: per-block partial written to escal via one thread per block
+    __shared__ double sh[LN_TB];
+    sh[tid] = (double)eb; __syncthreads();
+    for (int o = LN_TB / 2; o > 0; o >>= 1) { if (tid < o) sh[tid] += sh[tid + o]; __syncthreads(); }
+    if (tid == 0) a.escal[3 + B] = sh[0];                // per-block bond partials follow the 3 totals
+}
+// totals of this rank: e_noe, e_vdw (tile kernel partials), e_bond (reduce kernel partials), fixed order
+__global__ void ln_energy_kernel(const double* epart, int ncta, double* escal, int nblk) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double e0 = 0, e1 = 0, e2 = 0;
+    for (int c = 0; c < ncta; c++) { e0 += epart[2 * c]; e1 += epart[2 * c + 1]; }
+    for (int b = 0; b < nblk; b++) e2 += escal[3 + b];
+    escal[0] = e0; escal[1] = e1; escal[2] = e2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident control state and the vector kernels of MD / L-BFGS
+// ------------------------------------------------------------------------------------------------
+struct LnState {
+    double E, Enoe, Evdw, Ebond, gg, gp, tstep, ke, lam;
+    double B[LN_MAXB * LN_MAXB]; double delta[LN_MAXB];
+    double e_saved;
+    int cnt, head, it, ls, done, accepted, keep, have_E, hand, cur_image, nsteps, fresh;
+    long long nevals;
+};
+
+struct LnVec {     // all float4[N]
+    float4 *x, *xb, *g, *p, *v, *f, *S, *Y;   // S, Y: m * N
+    int N, m;
+};
+
+__device__ __forceinline__ float dot3(const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+
+// x = xb + t p  (trial point); skipped when the minimiser is done
+__global__ void ln_min_trial_kernel(LnVec v, const LnState* st) {
+    if (st->done) return;
+    const float t = (float)st->tstep;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
+        float4 b = v.xb[i], p = v.p[i];
+        v.x[i] = make_float4(fmaf(t, p.x, b.x), fmaf(t, p.y, b.y), fmaf(t, p.z, b.z), 0.f);
+    }
+}
+// per-block partial inner products of (s, y, g') with the basis; layout part[block][K]
+#define LDOT_L(l, w) (6 * (l) + (w))
+#define LDOT_X(m, w) (6 * (m) + (w))
+__global__ void __launch_bounds__(256) ln_min_dots_kernel(LnVec v, const LnState* st, double* part) {
+    const int m = v.m, K = 6 * m + 6, head = st->head;
+    __shared__ float sh[8][LN_KMAX];
+    float acc[LN_KMAX];
+#pragma unroll 1
+    for (int k = 0; k < K; k++) acc[k] = 0.f;
+    if (!st->done) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
+            float4 x = v.x[i], xb = v.xb[i], f = v.f[i], g = v.g[i];
+            float4 s = make_float4(x.x - xb.x, x.y - xb.y, x.z - xb.z, 0.f);
+            float4 gn = make_float4(-f.x, -f.y, -f.z, 0.f);
+            float4 y = make_float4(gn.x - g.x, gn.y - g.y, gn.z - g.z, 0.f);
+            for (int l = 0; l < m; l++) {
+                if (l == head) continue;
+                float4 sl = v.S[(size_t)l * v.N + i], yl = v.Y[(size_t)l * v.N + i];
+                acc[LDOT_L(l, 0)] += dot3(s, sl); acc[LDOT_L(l, 1)] += dot3(s, yl); acc[LDOT_L(l, 2)] += dot3(y, sl);
+                acc[LDOT_L(l, 3)] += dot3(y, yl); acc[LDOT_L(l, 4)] += dot3(gn, sl); acc[LDOT_L(l, 5)] += dot3(gn, yl);
+            }
+            acc[LDOT_X(m, 0)] += dot3(s, s); acc[LDOT_X(m, 1)] += dot3(s, y); acc[LDOT_X(m, 2)] += dot3(s, gn);
+            acc[LDOT_X(m, 3)] += dot3(y, y); acc[LDOT_X(m, 4)] += dot3(y, gn); acc[LDOT_X(m, 5)] += dot3(gn, gn);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        float s = acc[k];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sh[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double s = 0;
+        for (int w = 0; w < 8; w++) s += (double)sh[w][threadIdx.x];
+        part[(size_t)blockIdx.x * LN_KMAX + threadIdx.x] = s;
+    }
+}
+
+// vector-free L-BFGS direction on the Gram matrix (same recursion as sa_ensemble.cu)
+__device__ double ln_direction(double* B, double* delta, int m, int cnt, int head) {
+    const int nb = 2 * m + 1, ig = 2 * m;
+    double al[CHR3D_LBFGS_MAX_M];
+    for (int l = 0; l < nb; l++) delta[l] = 0.0;
+    delta[ig] = 1.0;
+    for (int k = 0; k < cnt; k++) {
+        int idx = ((head - 1 - k) % m + m) % m;
+        double s = delta[ig] * B[ig * LN_MAXB + idx];
+        for (int kk = 0; kk < cnt; kk++) { int l = ((head - 1 - kk) % m + m) % m;
+            s += delta[l] * B[l * LN_MAXB + idx] + delta[m + l] * B[(m + l) * LN_MAXB + idx]; }
+        al[idx] = s / B[idx * LN_MAXB + m + idx];
+        delta[m + idx] -= al[idx];
+    }
+    int nw = ((head - 1) % m + m) % m;
+    double gam = B[nw * LN_MAXB + m + nw] / B[(m + nw) * LN_MAXB + m + nw];
+    for (int l = 0; l < nb; l++) delta[l] *= gam;
+    for (int k = cnt - 1; k >= 0; k--) {
+        int idx = ((head - 1 - k) % m + m) % m;
+        double s = delta[ig] * B[ig * LN_MAXB + m + idx];
+        for (int kk = 0; kk < cnt; kk++) { int l = ((head - 1 - kk) % m + m) % m;
+            s += delta[l] * B[l * LN_MAXB + m + idx] + delta[m + l] * B[(m + l) * LN_MAXB + m + idx]; }
+        double be = s / B[idx * LN_MAXB + m + idx];
+        delta[idx] += al[idx] - be;
+    }
+    double gp = delta[ig] * B[ig * LN_MAXB + ig];
+    for (int kk = 0; kk < cnt; kk++) { int l = ((head - 1 - kk) % m + m) % m;
+        gp += delta[l] * B[l * LN_MAXB + ig] + delta[m + l] * B[(m + l) * LN_MAXB + ig]; }
+    return -gp;
+}
+
+struct LnMinCfg { int m, max_ls, nstep, nparts; double c1, gtol, ftol, drop; int N; };
+
+// one thread: sums the partial scalars in a fixed order and takes the line-search / history decision
+__global__ void ln_min_control_kernel(LnState* st, const double* part, const double* escal_all, LnMinCfg c, int init) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->done) { st->accepted = 0; return; }
+    const int m = c.m, K = 6 * m + 6;
+    double G[LN_KMAX];
+    for (int k = 0; k < K; k++) { double s = 0; for (int b = 0; b < c.nparts; b++) s += part[(size_t)b * LN_KMAX + k]; G[k] = s; }
+    const double Et = escal_all[0] + escal_all[1] + escal_all[2];
+    st->nevals++;
+    const double n3 = 3.0 * c.N;
+    if (init) {             // first evaluation of a MINIMIZE op: x = xb, g' = g
+        st->E = Et; st->Enoe = escal_all[0]; st->Evdw = escal_all[1]; st->Ebond = escal_all[2];
+        st->gg = G[LDOT_X(m, 5)]; st->cnt = 0; st->head = 0; st->it = 0; st->ls = 0; st->accepted = 2;   // 2: adopt g, steepest descent
+        st->gp = -st->gg;
+        if (sqrt(st->gg / n3) < c.gtol || c.nstep <= 0) { st->done = 1; return; }
+        st->tstep = c.drop > 0 ? fmin(1.0, c.drop / st->gg) : fmin(1.0, 1.0 / sqrt(st->gg));
+        return;
+    }
+    st->accepted = 0;
+    const double ts = st->tstep;
+    if (Et < st->E && Et <= st->E + c.c1 * ts * st->gp) {
+        // accept
+        const double ss = G[LDOT_X(m, 0)], sy = G[LDOT_X(m, 1)], yy = G[LDOT_X(m, 3)];
+        const bool keep = sy > 1e-10 * sqrt(ss * yy);
+        const bool small = st->cnt > 0 && (st->E - Et) <= c.ftol * fmax(fabs(Et), 1.0);
+        st->E = Et; st->Enoe = escal_all[0]; st->Evdw = escal_all[1]; st->Ebond = escal_all[2];
+        st->gg = G[LDOT_X(m, 5)];
+        st->it++; st->ls = 0;
+        st->keep = keep ? 1 : 0; st->accepted = 1;
+        if (keep) {
+            double* B = st->B; const int ig = 2 * m, h = st->head;
+            for (int l = 0; l < m; l++) {
+                if (l == h) continue;
+                B[h * LN_MAXB + l] = B[l * LN_MAXB + h] = G[LDOT_L(l, 0)];
+                B[h * LN_MAXB + m + l] = B[(m + l) * LN_MAXB + h] = G[LDOT_L(l, 1)];
+                B[(m + h) * LN_MAXB + l] = B[l * LN_MAXB + m + h] = G[LDOT_L(l, 2)];
+                B[(m + h) * LN_MAXB + m + l] = B[(m + l) * LN_MAXB + m + h] = G[LDOT_L(l, 3)];
+                B[ig * LN_MAXB + l] = B[l * LN_MAXB + ig] = G[LDOT_L(l, 4)];
+                B[ig * LN_MAXB + m + l] = B[(m + l) * LN_MAXB + ig] = G[LDOT_L(l, 5)];
+            }
+            B[h * LN_MAXB + h] = ss; B[h * LN_MAXB + m + h] = B[(m + h) * LN_MAXB + h] = sy; B[(m + h) * LN_MAXB + m + h] = yy;
+            B[ig * LN_MAXB + h] = B[h * LN_MAXB + ig] = G[LDOT_X(m, 2)];
+            B[ig * LN_MAXB + m + h] = B[(m + h) * LN_MAXB + ig] = G[LDOT_X(m, 4)];
+            B[ig * LN_MAXB + ig] = st->gg;
+            st->head = (h + 1) % m; if (st->cnt < m) st->cnt++;
+            st->gp = ln_direction(st->B, st->delta, m, st->cnt, st->head);
+            st->tstep = 1.0;
+        } else {
+            st->cnt = 0;
+        }
+        if (small || st->it >= c.nstep || sqrt(st->gg / n3) < c.gtol) { st->done = 1; return; }
+        if (st->cnt == 0 || !(st->gp < 0.0)) {      // steepest descent restart
+            st->cnt = 0; st->gp = -st->gg;
+            st->tstep = c.drop > 0 ? fmin(1.0, c.drop / st->gg) : fmin(1.0, 1.0 / sqrt(st->gg));
+            st->accepted = 3;                         // 3: accepted, next direction = -g
+        }
+    } else {
+        st->ls++;
+        if (st->ls > c.max_ls) {
+            st->it++; st->ls = 0;
+            if (st->cnt == 0 || st->it >= c.nstep) { st->done = 1; st->accepted = 4; return; }   // 4: restore xb
+            st->cnt = 0; st->gp = -st->gg;
+            st->tstep = c.drop > 0 ? fmin(1.0, c.drop / st->gg) : fmin(1.0, 1.0 / sqrt(st->gg));
+            st->accepted = 5;                         // 5: rejected, restart from -g at xb
+        } else {
+            st->tstep = ts * 0.5;
+        }
+    }
+}
+// applies the decision to the vectors
+__global__ void ln_min_update_kernel(LnVec v, const LnState* st) {
+    const int acc = st->accepted;
+    if (acc == 0) return;
+    const int m = v.m, cnt = st->cnt, head = st->head;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
+        if (acc == 4) { v.x[i] = v.xb[i]; continue; }
+        if (acc == 5) { float4 g = v.g[i]; v.p[i] = make_float4(-g.x, -g.y, -g.z, 0.f); continue; }
+        float4 x = v.x[i], f = v.f[i];
+        float4 gn = make_float4(-f.x, -f.y, -f.z, 0.f);
+        if (acc == 1 && st->keep) {
+            const int h = ((head - 1) % m + m) % m;      // slot just filled
+            float4 xb = v.xb[i], g = v.g[i];
+            v.S[(size_t)h * v.N + i] = make_float4(x.x - xb.x, x.y - xb.y, x.z - xb.z, 0.f);
+            v.Y[(size_t)h * v.N + i] = make_float4(gn.x - g.x, gn.y - g.y, gn.z - g.z, 0.f);
+        }
+        v.xb[i] = x; v.g[i] = gn;
+        if (acc == 2 || acc == 3 || cnt == 0) { v.p[i] = make_float4(-gn.x, -gn.y, -gn.z, 0.f); continue; }
+        float ax = (float)st->delta[2 * m] * gn.x, ay = (float)st->delta[2 * m] * gn.y, az = (float)st->delta[2 * m] * gn.z;
+        for (int kk = 0; kk < cnt; kk++) {
+            int l = ((head - 1 - kk) % m + m) % m;
+            float ds = (float)st->delta[l], dy = (float)st->delta[m + l];
+            float4 sl = v.S[(size_t)l * v.N + i], yl = v.Y[(size_t)l * v.N + i];
+            ax = fmaf(ds, sl.x, fmaf(dy, yl.x, ax)); ay = fmaf(ds, sl.y, fmaf(dy, yl.y, ay)); az = fmaf(ds, sl.z, fmaf(dy, yl.z, az));
+        }
+        v.p[i] = make_float4(-ax, -ay, -az, 0.f);
+    }
+}
+
+// ---- MD --------------------------------------------------------------------------------------
+struct LnMdCfg { float dt_akma, h; double dt_ps, temp, fbeta, kboltz, mass; int flag, N, nparts, count; };
+__global__ void ln_md_pre_kernel(LnVec v, const LnState* st, LnMdCfg c) {
+    const float lam = (float)st->lam;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
+        float4 vv = v.v[i], f = v.f[i], x = v.x[i];
+        vv.x = fmaf(c.h, f.x, lam * vv.x); vv.y = fmaf(c.h, f.y, lam * vv.y); vv.z = fmaf(c.h, f.z, lam * vv.z);
+        x.x = fmaf(c.dt_akma, vv.x, x.x); x.y = fmaf(c.dt_akma, vv.y, x.y); x.z = fmaf(c.dt_akma, vv.z, x.z);
+        v.v[i] = vv; v.x[i] = x;
+    }
+}
+// v += h f (skipped for the initial evaluation), kinetic-energy partials
+__global__ void __launch_bounds__(256) ln_md_post_kernel(LnVec v, LnMdCfg c, int kick, double* part) {
+    float k2 = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
+        float4 vv = v.v[i];
+        if (kick) { float4 f = v.f[i]; vv.x = fmaf(c.h, f.x, vv.x); vv.y = fmaf(c.h, f.y, vv.y); vv.z = fmaf(c.h, f.z, vv.z); v.v[i] = vv; }
+        k2 += dot3(vv, vv);
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = (double)k2; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * LN_KMAX] = sh[0];
+}
+__global__ void ln_md_control_kernel(LnState* st, const double* part, const double* escal, LnMdCfg c) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double k2 = 0; for (int b = 0; b < c.nparts; b++) k2 += part[(size_t)b * LN_KMAX];
+    const double ke = 0.5 * c.mass * k2, ndof = 3.0 * c.N - 3.0;
+    const double T = 2.0 * ke / (c.kboltz * ndof);
+    double lam = 1.0;
+    if (T > 0.0) {
+        if (c.flag == CHR3D_COUPLE_TCOUP) lam = sqrt(fmax(0.0, 1.0 + 2.0 * c.fbeta * c.dt_ps * (c.temp / T - 1.0)));
+        else if (c.flag == CHR3D_COUPLE_VSCALE) lam = sqrt(c.temp / T);
+    }
+    st->ke = ke; st->lam = lam; st->nevals += c.count;
+    st->E = escal[0] + escal[1] + escal[2]; st->Enoe = escal[0]; st->Evdw = escal[1]; st->Ebond = escal[2];
+}
+// sums of a float4 array (COM velocity / geometric centre): partials then subtraction
+__global__ void __launch_bounds__(256) ln_sum3_kernel(const float4* a, int N, double* part) {
+    double sx = 0, sy = 0, sz = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) { float4 q = a[i]; sx += q.x; sy += q.y; sz += q.z; }
+    __shared__ double sh[3][256];
+    sh[0][threadIdx.x] = sx; sh[1][threadIdx.x] = sy; sh[2][threadIdx.x] = sz; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) for (int q = 0; q < 3; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) for (int q = 0; q < 3; q++) part[(size_t)blockIdx.x * LN_KMAX + q] = sh[q][0];
+}
+__global__ void ln_sub_mean_kernel(float4* a, int N, const double* part, int nparts) {
+    __shared__ float mean[3];
+    if (threadIdx.x == 0) for (int q = 0; q < 3; q++) { double s = 0; for (int b = 0; b < nparts; b++) s += part[(size_t)b * LN_KMAX + q]; mean[q] = (float)(s / N); }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) { float4 q = a[i]; q.x -= mean[0]; q.y -= mean[1]; q.z -= mean[2]; a[i] = q; }
+}
+__global__ void ln_init_kernel(LnVec v, const float* x0, int flag) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
+        v.x[i] = make_float4(x0[3 * i] * (float)flag, x0[3 * i + 1], x0[3 * i + 2], 0.f);
+        v.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__global__ void ln_copy_xb_kernel(LnVec v) {    // xb = x (start of a MINIMIZE op)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) v.xb[i] = v.x[i];
+}
+__global__ void ln_state_reset_kernel(LnState* st, int full) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    st->done = 0; st->accepted = 0; st->ls = 0; st->it = 0; st->cnt = 0; st->head = 0; st->lam = 1.0;
+    if (full) { st->nevals = 0; st->hand = 1; st->cur_image = 1; st->e_saved = 0; }
+}
+
+// Philox (same definition as the oracle / sa_ensemble.cu)
+__device__ inline void ln_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__global__ void ln_maxwell_kernel(LnVec v, unsigned long long seed, uint32_t stream, uint32_t model, double sd) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
+        uint32_t r[4]; ln_philox((uint32_t)i, stream, model, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const double s = 1.0 / 4294967296.0, twopi = 6.283185307179586476925286766559;
+        double u1 = (r[0] + 0.5) * s, u2 = (r[1] + 0.5) * s, u3 = (r[2] + 0.5) * s, u4 = (r[3] + 0.5) * s;
+        double ra = sqrt(-2.0 * log(u1)), rb = sqrt(-2.0 * log(u3));
+        v.v[i] = make_float4((float)(sd * ra * cos(twopi * u2)), (float)(sd * ra * sin(twopi * u2)), (float)(sd * rb * cos(twopi * u4)), 0.f);
+    }
+}
+__global__ void ln_save_kernel(LnVec v, float4* sx, float4* sv, LnState* st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->e_saved = st->E;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) { sx[i] = v.x[i]; sv[i] = v.v[i]; }
+}
+__global__ void ln_pick_kernel(LnVec v, const float4* sx, const float4* sv, LnState* st) {
+    const bool keep_cur = st->e_saved > st->E;          // C3D:1717-1721
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) if (!keep_cur) { v.x[i] = sx[i]; v.v[i] = sv[i]; }
+}
+__global__ void ln_pick_state_kernel(LnState* st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    st->hand = st->e_saved > st->E ? st->cur_image : 1;
+}
+__global__ void ln_set_image_kernel(LnState* st, int image) { if (threadIdx.x == 0 && blockIdx.x == 0) { st->cur_image = image; st->hand = image; } }
+
+// ------------------------------------------------------------------------------------------------
+// target construction (large L: no certification, blocked sum order — beyond the reference's cap)
+// ------------------------------------------------------------------------------------------------
+__global__ void ln_row_pow_sum_kernel(const double* __restrict__ IF, int L, double alpha, double* __restrict__ rows) {
+    // one warp per row, lane-strided partial sums combined in a fixed order
+    int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (row >= L) return;
+    double s = 0.0;
+    for (int j = lane; j < L; j += 32) s += pow(IF[(size_t)row * L + j], alpha);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) rows[row] = s;
+}
+__global__ void ln_sum_rows_kernel(const double* rows, int L, double* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = 0; for (int i = 0; i < L; i++) s += rows[i];
+    *out = s / ((double)L * (double)L);
+}
+__device__ __forceinline__ long long ln_round_tenths(double D) {
+    if (D >= 4.0e15) return (long long)D * 10;
+    double n = floor(D * 10.0);
+    if (fma(D, 10.0, -n) < 0.0) n -= 1.0; else if (fma(D, 10.0, -(n + 1.0)) >= 0.0) n += 1.0;
+    double r = fma(D, 10.0, -(n + 0.5));
+    long long ni = (long long)n;
+    return r > 0.0 ? ni + 1 : (r < 0.0 ? ni : ((ni & 1) ? ni + 1 : ni));
+}
+// tile-packed fp32 targets straight from IF (C3D:134-152 per cell, "%.1f" rounding, dist2rr filters)
+__global__ void __launch_bounds__(256) ln_build_tiles_kernel(const double* __restrict__ IF, int L, double alpha, double K, const double* mean_p,
+                                                              int min_sep, int vdw_min_sep, long long t0, long long t1, long long nT, float* __restrict__ Dt) {
+    const long long t = t0 + blockIdx.x;
+    if (t >= t1) return;
+    int I, J; tile_coords(t, nT, I, J);
+    const double mean = *mean_p;
+    float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
+    for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
+        const int r = k / LN_TB, c = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + c;
+        float v = -2.f;
+        if (i < L && j < L && j > i) {
+            const int sep = j - i;
+            v = sep >= vdw_min_sep ? -1.f : -2.f;
+            if (sep >= min_sep) {
+                double q = pow(IF[(size_t)i * L + j], alpha) / mean;
+                if (q != 0.0) { long long tt = ln_round_tenths(K / q); if (tt > 0) v = (float)((double)tt / 10.0); }
+            }
+        }
+        out[k] = v;
+    }
+}
+// tile-packed targets from the certified `%.1f` tenths (L within the reference's range: bit-exact table)
+__global__ void __launch_bounds__(256) ln_tiles_from_tenths_kernel(const long long* __restrict__ tenths, int L, int min_sep, int vdw_min_sep,
+                                                                    long long t0, long long t1, long long nT, float* __restrict__ Dt) {
+    const long long t = t0 + blockIdx.x;
+    if (t >= t1) return;
+    int I, J; tile_coords(t, nT, I, J);
+    float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
+    for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
+        const int r = k / LN_TB, c = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + c;
+        float v = -2.f;
+        if (i < L && j < L && j > i) {
+            const int sep = j - i;
+            v = sep >= vdw_min_sep ? -1.f : -2.f;
+            const long long tt = tenths[(size_t)i * L + j];
+            if (sep >= min_sep && tt > 0) v = (float)((double)tt / 10.0);
+        }
+        out[k] = v;
+    }
+}
+// restraint rows held by this rank (cells with a positive target)
+__global__ void __launch_bounds__(256) ln_count_rows_kernel(const float* __restrict__ Dt, long long n, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) c += Dt[k] > 0.f ? 1ull : 0ull;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+// dense [N][pitch] fp32 targets (small-N layout) -> tile-packed; used by tests to cross-check both engines
+__global__ void __launch_bounds__(256) ln_tiles_from_dense_kernel(const float* __restrict__ T, int N, int pitch, long long t0, long long t1, long long nT,
+                                                                   float* __restrict__ Dt) {
+    const long long t = t0 + blockIdx.x;
+    if (t >= t1) return;
+    int I, J; tile_coords(t, nT, I, J);
+    float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
+    for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
+        const int r = k / LN_TB, c = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + c;
+        out[k] = (i < N && j < N && j > i) ? T[(size_t)i * pitch + j] : -2.f;
+    }
+}
+
+// synthetic IF matrix of SURVEY §8(d) generated on the device (same definition as datasets.synthetic_if)
+__global__ void ln_synth_if_kernel(double* __restrict__ IF, int N, unsigned long long seed, double A, double slope, double sigma, double zero_frac) {
+    const long long n = (long long)N * N;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        int a = (int)(k / N), b = (int)(k % N);
+        int i = a < b ? a : b, j = a < b ? b : a;
+        unsigned long long lin = (unsigned long long)i * (unsigned long long)N + (unsigned long long)j;
+        uint32_t r[4]; ln_philox((uint32_t)lin, (uint32_t)(lin >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const double s = 1.0 / 4294967296.0, twopi = 6.283185307179586476925286766559;
+        double u1 = (r[0] + 0.5) * s, u2 = (r[1] + 0.5) * s, u3 = (r[2] + 0.5) * s;
+        double z = sqrt(-2.0 * log(u1)) * cos(twopi * u2);
+        double v;
+        if (i == j) v = 4.0 * A * exp(0.3 * z);
+        else { v = A * pow((double)(j - i), slope) * exp(sigma * z); if (u3 < zero_frac) v = 0.0; }
+        IF[k] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+struct LnEngine {
+    int N = 0, nT = 0, rank = 0, world = 1, m = 5, ncta = 0, maxseg = 0, nblk = 0, nparts = 0;
+    long long n_tiles = 0, t0 = 0, t1 = 0, pairs_total = 0;
+    DevBuf<float> Dt, colpart, x0; DevBuf<float4> rowpart, vx, vxb, vg, vp, vv, vf, vS, vY, sx, sv;
+    DevBuf<int> seg_I; DevBuf<double> epart, escal, part; DevBuf<LnState> st;
+    chr3d_sa_params prm; unsigned long long seed = 0;
+    cudaStream_t stream = nullptr;
+    long long n_launches = 0;
+#ifdef CHR3D_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+    LnVec vec() { LnVec v; v.x = vx.p; v.xb = vxb.p; v.g = vg.p; v.p = vp.p; v.v = vv.p; v.f = vf.p; v.S = vS.p; v.Y = vY.p; v.N = N; v.m = m; return v; }
+};
+
+static int ln_alloc(LnEngine& e) {
+    const int N = e.N;
+    e.nT = (N + LN_TB - 1) / LN_TB; e.nblk = e.nT;
+    e.n_tiles = (long long)e.nT * (e.nT + 1) / 2;
+    e.t0 = e.n_tiles * e.rank / e.world; e.t1 = e.n_tiles * (e.rank + 1) / e.world;
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntl = e.t1 - e.t0;
+    e.ncta = (int)std::max<long long>(1, std::min<long long>(sms, ntl));
+    // a CTA's contiguous tile range of length len touches at most len/(shortest row) + 2 tile rows
+    long long per = (ntl + e.ncta - 1) / e.ncta;
+    e.maxseg = (int)std::min<long long>(e.nT, per + 2);
+    e.nparts = std::min(64, std::max(1, (N + 255) / 256));
+    CHR3D_CUDA(e.Dt.alloc((size_t)std::max<long long>(ntl, 1) * LN_TILE_FLOATS));
+    CHR3D_CUDA(e.colpart.alloc((size_t)std::max<long long>(ntl, 1) * 3 * LN_TB));
+    CHR3D_CUDA(e.rowpart.alloc((size_t)e.ncta * e.maxseg * LN_TB));
+    CHR3D_CUDA(e.seg_I.alloc((size_t)e.ncta * e.maxseg));
+    CHR3D_CUDA(e.epart.alloc((size_t)e.ncta * 2));
+    CHR3D_CUDA(e.escal.alloc((size_t)3 + e.nblk));
+    CHR3D_CUDA(e.part.alloc((size_t)e.nparts * LN_KMAX));
+    CHR3D_CUDA(e.st.alloc(1));
+    CHR3D_CUDA(cudaMemset(e.st.p, 0, sizeof(LnState)));
+    const size_t n4 = (size_t)N + 1;
+    CHR3D_CUDA(e.vx.alloc(n4)); CHR3D_CUDA(e.vxb.alloc(n4)); CHR3D_CUDA(e.vg.alloc(n4)); CHR3D_CUDA(e.vp.alloc(n4));
+    CHR3D_CUDA(e.vv.alloc(n4)); CHR3D_CUDA(e.vf.alloc(n4)); CHR3D_CUDA(e.sx.alloc(n4)); CHR3D_CUDA(e.sv.alloc(n4));
+    CHR3D_CUDA(e.vS.alloc((size_t)e.m * N)); CHR3D_CUDA(e.vY.alloc((size_t)e.m * N));
+    CHR3D_CUDA(e.x0.alloc((size_t)N * 3));
+    CHR3D_CUDA(cudaMemset(e.vf.p, 0, sizeof(float4) * n4));
+    CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    return 0;
+}
+
+static void ln_terms(const chr3d_sa_params& p, const chr3d_stage& s, LnTerms& t) {
+    t.wnC = (float)(s.w_noe * p.noe_sqconst); t.wnC2m = -2.f * t.wnC; t.rsw = (float)p.noe_rswitch;
+    t.lo = p.noe_low_soft ? -(float)p.noe_rswitch : -INFINITY;
+    t.wv = (float)s.w_vdw; t.wv4 = 4.f * (float)s.w_vdw;
+    double r = s.repel * p.vdw_rmin; t.R2 = (float)(r * r);
+}
+
+static void ln_launch_tiles(LnEngine& e, const LnTileArgs& a, bool want_e) {
+    const bool soft = e.prm.noe_low_soft != 0;
+    if (want_e) { if (soft) ln_tile_kernel<true, true><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); else ln_tile_kernel<true, false><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); }
+    else { if (soft) ln_tile_kernel<false, true><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); else ln_tile_kernel<false, false><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); }
+}
+
+// one energy + force evaluation at e.vx: tile kernel, reduction, (all-reduce), totals in escal[0..2]
+static int ln_eval(LnEngine& e, const chr3d_stage& s, bool want_e = true) {
+    LnTileArgs a; a.Dt = e.Dt.p; a.t0 = e.t0; a.t1 = e.t1; a.nT = e.nT; a.N = e.N; a.x = e.vx.p; a.colpart = e.colpart.p;
+    a.rowpart = e.rowpart.p; a.seg_I = e.seg_I.p; a.epart = e.epart.p; a.maxseg = e.maxseg; ln_terms(e.prm, s, a.terms);
+    ln_launch_tiles(e, a, want_e);
+    LnReduceArgs r; r.colpart = e.colpart.p; r.rowpart = e.rowpart.p; r.seg_I = e.seg_I.p; r.epart = e.epart.p; r.t0 = e.t0; r.t1 = e.t1; r.nT = e.nT;
+    r.N = e.N; r.ncta = e.ncta; r.maxseg = e.maxseg; r.add_bond = e.rank == 0 ? 1 : 0; r.x = e.vx.p; r.f = e.vf.p; r.escal = e.escal.p;
+    r.w_bond = (float)s.w_bond; r.r0 = (float)e.prm.bond_r0;
+    ln_reduce_kernel<<<e.nblk, LN_TB, 0, e.stream>>>(r);
+    ln_energy_kernel<<<1, 32, 0, e.stream>>>(e.epart.p, e.ncta, e.escal.p, e.nblk);
+    e.n_launches += 3;
+#ifdef CHR3D_WITH_NCCL
+    if (e.world > 1 && e.comm) {
+        if (ncclAllReduce(e.vf.p, e.vf.p, (size_t)e.N * 4, ncclFloat, ncclSum, e.comm, e.stream) != ncclSuccess ||
+            ncclAllReduce(e.escal.p, e.escal.p, 3, ncclDouble, ncclSum, e.comm, e.stream) != ncclSuccess) {
+            set_error("ncclAllReduce failed"); return CHR3D_ERR_CUDA;
+        }
+    }
+#endif
+    CHR3D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int ln_poll_done(LnEngine& e, int* done) {
+    LnState h;
+    CHR3D_CUDA(cudaMemcpyAsync(&h, e.st.p, sizeof(LnState), cudaMemcpyDeviceToHost, e.stream));
+    CHR3D_CUDA(cudaStreamSynchronize(e.stream));
+    *done = h.done;
+    return 0;
+}
+
+static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
+    const int vb = std::min(296, (e.N + 255) / 256);
+    LnVec v = e.vec();
+    LnMinCfg c; c.m = e.m; c.max_ls = e.prm.lbfgs_max_ls; c.nstep = s.nstep; c.nparts = e.nparts; c.c1 = e.prm.lbfgs_c1; c.gtol = e.prm.lbfgs_gtol;
+    c.ftol = e.prm.lbfgs_ftol; c.drop = s.drop; c.N = e.N;
+    ln_state_reset_kernel<<<1, 32, 0, e.stream>>>(e.st.p, 0);
+    ln_copy_xb_kernel<<<vb, 256, 0, e.stream>>>(v);
+    // g := 0 so that the initial "y" is -f and g.g comes out of the same dots kernel
+    CHR3D_CUDA(cudaMemsetAsync(e.vg.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
+    if (int rc = ln_eval(e, s)) return rc;
+    ln_min_dots_kernel<<<e.nparts, 256, 0, e.stream>>>(v, e.st.p, e.part.p);
+    ln_min_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c, 1);
+    ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
+    e.n_launches += 6;
+    const long long max_trials = (long long)s.nstep * (e.prm.lbfgs_max_ls + 2) + 2;
+    const int poll_every = 32;
+    for (long long trial = 0; trial < max_trials;) {
+        for (int k = 0; k < poll_every; k++, trial++) {
+            ln_min_trial_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
+            if (int rc = ln_eval(e, s)) return rc;
+            ln_min_dots_kernel<<<e.nparts, 256, 0, e.stream>>>(v, e.st.p, e.part.p);
+            ln_min_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c, 0);
+            ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
+            e.n_launches += 4;
+        }
+        int done = 0;
+        if (int rc = ln_poll_done(e, &done)) return rc;
+        if (done) break;
+    }
+    // evaluations issued after `done` are no-ops on the state (control returns early) but x may hold a rejected trial:
+    // the update kernel restored x = xb when the search ended on a failure (accepted == 4); on success x == xb already.
+    return 0;
+}
+
+static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
+    const int vb = std::min(296, (e.N + 255) / 256);
+    LnVec v = e.vec();
+    LnMdCfg c; c.dt_akma = (float)(s.dt / CHR3D_TIMFAC); c.h = (float)(0.5 * (s.dt / CHR3D_TIMFAC) / e.prm.mass); c.dt_ps = s.dt; c.temp = s.temp;
+    c.fbeta = e.prm.fbeta; c.kboltz = CHR3D_KBOLTZ; c.mass = e.prm.mass; c.flag = s.flag; c.N = e.N; c.nparts = e.nparts; c.count = 1;
+    ln_sum3_kernel<<<e.nparts, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p);             // cmremove
+    ln_sub_mean_kernel<<<vb, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p, e.nparts);
+    if (int rc = ln_eval(e, s)) return rc;
+    ln_md_post_kernel<<<e.nparts, 256, 0, e.stream>>>(v, c, 0, e.part.p);
+    ln_md_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c);
+    e.n_launches += 4;
+    for (int step = 0; step < s.nstep; step++) {
+        ln_md_pre_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p, c);
+        if (int rc = ln_eval(e, s, step == s.nstep - 1)) return rc;     // energies only matter after the last step
+        ln_md_post_kernel<<<e.nparts, 256, 0, e.stream>>>(v, c, 1, e.part.p);
+        ln_md_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c);
+        e.n_launches += 3;
+    }
+    CHR3D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int ln_energy_only(LnEngine& e, const chr3d_stage& s, bool count) {
+    if (int rc = ln_eval(e, s)) return rc;
+    LnMdCfg c; memset(&c, 0, sizeof c); c.mass = e.prm.mass; c.kboltz = CHR3D_KBOLTZ; c.N = e.N; c.nparts = e.nparts; c.flag = 0; c.temp = 0; c.count = count ? 1 : 0;
+    LnVec v = e.vec();
+    ln_md_post_kernel<<<e.nparts, 256, 0, e.stream>>>(v, c, 0, e.part.p);
+    ln_md_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c);     // fills E terms (and counts the evaluation)
+    e.n_launches += 2;
+    return 0;
+}
+
+static int ln_run_program(LnEngine& e, const chr3d_stage* prog, int nst) {
+    const int vb = std::min(296, (e.N + 255) / 256);
+    LnVec v = e.vec();
+    ln_state_reset_kernel<<<1, 32, 0, e.stream>>>(e.st.p, 1);
+    for (int k = 0; k < nst; k++) {
+        const chr3d_stage& s = prog[k];
+        switch (s.op) {
+        case CHR3D_OP_INIT:
+            ln_init_kernel<<<vb, 256, 0, e.stream>>>(v, e.x0.p, s.flag);
+            ln_set_image_kernel<<<1, 32, 0, e.stream>>>(e.st.p, s.flag);
+            break;
+        case CHR3D_OP_MINIMIZE: if (int rc = ln_minimize(e, s)) return rc; break;
+        case CHR3D_OP_MAXWELL:
+            ln_maxwell_kernel<<<vb, 256, 0, e.stream>>>(v, e.seed, 0x100000u + (uint32_t)k, 0u, sqrt(CHR3D_KBOLTZ * s.temp / e.prm.mass));
+            break;
+        case CHR3D_OP_DYNAMICS: if (int rc = ln_dynamics(e, s)) return rc; break;
+        case CHR3D_OP_SAVE:
+            if (int rc = ln_energy_only(e, s, true)) return rc;
+            ln_save_kernel<<<vb, 256, 0, e.stream>>>(v, e.sx.p, e.sv.p, e.st.p);
+            break;
+        case CHR3D_OP_PICK:
+            if (int rc = ln_energy_only(e, s, true)) return rc;
+            ln_pick_kernel<<<vb, 256, 0, e.stream>>>(v, e.sx.p, e.sv.p, e.st.p);
+            ln_pick_state_kernel<<<1, 32, 0, e.stream>>>(e.st.p);
+            break;
+        case CHR3D_OP_CENTER:
+            ln_sum3_kernel<<<e.nparts, 256, 0, e.stream>>>(e.vx.p, e.N, e.part.p);
+            ln_sub_mean_kernel<<<vb, 256, 0, e.stream>>>(e.vx.p, e.N, e.part.p, e.nparts);
+            break;
+        case CHR3D_OP_ENERGY: if (int rc = ln_energy_only(e, s, false)) return rc; break;
+        default: break;
+        }
+        CHR3D_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace chr3d
+
+using namespace chr3d;
+
+struct chr3d_single { LnEngine e; cudaEvent_t ev0 = nullptr, ev1 = nullptr; std::vector<chr3d_stage> prog; };
+
+// job: IF (host, N*N) or synthetic (IF == NULL, synth_seed != 0); x0 optional.
+CHR3D_API int chr3d_single_create(const double* IF, int32_t N, double alpha, double K, int32_t min_sep, uint64_t synth_seed,
+                                  const double* x0, uint64_t seed, const chr3d_sa_params* p, const chr3d_stage* program, int32_t nstages,
+                                  int32_t rank, int32_t world, const void* nccl_id, chr3d_single** out) {
+    if (N < 2 || !p || !program || nstages < 1 || !out || rank < 0 || world < 1 || rank >= world) { set_error("chr3d_single_create: bad arguments"); return CHR3D_ERR_ARG; }
+    if (!IF && !synth_seed) { set_error("chr3d_single_create: need an IF matrix or a synthetic seed"); return CHR3D_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    std::unique_ptr<chr3d_single> h(new chr3d_single());
+    LnEngine& e = h->e;
+    e.N = N; e.rank = rank; e.world = world; e.prm = *p; e.seed = seed ? seed : p->seed;
+    e.m = std::max(1, std::min((int)p->lbfgs_m, CHR3D_LBFGS_MAX_M));
+    h->prog.assign(program, program + nstages);
+    if (world > 1) {
+#ifdef CHR3D_WITH_NCCL
+        // nccl_id == NULL: shard without a communicator — forces/energies stay this rank's partial sums and the caller
+        // reduces them (used to check the partition on one GPU; chr3d_single_run refuses to integrate in that mode)
+        if (nccl_id) {
+            ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
+            if (ncclCommInitRank(&e.comm, world, id, rank) != ncclSuccess) { set_error("ncclCommInitRank failed"); return CHR3D_ERR_CUDA; }
+        }
+#else
+        set_error("libchr3d was built without NCCL"); return CHR3D_ERR_ARG;
+#endif
+    }
+    if (int rc = ln_alloc(e)) return rc;
+    {   // targets
+        DevBuf<double> dIF, rows, mean; DevBuf<long long> dT;
+        const size_t n2 = (size_t)N * N;
+        const long long ntl = e.t1 - e.t0;
+        if (IF && N <= CHR3D_EXACT_TABLE_MAX_L) {
+            // within the reference's reach: the certified, bit-exact table of restraints.cu (sequential mean, libm-checked rounding)
+            if (int rc = if_to_tenths_certified(IF, N, alpha, K, dIF, dT, nullptr, 0)) return rc;
+            if (ntl > 0) ln_tiles_from_tenths_kernel<<<(unsigned)ntl, 256>>>(dT.p, N, min_sep, p->vdw_min_sep, e.t0, e.t1, e.nT, e.Dt.p);
+        } else {
+            CHR3D_CUDA(dIF.alloc(n2)); CHR3D_CUDA(rows.alloc(N)); CHR3D_CUDA(mean.alloc(1));
+            if (IF) CHR3D_CUDA(cudaMemcpy(dIF.p, IF, sizeof(double) * n2, cudaMemcpyHostToDevice));
+            else { ln_synth_if_kernel<<<148 * 8, 256>>>(dIF.p, N, synth_seed, 6.8e4, -0.95, 0.6, 5e-4); CHR3D_CUDA(cudaGetLastError()); }
+            ln_row_pow_sum_kernel<<<(N + 7) / 8, 256>>>(dIF.p, N, alpha, rows.p);
+            ln_sum_rows_kernel<<<1, 32>>>(rows.p, N, mean.p);
+            if (ntl > 0) ln_build_tiles_kernel<<<(unsigned)ntl, 256>>>(dIF.p, N, alpha, K, mean.p, min_sep, p->vdw_min_sep, e.t0, e.t1, e.nT, e.Dt.p);
+        }
+        CHR3D_CUDA(cudaGetLastError());
+        DevBuf<unsigned long long> cnt; CHR3D_CUDA(cnt.alloc(1)); CHR3D_CUDA(cudaMemset(cnt.p, 0, sizeof(unsigned long long)));
+        if (ntl > 0) ln_count_rows_kernel<<<148 * 4, 256>>>(e.Dt.p, ntl * (long long)LN_TILE_FLOATS, cnt.p);
+        unsigned long long hc = 0;
+        CHR3D_CUDA(cudaMemcpy(&hc, cnt.p, sizeof hc, cudaMemcpyDeviceToHost));
+        e.pairs_total = (long long)hc;          // restraint rows whose tile this rank owns
+    }
+    if (x0) {
+        std::vector<float> hx((size_t)N * 3);
+        for (size_t k = 0; k < hx.size(); k++) hx[k] = (float)x0[k];
+        CHR3D_CUDA(cudaMemcpy(e.x0.p, hx.data(), sizeof(float) * hx.size(), cudaMemcpyHostToDevice));
+    } else {
+        if (int rc = dev_random_coil(e.x0.p, N, 1, 0, p->bond_r0, e.seed, 0)) return rc;
+    }
+    CHR3D_CUDA(cudaEventCreate(&h->ev0)); CHR3D_CUDA(cudaEventCreate(&h->ev1));
+    CHR3D_CUDA(cudaDeviceSynchronize());
+    *out = h.release();
+    return 0;
+}
+
+CHR3D_API int chr3d_single_run(chr3d_single* h, void* stream) {
+    if (!h) { set_error("chr3d_single_run: null handle"); return CHR3D_ERR_ARG; }
+#ifdef CHR3D_WITH_NCCL
+    if (h->e.world > 1 && !h->e.comm) {
+        bool integrates = false;
+        for (const chr3d_stage& s : h->prog) if (s.op == CHR3D_OP_MINIMIZE || s.op == CHR3D_OP_DYNAMICS) integrates = true;
+        if (integrates) { set_error("chr3d_single_run: a sharded structure without a communicator can only evaluate (INIT/ENERGY)"); return CHR3D_ERR_ARG; }
+    }
+#endif
+    h->e.stream = (cudaStream_t)stream; h->e.n_launches = 0;
+    CHR3D_CUDA(cudaEventRecord(h->ev0, h->e.stream));
+    if (int rc = ln_run_program(h->e, h->prog.data(), (int)h->prog.size())) return rc;
+    CHR3D_CUDA(cudaEventRecord(h->ev1, h->e.stream));
+    return 0;
+}
+
+// `reps` force evaluations at the start coordinates, timed on the device: the roofline measurement of ln_tile_kernel.
+CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t reps, int32_t want_energy, double* tile_ms, double* eval_ms) {
+    if (!h || reps < 1) { set_error("chr3d_single_eval_bench: bad arguments"); return CHR3D_ERR_ARG; }
+    LnEngine& e = h->e; e.stream = (cudaStream_t)stream;
+    LnVec v = e.vec();
+    ln_init_kernel<<<std::min(296, (e.N + 255) / 256), 256, 0, e.stream>>>(v, e.x0.p, 1);
+    chr3d_stage s = h->prog.back();
+    cudaEvent_t a, b; CHR3D_CUDA(cudaEventCreate(&a)); CHR3D_CUDA(cudaEventCreate(&b));
+    LnTileArgs ta; ta.Dt = e.Dt.p; ta.t0 = e.t0; ta.t1 = e.t1; ta.nT = e.nT; ta.N = e.N; ta.x = e.vx.p; ta.colpart = e.colpart.p;
+    ta.rowpart = e.rowpart.p; ta.seg_I = e.seg_I.p; ta.epart = e.epart.p; ta.maxseg = e.maxseg; ln_terms(e.prm, s, ta.terms);
+    for (int w = 0; w < 3; w++) ln_launch_tiles(e, ta, want_energy != 0);
+    CHR3D_CUDA(cudaEventRecord(a, e.stream));
+    for (int r = 0; r < reps; r++) ln_launch_tiles(e, ta, want_energy != 0);
+    CHR3D_CUDA(cudaEventRecord(b, e.stream));
+    CHR3D_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f; CHR3D_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (tile_ms) *tile_ms = ms / reps;
+    for (int w = 0; w < 2; w++) if (int rc = ln_eval(e, s, want_energy != 0)) return rc;
+    CHR3D_CUDA(cudaEventRecord(a, e.stream));
+    for (int r = 0; r < reps; r++) if (int rc = ln_eval(e, s, want_energy != 0)) return rc;
+    CHR3D_CUDA(cudaEventRecord(b, e.stream));
+    CHR3D_CUDA(cudaEventSynchronize(b));
+    CHR3D_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (eval_ms) *eval_ms = ms / reps;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return 0;
+}
+
+CHR3D_API int chr3d_single_fetch(chr3d_single* h, double* xyz, double* energies4, double* forces, int64_t* force_evals, int32_t* hand,
+                                 double* device_ms, int64_t* n_launches, int64_t* restraint_pairs) {
+    if (!h) { set_error("chr3d_single_fetch: null handle"); return CHR3D_ERR_ARG; }
+    LnEngine& e = h->e;
+    CHR3D_CUDA(cudaStreamSynchronize(e.stream));
+    LnState st;
+    CHR3D_CUDA(cudaMemcpy(&st, e.st.p, sizeof st, cudaMemcpyDeviceToHost));
+    std::vector<float4> buf((size_t)e.N);
+    if (xyz) {
+        CHR3D_CUDA(cudaMemcpy(buf.data(), e.vx.p, sizeof(float4) * e.N, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < e.N; i++) { xyz[3 * i] = buf[i].x; xyz[3 * i + 1] = buf[i].y; xyz[3 * i + 2] = buf[i].z; }
+    }
+    if (forces) {
+        CHR3D_CUDA(cudaMemcpy(buf.data(), e.vf.p, sizeof(float4) * e.N, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < e.N; i++) { forces[3 * i] = buf[i].x; forces[3 * i + 1] = buf[i].y; forces[3 * i + 2] = buf[i].z; }
+    }
+    if (energies4) { energies4[CHR3D_E_OVERALL] = st.E; energies4[CHR3D_E_BON] = st.Ebond; energies4[CHR3D_E_VDW] = st.Evdw; energies4[CHR3D_E_NOE] = st.Enoe; }
+    if (force_evals) *force_evals = st.nevals;
+    if (hand) *hand = st.hand;
+    if (device_ms) { float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) { ms = 0.f; cudaGetLastError(); } *device_ms = ms; }
+    if (n_launches) *n_launches = e.n_launches;
+    if (restraint_pairs) *restraint_pairs = e.pairs_total;
+    return 0;
+}
+
+CHR3D_API int chr3d_single_info(const chr3d_single* h, int64_t* n_tiles, int64_t* tiles_this_rank, int32_t* ctas, int64_t* target_bytes) {
+    if (!h) { set_error("chr3d_single_info: null handle"); return CHR3D_ERR_ARG; }
+    if (n_tiles) *n_tiles = h->e.n_tiles;
+    if (tiles_this_rank) *tiles_this_rank = h->e.t1 - h->e.t0;
+    if (ctas) *ctas = h->e.ncta;
+    if (target_bytes) *target_bytes = (h->e.t1 - h->e.t0) * (long long)LN_TILE_FLOATS * 4;
+    return 0;
+}
+
+CHR3D_API int chr3d_single_destroy(chr3d_single* h) {
+    if (!h) return 0;
+#ifdef CHR3D_WITH_NCCL
+    if (h->e.comm) ncclCommDestroy(h->e.comm);
+#endif
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return 0;
+}
+
+CHR3D_API int chr3d_nccl_unique_id(void* out128) {
+#ifdef CHR3D_WITH_NCCL
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) { set_error("ncclGetUniqueId failed"); return CHR3D_ERR_CUDA; }
+    memcpy(out128, &id, sizeof id);
+    return 0;
+#else
+    (void)out128; set_error("libchr3d was built without NCCL"); return CHR3D_ERR_ARG;
+#endif
+}
+
+// synthetic IF matrix on the host side of the ABI (small sizes, for tests): generated on the device, copied back
+CHR3D_API int chr3d_synthetic_if(int32_t N, uint64_t seed, double* out) {
+    if (N < 1 || !out) { set_error("chr3d_synthetic_if: bad arguments"); return CHR3D_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    DevBuf<double> d; CHR3D_CUDA(d.alloc((size_t)N * N));
+    ln_synth_if_kernel<<<148 * 8, 256>>>(d.p, N, seed, 6.8e4, -0.95, 0.6, 5e-4);
+    CHR3D_CUDA(cudaGetLastError());
+    CHR3D_CUDA(cudaMemcpy(out, d.p, sizeof(double) * (size_t)N * N, cudaMemcpyDeviceToHost));
+    return 0;
+}

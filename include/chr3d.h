@@ -195,6 +195,37 @@ int chr3d_ensemble_info(const chr3d_ensemble* e, int32_t* cluster_size, int32_t*
                         int32_t* n_launches, int64_t* restraint_rows_total);
 int chr3d_ensemble_destroy(chr3d_ensemble* e);
 
+/* ------------- (3b) one large structure, optionally sharded over the GPUs of a node -------- */
+/* The same dgsa.inp run (C3D:254-289, protocol C3D:1573-1829) for one structure of thousands of
+ * beads, far beyond the reference's 663-bead cap (C3D:93-94).  The upper triangle of the target
+ * matrix lives in HBM as 128x128 fp32 tiles; rank `rank` of `world` owns a contiguous range of
+ * the tile list (balanced by pair count) and only derives/stores that part.  One process per
+ * GPU; with world > 1 every force evaluation ends in one NCCL all-reduce of the N float4 forces
+ * over NVLink (chr3d_nccl_unique_id() on rank 0, broadcast by the caller, e.g. torch.distributed).
+ *   IF        : host N*N row-major, or NULL with synth_seed != 0 (synthetic IF generated on the
+ *               device; parsing 25k^2 decimals is not part of the hot path)
+ *   x0        : optional N*3 start coordinates, NULL = seeded random coil                     */
+typedef struct chr3d_single chr3d_single;
+int chr3d_single_create(const double* IF, int32_t N, double alpha, double K, int32_t min_sep,
+                        uint64_t synth_seed, const double* x0, uint64_t seed,
+                        const chr3d_sa_params* p, const chr3d_stage* program, int32_t nstages,
+                        int32_t rank, int32_t world, const void* nccl_id /* 128 bytes or NULL */,
+                        chr3d_single** out);
+int chr3d_single_run(chr3d_single* h, void* stream);
+/* Measurement aid: `reps` force evaluations at the start coordinates, device-timed.
+ * tile_ms = the pair-tile kernel alone, eval_ms = the whole evaluation (+reduction, +all-reduce). */
+int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t reps, int32_t want_energy,
+                            double* tile_ms, double* eval_ms);
+int chr3d_single_fetch(chr3d_single* h, double* xyz, double* energies4, double* forces,
+                       int64_t* force_evals, int32_t* hand, double* device_ms,
+                       int64_t* n_launches, int64_t* restraint_pairs);
+int chr3d_single_info(const chr3d_single* h, int64_t* n_tiles, int64_t* tiles_this_rank,
+                      int32_t* ctas, int64_t* target_bytes);
+int chr3d_single_destroy(chr3d_single* h);
+int chr3d_nccl_unique_id(void* out128);
+/* Synthetic IF matrix of SURVEY 8(d) (N*N doubles, generated on the device, copied back).     */
+int chr3d_synthetic_if(int32_t N, uint64_t seed, double* out);
+
 /* --------------- (4) ranking, violation statistics, PDB  C3D:447-600, 769-880 ------------ */
 /* xyz are rounded to the 3-decimal PDB text first (C3D:727 works on the text fields).     */
 int chr3d_assess(const double* xyz, int32_t n_models, int32_t N,
