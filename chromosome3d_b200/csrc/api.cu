@@ -515,6 +515,24 @@ CHR3D_API int chr3d_assess(const double* xyz, int32_t n_models, int32_t N, const
     CHR3D_CUDA(cudaMemcpy(sum_dev, jd.dev.p, sizeof(double) * n_models, cudaMemcpyDeviceToHost));
     return 0;
 }
+CHR3D_API int chr3d_assess_rows(const double* xyz, int32_t N, const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr,
+                                int32_t* flag, double* dev, double* dist) {
+    if (!xyz || N < 1 || nr < 0 || (nr > 0 && (!ri || !rj || !rd || !flag || !dev || !dist))) { set_error("chr3d_assess_rows: bad arguments"); return CHR3D_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    JobDev jd;
+    if (int rc = upload_list(jd, ri, rj, rd, nr, 0)) return rc;
+    DevBuf<int32_t> df; DevBuf<double> dd, ds;
+    const size_t n1 = (size_t)std::max<long long>(nr, 1);
+    CHR3D_CUDA(jd.xyz_d.alloc((size_t)N * 3)); CHR3D_CUDA(df.alloc(n1)); CHR3D_CUDA(dd.alloc(n1)); CHR3D_CUDA(ds.alloc(n1));
+    CHR3D_CUDA(cudaMemcpy(jd.xyz_d.p, xyz, sizeof(double) * (size_t)N * 3, cudaMemcpyHostToDevice));
+    if (int rc = dev_assess_rows(jd.xyz_d.p, N, jd.ri.p, jd.rj.p, jd.rd.p, nr, df.p, dd.p, ds.p, 0)) return rc;
+    if (nr > 0) {
+        CHR3D_CUDA(cudaMemcpy(flag, df.p, sizeof(int32_t) * (size_t)nr, cudaMemcpyDeviceToHost));
+        CHR3D_CUDA(cudaMemcpy(dev, dd.p, sizeof(double) * (size_t)nr, cudaMemcpyDeviceToHost));
+        CHR3D_CUDA(cudaMemcpy(dist, ds.p, sizeof(double) * (size_t)nr, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
 CHR3D_API int chr3d_rank_models(const double* energies, int32_t n_models, int32_t* order) {
     if (!energies || !order || n_models < 1) { set_error("chr3d_rank_models: bad arguments"); return CHR3D_ERR_ARG; }
     std::vector<int32_t> idx(n_models);

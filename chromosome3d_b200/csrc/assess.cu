@@ -64,6 +64,24 @@ __global__ void assess_terms_kernel(const long long* __restrict__ mxyz, int n_mo
     if (dist < (D0 - D1 - 0.2)) dev += (D0 - D1) - dist; // C3D:595-597
     if (dense) dense[((size_t)m * N + i) * N + j] = dev; else listterms[(size_t)m * nr + k] = dev;
 }
+// per-restraint rows of contact_violation.txt for one model (count_satisfied_tbl_rows, C3D:458-475):
+// violation flag, deviation and the "%.3f" model distance
+__global__ void assess_rows_kernel(const long long* __restrict__ mxyz, const int32_t* __restrict__ ri, const int32_t* __restrict__ rj,
+                                   const double* __restrict__ rd, long long nr, int32_t* __restrict__ flag, double* __restrict__ devv,
+                                   double* __restrict__ distv) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nr) return;
+    const long long* a = mxyz + (size_t)ri[k] * 3; const long long* b = mxyz + (size_t)rj[k] * 3;
+    long long dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    unsigned long long d2 = (unsigned long long)(dx * dx) + (unsigned long long)(dy * dy) + (unsigned long long)(dz * dz);
+    double dist = (double)round_sqrt(d2) / 1000.0;
+    if (!(dist < 1000.0)) dist = 1000.0;                     // C3D:538, 546
+    const double D0 = rd[k], D1 = 0.0, D2 = 0.0, RELAX = 0.5;
+    int vf = 1; double dev = dist - (D0 + D2);               // C3D:459, 463
+    if (dist < (D0 + D2 + RELAX)) { vf = 0; dev = 0.0; }     // C3D:464-468
+    if (dist < (D0 - D1 - RELAX)) { vf = 1; dev = -(D0 - D1 - dist); }   // C3D:469-473
+    flag[k] = vf; devv[k] = dev; distv[k] = dist;
+}
 // sequential fp64 sum per model in key order (one thread per model)
 __global__ void seq_rows_sum_kernel(const double* __restrict__ terms, long long per_model, int n_models, double* __restrict__ out) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,6 +129,17 @@ int dev_assess(const double* d_xyz, int n_models, int N, const int32_t* d_ri, co
     CHR3D_CUDA(cudaGetLastError());
     if (dense) seq_sum_staged_kernel<<<n_models, 256, 0, s>>>(terms.p, per_model, d_dev);
     else block_sum_kernel<<<n_models, 256, 0, s>>>(terms.p, per_model, d_dev);
+    CHR3D_CUDA(cudaGetLastError());
+    CHR3D_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dev_assess_rows(const double* d_xyz, int N, const int32_t* d_ri, const int32_t* d_rj, const double* d_rd, long long nr,
+                    int32_t* d_flag, double* d_dev, double* d_dist, cudaStream_t s) {
+    DevBuf<long long> mx;
+    CHR3D_CUDA(mx.alloc((size_t)N * 3));
+    milli_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, s>>>(d_xyz, (long long)N * 3, mx.p);
+    if (nr > 0) assess_rows_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(mx.p, d_ri, d_rj, d_rd, nr, d_flag, d_dev, d_dist);
     CHR3D_CUDA(cudaGetLastError());
     CHR3D_CUDA(cudaStreamSynchronize(s));
     return 0;

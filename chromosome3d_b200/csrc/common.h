@@ -115,6 +115,8 @@ int dev_random_coil(float* d_x0, int N, int n_models, int first_model, double st
 // ---- assess.cu -------------------------------------------------------------------------------
 int dev_assess(const double* d_xyz, int n_models, int N, const int32_t* d_ri, const int32_t* d_rj,
                const double* d_rd, long long nr, int32_t* d_sat, double* d_dev, cudaStream_t s);
+int dev_assess_rows(const double* d_xyz, int N, const int32_t* d_ri, const int32_t* d_rj, const double* d_rd, long long nr,
+                    int32_t* d_flag, double* d_dev, double* d_dist, cudaStream_t s);
 int dev_spearman(const double* d_IF, int L, const double* d_xyz, int n_models, int range, double* rho_host,
                  cudaStream_t s);
 

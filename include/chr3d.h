@@ -231,6 +231,10 @@ int chr3d_synthetic_if(int32_t N, uint64_t seed, double* out);
 int chr3d_assess(const double* xyz, int32_t n_models, int32_t N,
                  const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr,
                  int32_t* satisfied, double* sum_dev);
+/* Rows of contact_violation.txt for ONE model (C3D:458-475): violation flag, deviation, "%.3f" distance. */
+int chr3d_assess_rows(const double* xyz, int32_t N,
+                      const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr,
+                      int32_t* flag, double* dev, double* dist);
 /* order[k] = model index of rank k (ascending int(noe), ties by model index; C3D:617,802,823) */
 int chr3d_rank_models(const double* energies, int32_t n_models, int32_t* order);
 /* CNS-style trial structure <ID>_k.pdb: REMARK energies + one CA ATOM per bead + END      */

@@ -1,0 +1,83 @@
+"""Multi-process host logic on CPU (gloo, world_size 2): ensemble job sharding covers every job exactly
+once, results come back in job order on every rank, and the tile-range partition of one large
+structure is a disjoint cover.  No GPU, no numerics (the per-shard numerics are GPU tests)."""
+import os
+import socket
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from chromosome3d_b200 import sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    beads = [455, 37, 229, 73, 455, 120, 300, 35, 229]
+    jobs = [("job%d" % k, n) for k, n in enumerate(beads)]
+    costs = [sharding.job_cost(n, 20) for n in beads]
+
+    def runner(my_jobs):                      # stands in for api.build_models on this rank's GPU
+        return [(name, n * n, rank) for name, n in my_jobs]
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    res = sharding.run_sharded(jobs, costs, runner, rank, world, gather)
+    tiles = [sharding.tile_range(24925, r, world) for r in range(world)]
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, res, tiles))
+
+
+@pytest.mark.parametrize("world", [2])
+def test_gloo_world2_job_sharding(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res0, res1 = got[0][1], got[1][1]
+    assert res0 == res1                                     # every rank sees all results, in job order
+    assert [r[0] for r in res0] == ["job%d" % k for k in range(9)]
+    ranks = [r[2] for r in res0]
+    assert set(ranks) == {0, 1}
+    load = [sum(r[1] for r in res0 if r[2] == q_) for q_ in range(2)]
+    assert max(load) <= 1.2 * min(load)                     # LPT balance on N^2*m
+    t = got[0][2]
+    assert t[0][0] == 0 and t[0][1] == t[1][0] and t[1][1] == 19110     # N=24,925: 195*196/2 tiles
+
+
+def test_partition_functions():
+    sys.path.insert(0, ROOT)
+    from chromosome3d_b200 import sharding
+    for N in (37, 455, 700, 4985):
+        nt = sharding.n_tiles(N)
+        for world in (1, 2, 3, 4, 8):
+            r = [sharding.tile_range(N, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == nt and all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+        seen = [sharding.tile_coords(t, N) for t in range(nt)]
+        n1 = (N + 127) // 128
+        assert seen == [(i, j) for i in range(n1) for j in range(i, n1)]
+    s = sharding.shard_jobs([5, 5, 3, 3, 2, 2], 2)
+    assert sorted(s[0] + s[1]) == list(range(6)) and abs(sum([5, 5, 3, 3, 2, 2][k] for k in s[0]) - 10) <= 1
+    assert sharding.shard_jobs([1.0], 4) == [[0], [], [], []]
