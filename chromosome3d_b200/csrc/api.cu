@@ -125,7 +125,7 @@ static const char* aa3(char c) {
 // ------------------------------------------------------------------------------------------------
 struct JobDev {
     int L = 0, n_models = 0; long long nr = 0; unsigned long long seed = 0;
-    DevBuf<float> T, x0, xout, scratch;
+    DevBuf<float> T, Tt, x0, xout, scratch;
     DevBuf<double> e, xyz_d, dev;
     DevBuf<long long> nev;
     DevBuf<int> hand, sat;
@@ -355,6 +355,8 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             if (int rc = upload_list(*jd, jb.ri, jb.rj, jb.rd, jb.nr, 0)) return rc;
             if (int rc = dev_list_to_targets(jd->ri.p, jd->rj.p, jd->rd.p, jb.nr, N, p->vdw_min_sep, jd->T.p, 0)) return rc;
         }
+        CHR3D_CUDA(jd->Tt.alloc(sa_tiles_floats(N)));
+        if (int rc = sa_pack_tiles(jd->T.p, N, pitch, jd->Tt.p, 0)) return rc;
         tr.lap("targets+list");
         e->rows_total += jd->nr * jb.n_models;
         const size_t nx = (size_t)jb.n_models * N * 3;
@@ -375,7 +377,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         jd->traj0 = (int)tds.size();
         for (int m = 0; m < jb.n_models; m++) {
             TrajDesc td; memset(&td, 0, sizeof td);
-            td.T = jd->T.p; td.x0 = jd->x0.p + (size_t)m * N * 3; td.x_out = jd->xout.p + (size_t)m * N * 3;
+            td.T = jd->Tt.p; td.x0 = jd->x0.p + (size_t)m * N * 3; td.x_out = jd->xout.p + (size_t)m * N * 3;
             td.f_out = want_forces ? (*fbufs)[jn].p + (size_t)m * N * 3 : nullptr;
             td.scratch = jd->scratch.p + (size_t)m * N * 6; td.e_out = jd->e.p + 4 * m; td.nevals_out = jd->nev.p + m;
             td.hand_out = jd->hand.p + m; td.N = N; td.pitch = pitch; td.model = m; td.seed = jd->seed;
@@ -388,7 +390,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         JobDev& jd = *e->jobs[jn];
         if (!e->groups.empty()) {
             LaunchGroup& g = e->groups.back();
-            if (g.cfg.cluster == jd.cfg.cluster && g.cfg.threads == jd.cfg.threads && g.cfg.stage_targets == jd.cfg.stage_targets) {
+            if (g.cfg.cluster == jd.cfg.cluster && g.cfg.threads == jd.cfg.threads) {
                 g.n_traj += jd.n_models; g.cfg.smem = std::max(g.cfg.smem, jd.cfg.smem); g.Nmax = std::max(g.Nmax, jd.L); continue;
             }
         }

@@ -94,7 +94,7 @@ int if_to_tenths_certified(const double* IF, int L, double alpha, double K, DevB
 
 // ---- sa_ensemble.cu --------------------------------------------------------------------------
 struct TrajDesc {
-    const float* T;        // dense targets [N][pitch]
+    const float* T;        // tile-packed lane-major targets (sa_pack_tiles)
     const float* x0;       // N*3 start coordinates
     float*  x_out;         // N*3
     float*  f_out;         // N*3 or nullptr (forces of the last evaluation)
@@ -105,7 +105,10 @@ struct TrajDesc {
     int     N, pitch, model, pad_;
     unsigned long long seed;
 };
-struct SaLaunchCfg { int cluster; int threads; int stage_targets; size_t smem; };
+struct SaLaunchCfg { int cluster; int threads; int stage_targets; size_t smem; };   // stage_targets: resident tile rounds
+// dense [N][pitch] targets -> 32x32 tile-packed lane-major layout of the SA kernel
+int sa_pack_tiles(const float* d_T, int N, int pitch, float* d_Tt, cudaStream_t s);
+size_t sa_tiles_floats(int N);
 int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg);
 int sa_launch(const TrajDesc* d_traj, int n_traj, int Nmax, const DevParams& P, const DevStage* d_prog, int nstages,
               const SaLaunchCfg& cfg, cudaStream_t s);

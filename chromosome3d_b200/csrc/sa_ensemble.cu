@@ -1,27 +1,33 @@
 // sa_ensemble.cu — the small-N hot path: one thread-block cluster per SA trajectory.
 //
 // Replaces the CNS `dgsa.inp` run (C3D:254-289 launches it; protocol text C3D:1573-1829) for
-// chromosomes up to ~1000 beads.  One launch anneals every model of every (matrix, alpha) job:
+// chromosomes up to ~1500 beads.  One launch anneals every model of every (matrix, alpha) job:
 //
-//   * a trajectory = one cluster of C CTAs (C = 1..8, chosen on the host from N and the number of
-//     trajectories so that the 148 SMs are filled);  CTA `rank` owns a contiguous block of beads
-//     ("rows"), integrates them, and after every update stores them into the coordinate array of
-//     every CTA of the cluster through distributed shared memory;
-//   * coordinates of all N beads live in shared memory (float4), the CTA's column block of the
-//     dense target-distance matrix is staged into shared memory once with TMA bulk copies
-//     (cp.async.bulk -> UBLKCP) when it fits, otherwise it is read through L2;
-//   * force evaluation is the "gather" form: thread (row i, chunk q) walks j over its chunk with
-//     x_j broadcast from shared memory and T[j][i] read conflict-free; no atomics, deterministic;
-//   * NOE soft-square + repel are fused in that one pair loop, the bond term is added by the row
-//     owner; energies are reduced with warp shuffles (fp64 across threads);
+//   * a trajectory = one cluster of C CTAs of W warps (C, W chosen on the host from N, the number
+//     of trajectories and the cluster occupancy of the device);
+//   * the unordered pair matrix is cut into 32x32 micro-tiles (I <= J); tile t belongs to CTA
+//     t mod C and there to warp (t / C) mod W, so CTAs and their schedulers carry equal shares.  A lane owns a 4-row x 8-column sub-block (32 pairs in registers),
+//     every pair is evaluated ONCE and its force goes to both beads; row/column partial sums are
+//     combined inside the warp by recursive-halving shuffles and stored (DSMEM) into the partial
+//     buffer of the CTA that owns the bead block; the owner adds its nb+1 partials in fixed order.
+//     No atomics anywhere: runs are bit-reproducible;
+//   * target distances are tile-packed "lane-major" (each lane's 32 values = 8 float4 strided by
+//     the warp), resident in shared memory when they fit, otherwise streamed coalesced from L2;
+//   * coordinates of all beads live in the shared memory of every CTA; bead blocks are owned by
+//     CTAs (contiguous ranges) whose threads integrate them and publish new coordinates to all
+//     CTAs through distributed shared memory;
+//   * NOE soft-square + repel are fused in the pair term, the bond term is added by the bead owner;
+//     energies and all other scalars are reduced in fp64 in a fixed order;
 //   * the whole stage program (pre-minimisation, hot MD, cooling, L-BFGS, C3D:1573-1829) runs
-//     inside the kernel; scalar reductions (energies, kinetic energy, L-BFGS inner products)
-//     cross the cluster with one DSMEM exchange + one cluster barrier.
+//     inside the kernel.  An MD step costs two cluster barriers: one after the pair phase (forces
+//     complete) and one after the owners published a = x + dt*h*f, b = dt*v and their kinetic-energy
+//     partials, from which every CTA rebuilds x' = a + lambda*b for all beads itself.
 //
 // L-BFGS is the vector-free formulation: all inner products of an iteration are reduced in one
 // exchange and the two-loop recursion runs on the (2m+1)x(2m+1) Gram matrix.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 #include "common.h"
 
 namespace cg = cooperative_groups;
@@ -29,7 +35,9 @@ namespace cg = cooperative_groups;
 namespace chr3d {
 
 #define SA_MAXC 8
-#define SA_KTOT 64           // scalars per all-reduce (2 pair energies + owner columns)
+#define SA_KTOT 64           // scalars per all-reduce (owner columns)
+#define SA_MAXW 20           // warps per CTA (kernel variants for <= 16 and <= 20 warps)
+#define SA_TILE_FLOATS 1024  // 32x32 micro-tile
 #define SA_MAXB (2 * CHR3D_LBFGS_MAX_M + 1)
 
 #define STREAM_COIL 0x00C011u
@@ -93,65 +101,133 @@ int dev_random_coil(float* d_x0, int N, int n_models, int first_model, double st
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tile-packed, lane-major targets.  Tile t = (I, J), I <= J, row-major over the upper triangle of
+// the nb x nb block grid.  Inside a tile lane l = 4*rg + cg owns rows rg + 8r (r = 0..3) and columns
+// cg + 4q (q = 0..7) — interleaved, so that the coordinate loads of a warp touch consecutive shared
+// memory words (no bank conflicts); its value (r, q) sits in float4 number k = 2r + q/4 (component
+// q%4) at Tt[t*1024 + (k*32 + l)*4 ..].  Values: >0 restraint distance, -1 none, -2 none and no repel
+// (also: i >= j of diagonal tiles and padding).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int sa_tile_index(int I, int J, int nb) { return I * nb - I * (I - 1) / 2 + (J - I); }
+__host__ __device__ inline void sa_tile_coords(int t, int nb, int& I, int& J) {
+    int i = 0;
+    while (sa_tile_index(i + 1, i + 1, nb) <= t) i++;
+    I = i; J = i + (t - sa_tile_index(i, i, nb));
+}
+__global__ void __launch_bounds__(256) sa_pack_tiles_kernel(const float* __restrict__ T, int N, int pitch, int nb, float* __restrict__ Tt) {
+    const int t = blockIdx.x;
+    int I, J; sa_tile_coords(t, nb, I, J);
+    for (int e = threadIdx.x; e < SA_TILE_FLOATS; e += blockDim.x) {
+        const int k = e >> 7, lane = (e >> 2) & 31, comp = e & 3;
+        const int rg = lane >> 2, cg = lane & 3, r = k >> 1, c = (k & 1) * 4 + comp;
+        const int i = 32 * I + rg + 8 * r, j = 32 * J + cg + 4 * c;
+        Tt[(size_t)t * SA_TILE_FLOATS + e] = (i < N && j < N && i < j) ? T[(size_t)i * pitch + j] : -2.f;
+    }
+}
+int sa_pack_tiles(const float* d_T, int N, int pitch, float* d_Tt, cudaStream_t s) {
+    const int nb = (N + 31) / 32;
+    sa_pack_tiles_kernel<<<nb * (nb + 1) / 2, 256, 0, s>>>(d_T, N, pitch, nb, d_Tt);
+    CHR3D_CUDA(cudaGetLastError());
+    return 0;
+}
+size_t sa_tiles_floats(int N) { const size_t nb = (size_t)(N + 31) / 32; return nb * (nb + 1) / 2 * SA_TILE_FLOATS; }
+
 // ------------------------------------------------------------------------------------------------
 // shared-memory layout (identical on host and device)
 // ------------------------------------------------------------------------------------------------
 struct SaShape {
-    int N, C, nthreads, nwarps, rw_max, rows_pad, Q, m, nvec, stage_targets;
+    int N, C, W, nthreads, nb, n32, ntiles, gwarps, rounds, own_max, rows_pad, m, nvec, res_rounds;
 };
 struct SaLayout {
-    size_t xs, fpart, vec, P, ewarp, slots, gsum, B, delta, mbar, tblk, total;
+    size_t ab, part, vec, P, eslots, kslots, slots, gsum, B, delta, tij, own, tres, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline void sa_shape(int N, int C, int nthreads, int m, int stage_targets, SaShape& s) {
-    s.N = N; s.C = C; s.nthreads = nthreads; s.nwarps = nthreads / 32; s.m = m; s.stage_targets = stage_targets;
-    int rw_total = (N + 31) / 32;
-    s.rw_max = (rw_total + C - 1) / C;
-    s.rows_pad = 32 * s.rw_max;
-    s.Q = s.nwarps / s.rw_max; if (s.Q < 1) s.Q = 1;
-    s.nvec = 3 + 2 * m;     // XB, G, PV, S[m], Y[m]
-}
 __host__ __device__ inline void sa_layout(const SaShape& s, SaLayout& L) {
     size_t o = 0;
-    L.xs = o;    o = align_up(o + sizeof(float4) * (size_t)(s.N + 1), 16);
-    L.fpart = o; o = align_up(o + sizeof(float4) * (size_t)s.Q * s.rows_pad, 16);
-    L.vec = o;   o = align_up(o + sizeof(float) * (size_t)s.nvec * 3 * s.rows_pad, 16);
-    L.P = o;     o = align_up(o + sizeof(float) * (size_t)(SA_KTOT - 2) * s.rows_pad, 16);
-    L.ewarp = o; o = align_up(o + sizeof(double) * 2 * (size_t)s.nwarps, 16);
-    L.slots = o; o = align_up(o + sizeof(double) * 2 * SA_MAXC * SA_KTOT, 16);
-    L.gsum = o;  o = align_up(o + sizeof(double) * SA_KTOT, 16);
-    L.B = o;     o = align_up(o + sizeof(double) * SA_MAXB * SA_MAXB, 16);
-    L.delta = o; o = align_up(o + sizeof(double) * (SA_MAXB + 3), 16);
-    L.mbar = o;  o = align_up(o + 16, 128);
-    L.tblk = o;
-    if (s.stage_targets) o += sizeof(float) * (size_t)s.N * s.rows_pad;
+    L.ab = o;     o = align_up(o + sizeof(float4) * 4 * (size_t)(s.n32 + 1), 16);   // [parity][a|b][n32+1]
+    L.part = o;   o = align_up(o + sizeof(float4) * (size_t)s.own_max * (s.nb + 1) * 32, 16);
+    L.vec = o;    o = align_up(o + sizeof(float) * (size_t)s.nvec * 3 * s.rows_pad, 16);
+    L.P = o;      o = align_up(o + sizeof(float) * (size_t)SA_KTOT * s.rows_pad, 16);
+    L.eslots = o; o = align_up(o + sizeof(double) * 2 * (size_t)s.gwarps, 16);
+    L.kslots = o; o = align_up(o + sizeof(double) * (size_t)s.C * s.own_max, 16);
+    L.slots = o;  o = align_up(o + sizeof(double) * 2 * SA_MAXC * SA_KTOT, 16);
+    L.gsum = o;   o = align_up(o + sizeof(double) * (SA_KTOT + 2), 16);
+    L.B = o;      o = align_up(o + sizeof(double) * SA_MAXB * SA_MAXB, 16);
+    L.delta = o;  o = align_up(o + sizeof(double) * (SA_MAXB + 3), 16);
+    L.tij = o;    o = align_up(o + 2 * (size_t)s.rounds * s.W, 16);
+    L.own = o;    o = align_up(o + 2 * (size_t)s.nb, 128);
+    L.tres = o;
+    o += sizeof(float) * SA_TILE_FLOATS * (size_t)s.res_rounds * s.W;
     L.total = o;
 }
+// res_rounds: how many of a warp's tiles stay resident in shared memory (decided from the dynamic smem size)
+__host__ __device__ inline void sa_shape(int N, int C, int W, int m, size_t smem_bytes, SaShape& s) {
+    s.N = N; s.C = C; s.W = W; s.nthreads = 32 * W; s.m = m;
+    s.nb = (N + 31) / 32; s.n32 = 32 * s.nb; s.ntiles = s.nb * (s.nb + 1) / 2; s.gwarps = C * W;
+    s.rounds = ((s.ntiles + C - 1) / C + W - 1) / W;       // tiles of the busiest warp
+    s.own_max = (s.nb + C - 1) / C; s.rows_pad = 32 * s.own_max;
+    s.nvec = 3 + 2 * m;     // XB, G, PV, S[m], Y[m]
+    s.res_rounds = 0;
+    SaLayout L; sa_layout(s, L);
+    if (smem_bytes > L.total) {
+        size_t r = (smem_bytes - L.total) / (sizeof(float) * SA_TILE_FLOATS * (size_t)W);
+        s.res_rounds = (int)(r < (size_t)s.rounds ? r : (size_t)s.rounds);
+    }
+}
+
+extern __shared__ __align__(128) unsigned char sa_smem[];
+
+// Development aid (-DSA_TIMING): SM-clock cycles spent in the phases of a force evaluation, summed over all
+// evaluations, for the first owner warp and the last warp of cluster rank 0 of trajectory 0.
+#ifdef SA_TIMING
+__device__ unsigned long long sa_dbg[2][16];
+#define TSTAMP(c, k) do { if ((c).tmark) { long long t_ = clock64(); (c).tacc[k] += t_ - (c).tlast; (c).tlast = t_; } } while (0)
+#else
+#define TSTAMP(c, k) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // device context
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
     // geometry
-    int N, C, rank, tid, lane, warp, nwarps, nthreads;
-    int r0, rows, rows_pad, Q;       // owned rows [r0, r0+rows)
-    int pw_row, pw_q, pw_active;     // pair-loop role of this warp
+    int N, C, W, rank, tid, lane, warp, nthreads, nb, n32p, gw, gwarps, my_rounds, res_rounds, own_max;
+    int rw0, nown, rows_pad;         // owned bead blocks [rw0, rw0 + nown)
     int m;
-    // smem
-    float4* xs; float4* fpart; float* vec; float* P; double* ewarp; double* slots; double* gsum; double* B;
-    double* delta;
-    const float* Tsrc; int tstride;  // T[j][r0+li] = Tsrc[j*tstride + li]
+    // smem byte offsets (accessed through the sa_smem symbol so that loads stay LDS/STS)
+    unsigned o_ab, o_kslots, o_part, o_vec, o_P, o_eslots, o_slots, o_gsum, o_B, o_delta, o_tij, o_own, o_tres;
+    const float4* Tt;                // tile-packed targets in global memory
     int par;
-    // owner state (valid when tid < rows_pad; row_ok when tid < rows)
+    // coordinates of every bead are x = a + lam*b, (a, b) double-buffered by parity `buf` (see dyn_after_eval)
+    int buf; float lam;
+    // owner state (valid when tid < rows_pad; row_ok when the thread owns a real bead)
     bool owner, row_ok; int row;
     float x[3], v[3], f[3];
     float ebond;
     long long nevals;
     DevParams prm;
+#ifdef SA_TIMING
+    bool tmark; long long tlast; long long tacc[10];
+#endif
 };
+#define S_AB(c) ((float4*)(sa_smem + (c).o_ab))
+#define S_KSLOTS(c) ((double*)(sa_smem + (c).o_kslots))
+#define S_PART(c) ((float4*)(sa_smem + (c).o_part))
+#define S_VEC(c) ((float*)(sa_smem + (c).o_vec))
+#define S_P(c) ((float*)(sa_smem + (c).o_P))
+#define S_ESLOTS(c) ((double*)(sa_smem + (c).o_eslots))
+#define S_SLOTS(c) ((double*)(sa_smem + (c).o_slots))
+#define S_GSUM(c) ((double*)(sa_smem + (c).o_gsum))
+#define S_B(c) ((double*)(sa_smem + (c).o_B))
+#define S_DELTA(c) ((double*)(sa_smem + (c).o_delta))
+#define S_TIJ(c) ((uchar2*)(sa_smem + (c).o_tij))
+#define S_OWN(c) ((uchar2*)(sa_smem + (c).o_own))
+#define S_TRES(c) ((float4*)(sa_smem + (c).o_tres))
 
-__device__ __forceinline__ float* vecp(const Ctx& c, int v, int comp) { return c.vec + ((size_t)(v * 3 + comp)) * c.rows_pad; }
+__device__ __forceinline__ float* vecp(const Ctx& c, int v, int comp) { return S_VEC(c) + ((size_t)(v * 3 + comp)) * c.rows_pad; }
 #define V_XB 0
 #define V_G 1
 #define V_PV 2
@@ -166,42 +242,63 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// store the owner's coordinates into the coordinate array of every CTA of the cluster
-__device__ __forceinline__ void publish_x(const Ctx& c) {
+// Coordinates.  Every CTA holds (a, b) of all beads; x = a + lam*b with the cluster-uniform scalar lam.
+// Publishing goes into the buffer of the other parity (readers of the current one may still be busy);
+// after the cluster barrier that follows every publish, flip() makes it current.
+__device__ __forceinline__ float4 ldx(const Ctx& c, int i) {
+    const float4* A = S_AB(c) + (size_t)(2 * c.buf) * c.n32p;
+    const float4 a = A[i], b = A[c.n32p + i];
+    return make_float4(fmaf(c.lam, b.x, a.x), fmaf(c.lam, b.y, a.y), fmaf(c.lam, b.z, a.z), 0.f);
+}
+__device__ __forceinline__ void publish_ab(const Ctx& c, float4 a, float4 b, bool with_b) {
     if (!c.row_ok) return;
-    float4 val = make_float4(c.x[0], c.x[1], c.x[2], 0.f);
+    float4* A = S_AB(c) + (size_t)(2 * (c.buf ^ 1)) * c.n32p + c.row;
     if (c.C > 1) {
         cg::cluster_group cl = cg::this_cluster();
-        for (int r = 0; r < c.C; r++) cl.map_shared_rank(c.xs, r)[c.row] = val;
-    } else {
-        c.xs[c.row] = val;
-    }
+        for (int r = 0; r < c.C; r++) { float4* R = cl.map_shared_rank(A, r); R[0] = a; if (with_b) R[c.n32p] = b; }
+    } else { A[0] = a; if (with_b) A[c.n32p] = b; }
 }
+// x of the owner -> a (lam becomes 0 at the flip, b is ignored)
+__device__ __forceinline__ void publish_x(const Ctx& c) {
+    publish_ab(c, make_float4(c.x[0], c.x[1], c.x[2], 0.f), make_float4(0.f, 0.f, 0.f, 0.f), false);
+}
+__device__ __forceinline__ void flip(Ctx& c, float lam) { c.buf ^= 1; c.lam = lam; }
+// publish_x + barrier + flip: the usual way an op installs new coordinates
+__device__ __forceinline__ void install_x(Ctx& c) { publish_x(c); csync(c); flip(c, 0.f); }
 
-// All-reduce of K owner columns (P) + the two pair-energy columns (ewarp) across the cluster.
+// All-reduce of K owner columns (P) across the cluster; with_e: also totals of the pair energies
+// every warp of the cluster left in eslots (complete in every CTA after the barrier inside eval).
 // Result: gsum[0]=E_noe, gsum[1]=E_vdw, gsum[2+k]=column k.  Every CTA sums the same partials in
 // the same order, so all ranks take identical decisions afterwards.
-__device__ void allreduce(Ctx& c, int K) {
+__device__ void allreduce(Ctx& c, int K, bool with_e) {
     __syncthreads();
-    const int total = K + 2;
-    for (int k = c.warp; k < total; k += c.nwarps) {
+    for (int k = c.warp; k < K; k += c.W) {
+        const float* col = S_P(c) + (size_t)k * c.rows_pad;
         double s = 0;
-        if (k < 2) { for (int w = c.lane; w < c.nwarps; w += 32) s += c.ewarp[w * 2 + k]; }
-        else { const float* col = c.P + (size_t)(k - 2) * c.rows_pad; for (int t = c.lane; t < c.rows_pad; t += 32) s += (double)col[t]; }
+        for (int t = c.lane; t < c.rows_pad; t += 32) s += (double)col[t];
         s = warp_sum(s);
         if (c.C > 1) {
             if (c.lane < c.C) {
-                double* remote = cg::this_cluster().map_shared_rank(c.slots, c.lane);
+                double* remote = cg::this_cluster().map_shared_rank(S_SLOTS(c), c.lane);
                 remote[((size_t)c.par * SA_MAXC + c.rank) * SA_KTOT + k] = s;
             }
-        } else if (c.lane == 0) c.gsum[k] = s;
+        } else if (c.lane == 0) S_GSUM(c)[2 + k] = s;
+    }
+    if (with_e) {
+        for (int e = 0; e < 2; e++) {
+            if (c.warp != (c.W - 1 - e) % c.W) continue;
+            double s = 0;
+            for (int g = c.lane; g < c.gwarps; g += 32) s += S_ESLOTS(c)[2 * g + e];
+            s = warp_sum(s);
+            if (c.lane == 0) S_GSUM(c)[e] = s;
+        }
     }
     if (c.C > 1) {
         cg::this_cluster().sync();
-        if (c.tid < total) {
+        if (c.tid < K) {
             double s = 0;
-            for (int r = 0; r < c.C; r++) s += c.slots[((size_t)c.par * SA_MAXC + r) * SA_KTOT + c.tid];
-            c.gsum[c.tid] = s;
+            for (int r = 0; r < c.C; r++) s += S_SLOTS(c)[((size_t)c.par * SA_MAXC + r) * SA_KTOT + c.tid];
+            S_GSUM(c)[2 + c.tid] = s;
         }
         c.par ^= 1;
     }
@@ -209,105 +306,176 @@ __device__ void allreduce(Ctx& c, int K) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// energy + forces for the owned rows.  On return: c.f (owner), c.ebond (owner partial),
-// c.ewarp[warp] = (E_noe, E_vdw) partials.  The caller must follow with allreduce().
+// pair term, symmetric: accumulates the force on i and on j and, if WANT_E, the energies.
+// r^2 carries a 1e-12 floor (coincident beads), as the oracle's max(r^2, 1e-12).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pair_default(const DevParams& p, float wnC, float wv4, float wv, float R2, float lo,
-                                             float xi, float yi, float zi, float4 xj, float d,
-                                             float& fx, float& fy, float& fz, float& en, float& ev) {
-    float dx = xi - xj.x, dy = yi - xj.y, dz = zi - xj.z;
-    float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-    float r2c = fmaxf(r2, 1e-12f);
-    float rinv = rsqrtf(r2c);
-    float r = r2c * rinv;
-    float delta = r - d;
-    float h = fminf(fmaxf(delta, lo), p.rsw);
-    float w = d > 0.f ? wnC : 0.f;            // w_noe * C
-    float wh = w * h;
-    en = fmaf(wh, 2.f * delta - h, en);
-    float tr = fmaxf(R2 - r2, 0.f);
+// r^-1/2 as one MUFU.RSQ (arguments here are >= 1e-12: no denormal handling needed)
+__device__ __forceinline__ float rsqrt_fast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+struct SaTerms { float wnC2m, rsw, wv, wv4, R2, wn, C, a, b, casym; int low_soft; };
+
+template <bool WANT_E, bool GENERAL>
+__device__ __forceinline__ void pair_sym(const SaTerms& t, float xi, float yi, float zi, float xj, float yj, float zj, float d,
+                                         float* fi, float* fj, float& en, float& ev) {
+    const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
+    const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, 1e-12f)));
+    const float rinv = rsqrt_fast(r2);
+    float tr = fmaxf(t.R2 - r2, 0.f);
     tr = d > -1.5f ? tr : 0.f;
-    ev = fmaf(wv * tr, tr, ev);
-    float coef = fmaf(wv4, tr, -2.f * wh * rinv);   // 4 w_vdw t - (dE_noe/dr)/r
-    fx = fmaf(coef, dx, fx); fy = fmaf(coef, dy, fy); fz = fmaf(coef, dz, fz);
-}
-__device__ __forceinline__ void pair_general(const DevParams& p, float wn, float wv4, float wv, float R2,
-                                             float xi, float yi, float zi, float4 xj, float d,
-                                             float& fx, float& fy, float& fz, float& en, float& ev) {
-    float dx = xi - xj.x, dy = yi - xj.y, dz = zi - xj.z;
-    float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-    float r2c = fmaxf(r2, 1e-12f);
-    float rinv = rsqrtf(r2c);
-    float r = r2c * rinv;
-    float e = 0.f, de = 0.f;
-    if (d > 0.f) {
-        float delta = r - d, u = fabsf(delta), sg = delta > 0.f ? 1.f : -1.f;
-        bool soft = u > p.rsw && (delta > 0.f || p.lo_clamp > -1e30f);
-        if (!soft) { e = p.C * u * u; de = 2.f * p.C * u * sg; }
-        else { e = p.a + p.b / u + p.casym * u; de = (p.casym - p.b / (u * u)) * sg; }
+    float coef;
+    if (!GENERAL) {
+        const float delta = fmaf(r2, rinv, -d);                    // r - d
+        const float h = fminf(delta, t.rsw);
+        const float w2h = (d > 0.f ? t.wnC2m : 0.f) * h;           // -2 w C h
+        if (WANT_E) en = fmaf(-0.5f * w2h, 2.f * delta - h, en);   // w C h (2 delta - h)
+        coef = fmaf(t.wv4, tr, w2h * rinv);                        // 4 w_vdw t - (dE_noe/dr)/r
+    } else {
+        const float r = r2 * rinv, delta = r - d, u = fabsf(delta), sg = delta > 0.f ? 1.f : -1.f;
+        const bool soft = u > t.rsw && (delta > 0.f || t.low_soft);
+        const float uinv = 1.f / fmaxf(u, 1e-20f);
+        const float e = soft ? t.a + t.b * uinv + t.casym * u : t.C * u * u;
+        const float de = soft ? (t.casym - t.b * uinv * uinv) * sg : 2.f * t.C * u * sg;
+        const float w = d > 0.f ? t.wn : 0.f;
+        if (WANT_E) en = fmaf(w, e, en);
+        coef = fmaf(t.wv4, tr, -w * de * rinv);
     }
-    en = fmaf(wn, e, en);
-    float tr = fmaxf(R2 - r2, 0.f);
-    tr = d > -1.5f ? tr : 0.f;
-    ev = fmaf(wv * tr, tr, ev);
-    float coef = fmaf(wv4, tr, -wn * de * rinv);
-    fx = fmaf(coef, dx, fx); fy = fmaf(coef, dy, fy); fz = fmaf(coef, dz, fz);
+    if (WANT_E) ev = fmaf(t.wv * tr, tr, ev);
+    fi[0] = fmaf(coef, dx, fi[0]); fi[1] = fmaf(coef, dy, fi[1]); fi[2] = fmaf(coef, dz, fi[2]);
+    fj[0] = fmaf(-coef, dx, fj[0]); fj[1] = fmaf(-coef, dy, fj[1]); fj[2] = fmaf(-coef, dz, fj[2]);
 }
 
-__device__ void eval(Ctx& c, const DevStage& st, bool count) {
-    csync(c);                                       // coordinates of every CTA are in place
-    const DevParams& p = c.prm;
-    float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f, ev = 0.f;
-    if (c.pw_active) {
-        const int li = 32 * c.pw_row + c.lane;
-        int i = c.r0 + li; if (i >= c.N) i = c.N - 1;
-        const float4 xi4 = c.xs[i];
-        const float xi = xi4.x, yi = xi4.y, zi = xi4.z;
-        const int j0 = (int)(((long long)c.N * c.pw_q) / c.Q), j1 = (int)(((long long)c.N * (c.pw_q + 1)) / c.Q);
-        const float* tp = c.Tsrc + li;
-        const int ts = c.tstride;
-        const float wv = st.w_vdw, wv4 = 4.f * st.w_vdw, R2 = st.R2;
-        if (!p.general_noe) {
-            const float wnC = st.w_noe * p.C, lo = p.lo_clamp;
-            int j = j0;
-            for (; j + 4 <= j1; j += 4) {
-                float4 a0 = c.xs[j], a1 = c.xs[j + 1], a2 = c.xs[j + 2], a3 = c.xs[j + 3];
-                float d0 = tp[(size_t)j * ts], d1 = tp[(size_t)(j + 1) * ts], d2 = tp[(size_t)(j + 2) * ts], d3 = tp[(size_t)(j + 3) * ts];
-                pair_default(p, wnC, wv4, wv, R2, lo, xi, yi, zi, a0, d0, fx, fy, fz, en, ev);
-                pair_default(p, wnC, wv4, wv, R2, lo, xi, yi, zi, a1, d1, fx, fy, fz, en, ev);
-                pair_default(p, wnC, wv4, wv, R2, lo, xi, yi, zi, a2, d2, fx, fy, fz, en, ev);
-                pair_default(p, wnC, wv4, wv, R2, lo, xi, yi, zi, a3, d3, fx, fy, fz, en, ev);
-            }
-            for (; j < j1; j++) pair_default(p, wnC, wv4, wv, R2, lo, xi, yi, zi, c.xs[j], tp[(size_t)j * ts], fx, fy, fz, en, ev);
+// ------------------------------------------------------------------------------------------------
+// energy + forces.  On return: c.f (owner), c.ebond (owner partial); if WANT_E the pair-energy
+// partials of every warp of the cluster are in eslots (pick them up with allreduce(.., true)).
+// ------------------------------------------------------------------------------------------------
+template <bool WANT_E, bool GENERAL>
+__device__ __forceinline__ void eval_t(Ctx& c, const DevStage& st, bool count) {
+    const DevParams& p = c.prm;                     // precondition: coordinates installed (publish, cluster barrier, flip)
+    SaTerms tm;
+    tm.wnC2m = -2.f * st.w_noe * p.C; tm.rsw = p.rsw; tm.wv = st.w_vdw; tm.wv4 = 4.f * st.w_vdw; tm.R2 = st.R2;
+    tm.wn = st.w_noe; tm.C = p.C; tm.a = p.a; tm.b = p.b; tm.casym = p.casym; tm.low_soft = p.lo_clamp > -1e30f ? 1 : 0;
+    const int lane = c.lane, rg = lane >> 2, cg4 = lane & 3;
+    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8, b4 = lane & 16;
+    float en = 0.f, ev = 0.f;
+    TSTAMP(c, 0);                                   // everything since the last stamp: control, reductions
+    for (int k = 0; k < c.my_rounds; k++) {
+        const uchar2 ij = S_TIJ(c)[k * c.W + c.warp];
+        const int I = ij.x, J = ij.y;
+        float4 d[8];
+        if (k < c.res_rounds) {
+            const float4* tp = S_TRES(c) + ((size_t)(k * c.W + c.warp) * 256 + lane);
+#pragma unroll
+            for (int q = 0; q < 8; q++) d[q] = tp[q * 32];
         } else {
-            for (int j = j0; j < j1; j++) pair_general(p, st.w_noe, wv4, wv, R2, xi, yi, zi, c.xs[j], tp[(size_t)j * ts], fx, fy, fz, en, ev);
+            const float4* gp = c.Tt + ((size_t)(c.rank + c.C * (c.warp + c.W * k)) * 256 + lane);
+#pragma unroll
+            for (int q = 0; q < 8; q++) d[q] = __ldg(gp + q * 32);
         }
-        c.fpart[(size_t)c.pw_q * c.rows_pad + li] = make_float4(fx, fy, fz, 0.f);
-    }
-    // every unordered pair is visited from both of its rows
-    double den = warp_sum(0.5 * (double)en), dev = warp_sum(0.5 * (double)ev);
-    if (c.lane == 0) { c.ewarp[c.warp * 2] = den; c.ewarp[c.warp * 2 + 1] = dev; }
-    __syncthreads();
-    if (c.owner) {
-        float gx = 0.f, gy = 0.f, gz = 0.f, eb = 0.f;
-        if (c.row_ok) {
-            for (int q = 0; q < c.Q; q++) { float4 t = c.fpart[(size_t)q * c.rows_pad + c.tid]; gx += t.x; gy += t.y; gz += t.z; }
-            const float4 xi = c.xs[c.row];
-            for (int s = -1; s <= 1; s += 2) {          // bonds (i-1,i) and (i,i+1)
-                int nb = c.row + s;
-                if (nb < 0 || nb >= c.N) continue;
-                const float4 xn = c.xs[nb];
-                float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
-                float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f);
-                float rinv = rsqrtf(r2), r = r2 * rinv, u = r - p.r0;
-                float g = 2.f * st.w_bond * u * rinv;
-                gx -= g * dx; gy -= g * dy; gz -= g * dz;
-                if (s == 1) eb = st.w_bond * u * u;
+        float xj[8], yj[8], zj[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { const float4 t = ldx(c, 32 * J + cg4 + 4 * q); xj[q] = t.x; yj[q] = t.y; zj[q] = t.z; }
+        float fi[4][3], fj[8][3];
+#pragma unroll
+        for (int q = 0; q < 4; q++) fi[q][0] = fi[q][1] = fi[q][2] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) fj[q][0] = fj[q][1] = fj[q][2] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const float4 xi = ldx(c, 32 * I + rg + 8 * r);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const float4 d4 = d[2 * r + hh];
+                pair_sym<WANT_E, GENERAL>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 0], yj[4 * hh + 0], zj[4 * hh + 0], d4.x, fi[r], fj[4 * hh + 0], en, ev);
+                pair_sym<WANT_E, GENERAL>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 1], yj[4 * hh + 1], zj[4 * hh + 1], d4.y, fi[r], fj[4 * hh + 1], en, ev);
+                pair_sym<WANT_E, GENERAL>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 2], yj[4 * hh + 2], zj[4 * hh + 2], d4.z, fi[r], fj[4 * hh + 2], en, ev);
+                pair_sym<WANT_E, GENERAL>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 3], yj[4 * hh + 3], zj[4 * hh + 3], d4.w, fi[r], fj[4 * hh + 3], en, ev);
             }
         }
-        c.f[0] = gx; c.f[1] = gy; c.f[2] = gz; c.ebond = eb;
+        // rows: the 4 lanes that differ in bits 0-1 (column groups) share rows -> recursive halving
+        float rowf[3], colf[3];
+        {
+            float k0[2][3];
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float lo = fi[q][a], hi = fi[q + 2][a];
+                    k0[q][a] = (b0 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b0 ? lo : hi, 1);
+                }
+#pragma unroll
+            for (int a = 0; a < 3; a++) rowf[a] = (b1 ? k0[1][a] : k0[0][a]) + __shfl_xor_sync(0xffffffffu, b1 ? k0[0][a] : k0[1][a], 2);
+        }
+        // columns: the 8 lanes that differ in bits 2-4 (row groups) share columns
+        {
+            float k1[4][3], k2[2][3];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float lo = fj[q][a], hi = fj[q + 4][a];
+                    k1[q][a] = (b2 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b2 ? lo : hi, 4);
+                }
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float lo = k1[q][a], hi = k1[q + 2][a];
+                    k2[q][a] = (b3 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b3 ? lo : hi, 8);
+                }
+#pragma unroll
+            for (int a = 0; a < 3; a++) colf[a] = (b4 ? k2[1][a] : k2[0][a]) + __shfl_xor_sync(0xffffffffu, b4 ? k2[0][a] : k2[1][a], 16);
+        }
+        const int rsel = rg + 8 * ((b0 ? 2 : 0) + (b1 ? 1 : 0));        // row of this tile held by the lane
+        const int csel = cg4 + 4 * ((b2 ? 4 : 0) + (b3 ? 2 : 0) + (b4 ? 1 : 0));
+        const uchar2 oi = S_OWN(c)[I], oj = S_OWN(c)[J];
+        const int slot_i = J, slot_j = (I == J) ? c.nb : I;
+        float4* dst_i = S_PART(c) + ((size_t)(oi.y * (c.nb + 1) + slot_i) * 32 + rsel);
+        float4* dst_j = S_PART(c) + ((size_t)(oj.y * (c.nb + 1) + slot_j) * 32 + csel);
+        if (c.C > 1) {
+            cg::cluster_group cl = cg::this_cluster();
+            dst_i = cl.map_shared_rank(dst_i, oi.x); dst_j = cl.map_shared_rank(dst_j, oj.x);
+        }
+        *dst_i = make_float4(rowf[0], rowf[1], rowf[2], 0.f);
+        *dst_j = make_float4(colf[0], colf[1], colf[2], 0.f);
     }
+    if (WANT_E) {
+        const double den = warp_sum((double)en), dev = warp_sum((double)ev);
+        if (c.C > 1) {
+            if (lane < c.C) {
+                double* remote = cg::this_cluster().map_shared_rank(S_ESLOTS(c), lane);
+                remote[2 * c.gw] = den; remote[2 * c.gw + 1] = dev;
+            }
+        } else if (lane == 0) { S_ESLOTS(c)[2 * c.gw] = den; S_ESLOTS(c)[2 * c.gw + 1] = dev; }
+    }
+    TSTAMP(c, 1);                                   // pair phase (own tiles)
+    csync(c);                                       // every partial of every owned bead has arrived
+    TSTAMP(c, 2);                                   // force barrier
+    float gx = 0.f, gy = 0.f, gz = 0.f, eb = 0.f;
+    if (c.row_ok) {
+        const float4* pp = S_PART(c) + ((size_t)(c.tid >> 5) * (c.nb + 1)) * 32 + lane;
+        int s = 0;
+        for (; s + 4 <= c.nb + 1; s += 4) {         // fixed summation order, loads issued four at a time
+            const float4 t0 = pp[s * 32], t1 = pp[(s + 1) * 32], t2 = pp[(s + 2) * 32], t3 = pp[(s + 3) * 32];
+            gx += t0.x; gy += t0.y; gz += t0.z; gx += t1.x; gy += t1.y; gz += t1.z;
+            gx += t2.x; gy += t2.y; gz += t2.z; gx += t3.x; gy += t3.y; gz += t3.z;
+        }
+        for (; s <= c.nb; s++) { const float4 t = pp[s * 32]; gx += t.x; gy += t.y; gz += t.z; }
+        const float4 xi = ldx(c, c.row);
+        for (int s = -1; s <= 1; s += 2) {          // bonds (i-1,i) and (i,i+1)
+            const int nbr = c.row + s;
+            if (nbr < 0 || nbr >= c.N) continue;
+            const float4 xn = ldx(c, nbr);
+            const float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
+            const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f);
+            const float rinv = rsqrtf(r2), r = r2 * rinv, u = r - p.r0;
+            const float g = 2.f * st.w_bond * u * rinv;
+            gx -= g * dx; gy -= g * dy; gz -= g * dz;
+            if (s == 1) eb = st.w_bond * u * u;
+        }
+    }
+    c.f[0] = gx; c.f[1] = gy; c.f[2] = gz; c.ebond = eb;
     if (count) c.nevals++;
+    TSTAMP(c, 3);                                   // gather + bond
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -349,340 +517,404 @@ __device__ double lbfgs_direction(double* B, double* delta, int m, int cnt, int 
 #define DOT_L(l, w) (1 + 6 * (l) + (w))     // w: 0 s.S 1 s.Y 2 y.S 3 y.Y 4 g.S 5 g.Y
 #define DOT_X(m, w) (1 + 6 * (m) + (w))     // w: 0 ss 1 sy 2 sg 3 yy 4 yg 5 gg
 
-__device__ void op_minimize(Ctx& c, const DevStage& st) {
-    const DevParams& p = c.prm;
-    const int m = c.m, t = c.tid;
-    const double n3 = 3.0 * c.N;
-    eval(c, st, true);
+// Every op that needs forces is written as "prepare coordinates -> evaluate -> digest", so that the
+// kernel has exactly one evaluation site per energy flavour (the pair loop is the bulk of the code).
+struct OpState {
+    int phase, step, cnt, head, it, ls;
+    bool want_e, count;
+    double E, gg, gp, ts, ke;
+};
+
+// ---- L-BFGS (definition shared with the oracle's sim_minimize) ---------------------------------
+__device__ __forceinline__ void min_set_trial(Ctx& c, const OpState& os) {
     if (c.owner) {
-        float gg = 0.f;
-        for (int k = 0; k < 3; k++) { vecp(c, V_G, k)[t] = -c.f[k]; vecp(c, V_XB, k)[t] = c.x[k]; gg += c.f[k] * c.f[k]; }
-        c.P[t] = c.ebond; c.P[c.rows_pad + t] = c.row_ok ? gg : 0.f;
+        const int t = c.tid;
+        for (int k = 0; k < 3; k++) c.x[k] = vecp(c, V_XB, k)[t] + (float)os.ts * vecp(c, V_PV, k)[t];
     }
-    allreduce(c, 2);
-    double E = c.gsum[0] + c.gsum[1] + c.gsum[2], gg = c.gsum[3];
-    int cnt = 0, head = 0, it = 0;
-    double gp = 0.0;
-    while (it < st.nstep) {
-        if (sqrt(gg / n3) < (double)p.gtol) break;
+    install_x(c);
+}
+__device__ __forceinline__ void min_finish(Ctx& c) {       // leave x = last accepted point everywhere
+    if (c.owner) { for (int k = 0; k < 3; k++) c.x[k] = vecp(c, V_XB, k)[c.tid]; }
+    install_x(c);
+}
+// top of an iteration: choose the direction / first step, publish the trial point.  false = minimiser done.
+__device__ bool min_top(Ctx& c, const DevStage& st, OpState& os) {
+    const DevParams& p = c.prm;
+    const int t = c.tid;
+    const double n3 = 3.0 * c.N;
+    while (true) {
+        if (!(os.it < st.nstep)) break;
+        if (sqrt(os.gg / n3) < (double)p.gtol) break;
         double t0 = 1.0;
-        if (cnt == 0) {
+        if (os.cnt == 0) {
             if (c.owner) for (int k = 0; k < 3; k++) vecp(c, V_PV, k)[t] = -vecp(c, V_G, k)[t];
-            gp = -gg;
-            t0 = st.drop > 0.f ? fmin(1.0, (double)st.drop / gg) : fmin(1.0, 1.0 / sqrt(gg));
+            os.gp = -os.gg;
+            t0 = st.drop > 0.f ? fmin(1.0, (double)st.drop / os.gg) : fmin(1.0, 1.0 / sqrt(os.gg));
         }
-        if (!(gp < 0.0)) { if (cnt == 0) break; cnt = 0; continue; }
-        double ts = t0, Et = 0.0; bool ok = false;
-        float gn[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f}, yv[3] = {0.f, 0.f, 0.f};
-        for (int ls = 0; ls <= p.max_ls; ls++) {
-            if (c.owner) {
-                for (int k = 0; k < 3; k++) { sv[k] = (float)ts * vecp(c, V_PV, k)[t]; c.x[k] = vecp(c, V_XB, k)[t] + sv[k]; }
-                publish_x(c);
-            }
-            eval(c, st, true);
-            if (c.owner) {
-                for (int k = 0; k < 3; k++) { gn[k] = -c.f[k]; yv[k] = gn[k] - vecp(c, V_G, k)[t]; }
-                if (!c.row_ok) for (int k = 0; k < 3; k++) { gn[k] = sv[k] = yv[k] = 0.f; }
-                const int rp = c.rows_pad;
-                c.P[t] = c.ebond;
-                for (int l = 0; l < m; l++) {
-                    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (l != head) for (int k = 0; k < 3; k++) {
-                        float sl = vecp(c, V_S(l), k)[t], yl = vecp(c, V_Y(l), k)[t];
-                        a[0] = fmaf(sv[k], sl, a[0]); a[1] = fmaf(sv[k], yl, a[1]); a[2] = fmaf(yv[k], sl, a[2]);
-                        a[3] = fmaf(yv[k], yl, a[3]); a[4] = fmaf(gn[k], sl, a[4]); a[5] = fmaf(gn[k], yl, a[5]);
-                    }
-                    for (int w = 0; w < 6; w++) c.P[(size_t)DOT_L(l, w) * rp + t] = a[w];
-                }
-                float b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int k = 0; k < 3; k++) {
-                    b[0] = fmaf(sv[k], sv[k], b[0]); b[1] = fmaf(sv[k], yv[k], b[1]); b[2] = fmaf(sv[k], gn[k], b[2]);
-                    b[3] = fmaf(yv[k], yv[k], b[3]); b[4] = fmaf(yv[k], gn[k], b[4]); b[5] = fmaf(gn[k], gn[k], b[5]);
-                }
-                for (int w = 0; w < 6; w++) c.P[(size_t)DOT_X(m, w) * rp + t] = b[w];
-            }
-            allreduce(c, 1 + 6 * m + 6);
-            Et = c.gsum[0] + c.gsum[1] + c.gsum[2];
-            if (Et < E && Et <= E + (double)p.c1 * ts * gp) { ok = true; break; }
-            ts *= 0.5;
+        if (!(os.gp < 0.0)) { if (os.cnt == 0) break; os.cnt = 0; continue; }
+        os.ts = t0; os.ls = 0;
+        min_set_trial(c, os);
+        return true;
+    }
+    min_finish(c);
+    return false;
+}
+__device__ bool min_after_eval(Ctx& c, const DevStage& st, OpState& os) {
+    const DevParams& p = c.prm;
+    const int m = c.m, t = c.tid, rp = c.rows_pad;
+    float* P = S_P(c);
+    double* gsum = S_GSUM(c);
+    if (os.phase == 0) {                     // evaluation at the starting point
+        if (c.owner) {
+            float gg = 0.f;
+            for (int k = 0; k < 3; k++) { vecp(c, V_G, k)[t] = -c.f[k]; vecp(c, V_XB, k)[t] = c.x[k]; gg += c.f[k] * c.f[k]; }
+            P[t] = c.ebond; P[rp + t] = c.row_ok ? gg : 0.f;
         }
-        it++;
-        if (!ok) { if (cnt == 0) break; cnt = 0; continue; }
-        const double* G = c.gsum + 2;       // owner columns
-        double ss = G[DOT_X(m, 0)], sy = G[DOT_X(m, 1)], yy = G[DOT_X(m, 3)];
-        bool keep = sy > 1e-10 * sqrt(ss * yy);
+        allreduce(c, 2, true);
+        os.E = gsum[0] + gsum[1] + gsum[2]; os.gg = gsum[3];
+        os.cnt = 0; os.head = 0; os.it = 0; os.gp = 0.0; os.phase = 1;
+        return min_top(c, st, os);
+    }
+    // evaluation at a trial point x = xb + ts p
+    float gn[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f}, yv[3] = {0.f, 0.f, 0.f};
+    const int head = os.head;
+    if (c.owner) {
+        for (int k = 0; k < 3; k++) { sv[k] = (float)os.ts * vecp(c, V_PV, k)[t]; gn[k] = -c.f[k]; yv[k] = gn[k] - vecp(c, V_G, k)[t]; }
+        if (!c.row_ok) for (int k = 0; k < 3; k++) { gn[k] = sv[k] = yv[k] = 0.f; }
+        P[t] = c.ebond;
+        for (int l = 0; l < m; l++) {
+            float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (l != head) for (int k = 0; k < 3; k++) {
+                float sl = vecp(c, V_S(l), k)[t], yl = vecp(c, V_Y(l), k)[t];
+                a[0] = fmaf(sv[k], sl, a[0]); a[1] = fmaf(sv[k], yl, a[1]); a[2] = fmaf(yv[k], sl, a[2]);
+                a[3] = fmaf(yv[k], yl, a[3]); a[4] = fmaf(gn[k], sl, a[4]); a[5] = fmaf(gn[k], yl, a[5]);
+            }
+            for (int w = 0; w < 6; w++) P[(size_t)DOT_L(l, w) * rp + t] = a[w];
+        }
+        float b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < 3; k++) {
+            b[0] = fmaf(sv[k], sv[k], b[0]); b[1] = fmaf(sv[k], yv[k], b[1]); b[2] = fmaf(sv[k], gn[k], b[2]);
+            b[3] = fmaf(yv[k], yv[k], b[3]); b[4] = fmaf(yv[k], gn[k], b[4]); b[5] = fmaf(gn[k], gn[k], b[5]);
+        }
+        for (int w = 0; w < 6; w++) P[(size_t)DOT_X(m, w) * rp + t] = b[w];
+    }
+    allreduce(c, 1 + 6 * m + 6, true);
+    const double Et = gsum[0] + gsum[1] + gsum[2];
+    if (!(Et < os.E && Et <= os.E + (double)p.c1 * os.ts * os.gp)) {        // Armijo test failed
+        os.ts *= 0.5; os.ls++;
+        if (os.ls <= p.max_ls) { min_set_trial(c, os); return true; }
+        os.it++;
+        if (os.cnt == 0) { min_finish(c); return false; }
+        os.cnt = 0;
+        return min_top(c, st, os);
+    }
+    os.it++;
+    const double* G = gsum + 2;       // owner columns
+    const double ss = G[DOT_X(m, 0)], sy = G[DOT_X(m, 1)], yy = G[DOT_X(m, 3)];
+    const bool keep = sy > 1e-10 * sqrt(ss * yy);
+    if (c.owner) {
+        for (int k = 0; k < 3; k++) {
+            if (keep) { vecp(c, V_S(head), k)[t] = sv[k]; vecp(c, V_Y(head), k)[t] = yv[k]; }
+            vecp(c, V_XB, k)[t] = c.x[k]; vecp(c, V_G, k)[t] = gn[k];
+        }
+    }
+    const bool small = os.cnt > 0 && (os.E - Et) <= (double)p.ftol * fmax(fabs(Et), 1.0);
+    os.E = Et; os.gg = G[DOT_X(m, 5)];
+    if (small) { min_finish(c); return false; }
+    if (keep) {
+        double* B = S_B(c); double* delta = S_DELTA(c);
+        if (t == 0) {
+            const int ig = 2 * m, h = head;
+            for (int l = 0; l < m; l++) {
+                if (l == h) continue;
+                B[h * SA_MAXB + l] = B[l * SA_MAXB + h] = G[DOT_L(l, 0)];
+                B[h * SA_MAXB + m + l] = B[(m + l) * SA_MAXB + h] = G[DOT_L(l, 1)];
+                B[(m + h) * SA_MAXB + l] = B[l * SA_MAXB + m + h] = G[DOT_L(l, 2)];
+                B[(m + h) * SA_MAXB + m + l] = B[(m + l) * SA_MAXB + m + h] = G[DOT_L(l, 3)];
+                B[ig * SA_MAXB + l] = B[l * SA_MAXB + ig] = G[DOT_L(l, 4)];
+                B[ig * SA_MAXB + m + l] = B[(m + l) * SA_MAXB + ig] = G[DOT_L(l, 5)];
+            }
+            B[h * SA_MAXB + h] = ss; B[h * SA_MAXB + m + h] = B[(m + h) * SA_MAXB + h] = sy;
+            B[(m + h) * SA_MAXB + m + h] = yy;
+            B[ig * SA_MAXB + h] = B[h * SA_MAXB + ig] = G[DOT_X(m, 2)];
+            B[ig * SA_MAXB + m + h] = B[(m + h) * SA_MAXB + ig] = G[DOT_X(m, 4)];
+            B[ig * SA_MAXB + ig] = os.gg;
+        }
+        os.head = (head + 1) % m; if (os.cnt < m) os.cnt++;
+        if (t == 0) delta[SA_MAXB] = lbfgs_direction(B, delta, m, os.cnt, os.head);
+        __syncthreads();
+        os.gp = delta[SA_MAXB];
         if (c.owner) {
             for (int k = 0; k < 3; k++) {
-                if (keep) { vecp(c, V_S(head), k)[t] = sv[k]; vecp(c, V_Y(head), k)[t] = yv[k]; }
-                vecp(c, V_XB, k)[t] = c.x[k]; vecp(c, V_G, k)[t] = gn[k];
+                float acc = (float)delta[2 * m] * vecp(c, V_G, k)[t];
+                for (int kk = 0; kk < os.cnt; kk++) {
+                    int l = ((os.head - 1 - kk) % m + m) % m;
+                    acc = fmaf((float)delta[l], vecp(c, V_S(l), k)[t], acc);
+                    acc = fmaf((float)delta[m + l], vecp(c, V_Y(l), k)[t], acc);
+                }
+                vecp(c, V_PV, k)[t] = -acc;
             }
         }
-        const bool small = cnt > 0 && (E - Et) <= (double)p.ftol * fmax(fabs(Et), 1.0);
-        E = Et; gg = G[DOT_X(m, 5)];
-        if (small) break;
-        if (keep) {
-            if (t == 0) {
-                double* B = c.B; const int ig = 2 * m, h = head;
-                for (int l = 0; l < m; l++) {
-                    if (l == h) continue;
-                    B[h * SA_MAXB + l] = B[l * SA_MAXB + h] = G[DOT_L(l, 0)];
-                    B[h * SA_MAXB + m + l] = B[(m + l) * SA_MAXB + h] = G[DOT_L(l, 1)];
-                    B[(m + h) * SA_MAXB + l] = B[l * SA_MAXB + m + h] = G[DOT_L(l, 2)];
-                    B[(m + h) * SA_MAXB + m + l] = B[(m + l) * SA_MAXB + m + h] = G[DOT_L(l, 3)];
-                    B[ig * SA_MAXB + l] = B[l * SA_MAXB + ig] = G[DOT_L(l, 4)];
-                    B[ig * SA_MAXB + m + l] = B[(m + l) * SA_MAXB + ig] = G[DOT_L(l, 5)];
-                }
-                B[h * SA_MAXB + h] = ss; B[h * SA_MAXB + m + h] = B[(m + h) * SA_MAXB + h] = sy;
-                B[(m + h) * SA_MAXB + m + h] = yy;
-                B[ig * SA_MAXB + h] = B[h * SA_MAXB + ig] = G[DOT_X(m, 2)];
-                B[ig * SA_MAXB + m + h] = B[(m + h) * SA_MAXB + ig] = G[DOT_X(m, 4)];
-                B[ig * SA_MAXB + ig] = gg;
-            }
-            head = (head + 1) % m; if (cnt < m) cnt++;
-            if (t == 0) c.delta[SA_MAXB] = lbfgs_direction(c.B, c.delta, m, cnt, head);
-            __syncthreads();
-            gp = c.delta[SA_MAXB];
-            if (c.owner) {
-                for (int k = 0; k < 3; k++) {
-                    float acc = (float)c.delta[2 * m] * vecp(c, V_G, k)[t];
-                    for (int kk = 0; kk < cnt; kk++) {
-                        int l = ((head - 1 - kk) % m + m) % m;
-                        acc = fmaf((float)c.delta[l], vecp(c, V_S(l), k)[t], acc);
-                        acc = fmaf((float)c.delta[m + l], vecp(c, V_Y(l), k)[t], acc);
-                    }
-                    vecp(c, V_PV, k)[t] = -acc;
-                }
-            }
-            __syncthreads();   // delta is rewritten by thread 0 in the next iteration
-        } else {
-            cnt = 0;           // curvature condition failed: restart from steepest descent
-        }
+        __syncthreads();   // delta is rewritten by thread 0 in the next iteration
+    } else {
+        os.cnt = 0;        // curvature condition failed: restart from steepest descent
     }
-    // leave x = last accepted point everywhere
-    if (c.owner) { for (int k = 0; k < 3; k++) c.x[k] = vecp(c, V_XB, k)[t]; }
-    csync(c);
-    if (c.owner) publish_x(c);
+    return min_top(c, st, os);
 }
 
-__device__ void op_dynamics(Ctx& c, const DevStage& st) {
-    const DevParams& p = c.prm;
+// ---- Verlet MD (definition shared with the oracle's sim_dynamics) ------------------------------
+__device__ void dyn_begin(Ctx& c) {          // cmremove=true
     const int t = c.tid, rp = c.rows_pad;
-    // cmremove=true
-    if (c.owner) { for (int k = 0; k < 3; k++) c.P[(size_t)k * rp + t] = c.row_ok ? c.v[k] : 0.f; }
-    if (c.lane == 0) { c.ewarp[c.warp * 2] = 0.0; c.ewarp[c.warp * 2 + 1] = 0.0; }
-    allreduce(c, 3);
-    if (c.owner && c.row_ok) for (int k = 0; k < 3; k++) c.v[k] -= (float)(c.gsum[2 + k] / c.N);
-    eval(c, st, true);
-    if (c.owner) {
-        float ke = 0.f; if (c.row_ok) for (int k = 0; k < 3; k++) ke += c.v[k] * c.v[k];
-        c.P[t] = c.ebond; c.P[rp + t] = 0.5f * p.mass * ke;
-    }
-    allreduce(c, 2);
-    double ke = c.gsum[3];
-    const double ndof = 3.0 * c.N - 3.0;
+    float* P = S_P(c);
+    if (c.owner) { for (int k = 0; k < 3; k++) P[(size_t)k * rp + t] = c.row_ok ? c.v[k] : 0.f; }
+    allreduce(c, 3, false);
+    if (c.row_ok) for (int k = 0; k < 3; k++) c.v[k] -= (float)(S_GSUM(c)[2 + k] / c.N);
+}
+// One cluster barrier per step besides the force barrier: owners publish a = x + dt*h*f, b = dt*v (v after
+// the closing half kick) and their kinetic-energy partials; after the barrier every CTA knows the
+// temperature, hence lam, and x' = a + lam*b = x + dt*(lam*v + h*f) for all beads (read lazily by ldx).
+__device__ bool dyn_after_eval(Ctx& c, const DevStage& st, OpState& os) {
+    const DevParams& p = c.prm;
     const float h = 0.5f * st.dt_akma * p.inv_mass;
-    for (int step = 0; step < st.nstep; step++) {
-        double T = 2.0 * ke / ((double)p.kboltz * ndof), lam = 1.0;
-        if (T > 0.0) {
-            if (st.flag == CHR3D_COUPLE_TCOUP) lam = sqrt(fmax(0.0, 1.0 + 2.0 * (double)p.fbeta * (double)st.dt_ps * ((double)st.temp / T - 1.0)));
-            else if (st.flag == CHR3D_COUPLE_VSCALE) lam = sqrt((double)st.temp / T);
-        }
-        if (c.owner && c.row_ok) {
-            const float lf = (float)lam;
-            for (int k = 0; k < 3; k++) { c.v[k] = fmaf(h, c.f[k], lf * c.v[k]); c.x[k] = fmaf(st.dt_akma, c.v[k], c.x[k]); }
-            publish_x(c);
-        }
-        eval(c, st, true);
-        if (c.owner) {
-            float k2 = 0.f;
-            if (c.row_ok) for (int k = 0; k < 3; k++) { c.v[k] = fmaf(h, c.f[k], c.v[k]); k2 += c.v[k] * c.v[k]; }
-            c.P[t] = c.ebond; c.P[rp + t] = 0.5f * p.mass * k2;
-        }
-        allreduce(c, 2);
-        ke = c.gsum[3];
+    float k2 = 0.f;
+    if (c.row_ok) for (int k = 0; k < 3; k++) { if (os.phase) c.v[k] = fmaf(h, c.f[k], c.v[k]); k2 += c.v[k] * c.v[k]; }
+    os.phase = 1;
+    if (os.step >= st.nstep) return false;         // x, v, f of the owners are final
+    os.step++;
+    if (c.owner && c.tid < 32 * c.nown) {
+        const double kw = warp_sum((double)(0.5f * p.mass * k2));
+        const int slot = c.rank * c.own_max + (c.tid >> 5);
+        if (c.C > 1) { if (c.lane < c.C) cg::this_cluster().map_shared_rank(S_KSLOTS(c), c.lane)[slot] = kw; }
+        else if (c.lane == 0) S_KSLOTS(c)[slot] = kw;
     }
+    const float dth = st.dt_akma * h;
+    publish_ab(c, make_float4(fmaf(dth, c.f[0], c.x[0]), fmaf(dth, c.f[1], c.x[1]), fmaf(dth, c.f[2], c.x[2]), 0.f),
+               make_float4(st.dt_akma * c.v[0], st.dt_akma * c.v[1], st.dt_akma * c.v[2], 0.f), true);
+    TSTAMP(c, 4);                                   // kick, kinetic-energy partial, publish
+    csync(c);
+    TSTAMP(c, 5);                                   // coordinate barrier
+    double ke = c.lane < c.C * c.own_max ? S_KSLOTS(c)[c.lane] : 0.0;    // C*own_max <= 32 slots: one per lane,
+    ke = warp_sum(ke);                                                   // same butterfly order in every warp of the cluster
+    // lam = sqrt(1 + 2 fbeta dt (T0/T - 1)) (tcoupling) or sqrt(T0/T) (vscaling), T = 2 KE / (kB (3N-3)); the sum is fp64,
+    // the few scalar operations after it are fp32 (they sit on the critical path of every step)
+    const float kef = (float)ke;
+    float lf = 1.f;
+    if (kef > 0.f) {
+        const float tr = st.temp * (p.kboltz * (3.f * (float)c.N - 3.f)) / (2.f * kef);      // T0 / T
+        if (st.flag == CHR3D_COUPLE_TCOUP) lf = sqrtf(fmaxf(0.f, fmaf(2.f * p.fbeta * st.dt_ps, tr - 1.f, 1.f)));
+        else if (st.flag == CHR3D_COUPLE_VSCALE) lf = sqrtf(tr);
+    }
+    if (c.row_ok) {
+        for (int k = 0; k < 3; k++) {
+            const float a = fmaf(dth, c.f[k], c.x[k]), b = st.dt_akma * c.v[k];
+            c.x[k] = fmaf(lf, b, a);                // exactly what ldx() gives every other thread
+            c.v[k] = fmaf(h, c.f[k], lf * c.v[k]);
+        }
+    }
+    flip(c, lf);
+    TSTAMP(c, 6);                                   // temperature, lambda, owner update
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__global__ void __launch_bounds__(512, 1)
-sa_kernel(const TrajDesc* __restrict__ traj, DevParams prm, const DevStage* __restrict__ prog, int nstages,
-          int stage_targets) {
-    extern __shared__ __align__(128) unsigned char smem[];
+template <bool GENERAL, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, 1)
+sa_kernel(const TrajDesc* __restrict__ traj, DevParams prm, const DevStage* __restrict__ prog, int nstages, int smem_bytes) {
     cg::cluster_group cluster = cg::this_cluster();
     Ctx c;
     c.C = (int)cluster.num_blocks();
     c.rank = (int)cluster.block_rank();
     const TrajDesc td = traj[blockIdx.x / c.C];
     c.N = td.N; c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
-    c.nthreads = blockDim.x; c.nwarps = c.nthreads >> 5; c.m = prm.m; c.prm = prm; c.par = 0; c.nevals = 0;
+    c.nthreads = blockDim.x; c.W = c.nthreads >> 5; c.m = prm.m; c.prm = prm; c.par = 0; c.nevals = 0;
+    c.Tt = (const float4*)td.T;
 
-    SaShape sh; sa_shape(c.N, c.C, c.nthreads, c.m, stage_targets, sh);
+    SaShape sh; sa_shape(c.N, c.C, c.W, c.m, (size_t)smem_bytes, sh);
     SaLayout L; sa_layout(sh, L);
-    c.xs = (float4*)(smem + L.xs); c.fpart = (float4*)(smem + L.fpart); c.vec = (float*)(smem + L.vec);
-    c.P = (float*)(smem + L.P); c.ewarp = (double*)(smem + L.ewarp); c.slots = (double*)(smem + L.slots);
-    c.gsum = (double*)(smem + L.gsum); c.B = (double*)(smem + L.B); c.delta = (double*)(smem + L.delta);
-    c.rows_pad = sh.rows_pad; c.Q = sh.Q;
+    c.o_ab = (unsigned)L.ab; c.o_kslots = (unsigned)L.kslots; c.o_part = (unsigned)L.part; c.o_vec = (unsigned)L.vec; c.o_P = (unsigned)L.P;
+    c.o_eslots = (unsigned)L.eslots; c.o_slots = (unsigned)L.slots; c.o_gsum = (unsigned)L.gsum; c.o_B = (unsigned)L.B;
+    c.o_delta = (unsigned)L.delta; c.o_tij = (unsigned)L.tij; c.o_own = (unsigned)L.own; c.o_tres = (unsigned)L.tres;
+    c.nb = sh.nb; c.n32p = sh.n32 + 1; c.own_max = sh.own_max; c.buf = 0; c.lam = 0.f; c.gwarps = sh.gwarps; c.gw = c.rank * c.W + c.warp; c.res_rounds = sh.res_rounds; c.rows_pad = sh.rows_pad;
+    {   // tiles of this CTA: t = rank + C*lt, lt = 0..nloc-1; of this warp: lt = warp + W*k
+        const int nloc = sh.ntiles > c.rank ? (sh.ntiles - 1 - c.rank) / c.C + 1 : 0;
+        c.my_rounds = nloc > c.warp ? (nloc - 1 - c.warp) / c.W + 1 : 0;
+    }
 
-    // row-warps of this rank: balanced contiguous split of ceil(N/32) row-warps over C ranks
-    const int rw_total = (c.N + 31) / 32;
-    const int rw0 = (int)(((long long)rw_total * c.rank) / c.C), rw1 = (int)(((long long)rw_total * (c.rank + 1)) / c.C);
-    const int my_rw = rw1 - rw0;
-    c.r0 = rw0 * 32;
-    c.rows = min(c.N, rw1 * 32) - c.r0; if (c.rows < 0) c.rows = 0;
-    // pair-loop role: warp -> (row-warp, chunk); Q chunks for every row-warp of this rank
-    c.pw_row = my_rw > 0 ? c.warp % my_rw : 0;
-    c.pw_q = my_rw > 0 ? c.warp / my_rw : 0;
-    c.pw_active = (my_rw > 0 && c.pw_q < c.Q) ? 1 : 0;
+    // bead blocks of this rank: balanced contiguous split of the nb blocks over C ranks
+    c.rw0 = (int)(((long long)c.nb * c.rank) / c.C);
+    c.nown = (int)(((long long)c.nb * (c.rank + 1)) / c.C) - c.rw0;
     c.owner = c.tid < c.rows_pad;
-    c.row_ok = c.tid < c.rows;
-    c.row = c.r0 + c.tid;
+    c.row = 32 * c.rw0 + c.tid;
+    c.row_ok = c.tid < 32 * c.nown && c.row < c.N;
     for (int k = 0; k < 3; k++) { c.x[k] = 0.f; c.v[k] = 0.f; c.f[k] = 0.f; }
     c.ebond = 0.f;
 
-    // fpart rows of inactive chunks / padded rows must read as zero
-    for (int i = c.tid; i < c.Q * c.rows_pad; i += c.nthreads) c.fpart[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = c.tid; i < 2 * SA_MAXC * SA_KTOT; i += c.nthreads) c.slots[i] = 0.0;
-    for (int i = c.tid; i < SA_MAXB * SA_MAXB; i += c.nthreads) c.B[i] = 0.0;
-    if (c.tid == 0) c.xs[c.N] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // targets: column block [r0, r0+rows_pad) of the symmetric matrix, i.e. T[j][r0+li]
-    if (stage_targets && my_rw > 0) {
-        float* tblk = (float*)(smem + L.tblk);
-        uint64_t* mbar = (uint64_t*)(smem + L.mbar);
-        const uint32_t row_bytes = (uint32_t)(my_rw * 32 * sizeof(float));
-        if (c.tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (c.warp == 0) {
-            if (c.lane == 0)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(row_bytes * (uint32_t)c.N) : "memory");
-            __syncwarp();
-            for (int j = c.lane; j < c.N; j += 32) {
-                const float* src = td.T + (size_t)j * td.pitch + c.r0;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(tblk + (size_t)j * c.rows_pad)), "l"(src), "r"(row_bytes), "r"(smem_u32(mbar)) : "memory");
-            }
-        }
-        // wait for phase 0
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(done) : "r"(smem_u32(mbar)), "r"(0) : "memory");
-        }
-        // pad columns beyond this rank's rows (only when my_rw < rw_max) are never read
-        c.Tsrc = tblk; c.tstride = c.rows_pad;
-    } else {
-        c.Tsrc = td.T + c.r0; c.tstride = td.pitch;
+    for (int i = c.tid; i < 4 * c.n32p; i += c.nthreads) S_AB(c)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = c.tid; i < c.C * c.own_max; i += c.nthreads) S_KSLOTS(c)[i] = 0.0;
+    for (int i = c.tid; i < 2 * SA_MAXC * SA_KTOT; i += c.nthreads) S_SLOTS(c)[i] = 0.0;
+    for (int i = c.tid; i < 2 * sh.gwarps; i += c.nthreads) S_ESLOTS(c)[i] = 0.0;
+    for (int i = c.tid; i < SA_MAXB * SA_MAXB; i += c.nthreads) S_B(c)[i] = 0.0;
+    for (int i = c.tid; i < SA_KTOT * c.rows_pad; i += c.nthreads) S_P(c)[i] = 0.f;
+    for (int b = c.tid; b < c.nb; b += c.nthreads) {           // owner rank / local index of every bead block
+        int r = 0;
+        while ((int)(((long long)c.nb * (r + 1)) / c.C) <= b) r++;
+        S_OWN(c)[b] = make_uchar2((unsigned char)r, (unsigned char)(b - (int)(((long long)c.nb * r) / c.C)));
+    }
+    if (c.lane == 0) for (int k = 0; k < c.my_rounds; k++) {   // this warp's tiles
+        int I, J; sa_tile_coords(c.rank + c.C * (c.warp + c.W * k), c.nb, I, J);
+        S_TIJ(c)[k * c.W + c.warp] = make_uchar2((unsigned char)I, (unsigned char)J);
+    }
+    for (int k = 0; k < c.my_rounds && k < c.res_rounds; k++) {   // resident targets: each warp stages its own tiles (coalesced)
+        const float4* gp = c.Tt + ((size_t)(c.rank + c.C * (c.warp + c.W * k)) * 256 + c.lane);
+        float4* sp = S_TRES(c) + ((size_t)(k * c.W + c.warp) * 256 + c.lane);
+#pragma unroll
+        for (int q = 0; q < 8; q++) sp[q * 32] = __ldg(gp + q * 32);
     }
     __syncthreads();
     csync(c);
+#ifdef SA_TIMING
+    c.tmark = blockIdx.x == 0 && c.lane == 0 && (c.warp == 0 || c.warp == c.W - 1);
+    c.tlast = clock64(); for (int q = 0; q < 10; q++) c.tacc[q] = 0;
+#endif
 
     int cur_image = 1, hand = 1;
     double e_saved = 0.0;
     double e4[4] = {0, 0, 0, 0};
     for (int k = 0; k < nstages; k++) {
         const DevStage st = prog[k];
+        OpState os;
+        os.phase = 0; os.step = 0; os.cnt = 0; os.head = 0; os.it = 0; os.ls = 0; os.want_e = true; os.count = true;
+        os.E = os.gg = os.gp = os.ts = os.ke = 0.0;
+        bool more = false;
         switch (st.op) {
-        case CHR3D_OP_INIT: {
-            csync(c);
-            if (c.owner && c.row_ok) {
+        case CHR3D_OP_INIT:
+            if (c.row_ok) {
                 c.x[0] = td.x0[3 * c.row] * (float)st.flag; c.x[1] = td.x0[3 * c.row + 1]; c.x[2] = td.x0[3 * c.row + 2];
                 c.v[0] = c.v[1] = c.v[2] = 0.f;
-                publish_x(c);
             }
+            install_x(c);
             cur_image = st.flag; hand = cur_image;
-            break; }
-        case CHR3D_OP_MINIMIZE: op_minimize(c, st); break;
-        case CHR3D_OP_MAXWELL: {
-            if (c.owner && c.row_ok) {
+            break;
+        case CHR3D_OP_MAXWELL:
+            if (c.row_ok) {
                 double z[3]; normal3(td.seed, (uint32_t)c.row, STREAM_MAXWELL + (uint32_t)k, (uint32_t)td.model, z);
                 double sd = sqrt((double)prm.kboltz * (double)st.temp / (double)prm.mass);
                 for (int q = 0; q < 3; q++) c.v[q] = (float)(sd * z[q]);
             }
-            break; }
-        case CHR3D_OP_DYNAMICS: op_dynamics(c, st); break;
-        case CHR3D_OP_SAVE: case CHR3D_OP_PICK: case CHR3D_OP_ENERGY: {
-            eval(c, st, st.op != CHR3D_OP_ENERGY);
-            if (c.owner) c.P[c.tid] = c.ebond;
-            allreduce(c, 1);
-            double e = c.gsum[0] + c.gsum[1] + c.gsum[2];
-            if (st.op == CHR3D_OP_SAVE) {
-                e_saved = e;
-                if (c.owner && c.row_ok) for (int q = 0; q < 3; q++) { td.scratch[3 * c.row + q] = c.x[q]; td.scratch[3 * (c.N + c.row) + q] = c.v[q]; }
-            } else if (st.op == CHR3D_OP_PICK) {
-                if (e_saved > e) hand = cur_image;                 // C3D:1717-1721
-                else {
-                    hand = 1;
-                    if (c.owner && c.row_ok) {
-                        for (int q = 0; q < 3; q++) { c.x[q] = td.scratch[3 * c.row + q]; c.v[q] = td.scratch[3 * (c.N + c.row) + q]; }
-                        publish_x(c);
-                    }
-                }
-            } else {
-                e4[CHR3D_E_OVERALL] = e; e4[CHR3D_E_BON] = c.gsum[2]; e4[CHR3D_E_VDW] = c.gsum[1]; e4[CHR3D_E_NOE] = c.gsum[0];
-                if (td.f_out && c.owner && c.row_ok) for (int q = 0; q < 3; q++) td.f_out[3 * c.row + q] = c.f[q];
-            }
-            break; }
-        case CHR3D_OP_CENTER: {
-            if (c.owner) for (int q = 0; q < 3; q++) c.P[(size_t)q * c.rows_pad + c.tid] = c.row_ok ? c.x[q] : 0.f;
-            if (c.lane == 0) { c.ewarp[c.warp * 2] = 0.0; c.ewarp[c.warp * 2 + 1] = 0.0; }
-            allreduce(c, 3);
-            if (c.owner && c.row_ok) { for (int q = 0; q < 3; q++) c.x[q] -= (float)(c.gsum[2 + q] / c.N); publish_x(c); }
-            break; }
+            break;
+        case CHR3D_OP_CENTER:
+            if (c.owner) for (int q = 0; q < 3; q++) S_P(c)[(size_t)q * c.rows_pad + c.tid] = c.row_ok ? c.x[q] : 0.f;
+            allreduce(c, 3, false);
+            if (c.row_ok) { for (int q = 0; q < 3; q++) c.x[q] -= (float)(S_GSUM(c)[2 + q] / c.N); }
+            install_x(c);
+            break;
+        case CHR3D_OP_MINIMIZE: more = true; break;
+        case CHR3D_OP_DYNAMICS: dyn_begin(c); os.want_e = false; more = true; break;
+        case CHR3D_OP_SAVE: case CHR3D_OP_PICK: more = true; break;
+        case CHR3D_OP_ENERGY: os.count = false; more = true; break;
         default: break;
         }
+        while (more) {
+            if (os.want_e) eval_t<true, GENERAL>(c, st, os.count); else eval_t<false, GENERAL>(c, st, os.count);
+            if (st.op == CHR3D_OP_MINIMIZE) { more = min_after_eval(c, st, os); TSTAMP(c, 7); }
+            else if (st.op == CHR3D_OP_DYNAMICS) more = dyn_after_eval(c, st, os);
+            else {
+                more = false;
+                if (c.owner) S_P(c)[c.tid] = c.ebond;
+                allreduce(c, 1, true);
+                const double* gsum = S_GSUM(c);
+                const double e = gsum[0] + gsum[1] + gsum[2];
+                if (st.op == CHR3D_OP_SAVE) {
+                    e_saved = e;
+                    if (c.row_ok) for (int q = 0; q < 3; q++) { td.scratch[3 * c.row + q] = c.x[q]; td.scratch[3 * (c.N + c.row) + q] = c.v[q]; }
+                } else if (st.op == CHR3D_OP_PICK) {
+                    if (e_saved > e) hand = cur_image;                 // C3D:1717-1721
+                    else {
+                        hand = 1;
+                        if (c.row_ok) {
+                            for (int q = 0; q < 3; q++) { c.x[q] = td.scratch[3 * c.row + q]; c.v[q] = td.scratch[3 * (c.N + c.row) + q]; }
+                        }
+                        install_x(c);
+                    }
+                } else {
+                    e4[CHR3D_E_OVERALL] = e; e4[CHR3D_E_BON] = gsum[2]; e4[CHR3D_E_VDW] = gsum[1]; e4[CHR3D_E_NOE] = gsum[0];
+                    if (td.f_out && c.row_ok) for (int q = 0; q < 3; q++) td.f_out[3 * c.row + q] = c.f[q];
+                }
+            }
+        }
     }
-    if (c.owner && c.row_ok) for (int q = 0; q < 3; q++) td.x_out[3 * c.row + q] = c.x[q];
+    if (c.row_ok) for (int q = 0; q < 3; q++) td.x_out[3 * c.row + q] = c.x[q];
     if (c.rank == 0 && c.tid == 0) {
         for (int q = 0; q < 4; q++) td.e_out[q] = e4[q];
         *td.nevals_out = c.nevals; *td.hand_out = hand;
     }
+#ifdef SA_TIMING
+    if (c.tmark) for (int q = 0; q < 10; q++) sa_dbg[c.warp == 0 ? 0 : 1][q] = (unsigned long long)c.tacc[q];
+    if (c.tmark) sa_dbg[c.warp == 0 ? 0 : 1][10] = (unsigned long long)c.nevals;
+#endif
     csync(c);   // no CTA may exit while peers can still write into its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side: configuration choice and launch
 // ------------------------------------------------------------------------------------------------
-static size_t smem_for(int N, int C, int threads, int m, int stage) {
-    SaShape sh; sa_shape(N, C, threads, m, stage, sh);
+static size_t smem_fixed(int N, int C, int W, int m) {
+    SaShape sh; sa_shape(N, C, W, m, 0, sh);
     SaLayout L; sa_layout(sh, L);
     return L.total;
 }
+static int max_active_clusters(int C, int threads, size_t smem) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(C * 148), 1, 1); lc.blockDim = dim3((unsigned)threads, 1, 1); lc.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    int n = 0;
+    if ((threads > 512 ? cudaOccupancyMaxActiveClusters(&n, sa_kernel<false, 20>, &lc) : cudaOccupancyMaxActiveClusters(&n, sa_kernel<false, 16>, &lc)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
-    int dev = 0, sms = 148, smem_max = 227 * 1024;
+    int dev = 0, smem_max = 227 * 1024;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int rw_total = (N + 31) / 32;
+    if (cudaFuncSetAttribute(sa_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncSetAttribute(sa_kernel<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) cudaGetLastError();
+    const int nb = (N + 31) / 32, ntiles = nb * (nb + 1) / 2;
+    const int force_c = getenv("CHR3D_SA_CLUSTER") ? atoi(getenv("CHR3D_SA_CLUSTER")) : 0;
+    const int force_w = getenv("CHR3D_SA_WARPS") ? atoi(getenv("CHR3D_SA_WARPS")) : 0;
     double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0};
-    for (int C = 1; C <= SA_MAXC; C++) {
-        if (C > rw_total) break;
-        int rw_max = (rw_total + C - 1) / C;
-        // threads: enough chunks per row-warp to give every SM sub-partition several warps
-        int Q = 1; while (rw_max * (Q + 1) * 32 <= 512 && (Q + 1) <= (N + 31) / 32 + 1) Q++;
-        int threads = rw_max * Q * 32; if (threads < 64) threads = 64; if (threads > 512) continue;
-        int stage = 1; size_t sm = smem_for(N, C, threads, m, 1);
-        if (sm > (size_t)smem_max) { stage = 0; sm = smem_for(N, C, threads, m, 0); }
-        if (sm > (size_t)smem_max) continue;
-        // co-resident clusters (approximation: one CTA per SM for the big shapes, more for small ones)
-        int cta_per_sm = (int)((size_t)smem_max / (sm + 1024)); if (cta_per_sm < 1) cta_per_sm = 1;
-        int by_thr = 2048 / threads; if (cta_per_sm > by_thr) cta_per_sm = by_thr; if (cta_per_sm < 1) cta_per_sm = 1;
-        int resident = (sms * cta_per_sm) / C; if (C > 1) resident = (int)(resident * 0.9); if (resident < 1) resident = 1;
-        int waves = (n_traj + resident - 1) / resident;
-        // cost model per force evaluation: pair work per thread + fixed barrier/reduction overhead
-        double pair_cycles = (double)N / Q * 30.0 * ((double)(rw_max * Q) / 4.0 > 1.0 ? (double)(rw_max * Q) / 4.0 : 1.0);
-        double over = 600.0 + (C > 1 ? 1200.0 : 0.0);
-        double cost = waves * (pair_cycles + over);
-        if (cost < best) { best = cost; bc.cluster = C; bc.threads = threads; bc.stage_targets = stage; bc.smem = sm; }
+    const int Cs[] = {1, 2, 3, 4, 5, 6, 8};
+    for (int C : Cs) {
+        if (force_c && C != force_c) continue;
+        if (C > nb && C > 1) continue;
+        for (int W = 4; W <= SA_MAXW; W += 4) {
+            if (force_w && W != force_w) continue;
+            const int own_max = (nb + C - 1) / C;
+            if (own_max > W || C * own_max > 32) continue;       // every owned bead needs its own thread; one KE slot per lane
+            const size_t fixed = smem_fixed(N, C, W, m);
+            if (fixed > (size_t)smem_max) continue;
+            const int rounds = ((ntiles + C - 1) / C + W - 1) / W;
+            // resident targets when they fit, otherwise as many rounds as fit (the rest streams from L2)
+            size_t want = fixed + (size_t)rounds * W * SA_TILE_FLOATS * sizeof(float);
+            size_t smem = want <= (size_t)smem_max ? want : (size_t)smem_max;
+            int res_rounds = (int)((smem - fixed) / ((size_t)W * SA_TILE_FLOATS * sizeof(float)));
+            int resident = max_active_clusters(C, 32 * W, smem);
+            if (resident < 1 && smem > fixed) { smem = fixed; res_rounds = 0; resident = max_active_clusters(C, 32 * W, smem); }
+            if (resident < 1) continue;
+            const int waves = (n_traj + resident - 1) / resident;
+            // cost model per force evaluation (cycles): pair phase + fixed barrier / reduction overhead
+            const double warps_per_sched = W / 4.0;
+            const double tile_cycles = 1050.0 + (rounds > res_rounds ? 150.0 * (rounds - res_rounds) / rounds : 0.0);
+            const double pair_cycles = rounds * tile_cycles * warps_per_sched;
+            const double over = 1800.0 + (C > 1 ? 1500.0 : 0.0) + 40.0 * nb;
+            const double cost = waves * (pair_cycles + over);
+            if (cost < best) { best = cost; bc.cluster = C; bc.threads = 32 * W; bc.stage_targets = res_rounds; bc.smem = smem; }
+        }
     }
-    if (best >= 1e300) { set_error("no SA kernel configuration fits N=%d", N); return CHR3D_ERR_SIZE; }
+    if (best >= 1e300) { set_error("no SA kernel configuration fits N=%d (use the single-structure engine)", N); return CHR3D_ERR_SIZE; }
     *cfg = bc;
     return 0;
 }
@@ -690,7 +922,10 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
 int sa_launch(const TrajDesc* d_traj, int n_traj, int Nmax, const DevParams& P, const DevStage* d_prog, int nstages,
               const SaLaunchCfg& cfg, cudaStream_t s) {
     (void)Nmax;
-    CHR3D_CUDA(cudaFuncSetAttribute(sa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    const bool general = P.general_noe || P.lo_clamp > -1e30f;
+    const bool wide = cfg.threads > 512;
+    auto kern = general ? (wide ? sa_kernel<true, 20> : sa_kernel<true, 16>) : (wide ? sa_kernel<false, 20> : sa_kernel<false, 16>);
+    CHR3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(n_traj * cfg.cluster), 1, 1);
     lc.blockDim = dim3((unsigned)cfg.threads, 1, 1);
@@ -700,9 +935,15 @@ int sa_launch(const TrajDesc* d_traj, int n_traj, int Nmax, const DevParams& P, 
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)cfg.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    int st = cfg.stage_targets;
-    CHR3D_CUDA(cudaLaunchKernelEx(&lc, sa_kernel, d_traj, P, d_prog, nstages, st));
+    int sm = (int)cfg.smem;
+    CHR3D_CUDA(cudaLaunchKernelEx(&lc, kern, d_traj, P, d_prog, nstages, sm));
     return 0;
 }
 
 }  // namespace chr3d
+
+#ifdef SA_TIMING
+extern "C" __attribute__((visibility("default"))) int chr3d_debug_sa_timing(unsigned long long* out32) {
+    return cudaMemcpyFromSymbol(out32, chr3d::sa_dbg, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -3;
+}
+#endif
