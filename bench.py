@@ -27,11 +27,17 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: (matrix, alpha, models)
+    # ensembles — name: (matrix, alpha, models)                       BASELINE.json configs[1] is the default
     "chr1_500kb_a1.1_m20": ("chr1_500kb", 1.1, 20),
     "chr1_500kb_a0.5_m20": ("chr1_500kb", 0.5, 20),
     "chr21_1mb_a1.1_m10": ("chr21_1mb", 1.1, 10),
 }
+SINGLE_WORKLOADS = {
+    # one large structure (BASELINE.json configs[3], configs[4]) — name: (beads, alpha, synthetic seed)
+    "synth_50kb_single": (4985, 1.1, 20260001),
+    "synth_10kb_single": (24925, 1.1, 20260002),
+}
+BYTES_PER_PAIR_EVAL = 4.0      # one fp32 target per unordered pair per force evaluation
 FLOP_PER_PAIR_EVAL = 30.0      # canonical FP32 count per restraint-pair evaluation
 
 
@@ -143,17 +149,142 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def large_n_probe(api, N=24925, seed=20260002, reps=10):
+    """Force-evaluation throughput of the tile-streaming kernel on the synthetic 10 kb matrix (BASELINE configs[4]
+    shape), one GPU: the HBM-bound kernel of the path.  Device-timed inside chr3d_single_eval_bench."""
+    s = api.Single(N=N, alpha=1.1, synth_seed=seed)
+    try:
+        info = s.info()
+        rows = s.fetch()["restraint_rows"]
+        tile_ms, eval_ms = s.eval_bench(reps=reps, want_energy=False)
+        peaks, src = measured_peaks()
+        gbs = rows * BYTES_PER_PAIR_EVAL / (tile_ms * 1e-3) / 1e9
+        return {"beads": N, "restraint_rows": int(rows), "tile_kernel_ms": tile_ms, "force_eval_ms": eval_ms,
+                "pair_evals_per_sec": rows / (eval_ms * 1e-3), "launches": 3 * (reps + 2) + (reps + 3),
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                             "traffic": info["target_bytes"] + 32 * N, "kernel": "ln_tile_kernel",
+                             "algorithmic": "4 B per restraint-pair evaluation x %d rows per launch" % rows,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % src}}
+    finally:
+        s.close()
+
+
+def run_single(args, torch, dist, api, rank, world, local):
+    """One large structure (configs[3]/[4]); with N>1 GPUs the tile list is sharded (strong scaling) and every
+    force evaluation ends in one NCCL all-reduce of the forces."""
+    N, alpha, sseed = SINGLE_WORKLOADS[args.workload]
+    p = api.default_params()
+    if args.profile:
+        p.hot_step, p.cool_step, p.pow_step, p.pow_cycl, p.premin_step, p.images = 16, 80, 10, 1, 5, 1
+    nccl_id = None
+    if world > 1:
+        box = [api.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    stream = torch.cuda.current_stream()
+    single = api.Single(N=N, alpha=alpha, synth_seed=sseed, seed=82364, p=p, rank=rank, world=world, nccl_id=nccl_id)
+    info = single.info()
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        single.run(stream.cuda_stream)
+        e1.record(stream)
+        return e0, e1
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.time()
+    evs = [one_step() for _ in range(args.steps)]
+    barrier()
+    wall = time.time() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    step_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    res = single.fetch()
+    tile_ms, eval_ms = single.eval_bench(reps=10, want_energy=False, stream=stream.cuda_stream)
+    rows_rank = float(res["restraint_rows"])
+    # e2e: host IF matrix (pinned) -> create (H2D, target derivation) -> run -> fetch (D2H), world == 1 only
+    e2e = None
+    if world == 1:
+        try:
+            IF_np = api.synthetic_if(N, sseed)                      # the host buffer a caller would hold (outside the timed region)
+            IF = torch.from_numpy(IF_np).pin_memory().numpy()
+            del IF_np
+            ms = []
+            for k in range(2):
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                s2 = api.Single(IF=IF, alpha=alpha, seed=82364, p=p)
+                s2.run(stream.cuda_stream)
+                r2 = s2.fetch()
+                torch.cuda.synchronize()
+                ms.append(1e3 * (time.perf_counter() - t1))
+                s2.close()
+            e2e = {"value": r2["force_evals"] * float(r2["restraint_rows"]) / (ms[-1] * 1e-3), "unit": "pair-evals/s",
+                   "h2d_bytes_per_step": int(IF.nbytes), "d2h_bytes_per_step": int(r2["xyz"].nbytes + r2["forces"].nbytes + 32 + 24),
+                   "ms_per_step": ms[-1]}
+        except Exception as ex:
+            e2e = {"value": None, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)}
+    t = torch.tensor([step_ms, tile_ms, eval_ms], dtype=torch.float64, device="cuda")
+    w = torch.tensor([rows_rank], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    step_ms_max, tile_ms_max, eval_ms_max = t.tolist()
+    rows_all = w.item()
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        evals = float(res["force_evals"])
+        gbs = rows_rank * BYTES_PER_PAIR_EVAL / (tile_ms * 1e-3) / 1e9
+        line = {"metric": "restraint_pair_evals_per_sec", "value": evals * rows_all / (step_ms_max * 1e-3), "unit": "pair-evals/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic IF matrix (SURVEY 8(d) generator, Philox seed %d), seeded random-coil start" % sseed,
+                "config": {"workload": args.workload, "beads": N, "alpha": alpha, "K": 11, "restraint_rows": int(rows_all), "models": 1,
+                           "schedule": "dgsa.inp full (C3D:1573-1829)" if not args.profile else "PROFILE (shortened)", "force_evals_per_model": evals,
+                           "tiles": info["n_tiles"], "tiles_rank0": info["tiles_this_rank"], "target_bytes_rank0": info["target_bytes"],
+                           "l2": "flushed between steps (512 MB write); targets exceed L2 at this size" if N > 8000 else "flushed between steps (512 MB write); the 51 MB of targets are re-read from L2 inside a step",
+                           "parallelism": "tile-range shards + NCCL all-reduce of forces per evaluation" if world > 1 else "single GPU"},
+                "sa_models_per_sec": 1.0 / (step_ms_max * 1e-3),
+                "force_eval_ms": eval_ms_max, "tile_kernel_ms": tile_ms_max,
+                "e2e": e2e if e2e is not None else {"value": None, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                    "note": "e2e is measured at N=1 only"},
+                "gpu_launches": int(res["launches"]) * (args.steps + args.warmup),
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                             "traffic": info["target_bytes"] + 32 * N, "kernel": "ln_tile_kernel (TMA-fed 128x128 target tiles, symmetric pair evaluation)",
+                             "algorithmic": "4 B per restraint-pair evaluation x %d rows per launch (rank 0)" % int(rows_rank),
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % peak_src,
+                             "note": "achieved = algorithmic bytes / average ln_tile_kernel duration, CUDA events around back-to-back launches (chr3d_single_eval_bench)"},
+                "clocks": sampler.summary(), "wall_s": wall}
+        print(json.dumps(line), flush=True)
+    single.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="chr1_500kb_a1.1_m20", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="chr1_500kb_a1.1_m20", choices=sorted(WORKLOADS) + sorted(SINGLE_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large-n", action="store_true", help="skip the large-N kernel probe appended to the default line")
     ap.add_argument("--profile", action="store_true", help="short schedule for ncu captures (not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload in SINGLE_WORKLOADS:
+            args.workload = "chr1_500kb_a1.1_m20"
         return run_reference(args)
 
     import torch
@@ -167,6 +298,11 @@ def main():
     api.init(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.workload in SINGLE_WORKLOADS:
+        run_single(args, torch, dist, api, rank, world, local)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     name, alpha, m = WORKLOADS[args.workload]
     IF_np = ds.load_if_matrix(ds.input_path(name))
@@ -221,7 +357,7 @@ def main():
         torch.cuda.synchronize()
         if k >= args.warmup:
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
-        launches += info["launches"]
+        launches += info["launches"] + 14          # SA launch + restraint derivation, tile packing, coil, assessment kernels
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -262,12 +398,19 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
                          "traffic": prof.get("dram_bytes_per_launch"),
-                         "kernel": "sa_kernel (cluster-per-trajectory SA, targets staged in shared memory)",
+                         "kernel": "sa_kernel (cluster-per-trajectory SA, 32x32 symmetric micro-tiles, targets resident in shared memory)",
                          "algorithmic": "%d flop per restraint-pair evaluation x %.4g pair-evals per launch" % (FLOP_PER_PAIR_EVAL, pair_evals_step),
                          "peak_source": "FP32 FMA micro-benchmark run in this process (chr3d_fp32_peak); MEASURED_PEAKS.json (%s) has no FP32 entry: hbm %.0f GB/s" % (peak_src, peaks.get("hbm_gbs", 0)),
-                         "note": "kernel is FP32-pipe bound (targets live in shared memory, ~0 HBM traffic in steady state); north_star: 'FP32-pipe utilisation against peak, whichever bounds each kernel'"},
+                         "note": "FP32-pipe roofline (targets live in shared memory, ~0 HBM traffic in steady state); with 20 trajectories of 3.7k "
+                                 "sequential force evaluations each the kernel is bound by per-evaluation latency (cluster barriers, owner phases), see DESIGN.md"},
             "clocks": sampler.summary(), "wall_s": t_wall,
         }
+        if not args.no_large_n and world == 1 and not args.profile:
+            try:
+                line["large_n_probe"] = large_n_probe(api)
+                line["gpu_launches"] += line["large_n_probe"].pop("launches")
+            except Exception as ex:
+                line["large_n_probe"] = {"error": repr(ex)}
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload).items() if k in ("value", "unit", "cores", "kind", "sample")}

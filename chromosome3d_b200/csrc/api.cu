@@ -35,6 +35,16 @@ int require_device() {
         return CHR3D_ERR_NO_DEVICE;
     }
     if (g_device < 0) { g_device = 0; cudaGetDevice(&g_device); }
+    static int pool_ready = -1;
+    if (pool_ready != g_device) {           // keep freed blocks in the pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        pool_ready = g_device;
+    }
     return 0;
 }
 

@@ -27,7 +27,10 @@ int  require_device();                 // 0 or CHR3D_ERR_NO_DEVICE, sets the err
         }                                                                                        \
     } while (0)
 
-// RAII device buffer
+// RAII device buffer.  Stream-ordered allocation from the device's default memory pool (kept warm by
+// require_device(): release threshold = never), because cudaMalloc/cudaFree churn dominated the host-side
+// cost of one chr3d_run_ensemble call.  Allocation and release are ordered on the legacy default stream,
+// which synchronises with every blocking stream the kernels may be launched on.
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -40,9 +43,9 @@ struct DevBuf {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc((void**)&p, count * sizeof(T));
+        return cudaMallocAsync((void**)&p, count * sizeof(T), (cudaStream_t)0);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, (cudaStream_t)0); p = nullptr; n = 0; }
 };
 
 // ---- device-side views of the physics parameters / stage program (fp32 compute) -------------

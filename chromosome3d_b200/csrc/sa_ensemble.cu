@@ -28,6 +28,9 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "common.h"
 
 namespace cg = cooperative_groups;
@@ -876,15 +879,36 @@ static int max_active_clusters(int C, int threads, size_t smem) {
     return n;
 }
 
+// busiest scheduler of the busiest CTA: warps w = s, s+4, ... share scheduler s; warp w owns ceil((nloc - w) / W) tiles
+static int tiles_per_scheduler(int ntiles, int C, int W) {
+    const int nloc = (ntiles + C - 1) / C;
+    int worst = 0;
+    for (int sch = 0; sch < 4; sch++) {
+        int t = 0;
+        for (int w = sch; w < W; w += 4) if (nloc > w) t += (nloc - 1 - w) / W + 1;
+        worst = t > worst ? t : worst;
+    }
+    return worst;
+}
+
 int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
+    // the choice depends only on (N, n_traj, m) and the device: cached, the occupancy queries are slow
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int, int>, SaLaunchCfg> cache;
     int dev = 0, smem_max = 227 * 1024;
     cudaGetDevice(&dev);
+    const int force_c = getenv("CHR3D_SA_CLUSTER") ? atoi(getenv("CHR3D_SA_CLUSTER")) : 0;
+    const int force_w = getenv("CHR3D_SA_WARPS") ? atoi(getenv("CHR3D_SA_WARPS")) : 0;
+    const auto key = std::make_tuple(dev, N, n_traj, m);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end() && !force_c && !force_w) { *cfg = it->second; return 0; }
+    }
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (cudaFuncSetAttribute(sa_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) cudaGetLastError();
     if (cudaFuncSetAttribute(sa_kernel<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) cudaGetLastError();
     const int nb = (N + 31) / 32, ntiles = nb * (nb + 1) / 2;
-    const int force_c = getenv("CHR3D_SA_CLUSTER") ? atoi(getenv("CHR3D_SA_CLUSTER")) : 0;
-    const int force_w = getenv("CHR3D_SA_WARPS") ? atoi(getenv("CHR3D_SA_WARPS")) : 0;
     double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0};
     const int Cs[] = {1, 2, 3, 4, 5, 6, 8};
     for (int C : Cs) {
@@ -905,17 +929,20 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
             if (resident < 1 && smem > fixed) { smem = fixed; res_rounds = 0; resident = max_active_clusters(C, 32 * W, smem); }
             if (resident < 1) continue;
             const int waves = (n_traj + resident - 1) / resident;
-            // cost model per force evaluation (cycles): pair phase + fixed barrier / reduction overhead
-            const double warps_per_sched = W / 4.0;
-            const double tile_cycles = 1050.0 + (rounds > res_rounds ? 150.0 * (rounds - res_rounds) / rounds : 0.0);
-            const double pair_cycles = rounds * tile_cycles * warps_per_sched;
-            const double over = 1800.0 + (C > 1 ? 1500.0 : 0.0) + 40.0 * nb;
+            // cost model per force evaluation (SM cycles), fitted to the B200 sweep of scripts/sa_sweep.sh:
+            // pair phase = tiles of the busiest scheduler x ~1150 issue slots, stretched when few warps hide latency;
+            // fixed part = owner phases, reductions, barriers (grows with the warps that meet at them)
+            const double wps = W / 4.0;
+            const double tile_cycles = 1150.0 * (1.0 + 1.0 / wps) + (rounds > res_rounds ? 300.0 * (rounds - res_rounds) / rounds : 0.0);
+            const double pair_cycles = tiles_per_scheduler(ntiles, C, W) * tile_cycles;
+            const double over = 9000.0 + 150.0 * W + (C > 1 ? 2500.0 : 0.0);
             const double cost = waves * (pair_cycles + over);
             if (cost < best) { best = cost; bc.cluster = C; bc.threads = 32 * W; bc.stage_targets = res_rounds; bc.smem = smem; }
         }
     }
     if (best >= 1e300) { set_error("no SA kernel configuration fits N=%d (use the single-structure engine)", N); return CHR3D_ERR_SIZE; }
     *cfg = bc;
+    if (!force_c && !force_w) { std::lock_guard<std::mutex> g(mu); cache[key] = bc; }
     return 0;
 }
 
