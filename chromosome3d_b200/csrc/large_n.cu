@@ -46,18 +46,24 @@ struct LnTerms { float wnC, wnC2m, lo, rsw, wv, wv4, R2; };
 
 // one symmetric pair: accumulates the force on i (fi) and on j (fj) and, if WANT_E, the energies.
 // r^2 carries a 1e-12 floor folded into the FMA chain (coincident beads), as the oracle's max(r^2, 1e-12).
-template <bool WANT_E, bool LOW_SOFT>
+// r^-1/2 as one MUFU.RSQ (arguments are >= 1e-12: no denormal handling needed)
+__device__ __forceinline__ float ln_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// NEAR: the tile touches the diagonal band (J <= I + 1), where cells can carry the "no repel" sentinel -2
+// (bonded neighbours, the diagonal, the lower half of diagonal tiles).  Padding rows/columns of the last
+// tile row/column carry it too, so those tiles also take the NEAR path.
+template <bool WANT_E, bool LOW_SOFT, bool NEAR>
 __device__ __forceinline__ void pair_sym(const LnTerms& t, float xi, float yi, float zi, float xj, float yj, float zj, float d,
                                          float& fix, float& fiy, float& fiz, float& fjx, float& fjy, float& fjz, float& en, float& ev) {
     const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
     const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, 1e-12f)));
-    const float rinv = rsqrtf(r2);
+    const float rinv = ln_rsqrt(r2);
     const float delta = fmaf(r2, rinv, -d);                    // r - d
     float h = fminf(delta, t.rsw);
     if (LOW_SOFT) h = fmaxf(h, t.lo);
     const bool has = d > 0.f;
     float tr = fmaxf(t.R2 - r2, 0.f);
-    tr = d > -1.5f ? tr : 0.f;
+    if (NEAR) tr = d > -1.5f ? tr : 0.f;
     const float w2h = (has ? t.wnC2m : 0.f) * h;               // -2 w C h
     if (WANT_E) {
         en = fmaf(-0.5f * w2h, 2.f * delta - h, en);           // w C h (2 delta - h)
@@ -169,13 +175,26 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
         }
         mbar_wait(&bar[stage], phase[stage]); phase[stage] ^= 1;
         const float* D = dbuf + (size_t)stage * LN_TILE_FLOATS + (size_t)(warp * 8) * LN_TB + lane * 4;
+        // padding beads (index >= N) exist only in the last tile row / column; their cells are -2 like the diagonal band's
+        const bool near = J <= I + 1 || (J + 1) * LN_TB > a.N;
+        if (near) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const float4 d4 = *reinterpret_cast<const float4*>(D + r * LN_TB);
-            pair_sym<WANT_E, LOW_SOFT>(tm, xi[r], yi[r], zi[r], xj[0], yj[0], zj[0], d4.x, fix[r], fiy[r], fiz[r], fjx[0], fjy[0], fjz[0], en, ev);
-            pair_sym<WANT_E, LOW_SOFT>(tm, xi[r], yi[r], zi[r], xj[1], yj[1], zj[1], d4.y, fix[r], fiy[r], fiz[r], fjx[1], fjy[1], fjz[1], en, ev);
-            pair_sym<WANT_E, LOW_SOFT>(tm, xi[r], yi[r], zi[r], xj[2], yj[2], zj[2], d4.z, fix[r], fiy[r], fiz[r], fjx[2], fjy[2], fjz[2], en, ev);
-            pair_sym<WANT_E, LOW_SOFT>(tm, xi[r], yi[r], zi[r], xj[3], yj[3], zj[3], d4.w, fix[r], fiy[r], fiz[r], fjx[3], fjy[3], fjz[3], en, ev);
+            for (int r = 0; r < 8; r++) {
+                const float4 d4 = *reinterpret_cast<const float4*>(D + r * LN_TB);
+                pair_sym<WANT_E, LOW_SOFT, true>(tm, xi[r], yi[r], zi[r], xj[0], yj[0], zj[0], d4.x, fix[r], fiy[r], fiz[r], fjx[0], fjy[0], fjz[0], en, ev);
+                pair_sym<WANT_E, LOW_SOFT, true>(tm, xi[r], yi[r], zi[r], xj[1], yj[1], zj[1], d4.y, fix[r], fiy[r], fiz[r], fjx[1], fjy[1], fjz[1], en, ev);
+                pair_sym<WANT_E, LOW_SOFT, true>(tm, xi[r], yi[r], zi[r], xj[2], yj[2], zj[2], d4.z, fix[r], fiy[r], fiz[r], fjx[2], fjy[2], fjz[2], en, ev);
+                pair_sym<WANT_E, LOW_SOFT, true>(tm, xi[r], yi[r], zi[r], xj[3], yj[3], zj[3], d4.w, fix[r], fiy[r], fiz[r], fjx[3], fjy[3], fjz[3], en, ev);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const float4 d4 = *reinterpret_cast<const float4*>(D + r * LN_TB);
+                pair_sym<WANT_E, LOW_SOFT, false>(tm, xi[r], yi[r], zi[r], xj[0], yj[0], zj[0], d4.x, fix[r], fiy[r], fiz[r], fjx[0], fjy[0], fjz[0], en, ev);
+                pair_sym<WANT_E, LOW_SOFT, false>(tm, xi[r], yi[r], zi[r], xj[1], yj[1], zj[1], d4.y, fix[r], fiy[r], fiz[r], fjx[1], fjy[1], fjz[1], en, ev);
+                pair_sym<WANT_E, LOW_SOFT, false>(tm, xi[r], yi[r], zi[r], xj[2], yj[2], zj[2], d4.z, fix[r], fiy[r], fiz[r], fjx[2], fjy[2], fjz[2], en, ev);
+                pair_sym<WANT_E, LOW_SOFT, false>(tm, xi[r], yi[r], zi[r], xj[3], yj[3], zj[3], d4.w, fix[r], fiy[r], fiz[r], fjx[3], fjy[3], fjz[3], en, ev);
+            }
         }
         // column partials: [comp][warp][128], this lane's 4 consecutive columns
         float* cp = colp + (size_t)stage * 3 * 16 * LN_TB;

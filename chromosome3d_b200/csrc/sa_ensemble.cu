@@ -317,14 +317,16 @@ __device__ __forceinline__ float rsqrt_fast(float x) { float y; asm("rsqrt.appro
 
 struct SaTerms { float wnC2m, rsw, wv, wv4, R2, wn, C, a, b, casym; int low_soft; };
 
-template <bool WANT_E, bool GENERAL>
+// NEAR: the tile touches the diagonal band (J <= I + 1) or the padded last block column, the only places
+// where cells carry the "no repel" sentinel -2.
+template <bool WANT_E, bool GENERAL, bool NEAR>
 __device__ __forceinline__ void pair_sym(const SaTerms& t, float xi, float yi, float zi, float xj, float yj, float zj, float d,
                                          float* fi, float* fj, float& en, float& ev) {
     const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
     const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, 1e-12f)));
     const float rinv = rsqrt_fast(r2);
     float tr = fmaxf(t.R2 - r2, 0.f);
-    tr = d > -1.5f ? tr : 0.f;
+    if (NEAR) tr = d > -1.5f ? tr : 0.f;
     float coef;
     if (!GENERAL) {
         const float delta = fmaf(r2, rinv, -d);                    // r - d
@@ -382,16 +384,31 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevStage& st, bool count) {
         for (int q = 0; q < 4; q++) fi[q][0] = fi[q][1] = fi[q][2] = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; q++) fj[q][0] = fj[q][1] = fj[q][2] = 0.f;
+        if (J <= I + 1 || J == c.nb - 1) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const float4 xi = ldx(c, 32 * I + rg + 8 * r);
+            for (int r = 0; r < 4; r++) {
+                const float4 xi = ldx(c, 32 * I + rg + 8 * r);
 #pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                const float4 d4 = d[2 * r + hh];
-                pair_sym<WANT_E, GENERAL>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 0], yj[4 * hh + 0], zj[4 * hh + 0], d4.x, fi[r], fj[4 * hh + 0], en, ev);
-                pair_sym<WANT_E, GENERAL>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 1], yj[4 * hh + 1], zj[4 * hh + 1], d4.y, fi[r], fj[4 * hh + 1], en, ev);
-                pair_sym<WANT_E, GENERAL>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 2], yj[4 * hh + 2], zj[4 * hh + 2], d4.z, fi[r], fj[4 * hh + 2], en, ev);
-                pair_sym<WANT_E, GENERAL>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 3], yj[4 * hh + 3], zj[4 * hh + 3], d4.w, fi[r], fj[4 * hh + 3], en, ev);
+                for (int hh = 0; hh < 2; hh++) {
+                    const float4 d4 = d[2 * r + hh];
+                    pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 0], yj[4 * hh + 0], zj[4 * hh + 0], d4.x, fi[r], fj[4 * hh + 0], en, ev);
+                    pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 1], yj[4 * hh + 1], zj[4 * hh + 1], d4.y, fi[r], fj[4 * hh + 1], en, ev);
+                    pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 2], yj[4 * hh + 2], zj[4 * hh + 2], d4.z, fi[r], fj[4 * hh + 2], en, ev);
+                    pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 3], yj[4 * hh + 3], zj[4 * hh + 3], d4.w, fi[r], fj[4 * hh + 3], en, ev);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const float4 xi = ldx(c, 32 * I + rg + 8 * r);
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const float4 d4 = d[2 * r + hh];
+                    pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 0], yj[4 * hh + 0], zj[4 * hh + 0], d4.x, fi[r], fj[4 * hh + 0], en, ev);
+                    pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 1], yj[4 * hh + 1], zj[4 * hh + 1], d4.y, fi[r], fj[4 * hh + 1], en, ev);
+                    pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 2], yj[4 * hh + 2], zj[4 * hh + 2], d4.z, fi[r], fj[4 * hh + 2], en, ev);
+                    pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 3], yj[4 * hh + 3], zj[4 * hh + 3], d4.w, fi[r], fj[4 * hh + 3], en, ev);
+                }
             }
         }
         // rows: the 4 lanes that differ in bits 0-1 (column groups) share rows -> recursive halving
