@@ -13,7 +13,8 @@
 //   * coordinates / forces / L-BFGS vectors: float4 arrays of N.
 // Force evaluation = ln_tile_kernel (persistent CTAs, contiguous tile ranges, double-buffered TMA,
 // symmetric tile evaluation: every unordered pair is evaluated once and its force goes to both beads)
-//   - a warp owns 8 rows of the tile, a lane 4 columns: 32 pairs per thread per tile in registers;
+//   - a warp owns 8 rows of the tile, a lane the 4 columns {lane, lane+32, lane+64, lane+96} (stored as one float4 per row
+//     in the tile-packed layout, so target and coordinate reads are conflict-free): 32 pairs per thread per tile in registers;
 //   - row forces stay in registers while consecutive tiles share the tile row, column forces are
 //     reduced across the 16 warps through shared memory once per tile;
 //   - partial forces are written per tile / per row segment and summed in a fixed order by
@@ -75,7 +76,7 @@ __device__ __forceinline__ void pair_sym(const LnTerms& t, float xi, float yi, f
 }
 
 __host__ __device__ inline long long tile_index(long long I, long long J, long long nT) { return I * nT - I * (I - 1) / 2 + (J - I); }
-__device__ inline void tile_coords(long long t, long long nT, int& I, int& J) {
+__host__ __device__ inline void tile_coords(long long t, long long nT, int& I, int& J) {
     // largest I with I*nT - I(I-1)/2 <= t
     double a = (double)(2 * nT + 1);
     long long i = (long long)floor((a - sqrt(a * a - 8.0 * (double)t)) * 0.5);
@@ -98,7 +99,10 @@ struct LnTileArgs {
     const float* Dt;          // tile-packed targets of this rank: tiles [t0, t1)
     long long t0, t1, nT;
     int N;
-    const float4* x;
+    const float4* x;          // coordinates are x + lam * xb2 (lazy: the integrator publishes (a, b) and the scalar lam)
+    const float4* xb2;        // may be nullptr (then lam is ignored)
+    const float* lam;         // device scalar
+    const int* done;          // may be nullptr; *done != 0: the minimiser has finished, skip the evaluation
     float* colpart;           // [(t - t0)][3][128]
     float4* rowpart;          // [cta][maxseg][128]
     int* seg_I;               // [cta][maxseg] tile row of each segment (-1 unused)
@@ -108,7 +112,8 @@ struct LnTileArgs {
 };
 
 // dynamic smem: 2 x 64 KB tile buffers + 2 x colp[3][16][128] + 2 mbarriers
-#define LN_SMEM (2 * LN_TILE_FLOATS * 4 + 2 * 3 * 16 * LN_TB * 4 + 64)
+#define LN_CBUF_OFF (2 * LN_TILE_FLOATS * 4 + 2 * 3 * 16 * LN_TB * 4 + 64)
+#define LN_SMEM (LN_CBUF_OFF + 2 * 2 * LN_TB * 16)       // + column coordinates (a, b) of the current and the next tile
 
 template <bool WANT_E, bool LOW_SOFT>
 __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
@@ -116,7 +121,11 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
     float* dbuf = (float*)smem;
     float* colp = (float*)(smem + 2 * LN_TILE_FLOATS * 4);
     uint64_t* bar = (uint64_t*)(smem + 2 * LN_TILE_FLOATS * 4 + 2 * 3 * 16 * LN_TB * 4);
+    float4* cbuf = (float4*)(smem + LN_CBUF_OFF);       // [stage][a|b][128]
+    if (a.done && *a.done) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float lam = a.xb2 ? *a.lam : 0.f;
+    const float4* __restrict__ XB = a.xb2 ? a.xb2 : a.x;
     const long long ntl = a.t1 - a.t0;
     const long long c0 = a.t0 + (ntl * blockIdx.x) / gridDim.x, c1 = a.t0 + (ntl * (blockIdx.x + 1)) / gridDim.x;
     int* segI = a.seg_I + (size_t)blockIdx.x * a.maxseg;
@@ -134,9 +143,21 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
                        "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])) : "memory");
     };
     if (tid == 0) { if (c0 < c1) issue(c0, 0); if (c0 + 1 < c1) issue(c0 + 1, 1); }
+    // column coordinates of tile column Jn -> cbuf[stg] with cp.async (L2 latency hidden behind the previous tile's pairs)
+    auto prefetch_cols = [&](int Jn, int stg) {
+        if (tid < 2 * LN_TB) {
+            const int col = tid & (LN_TB - 1), which = tid >> 7;
+            int j = Jn * LN_TB + col; if (j >= a.N) j = a.N - 1;
+            const float4* src = (which ? XB : a.x) + j;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(cbuf + (stg * 2 + which) * LN_TB + col)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     int I = 0, J = 0;
-    if (c0 < c1) tile_coords(c0, a.nT, I, J);
+    if (c0 < c1) { tile_coords(c0, a.nT, I, J); prefetch_cols(J, 0); }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     int curI = -1, seg = -1;
     float xi[8], yi[8], zi[8], fix[8], fiy[8], fiz[8];
     float en = 0.f, ev = 0.f; double den = 0.0, dev = 0.0;
@@ -164,14 +185,16 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 int i = I * LN_TB + warp * 8 + r; if (i >= a.N) i = a.N - 1;
-                float4 p = a.x[i]; xi[r] = p.x; yi[r] = p.y; zi[r] = p.z; fix[r] = fiy[r] = fiz[r] = 0.f;
+                const float4 p = a.x[i], q = XB[i];
+                xi[r] = fmaf(lam, q.x, p.x); yi[r] = fmaf(lam, q.y, p.y); zi[r] = fmaf(lam, q.z, p.z); fix[r] = fiy[r] = fiz[r] = 0.f;
             }
         }
+        if (t + 1 < c1) { int Jn = J + 1; if (Jn == (int)a.nT) Jn = I + 1; prefetch_cols(Jn, stage ^ 1); }
         float xj[4], yj[4], zj[4], fjx[4] = {0.f, 0.f, 0.f, 0.f}, fjy[4] = {0.f, 0.f, 0.f, 0.f}, fjz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            int j = J * LN_TB + lane * 4 + c; if (j >= a.N) j = a.N - 1;
-            float4 p = a.x[j]; xj[c] = p.x; yj[c] = p.y; zj[c] = p.z;
+            const float4 p = cbuf[(stage * 2) * LN_TB + c * 32 + lane], q = cbuf[(stage * 2 + 1) * LN_TB + c * 32 + lane];   // column 32c + lane
+            xj[c] = fmaf(lam, q.x, p.x); yj[c] = fmaf(lam, q.y, p.y); zj[c] = fmaf(lam, q.z, p.z);
         }
         mbar_wait(&bar[stage], phase[stage]); phase[stage] ^= 1;
         const float* D = dbuf + (size_t)stage * LN_TILE_FLOATS + (size_t)(warp * 8) * LN_TB + lane * 4;
@@ -201,7 +224,8 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
         *reinterpret_cast<float4*>(cp + (0 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
         *reinterpret_cast<float4*>(cp + (1 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
         *reinterpret_cast<float4*>(cp + (2 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
-        __syncthreads();                 // tile buffer `stage` is free, column partials are complete
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                 // tile buffer `stage` is free, column partials are complete, next column coordinates have landed
         if (tid == 0 && t + 2 < c1) issue(t + 2, stage);
         if (tid < 3 * LN_TB) {
             const int comp = tid / LN_TB, col = tid % LN_TB;
@@ -228,49 +252,79 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
 // ------------------------------------------------------------------------------------------------
 // fixed-order reduction of the partial forces; rank 0 adds the bond term
 // ------------------------------------------------------------------------------------------------
+// partial forces of this rank -> force on bead (B*128 + tid): column partials of the tiles (I, B) this rank owns,
+// then the row partials of the CTA segments that walked tile row B (static CSR list built on the host), fixed order
+struct LnGather {
+    const float* colpart; const float4* rowpart; const int* rs_off; const int* rs_idx;
+    long long t0, t1, nT;
+};
+#define LN_GROUPS 4                     // the step kernels run LN_GROUPS x LN_TB threads: the column partials of a bead block
+#define LN_STEP_THREADS (LN_GROUPS * LN_TB)   // are summed by LN_GROUPS thread groups (I = grp, grp + LN_GROUPS, ...) in parallel
+__device__ __forceinline__ void ln_gather_part(const LnGather& g, int B, int tid, int grp, float& fx, float& fy, float& fz) {
+    fx = fy = fz = 0.f;
+    for (int I = grp; I <= B; I += LN_GROUPS) {
+        const long long t = tile_index(I, B, g.nT);
+        if (t < g.t0 || t >= g.t1) continue;
+        const float* cp = g.colpart + (size_t)(t - g.t0) * 3 * LN_TB + ((tid & 31) * 4 + (tid >> 5));   // column -> position 4*lane + c
+        fx += cp[0]; fy += cp[LN_TB]; fz += cp[2 * LN_TB];
+    }
+    if (grp == 0) for (int k = g.rs_off[B]; k < g.rs_off[B + 1]; k++) {
+        const float4 v = g.rowpart[(size_t)g.rs_idx[k] * LN_TB + tid];
+        fx += v.x; fy += v.y; fz += v.z;
+    }
+}
+// all LN_STEP_THREADS threads call; the result is valid in group 0 (fixed summation order: group 0, 1, 2, 3)
+__device__ __forceinline__ void ln_gather(const LnGather& g, int B, int tid, int grp, float& fx, float& fy, float& fz) {
+    __shared__ float gsh[LN_GROUPS - 1][3][LN_TB];
+    ln_gather_part(g, B, tid, grp, fx, fy, fz);
+    if (grp > 0) { gsh[grp - 1][0][tid] = fx; gsh[grp - 1][1][tid] = fy; gsh[grp - 1][2][tid] = fz; }
+    __syncthreads();
+    if (grp == 0) for (int q = 0; q < LN_GROUPS - 1; q++) { fx += gsh[q][0][tid]; fy += gsh[q][1][tid]; fz += gsh[q][2][tid]; }
+}
+// bond term of bead i at lazily defined coordinates x = a + lam*b
+__device__ __forceinline__ float4 ln_ldx(const float4* a, const float4* b, float lam, int i) {
+    const float4 p = a[i], q = b[i];
+    return make_float4(fmaf(lam, q.x, p.x), fmaf(lam, q.y, p.y), fmaf(lam, q.z, p.z), 0.f);
+}
+__device__ __forceinline__ void ln_bond(const float4* a, const float4* b, float lam, int i, int N, float w_bond, float r0,
+                                        float& fx, float& fy, float& fz, float& eb) {
+    const float4 xi = ln_ldx(a, b, lam, i);
+    for (int s = -1; s <= 1; s += 2) {
+        const int nb = i + s; if (nb < 0 || nb >= N) continue;
+        const float4 xn = ln_ldx(a, b, lam, nb);
+        const float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
+        const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f), rinv = ln_rsqrt(r2), r = r2 * rinv, u = r - r0;
+        const float g = 2.f * w_bond * u * rinv;
+        fx -= g * dx; fy -= g * dy; fz -= g * dz;
+        if (s == 1) eb = w_bond * u * u;
+    }
+}
+__device__ __forceinline__ double ln_block_sum(double v, double* sh, int tid, bool lead) {   // sum over the LN_TB lead threads; every thread of the block calls
+    __syncthreads();
+    if (lead) sh[tid] = v;
+    __syncthreads();
+    for (int o = LN_TB / 2; o > 0; o >>= 1) { if (lead && tid < o) sh[tid] += sh[tid + o]; __syncthreads(); }
+    return sh[0];
+}
+
 struct LnReduceArgs {
-    const float* colpart; const float4* rowpart; const int* seg_I; const double* epart;
-    long long t0, t1, nT; int N, ncta, maxseg, add_bond;
-    const float4* x; float4* f;         // f has N + 1 entries; entry N is unused padding
+    LnGather g; const double* epart;
+    int N, ncta, add_bond;
+    const float4* x; const float4* xb2; const float* lam;     // coordinates x + lam*xb2 (xb2 may be nullptr)
+    float4* f;                           // f has N + 1 entries; entry N is unused padding
     double* escal;                       // [3] e_noe, e_vdw, e_bond of this rank
     float w_bond, r0;
 };
-__global__ void __launch_bounds__(LN_TB) ln_reduce_kernel(LnReduceArgs a) {
-    const int B = blockIdx.x, tid = threadIdx.x, i = B * LN_TB + tid;
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    for (int I = 0; I <= B; I++) {                       // tiles (I, B): column partials
-        long long t = tile_index(I, B, a.nT);
-        if (t < a.t0 || t >= a.t1) continue;
-        const float* cp = a.colpart + (size_t)(t - a.t0) * 3 * LN_TB;
-        fx += cp[tid]; fy += cp[LN_TB + tid]; fz += cp[2 * LN_TB + tid];
-    }
-    for (int c = 0; c < a.ncta; c++)                      // row segments with tile row B
-        for (int s = 0; s < a.maxseg; s++) {
-            int sI = a.seg_I[(size_t)c * a.maxseg + s];
-            if (sI < 0) break;
-            if (sI != B) continue;
-            float4 v = a.rowpart[((size_t)c * a.maxseg + s) * LN_TB + tid];
-            fx += v.x; fy += v.y; fz += v.z;
-        }
-    float eb = 0.f;
-    if (a.add_bond && i < a.N) {
-        const float4 xi = a.x[i];
-        for (int s = -1; s <= 1; s += 2) {
-            int nb = i + s; if (nb < 0 || nb >= a.N) continue;
-            const float4 xn = a.x[nb];
-            float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
-            float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f), rinv = rsqrtf(r2), r = r2 * rinv, u = r - a.r0;
-            float g = 2.f * a.w_bond * u * rinv;
-            fx -= g * dx; fy -= g * dy; fz -= g * dz;
-            if (s == 1) eb = a.w_bond * u * u;
-        }
-    }
-    if (i < a.N) a.f[i] = make_float4(fx, fy, fz, 0.f);
-    // bond energy: block sum -> atomic-free two-level: per-block partial written to escal via one thread per block
+__global__ void __launch_bounds__(LN_STEP_THREADS) ln_reduce_kernel(LnReduceArgs a) {
+    const int B = blockIdx.x, tid = threadIdx.x & (LN_TB - 1), grp = threadIdx.x >> 7, i = B * LN_TB + tid;
+    const bool lead = grp == 0;
+    float fx, fy, fz, eb = 0.f;
+    ln_gather(a.g, B, tid, grp, fx, fy, fz);
+    if (lead && a.add_bond && i < a.N) ln_bond(a.x, a.xb2 ? a.xb2 : a.x, a.xb2 ? *a.lam : 0.f, i, a.N, a.w_bond, a.r0, fx, fy, fz, eb);
+    if (lead && i < a.N) a.f[i] = make_float4(fx, fy, fz, 0.f);
     __shared__ double sh[LN_TB];
-    sh[tid] = (double)eb; __syncthreads();
-    for (int o = LN_TB / 2; o > 0; o >>= 1) { if (tid < o) sh[tid] += sh[tid + o]; __syncthreads(); }
-    if (tid == 0) a.escal[3 + B] = sh[0];                // per-block bond partials follow the 3 totals
+    const double ebs = ln_block_sum((double)eb, sh, tid, lead);
+    if (threadIdx.x == 0) a.escal[3 + B] = ebs;          // per-block bond partials follow the 3 totals
 }
 // totals of this rank: e_noe, e_vdw (tile kernel partials), e_bond (reduce kernel partials), fixed order
 __global__ void ln_energy_kernel(const double* epart, int ncta, double* escal, int nblk) {
@@ -290,6 +344,8 @@ struct LnState {
     double e_saved;
     int cnt, head, it, ls, done, accepted, keep, have_E, hand, cur_image, nsteps, fresh;
     long long nevals;
+    float lamf, tstepf, zerof, pad_;      // device scalars read by the tile kernel: x = a + lamf*b (MD), x = xb + tstepf*p (L-BFGS)
+    unsigned int counter, pad2_;          // "last block done" counter of the fused step kernels
 };
 
 struct LnVec {     // all float4[N]
@@ -382,12 +438,9 @@ __device__ double ln_direction(double* B, double* delta, int m, int cnt, int hea
 struct LnMinCfg { int m, max_ls, nstep, nparts; double c1, gtol, ftol, drop; int N; };
 
 // one thread: sums the partial scalars in a fixed order and takes the line-search / history decision
-__global__ void ln_min_control_kernel(LnState* st, const double* part, const double* escal_all, LnMinCfg c, int init) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (st->done) { st->accepted = 0; return; }
-    const int m = c.m, K = 6 * m + 6;
-    double G[LN_KMAX];
-    for (int k = 0; k < K; k++) { double s = 0; for (int b = 0; b < c.nparts; b++) s += part[(size_t)b * LN_KMAX + k]; G[k] = s; }
+// (G: the 6m+6 inner products, escal_all: e_noe, e_vdw, e_bond of the evaluation just done)
+__device__ void ln_min_decide(LnState* st, const double* G, const double* escal_all, LnMinCfg c, int init) {
+    const int m = c.m;
     const double Et = escal_all[0] + escal_all[1] + escal_all[2];
     st->nevals++;
     const double n3 = 3.0 * c.N;
@@ -516,6 +569,165 @@ __global__ void ln_md_control_kernel(LnState* st, const double* part, const doub
     st->ke = ke; st->lam = lam; st->nevals += c.count;
     st->E = escal[0] + escal[1] + escal[2]; st->Enoe = escal[0]; st->Evdw = escal[1]; st->Ebond = escal[2];
 }
+
+// ------------------------------------------------------------------------------------------------
+// Fused per-evaluation kernels.  A force evaluation is two launches: ln_tile_kernel (pair tiles, lazy
+// coordinates) and one of the step kernels below, which gathers the partial forces of a bead block, adds
+// the bond term, advances the integrator / collects the L-BFGS inner products, and lets the last block
+// to finish ("last block done" counter) take the scalar decisions, so that no host round trip and no
+// extra launch is needed.  With several ranks the gather is preceded by the force exchange (see ln_eval).
+// ------------------------------------------------------------------------------------------------
+struct LnEnergySrc {        // where the energies of the evaluation come from
+    const double* epart; int ncta;      // local: per-CTA (e_noe, e_vdw) of the tile kernel
+    const double* escal;                // != nullptr: already summed over ranks [e_noe, e_vdw, e_bond]
+};
+// true in exactly one block: the last one to arrive; it sees every other block's writes
+__device__ __forceinline__ bool ln_last_block(unsigned int* counter, int nblk) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) { const unsigned int t = atomicAdd(counter, 1u); is_last = (t == (unsigned)nblk - 1u); }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last != 0;
+}
+
+struct LnMdStepArgs {
+    LnGather g; const float4* fsum;     // fsum != nullptr: total forces (bond included) already in fsum
+    const float4* a; const float4* b; const float* lam;     // coordinates of the evaluation just done: a + lam*b
+    float4 *x, *v, *f, *a_next, *b_next;
+    LnEnergySrc es;
+    LnState* st; double* blockpart; int nblk, N;
+    float w_bond, r0, h, dt_akma; int first, want_e;
+    LnMdCfg md;
+};
+// Verlet step (definition of the oracle's sim_dynamics):  x = a + lam*b are the coordinates the forces were just
+// computed at; v1 = lam*v + h*f_old is the velocity that led there; v2 = v1 + h*f closes the step.  Published for
+// the next step: a' = x + dt*h*f, b' = dt*v2; the last block turns the kinetic energy of v2 into lam'.
+__global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArgs p) {
+    const int B = blockIdx.x, tid = threadIdx.x & (LN_TB - 1), grp = threadIdx.x >> 7, i = B * LN_TB + tid;
+    const bool lead = grp == 0;
+    __shared__ double sh[LN_TB];
+    const float lam = *p.lam;
+    float fx = 0.f, fy = 0.f, fz = 0.f, eb = 0.f, k2 = 0.f;
+    if (p.fsum) { if (lead && i < p.N) { const float4 t = p.fsum[i]; fx = t.x; fy = t.y; fz = t.z; } }
+    else {
+        ln_gather(p.g, B, tid, grp, fx, fy, fz);
+        if (lead && i < p.N) ln_bond(p.a, p.b, lam, i, p.N, p.w_bond, p.r0, fx, fy, fz, eb);
+    }
+    if (lead && i < p.N) {
+        const float4 xi = ln_ldx(p.a, p.b, lam, i);
+        float4 vv = p.v[i];
+        if (!p.first) {
+            const float4 fo = p.f[i];
+            vv.x = fmaf(p.h, fo.x, lam * vv.x); vv.y = fmaf(p.h, fo.y, lam * vv.y); vv.z = fmaf(p.h, fo.z, lam * vv.z);   // v1
+            vv.x = fmaf(p.h, fx, vv.x); vv.y = fmaf(p.h, fy, vv.y); vv.z = fmaf(p.h, fz, vv.z);                          // v2
+        }
+        k2 = dot3(vv, vv);
+        const float dth = p.dt_akma * p.h;
+        p.x[i] = xi; p.v[i] = vv; p.f[i] = make_float4(fx, fy, fz, 0.f);
+        p.a_next[i] = make_float4(fmaf(dth, fx, xi.x), fmaf(dth, fy, xi.y), fmaf(dth, fz, xi.z), 0.f);
+        p.b_next[i] = make_float4(p.dt_akma * vv.x, p.dt_akma * vv.y, p.dt_akma * vv.z, 0.f);
+    }
+    const double kb = ln_block_sum((double)k2, sh, tid, lead), ebb = ln_block_sum((double)eb, sh, tid, lead);
+    if (threadIdx.x == 0) { p.blockpart[(size_t)B * LN_KMAX] = kb; p.blockpart[(size_t)B * LN_KMAX + 1] = ebb; }
+    if (!ln_last_block(&p.st->counter, p.nblk)) return;
+    if (threadIdx.x == 0) {
+        LnState* st = p.st;
+        double k2s = 0, e2 = 0;
+        for (int q = 0; q < p.nblk; q++) { k2s += p.blockpart[(size_t)q * LN_KMAX]; e2 += p.blockpart[(size_t)q * LN_KMAX + 1]; }
+        const double ke = 0.5 * p.md.mass * k2s, ndof = 3.0 * p.N - 3.0;
+        const double T = 2.0 * ke / (p.md.kboltz * ndof);
+        double l2 = 1.0;
+        if (T > 0.0) {
+            if (p.md.flag == CHR3D_COUPLE_TCOUP) l2 = sqrt(fmax(0.0, 1.0 + 2.0 * p.md.fbeta * p.md.dt_ps * (p.md.temp / T - 1.0)));
+            else if (p.md.flag == CHR3D_COUPLE_VSCALE) l2 = sqrt(p.md.temp / T);
+        }
+        st->ke = ke; st->lam = l2; st->lamf = (float)l2; st->nevals += p.md.count;
+        if (p.want_e) {
+            double e0 = 0, e1 = 0;
+            if (p.es.escal) { e0 = p.es.escal[0]; e1 = p.es.escal[1]; e2 = p.es.escal[2]; }
+            else for (int q = 0; q < p.es.ncta; q++) { e0 += p.es.epart[2 * q]; e1 += p.es.epart[2 * q + 1]; }
+            st->Enoe = e0; st->Evdw = e1; st->Ebond = e2; st->E = e0 + e1 + e2;
+        }
+        st->counter = 0;
+    }
+}
+
+struct LnMinStepArgs {
+    LnGather g; const float4* fsum;
+    LnVec v; const float* lam; int init;         // init: evaluation at the starting point (x = v.x, nothing pending)
+    LnEnergySrc es;
+    LnState* st; double* blockpart; int nblk;
+    float w_bond, r0;
+    LnMinCfg cfg;
+};
+// L-BFGS trial x = xb + t*p (t = *lam): forces, the 6m+6 inner products of (s, y, g') with the history, and in the
+// last block the line-search / history decision of ln_min_decide.  ln_min_update_kernel then applies it.
+__global__ void __launch_bounds__(LN_STEP_THREADS) ln_min_step_kernel(LnMinStepArgs p) {
+    if (p.st->done) { if (blockIdx.x == 0 && threadIdx.x == 0) p.st->accepted = 0; return; }   // later update launches are no-ops
+    const int B = blockIdx.x, tid = threadIdx.x & (LN_TB - 1), grp = threadIdx.x >> 7, i = B * LN_TB + tid, lane = tid & 31, warp = tid >> 5;
+    const bool lead = grp == 0;
+    const int m = p.v.m, K = 6 * m + 6, N = p.v.N, head = p.st->head;
+    __shared__ double sh[LN_TB];
+    __shared__ float shk[LN_TB / 32][LN_KMAX];
+    __shared__ double G[LN_KMAX];
+    const float lam = p.init ? 0.f : *p.lam;
+    const float4* A = p.init ? p.v.x : p.v.xb;
+    float fx = 0.f, fy = 0.f, fz = 0.f, eb = 0.f;
+    if (p.fsum) { if (lead && i < N) { const float4 t = p.fsum[i]; fx = t.x; fy = t.y; fz = t.z; } }
+    else {
+        ln_gather(p.g, B, tid, grp, fx, fy, fz);
+        if (lead && i < N) ln_bond(A, p.v.p, lam, i, N, p.w_bond, p.r0, fx, fy, fz, eb);
+    }
+    float acc[LN_KMAX];
+#pragma unroll 1
+    for (int k = 0; k < K; k++) acc[k] = 0.f;
+    if (lead && i < N) {
+        const float4 x = ln_ldx(A, p.v.p, lam, i), xb = p.v.xb[i], g = p.v.g[i];
+        const float4 s = make_float4(x.x - xb.x, x.y - xb.y, x.z - xb.z, 0.f);
+        const float4 gn = make_float4(-fx, -fy, -fz, 0.f);
+        const float4 y = make_float4(gn.x - g.x, gn.y - g.y, gn.z - g.z, 0.f);
+        p.v.x[i] = x; p.v.f[i] = make_float4(fx, fy, fz, 0.f);
+        for (int l = 0; l < m; l++) {
+            if (l == head) continue;
+            const float4 sl = p.v.S[(size_t)l * N + i], yl = p.v.Y[(size_t)l * N + i];
+            acc[LDOT_L(l, 0)] = dot3(s, sl); acc[LDOT_L(l, 1)] = dot3(s, yl); acc[LDOT_L(l, 2)] = dot3(y, sl);
+            acc[LDOT_L(l, 3)] = dot3(y, yl); acc[LDOT_L(l, 4)] = dot3(gn, sl); acc[LDOT_L(l, 5)] = dot3(gn, yl);
+        }
+        acc[LDOT_X(m, 0)] = dot3(s, s); acc[LDOT_X(m, 1)] = dot3(s, y); acc[LDOT_X(m, 2)] = dot3(s, gn);
+        acc[LDOT_X(m, 3)] = dot3(y, y); acc[LDOT_X(m, 4)] = dot3(y, gn); acc[LDOT_X(m, 5)] = dot3(gn, gn);
+    }
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        float s = acc[k];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lead && lane == 0) shk[warp][k] = s;
+    }
+    const double ebb = ln_block_sum((double)eb, sh, tid, lead);  // (its barriers also publish shk)
+    if (lead && tid < K) {
+        double s = 0;
+        for (int w = 0; w < LN_TB / 32; w++) s += (double)shk[w][tid];
+        p.blockpart[(size_t)B * LN_KMAX + tid] = s;
+    }
+    if (threadIdx.x == 0) p.blockpart[(size_t)B * LN_KMAX + K] = ebb;
+    if (!ln_last_block(&p.st->counter, p.nblk)) return;
+    if (lead && tid <= K) {
+        double s = 0;
+        for (int q = 0; q < p.nblk; q++) s += p.blockpart[(size_t)q * LN_KMAX + tid];
+        G[tid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double e3[3] = {0, 0, G[K]};
+        if (p.es.escal) { e3[0] = p.es.escal[0]; e3[1] = p.es.escal[1]; e3[2] = p.es.escal[2]; }
+        else for (int q = 0; q < p.es.ncta; q++) { e3[0] += p.es.epart[2 * q]; e3[1] += p.es.epart[2 * q + 1]; }
+        ln_min_decide(p.st, G, e3, p.cfg, p.init);
+        p.st->tstepf = (float)p.st->tstep;
+        p.st->counter = 0;
+    }
+}
+
 // sums of a float4 array (COM velocity / geometric centre): partials then subtraction
 __global__ void __launch_bounds__(256) ln_sum3_kernel(const float4* a, int N, double* part) {
     double sx = 0, sy = 0, sz = 0;
@@ -612,7 +824,7 @@ __global__ void __launch_bounds__(256) ln_build_tiles_kernel(const double* __res
     const double mean = *mean_p;
     float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
     for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
-        const int r = k / LN_TB, c = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + c;
+        const int r = k / LN_TB, q = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + (q & 3) * 32 + (q >> 2);   // position q = 4*lane + c holds column 32*c + lane
         float v = -2.f;
         if (i < L && j < L && j > i) {
             const int sep = j - i;
@@ -633,7 +845,7 @@ __global__ void __launch_bounds__(256) ln_tiles_from_tenths_kernel(const long lo
     int I, J; tile_coords(t, nT, I, J);
     float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
     for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
-        const int r = k / LN_TB, c = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + c;
+        const int r = k / LN_TB, q = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + (q & 3) * 32 + (q >> 2);   // position q = 4*lane + c holds column 32*c + lane
         float v = -2.f;
         if (i < L && j < L && j > i) {
             const int sep = j - i;
@@ -659,7 +871,7 @@ __global__ void __launch_bounds__(256) ln_tiles_from_dense_kernel(const float* _
     int I, J; tile_coords(t, nT, I, J);
     float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
     for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
-        const int r = k / LN_TB, c = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + c;
+        const int r = k / LN_TB, q = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + (q & 3) * 32 + (q >> 2);   // position q = 4*lane + c holds column 32*c + lane
         out[k] = (i < N && j < N && j > i) ? T[(size_t)i * pitch + j] : -2.f;
     }
 }
@@ -688,8 +900,8 @@ __global__ void ln_synth_if_kernel(double* __restrict__ IF, int N, unsigned long
 struct LnEngine {
     int N = 0, nT = 0, rank = 0, world = 1, m = 5, ncta = 0, maxseg = 0, nblk = 0, nparts = 0;
     long long n_tiles = 0, t0 = 0, t1 = 0, pairs_total = 0;
-    DevBuf<float> Dt, colpart, x0; DevBuf<float4> rowpart, vx, vxb, vg, vp, vv, vf, vS, vY, sx, sv;
-    DevBuf<int> seg_I; DevBuf<double> epart, escal, part; DevBuf<LnState> st;
+    DevBuf<float> Dt, colpart, x0; DevBuf<float4> rowpart, vx, vxb, vg, vp, vv, vf, vS, vY, sx, sv, va[2], vb[2], vfr;
+    DevBuf<int> seg_I, rs_off, rs_idx; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st;
     chr3d_sa_params prm; unsigned long long seed = 0;
     cudaStream_t stream = nullptr;
     long long n_launches = 0;
@@ -725,7 +937,26 @@ static int ln_alloc(LnEngine& e) {
     CHR3D_CUDA(e.vv.alloc(n4)); CHR3D_CUDA(e.vf.alloc(n4)); CHR3D_CUDA(e.sx.alloc(n4)); CHR3D_CUDA(e.sv.alloc(n4));
     CHR3D_CUDA(e.vS.alloc((size_t)e.m * N)); CHR3D_CUDA(e.vY.alloc((size_t)e.m * N));
     CHR3D_CUDA(e.x0.alloc((size_t)N * 3));
+    for (int q = 0; q < 2; q++) { CHR3D_CUDA(e.va[q].alloc(n4)); CHR3D_CUDA(e.vb[q].alloc(n4)); }
+    CHR3D_CUDA(e.vfr.alloc(n4)); CHR3D_CUDA(e.blockpart.alloc((size_t)e.nblk * LN_KMAX));
     CHR3D_CUDA(cudaMemset(e.vf.p, 0, sizeof(float4) * n4));
+    CHR3D_CUDA(cudaMemset(e.vp.p, 0, sizeof(float4) * n4));
+    {   // static CSR list: which (CTA, segment) row partials belong to tile row B (mirrors the walk of ln_tile_kernel)
+        std::vector<std::vector<int>> rows(e.nT);
+        for (int c = 0; c < e.ncta; c++) {
+            const long long c0 = e.t0 + (ntl * c) / e.ncta, c1 = e.t0 + (ntl * (c + 1)) / e.ncta;
+            int curI = -1, seg = -1;
+            for (long long t = c0; t < c1; t++) {
+                int I, J; tile_coords(t, e.nT, I, J);
+                if (I != curI) { curI = I; seg++; rows[I].push_back(c * e.maxseg + seg); }
+            }
+        }
+        std::vector<int> off(e.nT + 1, 0), idx;
+        for (int B = 0; B < e.nT; B++) { off[B + 1] = off[B] + (int)rows[B].size(); idx.insert(idx.end(), rows[B].begin(), rows[B].end()); }
+        CHR3D_CUDA(e.rs_off.alloc(off.size())); CHR3D_CUDA(e.rs_idx.alloc(std::max<size_t>(idx.size(), 1)));
+        CHR3D_CUDA(cudaMemcpy(e.rs_off.p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+        if (!idx.empty()) CHR3D_CUDA(cudaMemcpy(e.rs_idx.p, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+    }
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
@@ -746,17 +977,45 @@ static void ln_launch_tiles(LnEngine& e, const LnTileArgs& a, bool want_e) {
     else { if (soft) ln_tile_kernel<false, true><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); else ln_tile_kernel<false, false><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); }
 }
 
-// one energy + force evaluation at e.vx: tile kernel, reduction, (all-reduce), totals in escal[0..2]
-static int ln_eval(LnEngine& e, const chr3d_stage& s, bool want_e = true) {
-    LnTileArgs a; a.Dt = e.Dt.p; a.t0 = e.t0; a.t1 = e.t1; a.nT = e.nT; a.N = e.N; a.x = e.vx.p; a.colpart = e.colpart.p;
-    a.rowpart = e.rowpart.p; a.seg_I = e.seg_I.p; a.epart = e.epart.p; a.maxseg = e.maxseg; ln_terms(e.prm, s, a.terms);
+static LnGather ln_gather_args(LnEngine& e) {
+    LnGather g; g.colpart = e.colpart.p; g.rowpart = e.rowpart.p; g.rs_off = e.rs_off.p; g.rs_idx = e.rs_idx.p; g.t0 = e.t0; g.t1 = e.t1; g.nT = e.nT;
+    return g;
+}
+// pair tiles at the coordinates x + lam*xb2 (xb2 == nullptr: plain x)
+static void ln_tiles(LnEngine& e, const chr3d_stage& s, const float4* x, const float4* xb2, const float* lam, const int* done, bool want_e) {
+    LnTileArgs a; a.Dt = e.Dt.p; a.t0 = e.t0; a.t1 = e.t1; a.nT = e.nT; a.N = e.N; a.x = x; a.xb2 = xb2; a.lam = lam; a.done = done;
+    a.colpart = e.colpart.p; a.rowpart = e.rowpart.p; a.seg_I = e.seg_I.p; a.epart = e.epart.p; a.maxseg = e.maxseg; ln_terms(e.prm, s, a.terms);
     ln_launch_tiles(e, a, want_e);
-    LnReduceArgs r; r.colpart = e.colpart.p; r.rowpart = e.rowpart.p; r.seg_I = e.seg_I.p; r.epart = e.epart.p; r.t0 = e.t0; r.t1 = e.t1; r.nT = e.nT;
-    r.N = e.N; r.ncta = e.ncta; r.maxseg = e.maxseg; r.add_bond = e.rank == 0 ? 1 : 0; r.x = e.vx.p; r.f = e.vf.p; r.escal = e.escal.p;
-    r.w_bond = (float)s.w_bond; r.r0 = (float)e.prm.bond_r0;
-    ln_reduce_kernel<<<e.nblk, LN_TB, 0, e.stream>>>(r);
+    e.n_launches++;
+}
+// several ranks: reduce this rank's partial forces (+ bond on rank 0) into vfr, sum vfr and the three energies over the
+// ranks with NCCL; afterwards every rank holds the total force in vfr and the totals in escal[0..2]
+static int ln_exchange(LnEngine& e, const chr3d_stage& s, const float4* x, const float4* xb2, const float* lam) {
+    LnReduceArgs r; r.g = ln_gather_args(e); r.epart = e.epart.p; r.N = e.N; r.ncta = e.ncta; r.add_bond = e.rank == 0 ? 1 : 0;
+    r.x = x; r.xb2 = xb2; r.lam = lam; r.f = e.vfr.p; r.escal = e.escal.p; r.w_bond = (float)s.w_bond; r.r0 = (float)e.prm.bond_r0;
+    ln_reduce_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(r);
     ln_energy_kernel<<<1, 32, 0, e.stream>>>(e.epart.p, e.ncta, e.escal.p, e.nblk);
-    e.n_launches += 3;
+    e.n_launches += 2;
+#ifdef CHR3D_WITH_NCCL
+    if (e.world > 1 && e.comm) {
+        if (ncclAllReduce(e.vfr.p, e.vfr.p, (size_t)e.N * 4, ncclFloat, ncclSum, e.comm, e.stream) != ncclSuccess ||
+            ncclAllReduce(e.escal.p, e.escal.p, 3, ncclDouble, ncclSum, e.comm, e.stream) != ncclSuccess) {
+            set_error("ncclAllReduce failed"); return CHR3D_ERR_CUDA;
+        }
+        e.n_launches += 2;
+    }
+#endif
+    CHR3D_CUDA(cudaGetLastError());
+    return 0;
+}
+// one energy + force evaluation at explicit coordinates e.vx, forces into e.vf, totals in escal[0..2] (SAVE / PICK / ENERGY / bench)
+static int ln_eval(LnEngine& e, const chr3d_stage& s, bool want_e = true) {
+    ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, want_e);
+    LnReduceArgs r; r.g = ln_gather_args(e); r.epart = e.epart.p; r.N = e.N; r.ncta = e.ncta; r.add_bond = e.rank == 0 ? 1 : 0;
+    r.x = e.vx.p; r.xb2 = nullptr; r.lam = nullptr; r.f = e.vf.p; r.escal = e.escal.p; r.w_bond = (float)s.w_bond; r.r0 = (float)e.prm.bond_r0;
+    ln_reduce_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(r);
+    ln_energy_kernel<<<1, 32, 0, e.stream>>>(e.epart.p, e.ncta, e.escal.p, e.nblk);
+    e.n_launches += 2;
 #ifdef CHR3D_WITH_NCCL
     if (e.world > 1 && e.comm) {
         if (ncclAllReduce(e.vf.p, e.vf.p, (size_t)e.N * 4, ncclFloat, ncclSum, e.comm, e.stream) != ncclSuccess ||
@@ -770,64 +1029,80 @@ static int ln_eval(LnEngine& e, const chr3d_stage& s, bool want_e = true) {
 }
 
 static int ln_poll_done(LnEngine& e, int* done) {
-    LnState h;
-    CHR3D_CUDA(cudaMemcpyAsync(&h, e.st.p, sizeof(LnState), cudaMemcpyDeviceToHost, e.stream));
+    int h = 0;
+    CHR3D_CUDA(cudaMemcpyAsync(&h, &e.st.p->done, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
     CHR3D_CUDA(cudaStreamSynchronize(e.stream));
-    *done = h.done;
+    *done = h;
     return 0;
 }
 
+// L-BFGS: per trial three launches (tiles at xb + t*p, ln_min_step_kernel, ln_min_update_kernel); the host only polls
+// the `done` flag every 32 trials, launches after `done` return immediately
 static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
     const int vb = std::min(296, (e.N + 255) / 256);
     LnVec v = e.vec();
+    const bool multi = e.world > 1;
     LnMinCfg c; c.m = e.m; c.max_ls = e.prm.lbfgs_max_ls; c.nstep = s.nstep; c.nparts = e.nparts; c.c1 = e.prm.lbfgs_c1; c.gtol = e.prm.lbfgs_gtol;
     c.ftol = e.prm.lbfgs_ftol; c.drop = s.drop; c.N = e.N;
+    LnMinStepArgs m; m.g = ln_gather_args(e); m.fsum = multi ? e.vfr.p : nullptr; m.v = v; m.lam = &e.st.p->tstepf; m.init = 1;
+    m.es.epart = e.epart.p; m.es.ncta = e.ncta; m.es.escal = multi ? e.escal.p : nullptr; m.st = e.st.p; m.blockpart = e.blockpart.p; m.nblk = e.nblk;
+    m.w_bond = (float)s.w_bond; m.r0 = (float)e.prm.bond_r0; m.cfg = c;
     ln_state_reset_kernel<<<1, 32, 0, e.stream>>>(e.st.p, 0);
     ln_copy_xb_kernel<<<vb, 256, 0, e.stream>>>(v);
-    // g := 0 so that the initial "y" is -f and g.g comes out of the same dots kernel
+    // g := 0 so that the initial "y" is -f and g.g comes out of the same inner products; p := 0 keeps x + 0*p finite
     CHR3D_CUDA(cudaMemsetAsync(e.vg.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
-    if (int rc = ln_eval(e, s)) return rc;
-    ln_min_dots_kernel<<<e.nparts, 256, 0, e.stream>>>(v, e.st.p, e.part.p);
-    ln_min_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c, 1);
+    CHR3D_CUDA(cudaMemsetAsync(e.vp.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
+    ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, true);
+    if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
+    ln_min_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(m);
     ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
     e.n_launches += 6;
+    m.init = 0;
     const long long max_trials = (long long)s.nstep * (e.prm.lbfgs_max_ls + 2) + 2;
     const int poll_every = 32;
     for (long long trial = 0; trial < max_trials;) {
         for (int k = 0; k < poll_every; k++, trial++) {
-            ln_min_trial_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
-            if (int rc = ln_eval(e, s)) return rc;
-            ln_min_dots_kernel<<<e.nparts, 256, 0, e.stream>>>(v, e.st.p, e.part.p);
-            ln_min_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c, 0);
+            ln_tiles(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf, &e.st.p->done, true);
+            if (multi) if (int rc = ln_exchange(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf)) return rc;
+            ln_min_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(m);
             ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
-            e.n_launches += 4;
+            e.n_launches += 2;
         }
         int done = 0;
         if (int rc = ln_poll_done(e, &done)) return rc;
         if (done) break;
     }
-    // evaluations issued after `done` are no-ops on the state (control returns early) but x may hold a rejected trial:
-    // the update kernel restored x = xb when the search ended on a failure (accepted == 4); on success x == xb already.
+    CHR3D_CUDA(cudaGetLastError());
     return 0;
 }
 
+// Verlet MD: per step two launches (tiles at a + lam*b, ln_md_step_kernel); (a, b) double-buffered by parity
 static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
     const int vb = std::min(296, (e.N + 255) / 256);
-    LnVec v = e.vec();
+    const bool multi = e.world > 1;
     LnMdCfg c; c.dt_akma = (float)(s.dt / CHR3D_TIMFAC); c.h = (float)(0.5 * (s.dt / CHR3D_TIMFAC) / e.prm.mass); c.dt_ps = s.dt; c.temp = s.temp;
     c.fbeta = e.prm.fbeta; c.kboltz = CHR3D_KBOLTZ; c.mass = e.prm.mass; c.flag = s.flag; c.N = e.N; c.nparts = e.nparts; c.count = 1;
     ln_sum3_kernel<<<e.nparts, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p);             // cmremove
     ln_sub_mean_kernel<<<vb, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p, e.nparts);
-    if (int rc = ln_eval(e, s)) return rc;
-    ln_md_post_kernel<<<e.nparts, 256, 0, e.stream>>>(v, c, 0, e.part.p);
-    ln_md_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c);
-    e.n_launches += 4;
+    e.n_launches += 2;
+    LnMdStepArgs p; p.g = ln_gather_args(e); p.fsum = multi ? e.vfr.p : nullptr; p.x = e.vx.p; p.v = e.vv.p; p.f = e.vf.p;
+    p.es.epart = e.epart.p; p.es.ncta = e.ncta; p.es.escal = multi ? e.escal.p : nullptr; p.st = e.st.p; p.blockpart = e.blockpart.p; p.nblk = e.nblk; p.N = e.N;
+    p.w_bond = (float)s.w_bond; p.r0 = (float)e.prm.bond_r0; p.h = c.h; p.dt_akma = c.dt_akma; p.md = c;
+    // evaluation at the starting point: explicit x, nothing pending
+    ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, false);
+    if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
+    p.a = e.vx.p; p.b = e.vx.p; p.lam = &e.st.p->zerof; p.a_next = e.va[0].p; p.b_next = e.vb[0].p; p.first = 1; p.want_e = 0;
+    ln_md_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(p);
+    e.n_launches++;
+    int par = 0;
     for (int step = 0; step < s.nstep; step++) {
-        ln_md_pre_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p, c);
-        if (int rc = ln_eval(e, s, step == s.nstep - 1)) return rc;     // energies only matter after the last step
-        ln_md_post_kernel<<<e.nparts, 256, 0, e.stream>>>(v, c, 1, e.part.p);
-        ln_md_control_kernel<<<1, 32, 0, e.stream>>>(e.st.p, e.part.p, e.escal.p, c);
-        e.n_launches += 3;
+        const bool want_e = step == s.nstep - 1;                               // energies only matter after the last step
+        ln_tiles(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf, nullptr, want_e);
+        if (multi) if (int rc = ln_exchange(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf)) return rc;
+        p.a = e.va[par].p; p.b = e.vb[par].p; p.lam = &e.st.p->lamf; p.a_next = e.va[par ^ 1].p; p.b_next = e.vb[par ^ 1].p; p.first = 0; p.want_e = want_e ? 1 : 0;
+        ln_md_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(p);
+        e.n_launches++;
+        par ^= 1;
     }
     CHR3D_CUDA(cudaGetLastError());
     return 0;
@@ -971,8 +1246,8 @@ CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t rep
     ln_init_kernel<<<std::min(296, (e.N + 255) / 256), 256, 0, e.stream>>>(v, e.x0.p, 1);
     chr3d_stage s = h->prog.back();
     cudaEvent_t a, b; CHR3D_CUDA(cudaEventCreate(&a)); CHR3D_CUDA(cudaEventCreate(&b));
-    LnTileArgs ta; ta.Dt = e.Dt.p; ta.t0 = e.t0; ta.t1 = e.t1; ta.nT = e.nT; ta.N = e.N; ta.x = e.vx.p; ta.colpart = e.colpart.p;
-    ta.rowpart = e.rowpart.p; ta.seg_I = e.seg_I.p; ta.epart = e.epart.p; ta.maxseg = e.maxseg; ln_terms(e.prm, s, ta.terms);
+    LnTileArgs ta; ta.Dt = e.Dt.p; ta.t0 = e.t0; ta.t1 = e.t1; ta.nT = e.nT; ta.N = e.N; ta.x = e.vx.p; ta.xb2 = nullptr; ta.lam = nullptr; ta.done = nullptr;
+    ta.colpart = e.colpart.p; ta.rowpart = e.rowpart.p; ta.seg_I = e.seg_I.p; ta.epart = e.epart.p; ta.maxseg = e.maxseg; ln_terms(e.prm, s, ta.terms);
     for (int w = 0; w < 3; w++) ln_launch_tiles(e, ta, want_energy != 0);
     CHR3D_CUDA(cudaEventRecord(a, e.stream));
     for (int r = 0; r < reps; r++) ln_launch_tiles(e, ta, want_energy != 0);
@@ -980,12 +1255,17 @@ CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t rep
     CHR3D_CUDA(cudaEventSynchronize(b));
     float ms = 0.f; CHR3D_CUDA(cudaEventElapsedTime(&ms, a, b));
     if (tile_ms) *tile_ms = ms / reps;
-    for (int w = 0; w < 2; w++) if (int rc = ln_eval(e, s, want_energy != 0)) return rc;
+    // a whole force evaluation as the integrator issues it: `reps` MD steps with dt = 0 (the state does not move)
+    chr3d_stage md = s; md.op = CHR3D_OP_DYNAMICS; md.dt = 0.0; md.temp = 0.0; md.flag = 0; md.nstep = 2;
+    CHR3D_CUDA(cudaMemsetAsync(e.vv.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
+    if (int rc = ln_dynamics(e, md)) return rc;
+    md.nstep = reps;
     CHR3D_CUDA(cudaEventRecord(a, e.stream));
-    for (int r = 0; r < reps; r++) if (int rc = ln_eval(e, s, want_energy != 0)) return rc;
+    if (int rc = ln_dynamics(e, md)) return rc;
     CHR3D_CUDA(cudaEventRecord(b, e.stream));
     CHR3D_CUDA(cudaEventSynchronize(b));
     CHR3D_CUDA(cudaEventElapsedTime(&ms, a, b));
+    ms = ms * reps / (reps + 1);                 // the stage's starting-point evaluation is one more
     if (eval_ms) *eval_ms = ms / reps;
     cudaEventDestroy(a); cudaEventDestroy(b);
     return 0;
