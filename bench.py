@@ -184,6 +184,14 @@ def run_single(args, torch, dist, api, rank, world, local):
     stream = torch.cuda.current_stream()
     single = api.Single(N=N, alpha=alpha, synth_seed=sseed, seed=82364, p=p, rank=rank, world=world, nccl_id=nccl_id)
     info = single.info()
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl all-reduce"
+        if os.environ.get("CHR3D_NO_P2P") != "1":
+            hs = [None] * world
+            dist.all_gather_object(hs, single.comm_handle())
+            single.comm_connect(hs)
+            exchange = "fused peer-memory exchange in the step kernel (NVLink remote stores + epoch flags)"
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
     def barrier():
@@ -255,7 +263,7 @@ def run_single(args, torch, dist, api, rank, world, local):
                            "schedule": "dgsa.inp full (C3D:1573-1829)" if not args.profile else "PROFILE (shortened)", "force_evals_per_model": evals,
                            "tiles": info["n_tiles"], "tiles_rank0": info["tiles_this_rank"], "target_bytes_rank0": info["target_bytes"],
                            "l2": "flushed between steps (512 MB write); targets exceed L2 at this size" if N > 8000 else "flushed between steps (512 MB write); the 51 MB of targets are re-read from L2 inside a step",
-                           "parallelism": "tile-range shards + NCCL all-reduce of forces per evaluation" if world > 1 else "single GPU"},
+                           "parallelism": ("tile-range shards; force exchange per evaluation: " + exchange) if world > 1 else "single GPU"},
                 "sa_models_per_sec": 1.0 / (step_ms_max * 1e-3),
                 "force_eval_ms": eval_ms_max, "tile_kernel_ms": tile_ms_max,
                 "e2e": e2e if e2e is not None else {"value": None, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

@@ -348,6 +348,23 @@ class Single:
                                          C.c_uint64(seed), C.byref(self.p), self.program, len(self.program), int(rank), int(world),
                                          idbuf, C.byref(self._h)))
 
+    def comm_handle(self):
+        """64-byte CUDA IPC handle of this rank's exchange buffer (world > 1)."""
+        buf = (C.c_ubyte * 64)()
+        _check(lib().chr3d_single_comm_handle(self._h, buf))
+        return bytes(buf)
+
+    def comm_connect(self, handles):
+        """handles: the comm_handle() of every rank, in rank order.  Switches the force exchange from NCCL all-reduce
+        to the exchange fused into the step kernels (remote stores + flags over NVLink peer memory)."""
+        blob = b"".join(bytes(h) for h in handles)
+        _check(lib().chr3d_single_comm_connect(self._h, (C.c_ubyte * len(blob)).from_buffer_copy(blob), len(handles)))
+
+    def comm_error(self):
+        e = C.c_int32(0)
+        _check(lib().chr3d_single_comm_error(self._h, C.byref(e)))
+        return e.value
+
     def run(self, stream=None):
         _check(lib().chr3d_single_run(self._h, C.c_void_p(stream or 0)))
 

@@ -261,13 +261,25 @@ struct LnGather {
 #define LN_GROUPS 4                     // the step kernels run LN_GROUPS x LN_TB threads: the column partials of a bead block
 #define LN_STEP_THREADS (LN_GROUPS * LN_TB)   // are summed by LN_GROUPS thread groups (I = grp, grp + LN_GROUPS, ...) in parallel
 __device__ __forceinline__ void ln_gather_part(const LnGather& g, int B, int tid, int grp, float& fx, float& fy, float& fz) {
-    fx = fy = fz = 0.f;
-    for (int I = grp; I <= B; I += LN_GROUPS) {
-        const long long t = tile_index(I, B, g.nT);
-        if (t < g.t0 || t >= g.t1) continue;
-        const float* cp = g.colpart + (size_t)(t - g.t0) * 3 * LN_TB + ((tid & 31) * 4 + (tid >> 5));   // column -> position 4*lane + c
-        fx += cp[0]; fy += cp[LN_TB]; fz += cp[2 * LN_TB];
+    // the tiles (I, B), I = 0..B, have increasing list positions, so the ones this rank owns are a contiguous I range
+    int lo = 0, hi = B + 1;
+    while (lo < hi && tile_index(lo, B, g.nT) < g.t0) lo++;
+    while (hi > lo && tile_index(hi - 1, B, g.nT) >= g.t1) hi--;
+    const float* base = g.colpart + ((tid & 31) * 4 + (tid >> 5));      // column -> position 4*lane + c inside a partial
+    float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f}, az[4] = {0.f, 0.f, 0.f, 0.f};
+    int I = lo + grp;
+    for (; I + 3 * LN_GROUPS < hi; I += 4 * LN_GROUPS) {               // four independent loads in flight per component
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float* cp = base + (size_t)(tile_index(I + u * LN_GROUPS, B, g.nT) - g.t0) * 3 * LN_TB;
+            ax[u] += cp[0]; ay[u] += cp[LN_TB]; az[u] += cp[2 * LN_TB];
+        }
     }
+    for (; I < hi; I += LN_GROUPS) {
+        const float* cp = base + (size_t)(tile_index(I, B, g.nT) - g.t0) * 3 * LN_TB;
+        ax[0] += cp[0]; ay[0] += cp[LN_TB]; az[0] += cp[2 * LN_TB];
+    }
+    fx = (ax[0] + ax[1]) + (ax[2] + ax[3]); fy = (ay[0] + ay[1]) + (ay[2] + ay[3]); fz = (az[0] + az[1]) + (az[2] + az[3]);
     if (grp == 0) for (int k = g.rs_off[B]; k < g.rs_off[B + 1]; k++) {
         const float4 v = g.rowpart[(size_t)g.rs_idx[k] * LN_TB + tid];
         fx += v.x; fy += v.y; fz += v.z;
@@ -592,8 +604,71 @@ __device__ __forceinline__ bool ln_last_block(unsigned int* counter, int nblk) {
     return is_last != 0;
 }
 
+
+// ---- force exchange over NVLink peer memory, fused into the step kernels ------------------------------------
+// Every rank owns a communication buffer (cudaMalloc + CUDA IPC) that its peers map:
+//   recv [2 parities][world][N + 1] float4   slot g = partial forces of rank g (no bond term)
+//   flags[world][nblk] u32                   flags[g][B] = epoch of the newest block-B partial of rank g that has landed here
+//   es   [2][world][2] double, eflag[world]  pair energies of rank g, and their epoch
+// Block B of the step kernel gathers this rank's partial force on its 128 beads, PUSHES it into slot `rank` of every
+// rank's recv (remote stores, fire-and-forget), fences, pushes the epoch into every rank's flags, then waits until
+// the block-B flags of all ranks show the epoch and sums the world slots locally in rank order (identical on every
+// rank, so the redundant integration stays bit-identical).  Parity double-buffering makes overwriting safe: a rank
+// cannot run two evaluations ahead of a peer, because each evaluation needs that peer's current flags.
+#define LN_MAXWORLD 8
+struct LnXchg {
+    int world, rank, nblk, n4;                 // n4 = N + 1
+    float4* recv[LN_MAXWORLD]; unsigned int* flags[LN_MAXWORLD]; double* es[LN_MAXWORLD]; unsigned int* eflag[LN_MAXWORLD];
+    unsigned int epoch; int parity;
+    int* err;                                  // set when a wait times out (a peer died): the host reports it
+};
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool ln_wait_flag(const unsigned int* p, unsigned int epoch, int* err) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(p) - epoch) < 0) {
+        if (clock64() - t0 > 4000000000ll) { *err = 1; return false; }          // ~2 s: give up instead of hanging the GPU
+    }
+    return true;
+}
+// all threads of the block call; (fx, fy, fz) of the lead threads: this rank's partial in, total over ranks out
+__device__ __forceinline__ void ln_exchange_forces(const LnXchg& x, int B, int tid, bool lead, int i, int N, float& fx, float& fy, float& fz) {
+    const size_t slot = ((size_t)x.parity * x.world + x.rank) * x.n4;
+    if (lead && i < N) {
+        const float4 v = make_float4(fx, fy, fz, 0.f);
+        for (int g = 0; g < x.world; g++) x.recv[g][slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < x.world) st_release_sys(x.flags[threadIdx.x] + (size_t)x.rank * x.nblk + B, x.epoch);
+    if (threadIdx.x < x.world) ln_wait_flag(x.flags[x.rank] + (size_t)threadIdx.x * x.nblk + B, x.epoch, x.err);
+    __syncthreads();
+    if (lead && i < N) {
+        fx = fy = fz = 0.f;
+        const float4* R = x.recv[x.rank] + (size_t)x.parity * x.world * x.n4 + i;
+        for (int g = 0; g < x.world; g++) { const float4 v = __ldcg(R + (size_t)g * x.n4); fx += v.x; fy += v.y; fz += v.z; }
+    }
+}
+// one thread (of the last block): pair energies of this rank in, totals over ranks out
+__device__ __forceinline__ void ln_exchange_energies(const LnXchg& x, double& e0, double& e1) {
+    for (int g = 0; g < x.world; g++) { double* d = x.es[g] + ((size_t)x.parity * x.world + x.rank) * 2; d[0] = e0; d[1] = e1; }
+    __threadfence_system();
+    for (int g = 0; g < x.world; g++) st_release_sys(x.eflag[g] + x.rank, x.epoch);
+    e0 = e1 = 0.0;
+    for (int g = 0; g < x.world; g++) {
+        if (!ln_wait_flag(x.eflag[x.rank] + g, x.epoch, x.err)) return;
+        const double* d = x.es[x.rank] + ((size_t)x.parity * x.world + g) * 2;
+        e0 += __ldcg(d); e1 += __ldcg(d + 1);
+    }
+}
+
 struct LnMdStepArgs {
-    LnGather g; const float4* fsum;     // fsum != nullptr: total forces (bond included) already in fsum
+    LnGather g; const float4* fsum;     // fsum != nullptr: total forces (bond included) already in fsum (NCCL path)
+    LnXchg xc;                          // xc.world > 1: fused peer-memory exchange
     const float4* a; const float4* b; const float* lam;     // coordinates of the evaluation just done: a + lam*b
     float4 *x, *v, *f, *a_next, *b_next;
     LnEnergySrc es;
@@ -613,6 +688,7 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArg
     if (p.fsum) { if (lead && i < p.N) { const float4 t = p.fsum[i]; fx = t.x; fy = t.y; fz = t.z; } }
     else {
         ln_gather(p.g, B, tid, grp, fx, fy, fz);
+        if (p.xc.world > 1) ln_exchange_forces(p.xc, B, tid, lead, i, p.N, fx, fy, fz);
         if (lead && i < p.N) ln_bond(p.a, p.b, lam, i, p.N, p.w_bond, p.r0, fx, fy, fz, eb);
     }
     if (lead && i < p.N) {
@@ -632,10 +708,22 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArg
     const double kb = ln_block_sum((double)k2, sh, tid, lead), ebb = ln_block_sum((double)eb, sh, tid, lead);
     if (threadIdx.x == 0) { p.blockpart[(size_t)B * LN_KMAX] = kb; p.blockpart[(size_t)B * LN_KMAX + 1] = ebb; }
     if (!ln_last_block(&p.st->counter, p.nblk)) return;
+    // the last block sums the per-block partials with all its threads (fixed tree order)
+    __shared__ double red[4][LN_STEP_THREADS];
+    {
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int q = threadIdx.x; q < p.nblk; q += LN_STEP_THREADS) { a0 += p.blockpart[(size_t)q * LN_KMAX]; a1 += p.blockpart[(size_t)q * LN_KMAX + 1]; }
+        if (p.want_e && !p.es.escal) for (int q = threadIdx.x; q < p.es.ncta; q += LN_STEP_THREADS) { a2 += p.es.epart[2 * q]; a3 += p.es.epart[2 * q + 1]; }
+        red[0][threadIdx.x] = a0; red[1][threadIdx.x] = a1; red[2][threadIdx.x] = a2; red[3][threadIdx.x] = a3;
+        __syncthreads();
+        for (int o = LN_STEP_THREADS / 2; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) for (int c = 0; c < 4; c++) red[c][threadIdx.x] += red[c][threadIdx.x + o];
+            __syncthreads();
+        }
+    }
     if (threadIdx.x == 0) {
         LnState* st = p.st;
-        double k2s = 0, e2 = 0;
-        for (int q = 0; q < p.nblk; q++) { k2s += p.blockpart[(size_t)q * LN_KMAX]; e2 += p.blockpart[(size_t)q * LN_KMAX + 1]; }
+        double k2s = red[0][0], e2 = red[1][0];
         const double ke = 0.5 * p.md.mass * k2s, ndof = 3.0 * p.N - 3.0;
         const double T = 2.0 * ke / (p.md.kboltz * ndof);
         double l2 = 1.0;
@@ -647,7 +735,10 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArg
         if (p.want_e) {
             double e0 = 0, e1 = 0;
             if (p.es.escal) { e0 = p.es.escal[0]; e1 = p.es.escal[1]; e2 = p.es.escal[2]; }
-            else for (int q = 0; q < p.es.ncta; q++) { e0 += p.es.epart[2 * q]; e1 += p.es.epart[2 * q + 1]; }
+            else {
+                e0 = red[2][0]; e1 = red[3][0];
+                if (p.xc.world > 1) ln_exchange_energies(p.xc, e0, e1);
+            }
             st->Enoe = e0; st->Evdw = e1; st->Ebond = e2; st->E = e0 + e1 + e2;
         }
         st->counter = 0;
@@ -655,7 +746,7 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArg
 }
 
 struct LnMinStepArgs {
-    LnGather g; const float4* fsum;
+    LnGather g; const float4* fsum; LnXchg xc;
     LnVec v; const float* lam; int init;         // init: evaluation at the starting point (x = v.x, nothing pending)
     LnEnergySrc es;
     LnState* st; double* blockpart; int nblk;
@@ -678,6 +769,7 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_min_step_kernel(LnMinStepA
     if (p.fsum) { if (lead && i < N) { const float4 t = p.fsum[i]; fx = t.x; fy = t.y; fz = t.z; } }
     else {
         ln_gather(p.g, B, tid, grp, fx, fy, fz);
+        if (p.xc.world > 1) ln_exchange_forces(p.xc, B, tid, lead, i, N, fx, fy, fz);
         if (lead && i < N) ln_bond(A, p.v.p, lam, i, N, p.w_bond, p.r0, fx, fy, fz, eb);
     }
     float acc[LN_KMAX];
@@ -712,16 +804,23 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_min_step_kernel(LnMinStepA
     }
     if (threadIdx.x == 0) p.blockpart[(size_t)B * LN_KMAX + K] = ebb;
     if (!ln_last_block(&p.st->counter, p.nblk)) return;
-    if (lead && tid <= K) {
+    {   // per-block partials -> totals with all threads of the last block: 8 slices of blocks per scalar, fixed order
+        __shared__ double red2[LN_STEP_THREADS / LN_KMAX][LN_KMAX];
+        const int k = threadIdx.x & (LN_KMAX - 1), sl = threadIdx.x / LN_KMAX;
         double s = 0;
-        for (int q = 0; q < p.nblk; q++) s += p.blockpart[(size_t)q * LN_KMAX + tid];
-        G[tid] = s;
+        if (k <= K) for (int q = sl; q < p.nblk; q += LN_STEP_THREADS / LN_KMAX) s += p.blockpart[(size_t)q * LN_KMAX + k];
+        red2[sl][k] = s;
+        __syncthreads();
+        if ((int)threadIdx.x <= K) { double t = 0; for (int q = 0; q < LN_STEP_THREADS / LN_KMAX; q++) t += red2[q][threadIdx.x]; G[threadIdx.x] = t; }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         double e3[3] = {0, 0, G[K]};
         if (p.es.escal) { e3[0] = p.es.escal[0]; e3[1] = p.es.escal[1]; e3[2] = p.es.escal[2]; }
-        else for (int q = 0; q < p.es.ncta; q++) { e3[0] += p.es.epart[2 * q]; e3[1] += p.es.epart[2 * q + 1]; }
+        else {
+            for (int q = 0; q < p.es.ncta; q++) { e3[0] += p.es.epart[2 * q]; e3[1] += p.es.epart[2 * q + 1]; }
+            if (p.xc.world > 1) ln_exchange_energies(p.xc, e3[0], e3[1]);
+        }
         ln_min_decide(p.st, G, e3, p.cfg, p.init);
         p.st->tstepf = (float)p.st->tstep;
         p.st->counter = 0;
@@ -908,6 +1007,28 @@ struct LnEngine {
 #ifdef CHR3D_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
+    // peer-memory exchange (world > 1): this rank's buffer, the mapped peer buffers, the evaluation counter
+    void* xbuf = nullptr; size_t xbytes = 0; void* peer[LN_MAXWORLD] = {nullptr}; bool p2p = false; unsigned int epoch = 0;
+    DevBuf<int> xerr;
+    static size_t up16(size_t v) { return (v + 15) / 16 * 16; }
+    size_t x_off_flags() const { return sizeof(float4) * 2 * (size_t)world * (N + 1); }
+    size_t x_off_es() const { return x_off_flags() + up16(sizeof(unsigned int) * (size_t)world * nblk); }
+    size_t x_off_eflag() const { return x_off_es() + sizeof(double) * 2 * 2 * (size_t)world; }
+    size_t x_total() const { return x_off_eflag() + up16(sizeof(unsigned int) * (size_t)world); }
+    LnXchg xchg_next() {            // descriptor of the next evaluation's exchange
+        LnXchg x; memset(&x, 0, sizeof x);
+        x.world = p2p ? world : 1; x.rank = rank; x.nblk = nblk; x.n4 = N + 1;
+        if (p2p) {
+            epoch++;
+            x.epoch = epoch; x.parity = (int)(epoch & 1u); x.err = xerr.p;
+            for (int g = 0; g < world; g++) {
+                char* base = (char*)peer[g];
+                x.recv[g] = (float4*)base; x.flags[g] = (unsigned int*)(base + x_off_flags());
+                x.es[g] = (double*)(base + x_off_es()); x.eflag[g] = (unsigned int*)(base + x_off_eflag());
+            }
+        }
+        return x;
+    }
     LnVec vec() { LnVec v; v.x = vx.p; v.xb = vxb.p; v.g = vg.p; v.p = vp.p; v.v = vv.p; v.f = vf.p; v.S = vS.p; v.Y = vY.p; v.N = N; v.m = m; return v; }
 };
 
@@ -1041,7 +1162,7 @@ static int ln_poll_done(LnEngine& e, int* done) {
 static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
     const int vb = std::min(296, (e.N + 255) / 256);
     LnVec v = e.vec();
-    const bool multi = e.world > 1;
+    const bool multi = e.world > 1 && !e.p2p;       // NCCL path; with p2p the exchange is fused into the step kernel
     LnMinCfg c; c.m = e.m; c.max_ls = e.prm.lbfgs_max_ls; c.nstep = s.nstep; c.nparts = e.nparts; c.c1 = e.prm.lbfgs_c1; c.gtol = e.prm.lbfgs_gtol;
     c.ftol = e.prm.lbfgs_ftol; c.drop = s.drop; c.N = e.N;
     LnMinStepArgs m; m.g = ln_gather_args(e); m.fsum = multi ? e.vfr.p : nullptr; m.v = v; m.lam = &e.st.p->tstepf; m.init = 1;
@@ -1054,6 +1175,7 @@ static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
     CHR3D_CUDA(cudaMemsetAsync(e.vp.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, true);
     if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
+    m.xc = e.xchg_next();
     ln_min_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(m);
     ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
     e.n_launches += 6;
@@ -1064,6 +1186,7 @@ static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
         for (int k = 0; k < poll_every; k++, trial++) {
             ln_tiles(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf, &e.st.p->done, true);
             if (multi) if (int rc = ln_exchange(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf)) return rc;
+            m.xc = e.xchg_next();
             ln_min_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(m);
             ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
             e.n_launches += 2;
@@ -1079,7 +1202,7 @@ static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
 // Verlet MD: per step two launches (tiles at a + lam*b, ln_md_step_kernel); (a, b) double-buffered by parity
 static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
     const int vb = std::min(296, (e.N + 255) / 256);
-    const bool multi = e.world > 1;
+    const bool multi = e.world > 1 && !e.p2p;
     LnMdCfg c; c.dt_akma = (float)(s.dt / CHR3D_TIMFAC); c.h = (float)(0.5 * (s.dt / CHR3D_TIMFAC) / e.prm.mass); c.dt_ps = s.dt; c.temp = s.temp;
     c.fbeta = e.prm.fbeta; c.kboltz = CHR3D_KBOLTZ; c.mass = e.prm.mass; c.flag = s.flag; c.N = e.N; c.nparts = e.nparts; c.count = 1;
     ln_sum3_kernel<<<e.nparts, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p);             // cmremove
@@ -1092,6 +1215,7 @@ static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, false);
     if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
     p.a = e.vx.p; p.b = e.vx.p; p.lam = &e.st.p->zerof; p.a_next = e.va[0].p; p.b_next = e.vb[0].p; p.first = 1; p.want_e = 0;
+    p.xc = e.xchg_next();
     ln_md_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(p);
     e.n_launches++;
     int par = 0;
@@ -1100,6 +1224,7 @@ static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
         ln_tiles(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf, nullptr, want_e);
         if (multi) if (int rc = ln_exchange(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf)) return rc;
         p.a = e.va[par].p; p.b = e.vb[par].p; p.lam = &e.st.p->lamf; p.a_next = e.va[par ^ 1].p; p.b_next = e.vb[par ^ 1].p; p.first = 0; p.want_e = want_e ? 1 : 0;
+        p.xc = e.xchg_next();
         ln_md_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(p);
         e.n_launches++;
         par ^= 1;
@@ -1186,6 +1311,13 @@ CHR3D_API int chr3d_single_create(const double* IF, int32_t N, double alpha, dou
 #endif
     }
     if (int rc = ln_alloc(e)) return rc;
+    if (world > 1) {
+        if (world > LN_MAXWORLD) { set_error("chr3d_single_create: world %d exceeds %d", world, LN_MAXWORLD); return CHR3D_ERR_ARG; }
+        e.xbytes = e.x_total();
+        CHR3D_CUDA(cudaMalloc(&e.xbuf, e.xbytes));           // plain cudaMalloc: exportable through CUDA IPC
+        CHR3D_CUDA(cudaMemset(e.xbuf, 0, e.xbytes));
+        CHR3D_CUDA(e.xerr.alloc(1)); CHR3D_CUDA(cudaMemset(e.xerr.p, 0, sizeof(int)));
+    }
     {   // targets
         DevBuf<double> dIF, rows, mean; DevBuf<long long> dT;
         const size_t n2 = (size_t)N * N;
@@ -1312,7 +1444,41 @@ CHR3D_API int chr3d_single_destroy(chr3d_single* h) {
 #endif
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    cudaDeviceSynchronize();
+    for (int g = 0; g < h->e.world && g < LN_MAXWORLD; g++) if (h->e.peer[g] && g != h->e.rank) cudaIpcCloseMemHandle(h->e.peer[g]);
+    if (h->e.xbuf) cudaFree(h->e.xbuf);
+    cudaGetLastError();
     delete h;
+    return 0;
+}
+
+// Peer-memory exchange set-up (world > 1): every rank exports the IPC handle of its communication buffer
+// (64 bytes), the caller gathers the handles of all ranks in rank order (e.g. torch.distributed.all_gather_object)
+// and hands them to chr3d_single_comm_connect on every rank.  After that the force exchange of every evaluation
+// is fused into the step kernels (remote stores + flags over NVLink); without it the engine uses NCCL all-reduce.
+CHR3D_API int chr3d_single_comm_handle(chr3d_single* h, void* out64) {
+    if (!h || !out64 || !h->e.xbuf) { set_error("chr3d_single_comm_handle: no communication buffer (world == 1?)"); return CHR3D_ERR_ARG; }
+    cudaIpcMemHandle_t mh;
+    CHR3D_CUDA(cudaIpcGetMemHandle(&mh, h->e.xbuf));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out64, &mh, 64);
+    return 0;
+}
+CHR3D_API int chr3d_single_comm_connect(chr3d_single* h, const void* handles, int32_t world) {
+    if (!h || !handles || world != h->e.world || !h->e.xbuf) { set_error("chr3d_single_comm_connect: bad arguments"); return CHR3D_ERR_ARG; }
+    LnEngine& e = h->e;
+    for (int g = 0; g < world; g++) {
+        if (g == e.rank) { e.peer[g] = e.xbuf; continue; }
+        cudaIpcMemHandle_t mh; memcpy(&mh, (const char*)handles + 64 * (size_t)g, 64);
+        CHR3D_CUDA(cudaIpcOpenMemHandle(&e.peer[g], mh, cudaIpcMemLazyEnablePeerAccess));
+    }
+    e.p2p = true;
+    return 0;
+}
+CHR3D_API int chr3d_single_comm_error(chr3d_single* h, int32_t* err) {
+    if (!h || !err) { set_error("chr3d_single_comm_error: bad arguments"); return CHR3D_ERR_ARG; }
+    *err = 0;
+    if (h->e.xerr.p) CHR3D_CUDA(cudaMemcpy(err, h->e.xerr.p, sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -223,6 +223,12 @@ int chr3d_single_info(const chr3d_single* h, int64_t* n_tiles, int64_t* tiles_th
                       int32_t* ctas, int64_t* target_bytes);
 int chr3d_single_destroy(chr3d_single* h);
 int chr3d_nccl_unique_id(void* out128);
+/* Fused peer-memory force exchange (world > 1): export this rank's 64-byte CUDA IPC handle, gather the handles of
+ * all ranks in rank order, connect.  Afterwards the per-evaluation exchange runs inside the step kernels over
+ * NVLink (remote stores + epoch flags) instead of NCCL.  chr3d_single_comm_error reports a peer time-out.     */
+int chr3d_single_comm_handle(chr3d_single* h, void* out64);
+int chr3d_single_comm_connect(chr3d_single* h, const void* handles /* world*64 bytes */, int32_t world);
+int chr3d_single_comm_error(chr3d_single* h, int32_t* err);
 /* Synthetic IF matrix of SURVEY 8(d) (N*N doubles, generated on the device, copied back).     */
 int chr3d_synthetic_if(int32_t N, uint64_t seed, double* out);
 
