@@ -32,6 +32,12 @@ WORKLOADS = {
     "chr1_500kb_a0.5_m20": ("chr1_500kb", 0.5, 20),
     "chr21_1mb_a1.1_m10": ("chr21_1mb", 1.1, 10),
 }
+BATCH_WORKLOADS = {
+    # many (matrix, alpha) jobs in one call (the BASELINE.json configs[2] pattern) — name: (matrices, alphas, models)
+    "chr1_500kb_alpha_sweep_m20": (["chr1_500kb"], [round(0.1 * k, 1) for k in range(1, 21)], 20),
+    "all_inputs_a1.1_m20": ("ALL", [1.1], 20),
+    "all_inputs_alpha_sweep_m20": ("ALL", [round(0.1 * k, 1) for k in range(1, 21)], 20),
+}
 SINGLE_WORKLOADS = {
     # one large structure (BASELINE.json configs[3], configs[4]) — name: (beads, alpha, synthetic seed)
     "synth_50kb_single": (4985, 1.1, 20260001),
@@ -285,13 +291,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="chr1_500kb_a1.1_m20", choices=sorted(WORKLOADS) + sorted(SINGLE_WORKLOADS))
+    ap.add_argument("--workload", default="chr1_500kb_a1.1_m20", choices=sorted(WORKLOADS) + sorted(BATCH_WORKLOADS) + sorted(SINGLE_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-n", action="store_true", help="skip the large-N kernel probe appended to the default line")
     ap.add_argument("--profile", action="store_true", help="short schedule for ncu captures (not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.workload in SINGLE_WORKLOADS:
+        if args.workload not in WORKLOADS:
             args.workload = "chr1_500kb_a1.1_m20"
         return run_reference(args)
 
@@ -312,17 +318,35 @@ def main():
             dist.destroy_process_group()
         return
 
-    name, alpha, m = WORKLOADS[args.workload]
-    IF_np = ds.load_if_matrix(ds.input_path(name))
-    N = IF_np.shape[0]
-    IF_pinned = torch.from_numpy(IF_np).pin_memory()
-    IF = IF_pinned.numpy()
     p = api.default_params()
     if args.profile:
         p.hot_step, p.cool_step, p.pow_step, p.pow_cycl, p.premin_step, p.images = 64, 160, 50, 1, 10, 1
-    seed = 82364 + 1000 * rank          # every rank anneals its own ensemble (weak scaling)
-    job = api.Job(IF=IF, alpha=alpha, n_models=m, seed=seed)
-    ens = api.Ensemble([job], p)
+    seed = 82364 + 1000 * rank          # every rank anneals its own ensemble(s) (weak scaling)
+    if args.workload in BATCH_WORKLOADS:
+        mats, alphas, m = BATCH_WORKLOADS[args.workload]
+        names = ds.list_inputs() if mats == "ALL" else mats
+        pairs = [(nm, a) for nm in names for a in alphas]
+        if world > 1:                                   # job shards, no collective (chromosome3d_b200/sharding.py)
+            from chromosome3d_b200 import sharding
+            sizes = {nm: ds.load_if_matrix(ds.input_path(nm)).shape[0] for nm in names}
+            mine = sharding.shard_jobs([sharding.job_cost(sizes[nm], m) for nm, _ in pairs], world)[rank]
+            pairs = [pairs[k] for k in mine]
+        mats_np = {nm: torch.from_numpy(ds.load_if_matrix(ds.input_path(nm))).pin_memory().numpy() for nm in sorted(set(nm for nm, _ in pairs))}
+        def make_jobs():
+            return [api.Job(IF=mats_np[nm], alpha=a, n_models=m, seed=seed) for nm, a in pairs]
+        name, alpha = "%d jobs (%d matrices x %d alpha)" % (len(pairs), len(mats_np), len(alphas)), alphas[0] if len(alphas) == 1 else "0.1..2.0"
+        N = max(v.shape[0] for v in mats_np.values())
+        h2d_bytes = sum(mats_np[nm].nbytes for nm, _ in pairs)
+    else:
+        name, alpha, m = WORKLOADS[args.workload]
+        IF_np = ds.load_if_matrix(ds.input_path(name))
+        N = IF_np.shape[0]
+        IF = torch.from_numpy(IF_np).pin_memory().numpy()
+        def make_jobs():
+            return [api.Job(IF=IF, alpha=alpha, n_models=m, seed=seed)]
+        h2d_bytes = IF.nbytes
+    jobs = make_jobs()
+    ens = api.Ensemble(jobs, p)
     info = ens.info()
     stream = torch.cuda.current_stream()
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")     # > 126 MB L2
@@ -350,9 +374,11 @@ def main():
     barrier()
     t_wall = time.time() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    res = ens.fetch()[0]
+    all_res = ens.fetch()
+    res = all_res[0]
     kernel_ms = sum(step_ms) / len(step_ms)
-    pair_evals_step = float(res.force_evals.sum()) * res.n_restraints
+    pair_evals_step = sum(float(r.force_evals.sum()) * r.n_restraints for r in all_res)
+    n_models_rank = sum(j.n_models for j in jobs)
     launches = info["launches"] * (args.steps + args.warmup)
 
     # e2e: host buffers through the public call, copies inside the timed region
@@ -361,22 +387,28 @@ def main():
     for k in range(args.warmup + args.steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e2e_res = api.build_models([api.Job(IF=IF, alpha=alpha, n_models=m, seed=seed)], p)[0]
+        e2e_all = api.build_models(make_jobs(), p)
+        e2e_res = e2e_all[0]
         torch.cuda.synchronize()
+        last_ms = 1e3 * (time.perf_counter() - t0)
         if k >= args.warmup:
-            e2e_ms.append(1e3 * (time.perf_counter() - t0))
-        launches += info["launches"] + 14          # SA launch + restraint derivation, tile packing, coil, assessment kernels
+            e2e_ms.append(last_ms)
+        launches += info["launches"] + 14 * len(jobs)   # SA launches + per job: restraint derivation, tile packing, coil, assessment kernels
+        if args.workload in BATCH_WORKLOADS and k >= 1:
+            break                                   # the batch workloads are long: one warm-up and one timed pass
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    if not e2e_ms:
+        e2e_ms.append(last_ms)
     e2e_step_ms = sum(e2e_ms) / len(e2e_ms)
-    e2e_pair_evals = float(e2e_res.force_evals.sum()) * e2e_res.n_restraints
-    h2d = IF.nbytes
-    d2h = e2e_res.xyz.nbytes + e2e_res.energies.nbytes + e2e_res.force_evals.nbytes + e2e_res.hand.nbytes + e2e_res.satisfied.nbytes + e2e_res.sum_dev.nbytes
+    e2e_pair_evals = sum(float(r.force_evals.sum()) * r.n_restraints for r in e2e_all)
+    h2d = h2d_bytes
+    d2h = sum(r.xyz.nbytes + r.energies.nbytes + r.force_evals.nbytes + r.hand.nbytes + r.satisfied.nbytes + r.sum_dev.nbytes for r in e2e_all)
 
     # max over ranks
     t = torch.tensor([kernel_ms, e2e_step_ms], dtype=torch.float64, device="cuda")
-    w = torch.tensor([pair_evals_step, e2e_pair_evals, float(m)], dtype=torch.float64, device="cuda")
+    w = torch.tensor([pair_evals_step, e2e_pair_evals, float(n_models_rank)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
@@ -395,9 +427,10 @@ def main():
         line = {
             "metric": "restraint_pair_evals_per_sec", "value": value, "unit": "pair-evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kernel_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "reference input matrix %s_matrix.txt (real Hi-C IF), seeded random-coil starts" % name,
-            "config": {"workload": args.workload, "matrix": name, "beads": N, "alpha": alpha, "K": 11, "restraint_rows": int(res.n_restraints),
-                       "models_per_ensemble": m, "ensembles": world, "schedule": "dgsa.inp full (C3D:1573-1829)" if not args.profile else "PROFILE (shortened)",
+            "dtype": "f32", "data": "reference input matrices (real Hi-C IF): %s, seeded random-coil starts" % name,
+            "config": {"workload": args.workload, "matrix": name, "beads": N, "alpha": alpha, "K": 11,
+                       "restraint_rows": int(sum(r.n_restraints for r in all_res)), "jobs_per_rank": len(jobs),
+                       "models_per_ensemble": m, "ensembles": world * len(jobs), "sa_launches_per_step": info["launches"], "schedule": "dgsa.inp full (C3D:1573-1829)" if not args.profile else "PROFILE (shortened)",
                        "force_evals_per_model": float(res.force_evals.mean()), "cluster_size": info["cluster"], "threads_per_cta": info["threads"],
                        "l2": "flushed between steps (512 MB write, outside the per-step events)", "parallelism": "ensemble shards, no collectives"},
             "sa_models_per_sec": models_all / (kernel_ms_max * 1e-3),

@@ -167,8 +167,13 @@ struct chr3d_ensemble {
     int nstages = 0, n_traj = 0, n_launches = 0;
     long long rows_total = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaStream_t> gstreams; std::vector<cudaEvent_t> gevents;
     bool ran = false;
-    ~chr3d_ensemble() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
+    ~chr3d_ensemble() {
+        if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t ev : gevents) if (ev) cudaEventDestroy(ev);
+        for (cudaStream_t st : gstreams) if (st) cudaStreamDestroy(st);
+    }
 };
 
 // ---------------------------------- lifecycle ---------------------------------------------------
@@ -342,6 +347,8 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
     CHR3D_CUDA(cudaMemcpy(e->prog.p, hs.data(), sizeof(DevStage) * nstages, cudaMemcpyHostToDevice));
     std::vector<TrajDesc> tds;
     if (fbufs) { std::vector<DevBuf<float>> t(njobs); fbufs->swap(t); }
+    int total_traj = 0;                       // the launch shape of every job is chosen for the whole batch sharing the GPU
+    for (int jn = 0; jn < njobs; jn++) total_traj += std::max(jobs[jn].n_models, 0);
     for (int jn = 0; jn < njobs; jn++) {
         const chr3d_job& jb = jobs[jn];
         if (jb.L < 2 || jb.n_models < 1) { set_error("job %d: need L>=2 and n_models>=1", jn); return CHR3D_ERR_ARG; }
@@ -383,8 +390,8 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         }
         if (want_forces) CHR3D_CUDA((*fbufs)[jn].alloc(nx));
         tr.lap("alloc+coil");
-        if (int rc = sa_choose_config(N, jb.n_models, e->P.m, &jd->cfg)) return rc;
-        jd->traj0 = (int)tds.size();
+        if (int rc = sa_choose_config(N, total_traj, e->P.m, &jd->cfg)) return rc;
+        jd->traj0 = (int)tds.size();          // (position in creation order; the launch order is decided below)
         for (int m = 0; m < jb.n_models; m++) {
             TrajDesc td; memset(&td, 0, sizeof td);
             td.T = jd->Tt.p; td.x0 = jd->x0.p + (size_t)m * N * 3; td.x_out = jd->xout.p + (size_t)m * N * 3;
@@ -395,17 +402,39 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         }
         e->jobs.push_back(std::move(jd));
     }
-    // one launch per run of consecutive jobs that share a launch configuration
-    for (size_t jn = 0; jn < e->jobs.size(); jn++) {
-        JobDev& jd = *e->jobs[jn];
-        if (!e->groups.empty()) {
-            LaunchGroup& g = e->groups.back();
-            if (g.cfg.cluster == jd.cfg.cluster && g.cfg.threads == jd.cfg.threads) {
-                g.n_traj += jd.n_models; g.cfg.smem = std::max(g.cfg.smem, jd.cfg.smem); g.Nmax = std::max(g.Nmax, jd.L); continue;
+    // launch order: jobs grouped by launch shape, larger structures first inside a group (they finish last otherwise);
+    // one launch per group, groups run concurrently on their own streams
+    {
+        std::vector<int> order(e->jobs.size());
+        for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const JobDev& x = *e->jobs[a]; const JobDev& y = *e->jobs[b];
+            if (x.cfg.cluster != y.cfg.cluster) return x.cfg.cluster > y.cfg.cluster;
+            if (x.cfg.threads != y.cfg.threads) return x.cfg.threads > y.cfg.threads;
+            return x.L > y.L;
+        });
+        std::vector<TrajDesc> sorted; sorted.reserve(tds.size());
+        for (int jn : order) {
+            JobDev& jd = *e->jobs[jn];
+            const int pos = (int)sorted.size();
+            for (int m = 0; m < jd.n_models; m++) sorted.push_back(tds[jd.traj0 + m]);
+            if (!e->groups.empty()) {
+                LaunchGroup& g = e->groups.back();
+                if (g.cfg.cluster == jd.cfg.cluster && g.cfg.threads == jd.cfg.threads) {
+                    g.n_traj += jd.n_models; g.cfg.smem = std::max(g.cfg.smem, jd.cfg.smem); g.Nmax = std::max(g.Nmax, jd.L); continue;
+                }
             }
+            LaunchGroup g; g.cfg = jd.cfg; g.traj0 = pos; g.n_traj = jd.n_models; g.Nmax = jd.L;
+            e->groups.push_back(g);
         }
-        LaunchGroup g; g.cfg = jd.cfg; g.traj0 = jd.traj0; g.n_traj = jd.n_models; g.Nmax = jd.L;
-        e->groups.push_back(g);
+        tds.swap(sorted);
+    }
+    if (e->groups.size() > 1) {
+        e->gstreams.resize(e->groups.size()); e->gevents.resize(e->groups.size());
+        for (size_t k = 0; k < e->groups.size(); k++) {
+            CHR3D_CUDA(cudaStreamCreateWithFlags(&e->gstreams[k], cudaStreamNonBlocking));
+            CHR3D_CUDA(cudaEventCreateWithFlags(&e->gevents[k], cudaEventDisableTiming));
+        }
     }
     e->n_traj = (int)tds.size();
     CHR3D_CUDA(e->traj.alloc(tds.size()));
@@ -427,8 +456,12 @@ CHR3D_API int chr3d_ensemble_run(chr3d_ensemble* e, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     e->n_launches = 0;
     CHR3D_CUDA(cudaEventRecord(e->ev0, s));
-    for (const LaunchGroup& g : e->groups) {
-        if (int rc = sa_launch(e->traj.p + g.traj0, g.n_traj, g.Nmax, e->P, e->prog.p, e->nstages, g.cfg, s)) return rc;
+    for (size_t k = 0; k < e->groups.size(); k++) {
+        const LaunchGroup& g = e->groups[k];
+        cudaStream_t gs = e->gstreams.empty() ? s : e->gstreams[k];
+        if (gs != s) CHR3D_CUDA(cudaStreamWaitEvent(gs, e->ev0, 0));
+        if (int rc = sa_launch(e->traj.p + g.traj0, g.n_traj, g.Nmax, e->P, e->prog.p, e->nstages, g.cfg, gs)) return rc;
+        if (gs != s) { CHR3D_CUDA(cudaEventRecord(e->gevents[k], gs)); CHR3D_CUDA(cudaStreamWaitEvent(s, e->gevents[k], 0)); }
         e->n_launches++;
     }
     CHR3D_CUDA(cudaEventRecord(e->ev1, s));

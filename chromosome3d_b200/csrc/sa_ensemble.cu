@@ -31,16 +31,19 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <algorithm>
 #include "common.h"
 
 namespace cg = cooperative_groups;
 
 namespace chr3d {
 
-#define SA_MAXC 8
+#define SA_MAXC 16
 #define SA_KTOT 64           // scalars per all-reduce (owner columns)
 #define SA_MAXW 20           // warps per CTA (kernel variants for <= 16 and <= 20 warps)
 #define SA_TILE_FLOATS 1024  // 32x32 micro-tile
+#define SA_GEO_BYTES 256     // SaGeo (first 128 bytes) and the trajectory descriptor (next 128) at the start of shared memory
+#define SA_MAX_STAGES 160    // stage-program entries kept in shared memory (the dgsa.inp program has 113)
 #define SA_MAXB (2 * CHR3D_LBFGS_MAX_M + 1)
 
 #define STREAM_COIL 0x00C011u
@@ -141,19 +144,20 @@ size_t sa_tiles_floats(int N) { const size_t nb = (size_t)(N + 31) / 32; return 
 // shared-memory layout (identical on host and device)
 // ------------------------------------------------------------------------------------------------
 struct SaShape {
-    int N, C, W, nthreads, nb, n32, ntiles, gwarps, rounds, own_max, rows_pad, m, nvec, res_rounds;
+    int N, C, W, nthreads, nb, n32, ntiles, gwarps, rounds, own_max, rows_pad, m, nvec, res_rounds, nstages;
 };
 struct SaLayout {
-    size_t ab, part, vec, P, eslots, kslots, slots, gsum, B, delta, tij, own, tres, total;
+    size_t prog, ab, part, vec, P, eslots, kslots, slots, gsum, B, delta, tij, own, tres, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 __host__ __device__ inline void sa_layout(const SaShape& s, SaLayout& L) {
-    size_t o = 0;
+    size_t o = SA_GEO_BYTES;
+    L.prog = o;   o = align_up(o + sizeof(DevStage) * (size_t)s.nstages, 16);
     L.ab = o;     o = align_up(o + sizeof(float4) * 4 * (size_t)(s.n32 + 1), 16);   // [parity][a|b][n32+1]
     L.part = o;   o = align_up(o + sizeof(float4) * (size_t)s.own_max * (s.nb + 1) * 32, 16);
     L.vec = o;    o = align_up(o + sizeof(float) * (size_t)s.nvec * 3 * s.rows_pad, 16);
-    L.P = o;      o = align_up(o + sizeof(float) * (size_t)SA_KTOT * s.rows_pad, 16);
+    L.P = o;      o = align_up(o + sizeof(float) * (size_t)(7 + 6 * s.m) * s.rows_pad, 16);   // columns: bond energy + 6m+6 inner products
     L.eslots = o; o = align_up(o + sizeof(double) * 2 * (size_t)s.gwarps, 16);
     L.kslots = o; o = align_up(o + sizeof(double) * (size_t)s.C * s.own_max, 16);
     L.slots = o;  o = align_up(o + sizeof(double) * 2 * SA_MAXC * SA_KTOT, 16);
@@ -167,8 +171,8 @@ __host__ __device__ inline void sa_layout(const SaShape& s, SaLayout& L) {
     L.total = o;
 }
 // res_rounds: how many of a warp's tiles stay resident in shared memory (decided from the dynamic smem size)
-__host__ __device__ inline void sa_shape(int N, int C, int W, int m, size_t smem_bytes, SaShape& s) {
-    s.N = N; s.C = C; s.W = W; s.nthreads = 32 * W; s.m = m;
+__host__ __device__ inline void sa_shape(int N, int C, int W, int m, int nstages, size_t smem_bytes, SaShape& s) {
+    s.N = N; s.C = C; s.W = W; s.nthreads = 32 * W; s.m = m; s.nstages = nstages;
     s.nb = (N + 31) / 32; s.n32 = 32 * s.nb; s.ntiles = s.nb * (s.nb + 1) / 2; s.gwarps = C * W;
     s.rounds = ((s.ntiles + C - 1) / C + W - 1) / W;       // tiles of the busiest warp
     s.own_max = (s.nb + C - 1) / C; s.rows_pad = 32 * s.own_max;
@@ -183,6 +187,16 @@ __host__ __device__ inline void sa_shape(int N, int C, int W, int m, size_t smem
 
 extern __shared__ __align__(128) unsigned char sa_smem[];
 
+// Cluster-uniform geometry, layout offsets and the stage program live at the start of shared memory (read with
+// broadcast LDS when needed) instead of in per-thread registers: the pair loop needs the registers, and spilled
+// per-thread copies cost local-memory round trips on the latency-critical control path.
+struct SaGeo {
+    int N, C, W, nthreads, nb, n32p, gwarps, own_max, rows_pad, m, res_rounds, rw0, nown, nstages;
+    unsigned o_ab, o_kslots, o_part, o_vec, o_P, o_eslots, o_slots, o_gsum, o_B, o_delta, o_tij, o_own, o_tres, o_prog;
+};
+#define SGEO (*(const SaGeo*)sa_smem)
+#define STD (*(const TrajDesc*)(sa_smem + 128))
+
 // Development aid (-DSA_TIMING): SM-clock cycles spent in the phases of a force evaluation, summed over all
 // evaluations, for the first owner warp and the last warp of cluster rank 0 of trajectory 0.
 #ifdef SA_TIMING
@@ -196,12 +210,8 @@ __device__ unsigned long long sa_dbg[2][16];
 // device context
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
-    // geometry
-    int N, C, W, rank, tid, lane, warp, nthreads, nb, n32p, gw, gwarps, my_rounds, res_rounds, own_max;
-    int rw0, nown, rows_pad;         // owned bead blocks [rw0, rw0 + nown)
-    int m;
-    // smem byte offsets (accessed through the sa_smem symbol so that loads stay LDS/STS)
-    unsigned o_ab, o_kslots, o_part, o_vec, o_P, o_eslots, o_slots, o_gsum, o_B, o_delta, o_tij, o_own, o_tres;
+    // per-thread geometry (everything cluster-uniform is in SGEO)
+    int rank, tid, lane, warp, gw, my_rounds;
     const float4* Tt;                // tile-packed targets in global memory
     int par;
     // coordinates of every bead are x = a + lam*b, (a, b) double-buffered by parity `buf` (see dyn_after_eval)
@@ -211,34 +221,34 @@ struct Ctx {
     float x[3], v[3], f[3];
     float ebond;
     long long nevals;
-    DevParams prm;
 #ifdef SA_TIMING
     bool tmark; long long tlast; long long tacc[10];
 #endif
 };
-#define S_AB(c) ((float4*)(sa_smem + (c).o_ab))
-#define S_KSLOTS(c) ((double*)(sa_smem + (c).o_kslots))
-#define S_PART(c) ((float4*)(sa_smem + (c).o_part))
-#define S_VEC(c) ((float*)(sa_smem + (c).o_vec))
-#define S_P(c) ((float*)(sa_smem + (c).o_P))
-#define S_ESLOTS(c) ((double*)(sa_smem + (c).o_eslots))
-#define S_SLOTS(c) ((double*)(sa_smem + (c).o_slots))
-#define S_GSUM(c) ((double*)(sa_smem + (c).o_gsum))
-#define S_B(c) ((double*)(sa_smem + (c).o_B))
-#define S_DELTA(c) ((double*)(sa_smem + (c).o_delta))
-#define S_TIJ(c) ((uchar2*)(sa_smem + (c).o_tij))
-#define S_OWN(c) ((uchar2*)(sa_smem + (c).o_own))
-#define S_TRES(c) ((float4*)(sa_smem + (c).o_tres))
+#define S_AB(c) ((float4*)(sa_smem + SGEO.o_ab))
+#define S_KSLOTS(c) ((double*)(sa_smem + SGEO.o_kslots))
+#define S_PART(c) ((float4*)(sa_smem + SGEO.o_part))
+#define S_VEC(c) ((float*)(sa_smem + SGEO.o_vec))
+#define S_P(c) ((float*)(sa_smem + SGEO.o_P))
+#define S_ESLOTS(c) ((double*)(sa_smem + SGEO.o_eslots))
+#define S_SLOTS(c) ((double*)(sa_smem + SGEO.o_slots))
+#define S_GSUM(c) ((double*)(sa_smem + SGEO.o_gsum))
+#define S_B(c) ((double*)(sa_smem + SGEO.o_B))
+#define S_DELTA(c) ((double*)(sa_smem + SGEO.o_delta))
+#define S_TIJ(c) ((uchar2*)(sa_smem + SGEO.o_tij))
+#define S_OWN(c) ((uchar2*)(sa_smem + SGEO.o_own))
+#define S_TRES(c) ((float4*)(sa_smem + SGEO.o_tres))
+#define S_PROG(c) ((const DevStage*)(sa_smem + SGEO.o_prog))
 
-__device__ __forceinline__ float* vecp(const Ctx& c, int v, int comp) { return S_VEC(c) + ((size_t)(v * 3 + comp)) * c.rows_pad; }
+__device__ __forceinline__ float* vecp(const Ctx& c, int v, int comp) { return S_VEC(c) + ((size_t)(v * 3 + comp)) * SGEO.rows_pad; }
 #define V_XB 0
 #define V_G 1
 #define V_PV 2
 #define V_S(l) (3 + (l))
-#define V_Y(l) (3 + c.m + (l))
+#define V_Y(l) (3 + SGEO.m + (l))
 
 __device__ __forceinline__ void csync(const Ctx& c) {
-    if (c.C > 1) cg::this_cluster().sync(); else __syncthreads();
+    if (SGEO.C > 1) cg::this_cluster().sync(); else __syncthreads();
 }
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -249,17 +259,17 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Publishing goes into the buffer of the other parity (readers of the current one may still be busy);
 // after the cluster barrier that follows every publish, flip() makes it current.
 __device__ __forceinline__ float4 ldx(const Ctx& c, int i) {
-    const float4* A = S_AB(c) + (size_t)(2 * c.buf) * c.n32p;
-    const float4 a = A[i], b = A[c.n32p + i];
+    const float4* A = S_AB(c) + (size_t)(2 * c.buf) * SGEO.n32p;
+    const float4 a = A[i], b = A[SGEO.n32p + i];
     return make_float4(fmaf(c.lam, b.x, a.x), fmaf(c.lam, b.y, a.y), fmaf(c.lam, b.z, a.z), 0.f);
 }
 __device__ __forceinline__ void publish_ab(const Ctx& c, float4 a, float4 b, bool with_b) {
     if (!c.row_ok) return;
-    float4* A = S_AB(c) + (size_t)(2 * (c.buf ^ 1)) * c.n32p + c.row;
-    if (c.C > 1) {
+    float4* A = S_AB(c) + (size_t)(2 * (c.buf ^ 1)) * SGEO.n32p + c.row;
+    if (SGEO.C > 1) {
         cg::cluster_group cl = cg::this_cluster();
-        for (int r = 0; r < c.C; r++) { float4* R = cl.map_shared_rank(A, r); R[0] = a; if (with_b) R[c.n32p] = b; }
-    } else { A[0] = a; if (with_b) A[c.n32p] = b; }
+        for (int r = 0; r < SGEO.C; r++) { float4* R = cl.map_shared_rank(A, r); R[0] = a; if (with_b) R[SGEO.n32p] = b; }
+    } else { A[0] = a; if (with_b) A[SGEO.n32p] = b; }
 }
 // x of the owner -> a (lam becomes 0 at the flip, b is ignored)
 __device__ __forceinline__ void publish_x(const Ctx& c) {
@@ -275,13 +285,13 @@ __device__ __forceinline__ void install_x(Ctx& c) { publish_x(c); csync(c); flip
 // the same order, so all ranks take identical decisions afterwards.
 __device__ void allreduce(Ctx& c, int K, bool with_e) {
     __syncthreads();
-    for (int k = c.warp; k < K; k += c.W) {
-        const float* col = S_P(c) + (size_t)k * c.rows_pad;
+    for (int k = c.warp; k < K; k += SGEO.W) {
+        const float* col = S_P(c) + (size_t)k * SGEO.rows_pad;
         double s = 0;
-        for (int t = c.lane; t < c.rows_pad; t += 32) s += (double)col[t];
+        for (int t = c.lane; t < SGEO.rows_pad; t += 32) s += (double)col[t];
         s = warp_sum(s);
-        if (c.C > 1) {
-            if (c.lane < c.C) {
+        if (SGEO.C > 1) {
+            if (c.lane < SGEO.C) {
                 double* remote = cg::this_cluster().map_shared_rank(S_SLOTS(c), c.lane);
                 remote[((size_t)c.par * SA_MAXC + c.rank) * SA_KTOT + k] = s;
             }
@@ -289,18 +299,18 @@ __device__ void allreduce(Ctx& c, int K, bool with_e) {
     }
     if (with_e) {
         for (int e = 0; e < 2; e++) {
-            if (c.warp != (c.W - 1 - e) % c.W) continue;
+            if (c.warp != (SGEO.W - 1 - e) % SGEO.W) continue;
             double s = 0;
-            for (int g = c.lane; g < c.gwarps; g += 32) s += S_ESLOTS(c)[2 * g + e];
+            for (int g = c.lane; g < SGEO.gwarps; g += 32) s += S_ESLOTS(c)[2 * g + e];
             s = warp_sum(s);
             if (c.lane == 0) S_GSUM(c)[e] = s;
         }
     }
-    if (c.C > 1) {
+    if (SGEO.C > 1) {
         cg::this_cluster().sync();
         if (c.tid < K) {
             double s = 0;
-            for (int r = 0; r < c.C; r++) s += S_SLOTS(c)[((size_t)c.par * SA_MAXC + r) * SA_KTOT + c.tid];
+            for (int r = 0; r < SGEO.C; r++) s += S_SLOTS(c)[((size_t)c.par * SA_MAXC + r) * SA_KTOT + c.tid];
             S_GSUM(c)[2 + c.tid] = s;
         }
         c.par ^= 1;
@@ -354,8 +364,8 @@ __device__ __forceinline__ void pair_sym(const SaTerms& t, float xi, float yi, f
 // partials of every warp of the cluster are in eslots (pick them up with allreduce(.., true)).
 // ------------------------------------------------------------------------------------------------
 template <bool WANT_E, bool GENERAL>
-__device__ __forceinline__ void eval_t(Ctx& c, const DevStage& st, bool count) {
-    const DevParams& p = c.prm;                     // precondition: coordinates installed (publish, cluster barrier, flip)
+__device__ __forceinline__ void eval_t(Ctx& c, const DevParams& prm, const DevStage& st, bool count) {
+    const DevParams& p = prm;                       // precondition: coordinates installed (publish, cluster barrier, flip)
     SaTerms tm;
     tm.wnC2m = -2.f * st.w_noe * p.C; tm.rsw = p.rsw; tm.wv = st.w_vdw; tm.wv4 = 4.f * st.w_vdw; tm.R2 = st.R2;
     tm.wn = st.w_noe; tm.C = p.C; tm.a = p.a; tm.b = p.b; tm.casym = p.casym; tm.low_soft = p.lo_clamp > -1e30f ? 1 : 0;
@@ -364,15 +374,15 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevStage& st, bool count) {
     float en = 0.f, ev = 0.f;
     TSTAMP(c, 0);                                   // everything since the last stamp: control, reductions
     for (int k = 0; k < c.my_rounds; k++) {
-        const uchar2 ij = S_TIJ(c)[k * c.W + c.warp];
+        const uchar2 ij = S_TIJ(c)[k * SGEO.W + c.warp];
         const int I = ij.x, J = ij.y;
         float4 d[8];
-        if (k < c.res_rounds) {
-            const float4* tp = S_TRES(c) + ((size_t)(k * c.W + c.warp) * 256 + lane);
+        if (k < SGEO.res_rounds) {
+            const float4* tp = S_TRES(c) + ((size_t)(k * SGEO.W + c.warp) * 256 + lane);
 #pragma unroll
             for (int q = 0; q < 8; q++) d[q] = tp[q * 32];
         } else {
-            const float4* gp = c.Tt + ((size_t)(c.rank + c.C * (c.warp + c.W * k)) * 256 + lane);
+            const float4* gp = c.Tt + ((size_t)(c.rank + SGEO.C * (c.warp + SGEO.W * k)) * 256 + lane);
 #pragma unroll
             for (int q = 0; q < 8; q++) d[q] = __ldg(gp + q * 32);
         }
@@ -384,7 +394,7 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevStage& st, bool count) {
         for (int q = 0; q < 4; q++) fi[q][0] = fi[q][1] = fi[q][2] = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; q++) fj[q][0] = fj[q][1] = fj[q][2] = 0.f;
-        if (J <= I + 1 || J == c.nb - 1) {
+        if (J <= I + 1 || J == SGEO.nb - 1) {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const float4 xi = ldx(c, 32 * I + rg + 8 * r);
@@ -448,10 +458,10 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevStage& st, bool count) {
         const int rsel = rg + 8 * ((b0 ? 2 : 0) + (b1 ? 1 : 0));        // row of this tile held by the lane
         const int csel = cg4 + 4 * ((b2 ? 4 : 0) + (b3 ? 2 : 0) + (b4 ? 1 : 0));
         const uchar2 oi = S_OWN(c)[I], oj = S_OWN(c)[J];
-        const int slot_i = J, slot_j = (I == J) ? c.nb : I;
-        float4* dst_i = S_PART(c) + ((size_t)(oi.y * (c.nb + 1) + slot_i) * 32 + rsel);
-        float4* dst_j = S_PART(c) + ((size_t)(oj.y * (c.nb + 1) + slot_j) * 32 + csel);
-        if (c.C > 1) {
+        const int slot_i = J, slot_j = (I == J) ? SGEO.nb : I;
+        float4* dst_i = S_PART(c) + ((size_t)(oi.y * (SGEO.nb + 1) + slot_i) * 32 + rsel);
+        float4* dst_j = S_PART(c) + ((size_t)(oj.y * (SGEO.nb + 1) + slot_j) * 32 + csel);
+        if (SGEO.C > 1) {
             cg::cluster_group cl = cg::this_cluster();
             dst_i = cl.map_shared_rank(dst_i, oi.x); dst_j = cl.map_shared_rank(dst_j, oj.x);
         }
@@ -460,8 +470,8 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevStage& st, bool count) {
     }
     if (WANT_E) {
         const double den = warp_sum((double)en), dev = warp_sum((double)ev);
-        if (c.C > 1) {
-            if (lane < c.C) {
+        if (SGEO.C > 1) {
+            if (lane < SGEO.C) {
                 double* remote = cg::this_cluster().map_shared_rank(S_ESLOTS(c), lane);
                 remote[2 * c.gw] = den; remote[2 * c.gw + 1] = dev;
             }
@@ -472,18 +482,18 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevStage& st, bool count) {
     TSTAMP(c, 2);                                   // force barrier
     float gx = 0.f, gy = 0.f, gz = 0.f, eb = 0.f;
     if (c.row_ok) {
-        const float4* pp = S_PART(c) + ((size_t)(c.tid >> 5) * (c.nb + 1)) * 32 + lane;
+        const float4* pp = S_PART(c) + ((size_t)(c.tid >> 5) * (SGEO.nb + 1)) * 32 + lane;
         int s = 0;
-        for (; s + 4 <= c.nb + 1; s += 4) {         // fixed summation order, loads issued four at a time
+        for (; s + 4 <= SGEO.nb + 1; s += 4) {         // fixed summation order, loads issued four at a time
             const float4 t0 = pp[s * 32], t1 = pp[(s + 1) * 32], t2 = pp[(s + 2) * 32], t3 = pp[(s + 3) * 32];
             gx += t0.x; gy += t0.y; gz += t0.z; gx += t1.x; gy += t1.y; gz += t1.z;
             gx += t2.x; gy += t2.y; gz += t2.z; gx += t3.x; gy += t3.y; gz += t3.z;
         }
-        for (; s <= c.nb; s++) { const float4 t = pp[s * 32]; gx += t.x; gy += t.y; gz += t.z; }
+        for (; s <= SGEO.nb; s++) { const float4 t = pp[s * 32]; gx += t.x; gy += t.y; gz += t.z; }
         const float4 xi = ldx(c, c.row);
         for (int s = -1; s <= 1; s += 2) {          // bonds (i-1,i) and (i,i+1)
             const int nbr = c.row + s;
-            if (nbr < 0 || nbr >= c.N) continue;
+            if (nbr < 0 || nbr >= SGEO.N) continue;
             const float4 xn = ldx(c, nbr);
             const float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
             const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f);
@@ -558,10 +568,10 @@ __device__ __forceinline__ void min_finish(Ctx& c) {       // leave x = last acc
     install_x(c);
 }
 // top of an iteration: choose the direction / first step, publish the trial point.  false = minimiser done.
-__device__ bool min_top(Ctx& c, const DevStage& st, OpState& os) {
-    const DevParams& p = c.prm;
+__device__ bool min_top(Ctx& c, const DevParams& prm, const DevStage& st, OpState& os) {
+    const DevParams& p = prm;
     const int t = c.tid;
-    const double n3 = 3.0 * c.N;
+    const double n3 = 3.0 * SGEO.N;
     while (true) {
         if (!(os.it < st.nstep)) break;
         if (sqrt(os.gg / n3) < (double)p.gtol) break;
@@ -579,9 +589,9 @@ __device__ bool min_top(Ctx& c, const DevStage& st, OpState& os) {
     min_finish(c);
     return false;
 }
-__device__ bool min_after_eval(Ctx& c, const DevStage& st, OpState& os) {
-    const DevParams& p = c.prm;
-    const int m = c.m, t = c.tid, rp = c.rows_pad;
+__device__ bool min_after_eval(Ctx& c, const DevParams& prm, const DevStage& st, OpState& os) {
+    const DevParams& p = prm;
+    const int m = SGEO.m, t = c.tid, rp = SGEO.rows_pad;
     float* P = S_P(c);
     double* gsum = S_GSUM(c);
     if (os.phase == 0) {                     // evaluation at the starting point
@@ -593,7 +603,7 @@ __device__ bool min_after_eval(Ctx& c, const DevStage& st, OpState& os) {
         allreduce(c, 2, true);
         os.E = gsum[0] + gsum[1] + gsum[2]; os.gg = gsum[3];
         os.cnt = 0; os.head = 0; os.it = 0; os.gp = 0.0; os.phase = 1;
-        return min_top(c, st, os);
+        return min_top(c, prm, st, os);
     }
     // evaluation at a trial point x = xb + ts p
     float gn[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f}, yv[3] = {0.f, 0.f, 0.f};
@@ -626,7 +636,7 @@ __device__ bool min_after_eval(Ctx& c, const DevStage& st, OpState& os) {
         os.it++;
         if (os.cnt == 0) { min_finish(c); return false; }
         os.cnt = 0;
-        return min_top(c, st, os);
+        return min_top(c, prm, st, os);
     }
     os.it++;
     const double* G = gsum + 2;       // owner columns
@@ -679,32 +689,32 @@ __device__ bool min_after_eval(Ctx& c, const DevStage& st, OpState& os) {
     } else {
         os.cnt = 0;        // curvature condition failed: restart from steepest descent
     }
-    return min_top(c, st, os);
+    return min_top(c, prm, st, os);
 }
 
 // ---- Verlet MD (definition shared with the oracle's sim_dynamics) ------------------------------
 __device__ void dyn_begin(Ctx& c) {          // cmremove=true
-    const int t = c.tid, rp = c.rows_pad;
+    const int t = c.tid, rp = SGEO.rows_pad;
     float* P = S_P(c);
     if (c.owner) { for (int k = 0; k < 3; k++) P[(size_t)k * rp + t] = c.row_ok ? c.v[k] : 0.f; }
     allreduce(c, 3, false);
-    if (c.row_ok) for (int k = 0; k < 3; k++) c.v[k] -= (float)(S_GSUM(c)[2 + k] / c.N);
+    if (c.row_ok) for (int k = 0; k < 3; k++) c.v[k] -= (float)(S_GSUM(c)[2 + k] / SGEO.N);
 }
 // One cluster barrier per step besides the force barrier: owners publish a = x + dt*h*f, b = dt*v (v after
 // the closing half kick) and their kinetic-energy partials; after the barrier every CTA knows the
 // temperature, hence lam, and x' = a + lam*b = x + dt*(lam*v + h*f) for all beads (read lazily by ldx).
-__device__ bool dyn_after_eval(Ctx& c, const DevStage& st, OpState& os) {
-    const DevParams& p = c.prm;
+__device__ bool dyn_after_eval(Ctx& c, const DevParams& prm, const DevStage& st, OpState& os) {
+    const DevParams& p = prm;
     const float h = 0.5f * st.dt_akma * p.inv_mass;
     float k2 = 0.f;
     if (c.row_ok) for (int k = 0; k < 3; k++) { if (os.phase) c.v[k] = fmaf(h, c.f[k], c.v[k]); k2 += c.v[k] * c.v[k]; }
     os.phase = 1;
     if (os.step >= st.nstep) return false;         // x, v, f of the owners are final
     os.step++;
-    if (c.owner && c.tid < 32 * c.nown) {
+    if (c.owner && c.tid < 32 * SGEO.nown) {
         const double kw = warp_sum((double)(0.5f * p.mass * k2));
-        const int slot = c.rank * c.own_max + (c.tid >> 5);
-        if (c.C > 1) { if (c.lane < c.C) cg::this_cluster().map_shared_rank(S_KSLOTS(c), c.lane)[slot] = kw; }
+        const int slot = c.rank * SGEO.own_max + (c.tid >> 5);
+        if (SGEO.C > 1) { if (c.lane < SGEO.C) cg::this_cluster().map_shared_rank(S_KSLOTS(c), c.lane)[slot] = kw; }
         else if (c.lane == 0) S_KSLOTS(c)[slot] = kw;
     }
     const float dth = st.dt_akma * h;
@@ -713,14 +723,14 @@ __device__ bool dyn_after_eval(Ctx& c, const DevStage& st, OpState& os) {
     TSTAMP(c, 4);                                   // kick, kinetic-energy partial, publish
     csync(c);
     TSTAMP(c, 5);                                   // coordinate barrier
-    double ke = c.lane < c.C * c.own_max ? S_KSLOTS(c)[c.lane] : 0.0;    // C*own_max <= 32 slots: one per lane,
+    double ke = c.lane < SGEO.C * SGEO.own_max ? S_KSLOTS(c)[c.lane] : 0.0;    // C*own_max <= 32 slots: one per lane,
     ke = warp_sum(ke);                                                   // same butterfly order in every warp of the cluster
     // lam = sqrt(1 + 2 fbeta dt (T0/T - 1)) (tcoupling) or sqrt(T0/T) (vscaling), T = 2 KE / (kB (3N-3)); the sum is fp64,
     // the few scalar operations after it are fp32 (they sit on the critical path of every step)
     const float kef = (float)ke;
     float lf = 1.f;
     if (kef > 0.f) {
-        const float tr = st.temp * (p.kboltz * (3.f * (float)c.N - 3.f)) / (2.f * kef);      // T0 / T
+        const float tr = st.temp * (p.kboltz * (3.f * (float)SGEO.N - 3.f)) / (2.f * kef);      // T0 / T
         if (st.flag == CHR3D_COUPLE_TCOUP) lf = sqrtf(fmaxf(0.f, fmaf(2.f * p.fbeta * st.dt_ps, tr - 1.f, 1.f)));
         else if (st.flag == CHR3D_COUPLE_VSCALE) lf = sqrtf(tr);
     }
@@ -741,69 +751,77 @@ __device__ bool dyn_after_eval(Ctx& c, const DevStage& st, OpState& os) {
 // ------------------------------------------------------------------------------------------------
 template <bool GENERAL, int MAXW>
 __global__ void __launch_bounds__(32 * MAXW, 1)
-sa_kernel(const TrajDesc* __restrict__ traj, DevParams prm, const DevStage* __restrict__ prog, int nstages, int smem_bytes) {
+sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams prm, const DevStage* __restrict__ prog, int nstages, int smem_bytes) {
     cg::cluster_group cluster = cg::this_cluster();
     Ctx c;
-    c.C = (int)cluster.num_blocks();
     c.rank = (int)cluster.block_rank();
-    const TrajDesc td = traj[blockIdx.x / c.C];
-    c.N = td.N; c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
-    c.nthreads = blockDim.x; c.W = c.nthreads >> 5; c.m = prm.m; c.prm = prm; c.par = 0; c.nevals = 0;
-    c.Tt = (const float4*)td.T;
-
-    SaShape sh; sa_shape(c.N, c.C, c.W, c.m, (size_t)smem_bytes, sh);
-    SaLayout L; sa_layout(sh, L);
-    c.o_ab = (unsigned)L.ab; c.o_kslots = (unsigned)L.kslots; c.o_part = (unsigned)L.part; c.o_vec = (unsigned)L.vec; c.o_P = (unsigned)L.P;
-    c.o_eslots = (unsigned)L.eslots; c.o_slots = (unsigned)L.slots; c.o_gsum = (unsigned)L.gsum; c.o_B = (unsigned)L.B;
-    c.o_delta = (unsigned)L.delta; c.o_tij = (unsigned)L.tij; c.o_own = (unsigned)L.own; c.o_tres = (unsigned)L.tres;
-    c.nb = sh.nb; c.n32p = sh.n32 + 1; c.own_max = sh.own_max; c.buf = 0; c.lam = 0.f; c.gwarps = sh.gwarps; c.gw = c.rank * c.W + c.warp; c.res_rounds = sh.res_rounds; c.rows_pad = sh.rows_pad;
-    {   // tiles of this CTA: t = rank + C*lt, lt = 0..nloc-1; of this warp: lt = warp + W*k
-        const int nloc = sh.ntiles > c.rank ? (sh.ntiles - 1 - c.rank) / c.C + 1 : 0;
-        c.my_rounds = nloc > c.warp ? (nloc - 1 - c.warp) / c.W + 1 : 0;
+    const int nclu = (int)cluster.num_blocks();
+    c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+    c.par = 0; c.nevals = 0; c.buf = 0; c.lam = 0.f;
+    {   // trajectory descriptor, geometry and layout: set up once by thread 0 in shared memory
+        if (c.tid == 0) {
+            const TrajDesc td = traj[blockIdx.x / nclu];
+            *(TrajDesc*)(sa_smem + 128) = td;
+            SaShape sh; sa_shape(td.N, nclu, (int)(blockDim.x >> 5), prm.m, nstages, (size_t)smem_bytes, sh);
+            SaLayout L; sa_layout(sh, L);
+            SaGeo* g = (SaGeo*)sa_smem;
+            g->N = sh.N; g->C = sh.C; g->W = sh.W; g->nthreads = sh.nthreads; g->nb = sh.nb; g->n32p = sh.n32 + 1; g->gwarps = sh.gwarps;
+            g->own_max = sh.own_max; g->rows_pad = sh.rows_pad; g->m = sh.m; g->res_rounds = sh.res_rounds; g->nstages = nstages;
+            g->rw0 = (int)(((long long)sh.nb * c.rank) / sh.C);
+            g->nown = (int)(((long long)sh.nb * (c.rank + 1)) / sh.C) - g->rw0;
+            g->o_prog = (unsigned)L.prog; g->o_ab = (unsigned)L.ab; g->o_kslots = (unsigned)L.kslots; g->o_part = (unsigned)L.part; g->o_vec = (unsigned)L.vec;
+            g->o_P = (unsigned)L.P; g->o_eslots = (unsigned)L.eslots; g->o_slots = (unsigned)L.slots; g->o_gsum = (unsigned)L.gsum; g->o_B = (unsigned)L.B;
+            g->o_delta = (unsigned)L.delta; g->o_tij = (unsigned)L.tij; g->o_own = (unsigned)L.own; g->o_tres = (unsigned)L.tres;
+        }
+        __syncthreads();
     }
-
+    c.Tt = (const float4*)STD.T;
+    const int ntiles = SGEO.nb * (SGEO.nb + 1) / 2;
+    c.gw = c.rank * SGEO.W + c.warp;
+    {   // tiles of this CTA: t = rank + C*lt, lt = 0..nloc-1; of this warp: lt = warp + W*k
+        const int nloc = ntiles > c.rank ? (ntiles - 1 - c.rank) / SGEO.C + 1 : 0;
+        c.my_rounds = nloc > c.warp ? (nloc - 1 - c.warp) / SGEO.W + 1 : 0;
+    }
     // bead blocks of this rank: balanced contiguous split of the nb blocks over C ranks
-    c.rw0 = (int)(((long long)c.nb * c.rank) / c.C);
-    c.nown = (int)(((long long)c.nb * (c.rank + 1)) / c.C) - c.rw0;
-    c.owner = c.tid < c.rows_pad;
-    c.row = 32 * c.rw0 + c.tid;
-    c.row_ok = c.tid < 32 * c.nown && c.row < c.N;
+    c.owner = c.tid < SGEO.rows_pad;
+    c.row = 32 * SGEO.rw0 + c.tid;
+    c.row_ok = c.tid < 32 * SGEO.nown && c.row < SGEO.N;
     for (int k = 0; k < 3; k++) { c.x[k] = 0.f; c.v[k] = 0.f; c.f[k] = 0.f; }
     c.ebond = 0.f;
 
-    for (int i = c.tid; i < 4 * c.n32p; i += c.nthreads) S_AB(c)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = c.tid; i < c.C * c.own_max; i += c.nthreads) S_KSLOTS(c)[i] = 0.0;
-    for (int i = c.tid; i < 2 * SA_MAXC * SA_KTOT; i += c.nthreads) S_SLOTS(c)[i] = 0.0;
-    for (int i = c.tid; i < 2 * sh.gwarps; i += c.nthreads) S_ESLOTS(c)[i] = 0.0;
-    for (int i = c.tid; i < SA_MAXB * SA_MAXB; i += c.nthreads) S_B(c)[i] = 0.0;
-    for (int i = c.tid; i < SA_KTOT * c.rows_pad; i += c.nthreads) S_P(c)[i] = 0.f;
-    for (int b = c.tid; b < c.nb; b += c.nthreads) {           // owner rank / local index of every bead block
+    for (int i = c.tid; i < nstages * (int)(sizeof(DevStage) / 4); i += SGEO.nthreads) ((int*)(sa_smem + SGEO.o_prog))[i] = ((const int*)prog)[i];
+    for (int i = c.tid; i < 4 * SGEO.n32p; i += SGEO.nthreads) S_AB(c)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = c.tid; i < SGEO.C * SGEO.own_max; i += SGEO.nthreads) S_KSLOTS(c)[i] = 0.0;
+    for (int i = c.tid; i < 2 * SA_MAXC * SA_KTOT; i += SGEO.nthreads) S_SLOTS(c)[i] = 0.0;
+    for (int i = c.tid; i < 2 * SGEO.gwarps; i += SGEO.nthreads) S_ESLOTS(c)[i] = 0.0;
+    for (int i = c.tid; i < SA_MAXB * SA_MAXB; i += SGEO.nthreads) S_B(c)[i] = 0.0;
+    for (int i = c.tid; i < (7 + 6 * SGEO.m) * SGEO.rows_pad; i += SGEO.nthreads) S_P(c)[i] = 0.f;
+    for (int b = c.tid; b < SGEO.nb; b += SGEO.nthreads) {           // owner rank / local index of every bead block
         int r = 0;
-        while ((int)(((long long)c.nb * (r + 1)) / c.C) <= b) r++;
-        S_OWN(c)[b] = make_uchar2((unsigned char)r, (unsigned char)(b - (int)(((long long)c.nb * r) / c.C)));
+        while ((int)(((long long)SGEO.nb * (r + 1)) / SGEO.C) <= b) r++;
+        S_OWN(c)[b] = make_uchar2((unsigned char)r, (unsigned char)(b - (int)(((long long)SGEO.nb * r) / SGEO.C)));
     }
     if (c.lane == 0) for (int k = 0; k < c.my_rounds; k++) {   // this warp's tiles
-        int I, J; sa_tile_coords(c.rank + c.C * (c.warp + c.W * k), c.nb, I, J);
-        S_TIJ(c)[k * c.W + c.warp] = make_uchar2((unsigned char)I, (unsigned char)J);
+        int I, J; sa_tile_coords(c.rank + SGEO.C * (c.warp + SGEO.W * k), SGEO.nb, I, J);
+        S_TIJ(c)[k * SGEO.W + c.warp] = make_uchar2((unsigned char)I, (unsigned char)J);
     }
-    for (int k = 0; k < c.my_rounds && k < c.res_rounds; k++) {   // resident targets: each warp stages its own tiles (coalesced)
-        const float4* gp = c.Tt + ((size_t)(c.rank + c.C * (c.warp + c.W * k)) * 256 + c.lane);
-        float4* sp = S_TRES(c) + ((size_t)(k * c.W + c.warp) * 256 + c.lane);
+    for (int k = 0; k < c.my_rounds && k < SGEO.res_rounds; k++) {   // resident targets: each warp stages its own tiles (coalesced)
+        const float4* gp = c.Tt + ((size_t)(c.rank + SGEO.C * (c.warp + SGEO.W * k)) * 256 + c.lane);
+        float4* sp = S_TRES(c) + ((size_t)(k * SGEO.W + c.warp) * 256 + c.lane);
 #pragma unroll
         for (int q = 0; q < 8; q++) sp[q * 32] = __ldg(gp + q * 32);
     }
     __syncthreads();
     csync(c);
 #ifdef SA_TIMING
-    c.tmark = blockIdx.x == 0 && c.lane == 0 && (c.warp == 0 || c.warp == c.W - 1);
+    c.tmark = blockIdx.x == 0 && c.lane == 0 && (c.warp == 0 || c.warp == SGEO.W - 1);
     c.tlast = clock64(); for (int q = 0; q < 10; q++) c.tacc[q] = 0;
 #endif
 
     int cur_image = 1, hand = 1;
     double e_saved = 0.0;
-    double e4[4] = {0, 0, 0, 0};
     for (int k = 0; k < nstages; k++) {
-        const DevStage st = prog[k];
+        const DevStage& st = S_PROG(c)[k];
         OpState os;
         os.phase = 0; os.step = 0; os.cnt = 0; os.head = 0; os.it = 0; os.ls = 0; os.want_e = true; os.count = true;
         os.E = os.gg = os.gp = os.ts = os.ke = 0.0;
@@ -811,7 +829,7 @@ sa_kernel(const TrajDesc* __restrict__ traj, DevParams prm, const DevStage* __re
         switch (st.op) {
         case CHR3D_OP_INIT:
             if (c.row_ok) {
-                c.x[0] = td.x0[3 * c.row] * (float)st.flag; c.x[1] = td.x0[3 * c.row + 1]; c.x[2] = td.x0[3 * c.row + 2];
+                c.x[0] = STD.x0[3 * c.row] * (float)st.flag; c.x[1] = STD.x0[3 * c.row + 1]; c.x[2] = STD.x0[3 * c.row + 2];
                 c.v[0] = c.v[1] = c.v[2] = 0.f;
             }
             install_x(c);
@@ -819,15 +837,15 @@ sa_kernel(const TrajDesc* __restrict__ traj, DevParams prm, const DevStage* __re
             break;
         case CHR3D_OP_MAXWELL:
             if (c.row_ok) {
-                double z[3]; normal3(td.seed, (uint32_t)c.row, STREAM_MAXWELL + (uint32_t)k, (uint32_t)td.model, z);
+                double z[3]; normal3(STD.seed, (uint32_t)c.row, STREAM_MAXWELL + (uint32_t)k, (uint32_t)STD.model, z);
                 double sd = sqrt((double)prm.kboltz * (double)st.temp / (double)prm.mass);
                 for (int q = 0; q < 3; q++) c.v[q] = (float)(sd * z[q]);
             }
             break;
         case CHR3D_OP_CENTER:
-            if (c.owner) for (int q = 0; q < 3; q++) S_P(c)[(size_t)q * c.rows_pad + c.tid] = c.row_ok ? c.x[q] : 0.f;
+            if (c.owner) for (int q = 0; q < 3; q++) S_P(c)[(size_t)q * SGEO.rows_pad + c.tid] = c.row_ok ? c.x[q] : 0.f;
             allreduce(c, 3, false);
-            if (c.row_ok) { for (int q = 0; q < 3; q++) c.x[q] -= (float)(S_GSUM(c)[2 + q] / c.N); }
+            if (c.row_ok) { for (int q = 0; q < 3; q++) c.x[q] -= (float)(S_GSUM(c)[2 + q] / SGEO.N); }
             install_x(c);
             break;
         case CHR3D_OP_MINIMIZE: more = true; break;
@@ -837,9 +855,9 @@ sa_kernel(const TrajDesc* __restrict__ traj, DevParams prm, const DevStage* __re
         default: break;
         }
         while (more) {
-            if (os.want_e) eval_t<true, GENERAL>(c, st, os.count); else eval_t<false, GENERAL>(c, st, os.count);
-            if (st.op == CHR3D_OP_MINIMIZE) { more = min_after_eval(c, st, os); TSTAMP(c, 7); }
-            else if (st.op == CHR3D_OP_DYNAMICS) more = dyn_after_eval(c, st, os);
+            if (os.want_e) eval_t<true, GENERAL>(c, prm, st, os.count); else eval_t<false, GENERAL>(c, prm, st, os.count);
+            if (st.op == CHR3D_OP_MINIMIZE) { more = min_after_eval(c, prm, st, os); TSTAMP(c, 7); }
+            else if (st.op == CHR3D_OP_DYNAMICS) more = dyn_after_eval(c, prm, st, os);
             else {
                 more = false;
                 if (c.owner) S_P(c)[c.tid] = c.ebond;
@@ -848,27 +866,28 @@ sa_kernel(const TrajDesc* __restrict__ traj, DevParams prm, const DevStage* __re
                 const double e = gsum[0] + gsum[1] + gsum[2];
                 if (st.op == CHR3D_OP_SAVE) {
                     e_saved = e;
-                    if (c.row_ok) for (int q = 0; q < 3; q++) { td.scratch[3 * c.row + q] = c.x[q]; td.scratch[3 * (c.N + c.row) + q] = c.v[q]; }
+                    if (c.row_ok) for (int q = 0; q < 3; q++) { STD.scratch[3 * c.row + q] = c.x[q]; STD.scratch[3 * (SGEO.N + c.row) + q] = c.v[q]; }
                 } else if (st.op == CHR3D_OP_PICK) {
                     if (e_saved > e) hand = cur_image;                 // C3D:1717-1721
                     else {
                         hand = 1;
                         if (c.row_ok) {
-                            for (int q = 0; q < 3; q++) { c.x[q] = td.scratch[3 * c.row + q]; c.v[q] = td.scratch[3 * (c.N + c.row) + q]; }
+                            for (int q = 0; q < 3; q++) { c.x[q] = STD.scratch[3 * c.row + q]; c.v[q] = STD.scratch[3 * (SGEO.N + c.row) + q]; }
                         }
                         install_x(c);
                     }
                 } else {
-                    e4[CHR3D_E_OVERALL] = e; e4[CHR3D_E_BON] = gsum[2]; e4[CHR3D_E_VDW] = gsum[1]; e4[CHR3D_E_NOE] = gsum[0];
-                    if (td.f_out && c.row_ok) for (int q = 0; q < 3; q++) td.f_out[3 * c.row + q] = c.f[q];
+                    if (c.rank == 0 && c.tid == 0) {
+                        STD.e_out[CHR3D_E_OVERALL] = e; STD.e_out[CHR3D_E_BON] = gsum[2]; STD.e_out[CHR3D_E_VDW] = gsum[1]; STD.e_out[CHR3D_E_NOE] = gsum[0];
+                    }
+                    if (STD.f_out && c.row_ok) for (int q = 0; q < 3; q++) STD.f_out[3 * c.row + q] = c.f[q];
                 }
             }
         }
     }
-    if (c.row_ok) for (int q = 0; q < 3; q++) td.x_out[3 * c.row + q] = c.x[q];
+    if (c.row_ok) for (int q = 0; q < 3; q++) STD.x_out[3 * c.row + q] = c.x[q];
     if (c.rank == 0 && c.tid == 0) {
-        for (int q = 0; q < 4; q++) td.e_out[q] = e4[q];
-        *td.nevals_out = c.nevals; *td.hand_out = hand;
+        *STD.nevals_out = c.nevals; *STD.hand_out = hand;
     }
 #ifdef SA_TIMING
     if (c.tmark) for (int q = 0; q < 10; q++) sa_dbg[c.warp == 0 ? 0 : 1][q] = (unsigned long long)c.tacc[q];
@@ -881,7 +900,7 @@ sa_kernel(const TrajDesc* __restrict__ traj, DevParams prm, const DevStage* __re
 // host side: configuration choice and launch
 // ------------------------------------------------------------------------------------------------
 static size_t smem_fixed(int N, int C, int W, int m) {
-    SaShape sh; sa_shape(N, C, W, m, 0, sh);
+    SaShape sh; sa_shape(N, C, W, m, SA_MAX_STAGES, 0, sh);
     SaLayout L; sa_layout(sh, L);
     return L.total;
 }
@@ -923,16 +942,21 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
         if (it != cache.end() && !force_c && !force_w) { *cfg = it->second; return 0; }
     }
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (cudaFuncSetAttribute(sa_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) cudaGetLastError();
-    if (cudaFuncSetAttribute(sa_kernel<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) cudaGetLastError();
+    const int smem_hw = smem_max;
+    if (getenv("CHR3D_SA_SMEM_CAP")) smem_max = std::min(smem_max, atoi(getenv("CHR3D_SA_SMEM_CAP")));   // development: force >1 CTA per SM
+    if (cudaFuncSetAttribute(sa_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_hw) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncSetAttribute(sa_kernel<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_hw) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncSetAttribute(sa_kernel<false, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    if (cudaFuncSetAttribute(sa_kernel<false, 20>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
     const int nb = (N + 31) / 32, ntiles = nb * (nb + 1) / 2;
     double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0};
-    const int Cs[] = {1, 2, 3, 4, 5, 6, 8};
+    const int Cs[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};     // > 8: non-portable cluster sizes, two CTAs of different trajectories per SM
     for (int C : Cs) {
         if (force_c && C != force_c) continue;
         if (C > nb && C > 1) continue;
-        for (int W = 4; W <= SA_MAXW; W += 4) {
+        for (int W = 4; W <= SA_MAXW; W += 2) {
             if (force_w && W != force_w) continue;
+            if (!force_w && (W & 3)) continue;
             const int own_max = (nb + C - 1) / C;
             if (own_max > W || C * own_max > 32) continue;       // every owned bead needs its own thread; one KE slot per lane
             const size_t fixed = smem_fixed(N, C, W, m);
@@ -966,10 +990,12 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
 int sa_launch(const TrajDesc* d_traj, int n_traj, int Nmax, const DevParams& P, const DevStage* d_prog, int nstages,
               const SaLaunchCfg& cfg, cudaStream_t s) {
     (void)Nmax;
+    if (nstages > SA_MAX_STAGES) { set_error("stage program has %d entries, the SA kernel keeps at most %d", nstages, SA_MAX_STAGES); return CHR3D_ERR_SIZE; }
     const bool general = P.general_noe || P.lo_clamp > -1e30f;
     const bool wide = cfg.threads > 512;
     auto kern = general ? (wide ? sa_kernel<true, 20> : sa_kernel<true, 16>) : (wide ? sa_kernel<false, 20> : sa_kernel<false, 16>);
     CHR3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    if (cfg.cluster > 8) CHR3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(n_traj * cfg.cluster), 1, 1);
     lc.blockDim = dim3((unsigned)cfg.threads, 1, 1);
