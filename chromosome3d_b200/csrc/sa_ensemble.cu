@@ -73,36 +73,45 @@ __device__ inline void normal3(unsigned long long seed, uint32_t bead, uint32_t 
     z[0] = ra * cos(twopi * u2); z[1] = ra * sin(twopi * u2); z[2] = rb * cos(twopi * u4);
 }
 
-// seeded random-coil start: one thread per model walks the chain (N <= a few thousand)
-__global__ void coil_kernel(float* x0, int N, int n_models, int first_model, double step, unsigned long long seed) {
+// seeded random-coil start (stand-in for the DG embedding): unit steps in parallel (the Philox / Box-Muller part),
+// then one thread per model adds them up in chain order and centres — the same additions in the same order as the
+// oracle's orc_random_coil, so the start coordinates are bit-identical to it
+__global__ void coil_steps_kernel(double* __restrict__ d, int N, int n_models, int first_model, double step, unsigned long long seed) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (long long)N * n_models) return;
+    const int m = (int)(k / N), i = (int)(k % N);
+    double z[3] = {0, 0, 0};
+    if (i > 0) {
+        normal3(seed, (uint32_t)i, STREAM_COIL, (uint32_t)(first_model + m), z);
+        double nrm = sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+        if (nrm < 1e-12) { z[0] = 1; z[1] = z[2] = 0; nrm = 1; }
+        for (int q = 0; q < 3; q++) z[q] = step * z[q] / nrm;
+    }
+    for (int q = 0; q < 3; q++) d[3 * k + q] = z[q];
+}
+__global__ void coil_kernel(float* x0, const double* __restrict__ d, int N, int n_models) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_models) return;
     float* x = x0 + (size_t)m * N * 3;
+    const double* dm = d + (size_t)m * N * 3;
     double p[3] = {0, 0, 0}, c[3] = {0, 0, 0};
     for (int i = 0; i < N; i++) {
-        if (i > 0) {
-            double z[3]; normal3(seed, (uint32_t)i, STREAM_COIL, (uint32_t)(first_model + m), z);
-            double nrm = sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
-            if (nrm < 1e-12) { z[0] = 1; z[1] = z[2] = 0; nrm = 1; }
-            for (int k = 0; k < 3; k++) p[k] += step * z[k] / nrm;
-        }
+        if (i > 0) for (int k = 0; k < 3; k++) p[k] += dm[3 * i + k];
         for (int k = 0; k < 3; k++) c[k] += p[k];
     }
-    // second pass: recompute and centre (keeps the kernel free of per-model scratch)
     p[0] = p[1] = p[2] = 0;
     for (int i = 0; i < N; i++) {
-        if (i > 0) {
-            double z[3]; normal3(seed, (uint32_t)i, STREAM_COIL, (uint32_t)(first_model + m), z);
-            double nrm = sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
-            if (nrm < 1e-12) { z[0] = 1; z[1] = z[2] = 0; nrm = 1; }
-            for (int k = 0; k < 3; k++) p[k] += step * z[k] / nrm;
-        }
+        if (i > 0) for (int k = 0; k < 3; k++) p[k] += dm[3 * i + k];
         for (int k = 0; k < 3; k++) x[3 * i + k] = (float)(p[k] - c[k] / N);
     }
 }
 int dev_random_coil(float* d_x0, int N, int n_models, int first_model, double step, unsigned long long seed,
                     cudaStream_t s) {
-    coil_kernel<<<(n_models + 63) / 64, 64, 0, s>>>(d_x0, N, n_models, first_model, step, seed);
+    DevBuf<double> d;
+    CHR3D_CUDA(d.alloc((size_t)N * n_models * 3));
+    const long long n = (long long)N * n_models;
+    coil_steps_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d.p, N, n_models, first_model, step, seed);
+    coil_kernel<<<(n_models + 31) / 32, 32, 0, s>>>(d_x0, d.p, N, n_models);
     CHR3D_CUDA(cudaGetLastError());
     return 0;
 }
@@ -723,7 +732,8 @@ __device__ bool dyn_after_eval(Ctx& c, const DevParams& prm, const DevStage& st,
     TSTAMP(c, 4);                                   // kick, kinetic-energy partial, publish
     csync(c);
     TSTAMP(c, 5);                                   // coordinate barrier
-    double ke = c.lane < SGEO.C * SGEO.own_max ? S_KSLOTS(c)[c.lane] : 0.0;    // C*own_max <= 32 slots: one per lane,
+    double ke = 0.0;
+    for (int q = c.lane; q < SGEO.C * SGEO.own_max; q += 32) ke += S_KSLOTS(c)[q];     // usually one slot per lane,
     ke = warp_sum(ke);                                                   // same butterfly order in every warp of the cluster
     // lam = sqrt(1 + 2 fbeta dt (T0/T - 1)) (tcoupling) or sqrt(T0/T) (vscaling), T = 2 KE / (kB (3N-3)); the sum is fp64,
     // the few scalar operations after it are fp32 (they sit on the critical path of every step)
@@ -958,7 +968,7 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
             if (force_w && W != force_w) continue;
             if (!force_w && (W & 3)) continue;
             const int own_max = (nb + C - 1) / C;
-            if (own_max > W || C * own_max > 32) continue;       // every owned bead needs its own thread; one KE slot per lane
+            if (own_max > W) continue;                           // every owned bead needs its own thread
             const size_t fixed = smem_fixed(N, C, W, m);
             if (fixed > (size_t)smem_max) continue;
             const int rounds = ((ntiles + C - 1) / C + W - 1) / W;

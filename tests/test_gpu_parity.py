@@ -302,3 +302,15 @@ def test_spearman_ties_and_edges(gpu_api):
     assert np.isnan(gpu_api.spearman_IF_pdb(IF, xyz, 40)).all()   # SP:38-41
     const = np.ones((L, L))
     assert np.array_equal(gpu_api.spearman_IF_pdb(const, xyz, 3), np.zeros(4))   # zero variance -> 0
+
+
+def test_seeded_random_coil_start_equals_oracle(gpu_api):
+    """Trajectories without caller-supplied coordinates start from the Philox-seeded random coil; the device builds
+    it with the same additions in the same order as the oracle (bit-identical after the fp32 conversion)."""
+    for N, m, seed in ((37, 3, 82364), (455, 2, 7), (900, 1, 99)):
+        prog = abi.stage_array([abi.stage(abi.OP_INIT, flag=1)])
+        ri, rj, rd = np.array([0], np.int32), np.array([N - 1], np.int32), np.array([10.0])
+        r = gpu_api.build_models([gpu_api.Job(restraints=(ri, rj, rd), N=N, n_models=m, seed=seed)], gpu_api.default_params(), prog)[0]
+        for k in range(m):
+            ref = orc.random_coil(N, 3.8, seed, k).astype(np.float32).astype(np.float64)
+            assert np.array_equal(r.xyz[k], ref), (N, k)
