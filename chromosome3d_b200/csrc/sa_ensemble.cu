@@ -156,19 +156,20 @@ struct SaShape {
     int N, C, W, nthreads, nb, n32, ntiles, gwarps, rounds, own_max, rows_pad, m, nvec, res_rounds, nstages;
 };
 struct SaLayout {
-    size_t prog, ab, part, vec, P, eslots, kslots, slots, gsum, B, delta, tij, own, tres, total;
+    size_t prog, mbar, ab, part, vec, P, eslots, kslots, slots, gsum, B, delta, tij, own, tres, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 __host__ __device__ inline void sa_layout(const SaShape& s, SaLayout& L) {
     size_t o = SA_GEO_BYTES;
     L.prog = o;   o = align_up(o + sizeof(DevStage) * (size_t)s.nstages, 16);
+    L.mbar = o;   o = align_up(o + 16, 16);                            // two mbarriers: forces arrived, coordinates arrived
     L.ab = o;     o = align_up(o + sizeof(float4) * 4 * (size_t)(s.n32 + 1), 16);   // [parity][a|b][n32+1]
     L.part = o;   o = align_up(o + sizeof(float4) * (size_t)s.own_max * (s.nb + 1) * 32, 16);
     L.vec = o;    o = align_up(o + sizeof(float) * (size_t)s.nvec * 3 * s.rows_pad, 16);
     L.P = o;      o = align_up(o + sizeof(float) * (size_t)(7 + 6 * s.m) * s.rows_pad, 16);   // columns: bond energy + 6m+6 inner products
     L.eslots = o; o = align_up(o + sizeof(double) * 2 * (size_t)s.gwarps, 16);
-    L.kslots = o; o = align_up(o + sizeof(double) * (size_t)s.C * s.own_max, 16);
+    L.kslots = o; o = align_up(o + 2 * sizeof(double) * (size_t)s.nb, 16);              // one 16-byte slot per bead block (st.async granularity)
     L.slots = o;  o = align_up(o + sizeof(double) * 2 * SA_MAXC * SA_KTOT, 16);
     L.gsum = o;   o = align_up(o + sizeof(double) * (SA_KTOT + 2), 16);
     L.B = o;      o = align_up(o + sizeof(double) * SA_MAXB * SA_MAXB, 16);
@@ -201,7 +202,7 @@ extern __shared__ __align__(128) unsigned char sa_smem[];
 // per-thread copies cost local-memory round trips on the latency-critical control path.
 struct SaGeo {
     int N, C, W, nthreads, nb, n32p, gwarps, own_max, rows_pad, m, res_rounds, rw0, nown, nstages;
-    unsigned o_ab, o_kslots, o_part, o_vec, o_P, o_eslots, o_slots, o_gsum, o_B, o_delta, o_tij, o_own, o_tres, o_prog;
+    unsigned o_ab, o_kslots, o_part, o_vec, o_P, o_eslots, o_slots, o_gsum, o_B, o_delta, o_tij, o_own, o_tres, o_prog, o_mbar;
 };
 #define SGEO (*(const SaGeo*)sa_smem)
 #define STD (*(const TrajDesc*)(sa_smem + 128))
@@ -225,6 +226,7 @@ struct Ctx {
     int par;
     // coordinates of every bead are x = a + lam*b, (a, b) double-buffered by parity `buf` (see dyn_after_eval)
     int buf; float lam;
+    unsigned phF, phX;               // parities of the two mbarriers
     // owner state (valid when tid < rows_pad; row_ok when the thread owns a real bead)
     bool owner, row_ok; int row;
     float x[3], v[3], f[3];
@@ -272,21 +274,63 @@ __device__ __forceinline__ float4 ldx(const Ctx& c, int i) {
     const float4 a = A[i], b = A[SGEO.n32p + i];
     return make_float4(fmaf(c.lam, b.x, a.x), fmaf(c.lam, b.y, a.y), fmaf(c.lam, b.z, a.z), 0.f);
 }
+// ---- asynchronous cluster exchange ----------------------------------------------------------------------------
+// Producers push 16-byte pieces into the shared memory of the consumer CTA with st.async, which also credits the
+// bytes to an mbarrier of the consumer; the consumer declares how many bytes a phase brings (arrive.expect_tx by
+// one thread) and waits for the phase.  No cluster-wide barrier and no producer-side fence: a CTA proceeds as soon
+// as ITS inputs have landed.  Two barriers per CTA: MB_F (partial forces + pair energies), MB_X (coordinates +
+// kinetic-energy partials).  Phases cannot mix: a producer can only start the next phase after it has consumed
+// data that the consumer sent after completing the current one (see the header comment).
+#define MB_F 0
+#define MB_X 1
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, int rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void st_async16(uint32_t dst_cluster, uint32_t mbar_cluster, float4 v) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(dst_cluster), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+                   "r"(mbar_cluster) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_addr(const Ctx& c, int which) { return smem_u32(sa_smem + SGEO.o_mbar + 8 * which); }
+__device__ __forceinline__ void mbar_expect(const Ctx& c, int which, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr(c, which)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const Ctx& c, int which, unsigned& parity) {
+    const uint32_t bar = mbar_addr(c, which);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 20000000000ll) __trap();        // ~10 s: a peer died; fail instead of hanging the GPU
+    }
+    parity ^= 1u;
+}
+
+// Publish (a, b) of the owned bead to every CTA of the cluster (buffer of the other parity).
 __device__ __forceinline__ void publish_ab(const Ctx& c, float4 a, float4 b, bool with_b) {
     if (!c.row_ok) return;
-    float4* A = S_AB(c) + (size_t)(2 * (c.buf ^ 1)) * SGEO.n32p + c.row;
-    if (SGEO.C > 1) {
-        cg::cluster_group cl = cg::this_cluster();
-        for (int r = 0; r < SGEO.C; r++) { float4* R = cl.map_shared_rank(A, r); R[0] = a; if (with_b) R[SGEO.n32p] = b; }
-    } else { A[0] = a; if (with_b) A[SGEO.n32p] = b; }
+    const uint32_t A = smem_u32(S_AB(c) + (size_t)(2 * (c.buf ^ 1)) * SGEO.n32p + c.row);
+    const uint32_t bar = mbar_addr(c, MB_X);
+    for (int r = 0; r < SGEO.C; r++) {
+        const uint32_t rb = mapa_u32(bar, r), ra = mapa_u32(A, r);
+        st_async16(ra, rb, a);
+        if (with_b) st_async16(ra + 16u * (uint32_t)SGEO.n32p, rb, b);
+    }
 }
 // x of the owner -> a (lam becomes 0 at the flip, b is ignored)
 __device__ __forceinline__ void publish_x(const Ctx& c) {
     publish_ab(c, make_float4(c.x[0], c.x[1], c.x[2], 0.f), make_float4(0.f, 0.f, 0.f, 0.f), false);
 }
 __device__ __forceinline__ void flip(Ctx& c, float lam) { c.buf ^= 1; c.lam = lam; }
-// publish_x + barrier + flip: the usual way an op installs new coordinates
-__device__ __forceinline__ void install_x(Ctx& c) { publish_x(c); csync(c); flip(c, 0.f); }
+// every CTA waits until the coordinates of all N beads (16 or 32 bytes each, + `extra` bytes) have landed
+__device__ __forceinline__ void await_coords(Ctx& c, bool with_b, uint32_t extra) {
+    if (c.tid == 0) mbar_expect(c, MB_X, (uint32_t)SGEO.N * (with_b ? 32u : 16u) + extra);
+    mbar_wait(c, MB_X, c.phX);
+}
+// publish_x + wait + flip: the usual way an op installs new coordinates
+__device__ __forceinline__ void install_x(Ctx& c) { publish_x(c); await_coords(c, false, 0u); flip(c, 0.f); }
 
 // All-reduce of K owner columns (P) across the cluster; with_e: also totals of the pair energies
 // every warp of the cluster left in eslots (complete in every CTA after the barrier inside eval).
@@ -468,27 +512,26 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevParams& prm, const DevSt
         const int csel = cg4 + 4 * ((b2 ? 4 : 0) + (b3 ? 2 : 0) + (b4 ? 1 : 0));
         const uchar2 oi = S_OWN(c)[I], oj = S_OWN(c)[J];
         const int slot_i = J, slot_j = (I == J) ? SGEO.nb : I;
-        float4* dst_i = S_PART(c) + ((size_t)(oi.y * (SGEO.nb + 1) + slot_i) * 32 + rsel);
-        float4* dst_j = S_PART(c) + ((size_t)(oj.y * (SGEO.nb + 1) + slot_j) * 32 + csel);
-        if (SGEO.C > 1) {
-            cg::cluster_group cl = cg::this_cluster();
-            dst_i = cl.map_shared_rank(dst_i, oi.x); dst_j = cl.map_shared_rank(dst_j, oj.x);
-        }
-        *dst_i = make_float4(rowf[0], rowf[1], rowf[2], 0.f);
-        *dst_j = make_float4(colf[0], colf[1], colf[2], 0.f);
+        const uint32_t dst_i = smem_u32(S_PART(c) + ((size_t)(oi.y * (SGEO.nb + 1) + slot_i) * 32 + rsel));
+        const uint32_t dst_j = smem_u32(S_PART(c) + ((size_t)(oj.y * (SGEO.nb + 1) + slot_j) * 32 + csel));
+        const uint32_t barF = mbar_addr(c, MB_F);
+        st_async16(mapa_u32(dst_i, oi.x), mapa_u32(barF, oi.x), make_float4(rowf[0], rowf[1], rowf[2], 0.f));
+        st_async16(mapa_u32(dst_j, oj.x), mapa_u32(barF, oj.x), make_float4(colf[0], colf[1], colf[2], 0.f));
     }
-    if (WANT_E) {
+    if (WANT_E) {       // pair-energy partial of this warp -> slot gw of every CTA (16 bytes: two doubles)
         const double den = warp_sum((double)en), dev = warp_sum((double)ev);
-        if (SGEO.C > 1) {
-            if (lane < SGEO.C) {
-                double* remote = cg::this_cluster().map_shared_rank(S_ESLOTS(c), lane);
-                remote[2 * c.gw] = den; remote[2 * c.gw + 1] = dev;
-            }
-        } else if (lane == 0) { S_ESLOTS(c)[2 * c.gw] = den; S_ESLOTS(c)[2 * c.gw + 1] = dev; }
+        if (lane < SGEO.C) {
+            const uint32_t dst = smem_u32(S_ESLOTS(c) + 2 * c.gw);
+            st_async16(mapa_u32(dst, lane), mapa_u32(mbar_addr(c, MB_F), lane),
+                       make_float4(__int_as_float(__double2loint(den)), __int_as_float(__double2hiint(den)),
+                                   __int_as_float(__double2loint(dev)), __int_as_float(__double2hiint(dev))));
+        }
     }
     TSTAMP(c, 1);                                   // pair phase (own tiles)
-    csync(c);                                       // every partial of every owned bead has arrived
-    TSTAMP(c, 2);                                   // force barrier
+    // this CTA's inputs of the force phase: nb+1 partial vectors (512 B) per owned block, and the energy partials of every warp
+    if (c.tid == 0) mbar_expect(c, MB_F, (uint32_t)SGEO.nown * (uint32_t)(SGEO.nb + 1) * 512u + (WANT_E ? 16u * (uint32_t)SGEO.gwarps : 0u));
+    mbar_wait(c, MB_F, c.phF);
+    TSTAMP(c, 2);                                   // wait for the partial forces
     float gx = 0.f, gy = 0.f, gz = 0.f, eb = 0.f;
     if (c.row_ok) {
         const float4* pp = S_PART(c) + ((size_t)(c.tid >> 5) * (SGEO.nb + 1)) * 32 + lane;
@@ -525,29 +568,31 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevParams& prm, const DevSt
 __device__ double lbfgs_direction(double* B, double* delta, int m, int cnt, int head) {
     const int nb = 2 * m + 1, ig = 2 * m;
     double al[CHR3D_LBFGS_MAX_M];
+    int ring[CHR3D_LBFGS_MAX_M];                 // history slots, newest first (no integer modulo inside the loops)
+    { int l = head - 1; if (l < 0) l += m; for (int k = 0; k < cnt; k++) { ring[k] = l; l = l == 0 ? m - 1 : l - 1; } }
     for (int l = 0; l < nb; l++) delta[l] = 0.0;
     delta[ig] = 1.0;
     for (int k = 0; k < cnt; k++) {
-        int idx = ((head - 1 - k) % m + m) % m;
+        const int idx = ring[k];
         double s = delta[ig] * B[ig * SA_MAXB + idx];
-        for (int kk = 0; kk < cnt; kk++) { int l = ((head - 1 - kk) % m + m) % m;
+        for (int kk = 0; kk < cnt; kk++) { const int l = ring[kk];
             s += delta[l] * B[l * SA_MAXB + idx] + delta[m + l] * B[(m + l) * SA_MAXB + idx]; }
         al[idx] = s / B[idx * SA_MAXB + m + idx];
         delta[m + idx] -= al[idx];
     }
-    int nw = ((head - 1) % m + m) % m;
+    const int nw = ring[0];
     double gam = B[nw * SA_MAXB + m + nw] / B[(m + nw) * SA_MAXB + m + nw];
     for (int l = 0; l < nb; l++) delta[l] *= gam;
     for (int k = cnt - 1; k >= 0; k--) {
-        int idx = ((head - 1 - k) % m + m) % m;
+        const int idx = ring[k];
         double s = delta[ig] * B[ig * SA_MAXB + m + idx];
-        for (int kk = 0; kk < cnt; kk++) { int l = ((head - 1 - kk) % m + m) % m;
+        for (int kk = 0; kk < cnt; kk++) { const int l = ring[kk];
             s += delta[l] * B[l * SA_MAXB + m + idx] + delta[m + l] * B[(m + l) * SA_MAXB + m + idx]; }
         double be = s / B[idx * SA_MAXB + m + idx];
         delta[idx] += al[idx] - be;
     }
     double gp = delta[ig] * B[ig * SA_MAXB + ig];
-    for (int kk = 0; kk < cnt; kk++) { int l = ((head - 1 - kk) % m + m) % m;
+    for (int kk = 0; kk < cnt; kk++) { const int l = ring[kk];
         gp += delta[l] * B[l * SA_MAXB + ig] + delta[m + l] * B[(m + l) * SA_MAXB + ig]; }
     return -gp;
 }
@@ -686,10 +731,11 @@ __device__ bool min_after_eval(Ctx& c, const DevParams& prm, const DevStage& st,
         if (c.owner) {
             for (int k = 0; k < 3; k++) {
                 float acc = (float)delta[2 * m] * vecp(c, V_G, k)[t];
+                int l = os.head - 1; if (l < 0) l += m;
                 for (int kk = 0; kk < os.cnt; kk++) {
-                    int l = ((os.head - 1 - kk) % m + m) % m;
                     acc = fmaf((float)delta[l], vecp(c, V_S(l), k)[t], acc);
                     acc = fmaf((float)delta[m + l], vecp(c, V_Y(l), k)[t], acc);
+                    l = l == 0 ? m - 1 : l - 1;
                 }
                 vecp(c, V_PV, k)[t] = -acc;
             }
@@ -720,20 +766,23 @@ __device__ bool dyn_after_eval(Ctx& c, const DevParams& prm, const DevStage& st,
     os.phase = 1;
     if (os.step >= st.nstep) return false;         // x, v, f of the owners are final
     os.step++;
-    if (c.owner && c.tid < 32 * SGEO.nown) {
+    if (c.owner && c.tid < 32 * SGEO.nown) {        // kinetic-energy partial of this owner warp -> its 16-byte slot in every CTA
         const double kw = warp_sum((double)(0.5f * p.mass * k2));
-        const int slot = c.rank * SGEO.own_max + (c.tid >> 5);
-        if (SGEO.C > 1) { if (c.lane < SGEO.C) cg::this_cluster().map_shared_rank(S_KSLOTS(c), c.lane)[slot] = kw; }
-        else if (c.lane == 0) S_KSLOTS(c)[slot] = kw;
+        const int slot = SGEO.rw0 + (c.tid >> 5);    // = global bead-block index: nb slots in total
+        if (c.lane < SGEO.C) {
+            const uint32_t dst = smem_u32(S_KSLOTS(c) + 2 * slot);
+            st_async16(mapa_u32(dst, c.lane), mapa_u32(mbar_addr(c, MB_X), c.lane),
+                       make_float4(__int_as_float(__double2loint(kw)), __int_as_float(__double2hiint(kw)), 0.f, 0.f));
+        }
     }
     const float dth = st.dt_akma * h;
     publish_ab(c, make_float4(fmaf(dth, c.f[0], c.x[0]), fmaf(dth, c.f[1], c.x[1]), fmaf(dth, c.f[2], c.x[2]), 0.f),
                make_float4(st.dt_akma * c.v[0], st.dt_akma * c.v[1], st.dt_akma * c.v[2], 0.f), true);
     TSTAMP(c, 4);                                   // kick, kinetic-energy partial, publish
-    csync(c);
+    await_coords(c, true, 16u * (uint32_t)SGEO.nb);
     TSTAMP(c, 5);                                   // coordinate barrier
     double ke = 0.0;
-    for (int q = c.lane; q < SGEO.C * SGEO.own_max; q += 32) ke += S_KSLOTS(c)[q];     // usually one slot per lane,
+    for (int q = c.lane; q < SGEO.nb; q += 32) ke += S_KSLOTS(c)[2 * q];               // usually one slot per lane,
     ke = warp_sum(ke);                                                   // same butterfly order in every warp of the cluster
     // lam = sqrt(1 + 2 fbeta dt (T0/T - 1)) (tcoupling) or sqrt(T0/T) (vscaling), T = 2 KE / (kB (3N-3)); the sum is fp64,
     // the few scalar operations after it are fp32 (they sit on the critical path of every step)
@@ -779,13 +828,19 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
             g->own_max = sh.own_max; g->rows_pad = sh.rows_pad; g->m = sh.m; g->res_rounds = sh.res_rounds; g->nstages = nstages;
             g->rw0 = (int)(((long long)sh.nb * c.rank) / sh.C);
             g->nown = (int)(((long long)sh.nb * (c.rank + 1)) / sh.C) - g->rw0;
-            g->o_prog = (unsigned)L.prog; g->o_ab = (unsigned)L.ab; g->o_kslots = (unsigned)L.kslots; g->o_part = (unsigned)L.part; g->o_vec = (unsigned)L.vec;
+            g->o_prog = (unsigned)L.prog; g->o_mbar = (unsigned)L.mbar; g->o_ab = (unsigned)L.ab; g->o_kslots = (unsigned)L.kslots; g->o_part = (unsigned)L.part; g->o_vec = (unsigned)L.vec;
             g->o_P = (unsigned)L.P; g->o_eslots = (unsigned)L.eslots; g->o_slots = (unsigned)L.slots; g->o_gsum = (unsigned)L.gsum; g->o_B = (unsigned)L.B;
             g->o_delta = (unsigned)L.delta; g->o_tij = (unsigned)L.tij; g->o_own = (unsigned)L.own; g->o_tres = (unsigned)L.tres;
         }
         __syncthreads();
     }
     c.Tt = (const float4*)STD.T;
+    c.phF = 0u; c.phX = 0u;
+    if (c.tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr(c, MB_F)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr(c, MB_X)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int ntiles = SGEO.nb * (SGEO.nb + 1) / 2;
     c.gw = c.rank * SGEO.W + c.warp;
     {   // tiles of this CTA: t = rank + C*lt, lt = 0..nloc-1; of this warp: lt = warp + W*k
@@ -801,7 +856,7 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
 
     for (int i = c.tid; i < nstages * (int)(sizeof(DevStage) / 4); i += SGEO.nthreads) ((int*)(sa_smem + SGEO.o_prog))[i] = ((const int*)prog)[i];
     for (int i = c.tid; i < 4 * SGEO.n32p; i += SGEO.nthreads) S_AB(c)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = c.tid; i < SGEO.C * SGEO.own_max; i += SGEO.nthreads) S_KSLOTS(c)[i] = 0.0;
+    for (int i = c.tid; i < 2 * SGEO.nb; i += SGEO.nthreads) S_KSLOTS(c)[i] = 0.0;
     for (int i = c.tid; i < 2 * SA_MAXC * SA_KTOT; i += SGEO.nthreads) S_SLOTS(c)[i] = 0.0;
     for (int i = c.tid; i < 2 * SGEO.gwarps; i += SGEO.nthreads) S_ESLOTS(c)[i] = 0.0;
     for (int i = c.tid; i < SA_MAXB * SA_MAXB; i += SGEO.nthreads) S_B(c)[i] = 0.0;
@@ -842,6 +897,7 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
                 c.x[0] = STD.x0[3 * c.row] * (float)st.flag; c.x[1] = STD.x0[3 * c.row + 1]; c.x[2] = STD.x0[3 * c.row + 2];
                 c.v[0] = c.v[1] = c.v[2] = 0.f;
             }
+            csync(c);                   // two coordinate phases without a force phase in between must not mix
             install_x(c);
             cur_image = st.flag; hand = cur_image;
             break;

@@ -20,7 +20,7 @@ p = api.default_params()
 res = api.build_models([api.Job(IF=IF, alpha=1.1, n_models=20, seed=82364)], p)[0]
 out = (C.c_ulonglong * 32)()
 api.lib().chr3d_debug_sa_timing(out)
-names = ["control (MD)", "pair phase", "force barrier", "gather+bond", "kick+publish", "coord barrier", "lambda+update", "L-BFGS digest"]
+names = ["control (MD)", "pair phase", "wait forces", "gather+bond", "kick+publish", "wait coords", "lambda+update", "L-BFGS digest"]
 for w, nm in ((0, "owner warp 0"), (1, "last warp")):
     a = list(out[16 * w:16 * w + 11]); ne = a[10]
     print(nm, "evals", ne, "device_ms", res.device_ms)
