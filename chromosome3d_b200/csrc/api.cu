@@ -142,8 +142,13 @@ struct JobDev {
     DevBuf<int32_t> ri, rj; DevBuf<double> rd;
     SaLaunchCfg cfg;
     int traj0 = 0;
+    chr3d_single* big = nullptr;      // structures beyond the cluster kernel's capacity run on the tile-streaming engine
+    bool has_x0 = false;
+    ~JobDev();
 };
 struct LaunchGroup { SaLaunchCfg cfg; int traj0, n_traj, Nmax; };
+
+JobDev::~JobDev() { if (big) chr3d_single_destroy(big); }
 
 __global__ void f2d_kernel(const float* __restrict__ a, double* __restrict__ b, long long n) {
     long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,7 +395,15 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         }
         if (want_forces) CHR3D_CUDA((*fbufs)[jn].alloc(nx));
         tr.lap("alloc+coil");
-        if (int rc = sa_choose_config(N, total_traj, e->P.m, &jd->cfg)) return rc;
+        jd->has_x0 = jb.x0 != nullptr;
+        if (int rc = sa_choose_config(N, total_traj, e->P.m, &jd->cfg)) {
+            if (rc != CHR3D_ERR_SIZE) return rc;
+            // too large for one thread-block cluster: the single-structure engine anneals the models one after the other
+            if (int rc2 = chr3d_single_create_dense(jd->T.p, pitch, N, jd->seed, p, program, nstages, jd->nr, &jd->big)) return rc2;
+            jd->cfg.cluster = 0; jd->cfg.threads = 0;
+            e->jobs.push_back(std::move(jd));
+            continue;
+        }
         jd->traj0 = (int)tds.size();          // (position in creation order; the launch order is decided below)
         for (int m = 0; m < jb.n_models; m++) {
             TrajDesc td; memset(&td, 0, sizeof td);
@@ -416,6 +429,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         std::vector<TrajDesc> sorted; sorted.reserve(tds.size());
         for (int jn : order) {
             JobDev& jd = *e->jobs[jn];
+            if (jd.big) continue;
             const int pos = (int)sorted.size();
             for (int m = 0; m < jd.n_models; m++) sorted.push_back(tds[jd.traj0 + m]);
             if (!e->groups.empty()) {
@@ -437,8 +451,8 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         }
     }
     e->n_traj = (int)tds.size();
-    CHR3D_CUDA(e->traj.alloc(tds.size()));
-    CHR3D_CUDA(cudaMemcpy(e->traj.p, tds.data(), sizeof(TrajDesc) * tds.size(), cudaMemcpyHostToDevice));
+    CHR3D_CUDA(e->traj.alloc(std::max<size_t>(tds.size(), 1)));
+    if (!tds.empty()) CHR3D_CUDA(cudaMemcpy(e->traj.p, tds.data(), sizeof(TrajDesc) * tds.size(), cudaMemcpyHostToDevice));
     CHR3D_CUDA(cudaEventCreate(&e->ev0)); CHR3D_CUDA(cudaEventCreate(&e->ev1));
     CHR3D_CUDA(cudaDeviceSynchronize());
     tr.lap("finish");
@@ -463,6 +477,15 @@ CHR3D_API int chr3d_ensemble_run(chr3d_ensemble* e, void* stream) {
         if (int rc = sa_launch(e->traj.p + g.traj0, g.n_traj, g.Nmax, e->P, e->prog.p, e->nstages, g.cfg, gs)) return rc;
         if (gs != s) { CHR3D_CUDA(cudaEventRecord(e->gevents[k], gs)); CHR3D_CUDA(cudaStreamWaitEvent(s, e->gevents[k], 0)); }
         e->n_launches++;
+    }
+    for (auto& jp : e->jobs) {
+        JobDev& jd = *jp;
+        if (!jd.big) continue;
+        for (int m = 0; m < jd.n_models; m++) {
+            const size_t off = (size_t)m * jd.L * 3;
+            if (int rc = chr3d_single_run_model(jd.big, m, jd.has_x0 ? jd.x0.p + off : nullptr, s, jd.xout.p + off, jd.e.p + 4 * m, jd.nev.p + m, jd.hand.p + m)) return rc;
+            e->n_launches++;
+        }
     }
     CHR3D_CUDA(cudaEventRecord(e->ev1, s));
     e->ran = true;
@@ -497,9 +520,9 @@ CHR3D_API int chr3d_ensemble_fetch(chr3d_ensemble* e, chr3d_result* results) {
 }
 CHR3D_API int chr3d_ensemble_info(const chr3d_ensemble* e, int32_t* cluster_size, int32_t* threads, int32_t* n_launches,
                                   int64_t* restraint_rows_total) {
-    if (!e || e->groups.empty()) { set_error("chr3d_ensemble_info: bad handle"); return CHR3D_ERR_ARG; }
-    if (cluster_size) *cluster_size = e->groups[0].cfg.cluster;
-    if (threads) *threads = e->groups[0].cfg.threads;
+    if (!e) { set_error("chr3d_ensemble_info: bad handle"); return CHR3D_ERR_ARG; }
+    if (cluster_size) *cluster_size = e->groups.empty() ? 0 : e->groups[0].cfg.cluster;      // 0: only single-structure engine jobs
+    if (threads) *threads = e->groups.empty() ? 0 : e->groups[0].cfg.threads;
     if (n_launches) *n_launches = (int)e->groups.size();
     if (restraint_rows_total) *restraint_rows_total = e->rows_total;
     return 0;

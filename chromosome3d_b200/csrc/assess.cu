@@ -108,7 +108,9 @@ __global__ void block_sum_kernel(const double* __restrict__ terms, long long per
     if (threadIdx.x == 0) out[m] = sh[0];
 }
 
-#define ASSESS_DENSE_MAX_N 1536
+// up to 999 beads the `sort keys %tbl_hash` order (string order of the %3d-padded rows) is the numeric (i, j) order, which the dense
+// sequential sum reproduces; beyond that the Perl could not run anyway (C3D:93-94) and a fixed tree order is used
+#define ASSESS_DENSE_MAX_N 999
 
 int dev_assess(const double* d_xyz, int n_models, int N, const int32_t* d_ri, const int32_t* d_rj,
                const double* d_rd, long long nr, int32_t* d_sat, double* d_dev, cudaStream_t s) {

@@ -127,3 +127,9 @@ int dev_spearman(const double* d_IF, int L, const double* d_xyz, int n_models, i
                  cudaStream_t s);
 
 }  // namespace chr3d
+
+// ---- large_n.cu (internal entry points used by the ensemble API for structures beyond the cluster kernel's capacity)
+struct chr3d_single;
+int chr3d_single_create_dense(const float* d_T, int pitch, int32_t N, uint64_t seed, const chr3d_sa_params* p, const chr3d_stage* program,
+                              int32_t nstages, long long n_rows, chr3d_single** out);
+int chr3d_single_run_model(chr3d_single* h, int model, const float* d_x0, void* stream, float* d_xout, double* d_e4, long long* d_nevals, int* d_hand);

@@ -1001,7 +1001,7 @@ struct LnEngine {
     long long n_tiles = 0, t0 = 0, t1 = 0, pairs_total = 0;
     DevBuf<float> Dt, colpart, x0; DevBuf<float4> rowpart, vx, vxb, vg, vp, vv, vf, vS, vY, sx, sv, va[2], vb[2], vfr;
     DevBuf<int> seg_I, rs_off, rs_idx; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st;
-    chr3d_sa_params prm; unsigned long long seed = 0;
+    chr3d_sa_params prm; unsigned long long seed = 0; int model = 0;     // model: Philox stream of the coil / Maxwell draws
     cudaStream_t stream = nullptr;
     long long n_launches = 0;
 #ifdef CHR3D_WITH_NCCL
@@ -1256,7 +1256,7 @@ static int ln_run_program(LnEngine& e, const chr3d_stage* prog, int nst) {
             break;
         case CHR3D_OP_MINIMIZE: if (int rc = ln_minimize(e, s)) return rc; break;
         case CHR3D_OP_MAXWELL:
-            ln_maxwell_kernel<<<vb, 256, 0, e.stream>>>(v, e.seed, 0x100000u + (uint32_t)k, 0u, sqrt(CHR3D_KBOLTZ * s.temp / e.prm.mass));
+            ln_maxwell_kernel<<<vb, 256, 0, e.stream>>>(v, e.seed, 0x100000u + (uint32_t)k, (uint32_t)e.model, sqrt(CHR3D_KBOLTZ * s.temp / e.prm.mass));
             break;
         case CHR3D_OP_DYNAMICS: if (int rc = ln_dynamics(e, s)) return rc; break;
         case CHR3D_OP_SAVE:
@@ -1351,6 +1351,43 @@ CHR3D_API int chr3d_single_create(const double* IF, int32_t N, double alpha, dou
     CHR3D_CUDA(cudaEventCreate(&h->ev0)); CHR3D_CUDA(cudaEventCreate(&h->ev1));
     CHR3D_CUDA(cudaDeviceSynchronize());
     *out = h.release();
+    return 0;
+}
+
+// ---- internal: the ensemble API hands structures that exceed the cluster kernel's capacity to this engine ----------
+__global__ void ln_pack_result_kernel(const float4* __restrict__ x, int N, const LnState* st, float* __restrict__ xout, double* e4, long long* nevals, int* hand) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) { const float4 q = x[i]; xout[3 * i] = q.x; xout[3 * i + 1] = q.y; xout[3 * i + 2] = q.z; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        e4[CHR3D_E_OVERALL] = st->E; e4[CHR3D_E_BON] = st->Ebond; e4[CHR3D_E_VDW] = st->Evdw; e4[CHR3D_E_NOE] = st->Enoe;
+        *nevals = st->nevals; *hand = st->hand;
+    }
+}
+// targets from a dense [N][pitch] device matrix (restraint-list jobs); one GPU
+int chr3d_single_create_dense(const float* d_T, int pitch, int32_t N, uint64_t seed, const chr3d_sa_params* p, const chr3d_stage* program,
+                              int32_t nstages, long long n_rows, chr3d_single** out) {
+    std::unique_ptr<chr3d_single> h(new chr3d_single());
+    LnEngine& e = h->e;
+    e.N = N; e.rank = 0; e.world = 1; e.prm = *p; e.seed = seed ? seed : p->seed;
+    e.m = std::max(1, std::min((int)p->lbfgs_m, CHR3D_LBFGS_MAX_M));
+    h->prog.assign(program, program + nstages);
+    if (int rc = ln_alloc(e)) return rc;
+    ln_tiles_from_dense_kernel<<<(unsigned)e.n_tiles, 256>>>(d_T, N, pitch, e.t0, e.t1, e.nT, e.Dt.p);
+    CHR3D_CUDA(cudaGetLastError());
+    e.pairs_total = n_rows;
+    CHR3D_CUDA(cudaEventCreate(&h->ev0)); CHR3D_CUDA(cudaEventCreate(&h->ev1));
+    CHR3D_CUDA(cudaDeviceSynchronize());
+    *out = h.release();
+    return 0;
+}
+// one model: start coordinates (d_x0 == nullptr: seeded random coil of `model`), the stage program, results packed on the device
+int chr3d_single_run_model(chr3d_single* h, int model, const float* d_x0, void* stream, float* d_xout, double* d_e4, long long* d_nevals, int* d_hand) {
+    LnEngine& e = h->e;
+    e.stream = (cudaStream_t)stream; e.model = model;
+    if (d_x0) CHR3D_CUDA(cudaMemcpyAsync(e.x0.p, d_x0, sizeof(float) * 3 * (size_t)e.N, cudaMemcpyDeviceToDevice, e.stream));
+    else { if (int rc = dev_random_coil(e.x0.p, e.N, 1, model, e.prm.bond_r0, e.seed, e.stream)) return rc; }
+    if (int rc = ln_run_program(e, h->prog.data(), (int)h->prog.size())) return rc;
+    ln_pack_result_kernel<<<std::min(296, (e.N + 255) / 256), 256, 0, e.stream>>>(e.vx.p, e.N, e.st.p, d_xout, d_e4, d_nevals, d_hand);
+    CHR3D_CUDA(cudaGetLastError());
     return 0;
 }
 

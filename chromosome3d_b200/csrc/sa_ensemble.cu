@@ -113,6 +113,7 @@ int dev_random_coil(float* d_x0, int N, int n_models, int first_model, double st
     coil_steps_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d.p, N, n_models, first_model, step, seed);
     coil_kernel<<<(n_models + 31) / 32, 32, 0, s>>>(d_x0, d.p, N, n_models);
     CHR3D_CUDA(cudaGetLastError());
+    if (s != (cudaStream_t)0) CHR3D_CUDA(cudaStreamSynchronize(s));     // the scratch buffer is released on the default stream
     return 0;
 }
 

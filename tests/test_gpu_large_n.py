@@ -162,3 +162,34 @@ def test_tile_engine_full_schedule_statistics(gpu_api, mats):
     assert abs(rho_l - np.median(rho_s)) <= 0.03
     assert abs(r["energies"][3] - np.median(small.energies[:, 3])) <= 0.05 * np.median(small.energies[:, 3])
     assert np.abs(r["xyz"].mean(0)).max() < 1e-3
+
+
+def test_ensemble_api_hands_large_structures_to_the_tile_engine(gpu_api):
+    """chr3d_run_ensemble accepts structures beyond the cluster kernel's capacity (here 1,300 beads) and anneals them on
+    the tile-streaming engine, model after model: same results as driving that engine directly, scored like any job."""
+    N = 1300
+    IF = ds.synthetic_if(N, 31337)
+    w = dict(w_noe=2.0, w_bond=200.0, w_vdw=0.01, repel=0.9)
+    prog = abi.stage_array([abi.stage(abi.OP_INIT, flag=1), abi.stage(abi.OP_MAXWELL, temp=300.0),
+                            abi.stage(abi.OP_DYNAMICS, nstep=15, flag=abi.COUPLE_TCOUP, dt=0.003, temp=2000.0, **w),
+                            abi.stage(abi.OP_MINIMIZE, nstep=5, drop=10.0, **w), abi.stage(abi.OP_CENTER), abi.stage(abi.OP_ENERGY, **w)])
+    p = gpu_api.default_params()
+    small = ds.load_if_matrix(ds.input_path("chr21_1mb"))
+    res = gpu_api.build_models([gpu_api.Job(IF=IF, alpha=0.9, n_models=2, seed=5), gpu_api.Job(IF=small, alpha=0.5, n_models=3, seed=5)], p, prog)
+    big = res[0]
+    ri, rj, rd = gpu_api.if_to_restraints(IF, 0.9)
+    assert big.n_restraints == len(ri) and big.xyz.shape == (2, N, 3)
+    for k in range(2):
+        eo, _ = orc.energy_forces(big.xyz[k], ri, rj, rd, p, prog[-1])
+        assert np.allclose(big.energies[k], eo[0], rtol=2e-5, atol=2e-5 * abs(eo[0, 0])), k     # reported energies belong to the reported coordinates
+    assert not np.array_equal(big.xyz[0], big.xyz[1])
+    sat, dev = orc.assess(big.xyz, ri, rj, rd)
+    assert np.array_equal(sat, big.satisfied) and np.allclose(dev, big.sum_dev, rtol=1e-12)     # > 999 beads: summation order is ours
+    assert np.abs(big.xyz.mean(1)).max() < 1e-3 and (big.force_evals > 16).all()
+    assert np.isfinite(res[1].energies).all() and res[1].xyz.shape == (3, 37, 3)
+    # model 1 through the oracle (fp64, same seed / Philox streams) on the MD part alone (the line search takes discrete decisions)
+    prog_md = abi.stage_array([prog[0], prog[1], prog[2], prog[5]])
+    md = gpu_api.build_models([gpu_api.Job(IF=IF, alpha=0.9, n_models=2, seed=5)], p, prog_md)[0]
+    o = orc.run_model(N, ri, rj, rd, p, prog_md, 5, 1, None)
+    assert np.abs(md.xyz[1] - o["xyz"]).max() < 1e-3
+    assert np.allclose(md.energies[1], o["energies"], rtol=1e-5, atol=1e-5 * o["energies"][0])
