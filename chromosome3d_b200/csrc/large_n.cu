@@ -32,7 +32,41 @@
 #include <vector>
 #include "common.h"
 #ifdef CHR3D_WITH_NCCL
+#include <dlfcn.h>
 #include <nccl.h>
+// NCCL is bound at run time, when a multi-rank structure is first created: dlopen picks the libnccl.so.2 the process
+// already has (PyTorch brings its own), otherwise the system's.  Linking it at build time would pin whichever copy the
+// loader finds first and break a later `import torch` in the same process.
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+        }
+    }
+    return api;
+}
+}  // namespace
+#define ncclGetUniqueId nccl_api().GetUniqueId
+#define ncclCommInitRank nccl_api().CommInitRank
+#define ncclAllReduce nccl_api().AllReduce
+#define ncclCommDestroy nccl_api().CommDestroy
 #endif
 
 namespace chr3d {
@@ -1303,6 +1337,7 @@ CHR3D_API int chr3d_single_create(const double* IF, int32_t N, double alpha, dou
         // nccl_id == NULL: shard without a communicator — forces/energies stay this rank's partial sums and the caller
         // reduces them (used to check the partition on one GPU; chr3d_single_run refuses to integrate in that mode)
         if (nccl_id) {
+            if (!nccl_api().ok) { set_error("libnccl.so.2 could not be loaded"); return CHR3D_ERR_ARG; }
             ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
             if (ncclCommInitRank(&e.comm, world, id, rank) != ncclSuccess) { set_error("ncclCommInitRank failed"); return CHR3D_ERR_CUDA; }
         }
@@ -1521,6 +1556,7 @@ CHR3D_API int chr3d_single_comm_error(chr3d_single* h, int32_t* err) {
 
 CHR3D_API int chr3d_nccl_unique_id(void* out128) {
 #ifdef CHR3D_WITH_NCCL
+    if (!nccl_api().ok) { set_error("libnccl.so.2 could not be loaded"); return CHR3D_ERR_ARG; }
     ncclUniqueId id;
     if (ncclGetUniqueId(&id) != ncclSuccess) { set_error("ncclGetUniqueId failed"); return CHR3D_ERR_CUDA; }
     memcpy(out128, &id, sizeof id);

@@ -6,7 +6,7 @@ mkdir -p /tmp/satim
 for f in api restraints sa_ensemble assess microbench large_n; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr -DCHR3D_WITH_NCCL -DSA_TIMING -c -o /tmp/satim/$f.o $f.cu &
 done; wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o /tmp/satim/libchr3d.so /tmp/satim/*.o -Xcompiler -fPIC /usr/lib/x86_64-linux-gnu/libnccl.so
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o /tmp/satim/libchr3d.so /tmp/satim/*.o -Xcompiler -fPIC -ldl
 cd ../..
 cp chromosome3d_b200/libchr3d.so /tmp/satim/libchr3d.orig.so
 cp /tmp/satim/libchr3d.so chromosome3d_b200/libchr3d.so
