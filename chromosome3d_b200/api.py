@@ -77,6 +77,12 @@ def fp32_peak(reps=3):
     return v.value
 
 
+def fp32_peak_packed(reps=3):
+    v = C.c_double(0)
+    _check(lib().chr3d_fp32_peak_packed(reps, C.byref(v)))
+    return v.value
+
+
 def default_params():
     p = abi.SaParams()
     lib().chr3d_default_params(C.byref(p))

@@ -87,26 +87,35 @@ __device__ __forceinline__ float ln_rsqrt(float x) { float y; asm("rsqrt.approx.
 // NEAR: the tile touches the diagonal band (J <= I + 1), where cells can carry the "no repel" sentinel -2
 // (bonded neighbours, the diagonal, the lower half of diagonal tiles).  Padding rows/columns of the last
 // tile row/column carry it too, so those tiles also take the NEAR path.
+//
+// The pair term runs on Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2, PTX *.f32x2): one call evaluates the pairs
+// (row a, column j) and (row a+1, column j) in the two halves of 64-bit register pairs.  The kernel is issue-bound with
+// scalar FP32 (about 22 instructions per pair against 4 B of HBM traffic); packing halves the FMA-class instruction count.
+// Scalar operands (column coordinates, weights) ride as broadcast operands of the packed instructions.  Each half computes
+// exactly what the scalar form computed (same operations, same order), so results do not depend on the packing.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
 template <bool WANT_E, bool LOW_SOFT, bool NEAR>
-__device__ __forceinline__ void pair_sym(const LnTerms& t, float xi, float yi, float zi, float xj, float yj, float zj, float d,
-                                         float& fix, float& fiy, float& fiz, float& fjx, float& fjy, float& fjz, float& en, float& ev) {
-    const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
-    const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, 1e-12f)));
-    const float rinv = ln_rsqrt(r2);
-    const float delta = fmaf(r2, rinv, -d);                    // r - d
-    float h = fminf(delta, t.rsw);
-    if (LOW_SOFT) h = fmaxf(h, t.lo);
-    const bool has = d > 0.f;
-    float tr = fmaxf(t.R2 - r2, 0.f);
-    if (NEAR) tr = d > -1.5f ? tr : 0.f;
-    const float w2h = (has ? t.wnC2m : 0.f) * h;               // -2 w C h
+__device__ __forceinline__ void pair_sym2(const LnTerms& t, const float2 xi, const float2 yi, const float2 zi, float xj, float yj, float zj, const float2 d,
+                                          float2& fix, float2& fiy, float2& fiz, float2& gjx, float2& gjy, float2& gjz, float2& en, float2& ev) {
+    const float2 dx = __fadd2_rn(xi, bc(-xj)), dy = __fadd2_rn(yi, bc(-yj)), dz = __fadd2_rn(zi, bc(-zj));
+    const float2 r2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, bc(1e-12f))));
+    const float2 rinv = f2(ln_rsqrt(r2.x), ln_rsqrt(r2.y));
+    const float2 delta = __ffma2_rn(r2, rinv, f2(-d.x, -d.y));                          // r - d
+    float2 h = f2(fminf(delta.x, t.rsw), fminf(delta.y, t.rsw));
+    if (LOW_SOFT) h = f2(fmaxf(h.x, t.lo), fmaxf(h.y, t.lo));
+    const float2 has = f2(d.x > 0.f ? 1.f : 0.f, d.y > 0.f ? 1.f : 0.f);                // FSET.BF
+    float2 tr = __fadd2_rn(bc(t.R2), f2(-r2.x, -r2.y));
+    tr = f2(fmaxf(tr.x, 0.f), fmaxf(tr.y, 0.f));
+    if (NEAR) tr = f2(d.x > -1.5f ? tr.x : 0.f, d.y > -1.5f ? tr.y : 0.f);
+    const float2 w2h = __fmul2_rn(__fmul2_rn(has, bc(t.wnC2m)), h);                     // -2 w C h
     if (WANT_E) {
-        en = fmaf(-0.5f * w2h, 2.f * delta - h, en);           // w C h (2 delta - h)
-        ev = fmaf(t.wv * tr, tr, ev);
+        en = __ffma2_rn(__fmul2_rn(w2h, bc(-0.5f)), __ffma2_rn(delta, bc(2.f), f2(-h.x, -h.y)), en);   // w C h (2 delta - h)
+        ev = __ffma2_rn(__fmul2_rn(tr, bc(t.wv)), tr, ev);
     }
-    const float coef = fmaf(t.wv4, tr, w2h * rinv);            // 4 w_vdw t - (dE_noe/dr)/r
-    fix = fmaf(coef, dx, fix); fiy = fmaf(coef, dy, fiy); fiz = fmaf(coef, dz, fiz);
-    fjx = fmaf(-coef, dx, fjx); fjy = fmaf(-coef, dy, fjy); fjz = fmaf(-coef, dz, fjz);
+    const float2 coef = __ffma2_rn(bc(t.wv4), tr, __fmul2_rn(w2h, rinv));              // 4 w_vdw t - (dE_noe/dr)/r
+    fix = __ffma2_rn(coef, dx, fix); fiy = __ffma2_rn(coef, dy, fiy); fiz = __ffma2_rn(coef, dz, fiz);
+    gjx = __ffma2_rn(coef, dx, gjx); gjy = __ffma2_rn(coef, dy, gjy); gjz = __ffma2_rn(coef, dz, gjz);   // force on j = -(gj.x + gj.y)
 }
 
 __host__ __device__ inline long long tile_index(long long I, long long J, long long nT) { return I * nT - I * (I - 1) / 2 + (J - I); }
@@ -120,6 +129,15 @@ __host__ __device__ inline void tile_coords(long long t, long long nT, int& I, i
     I = (int)i; J = (int)(i + (t - tile_index(i, i, nT)));
 }
 
+// Position k of a tile-packed tile -> (row, column) inside the tile.  Thread (warp w, lane l) of ln_tile_kernel owns rows
+// 8w..8w+7 and columns l+32c (c = 0..3); its 32 cells are 8 float4, number q = 2*rp + ch (row pair rp, column half ch) at
+// float offset ((8w + q)*32 + l)*4, holding {(2rp, 2ch), (2rp+1, 2ch), (2rp, 2ch+1), (2rp+1, 2ch+1)}: two row-packed f32x2
+// operands per 128-bit shared-memory load, warp loads contiguous (conflict-free).
+__host__ __device__ inline void ln_tile_cell(int k, int& r, int& c) {
+    const int e = k & 3, l = (k >> 2) & 31, q = (k >> 7) & 7, w = k >> 10;
+    r = 8 * w + 2 * (q >> 1) + (e & 1);
+    c = 32 * (2 * (q & 1) + (e >> 1)) + l;
+}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
@@ -142,19 +160,25 @@ struct LnTileArgs {
     int* seg_I;               // [cta][maxseg] tile row of each segment (-1 unused)
     double* epart;            // [cta][2]
     int maxseg;
+    int dbg;                  // development probe (CHR3D_LN_DEBUG): 1 = stream tiles without the pair term, 2 = pair term without tile traffic
     LnTerms terms;
 };
 
-// dynamic smem: 2 x 64 KB tile buffers + 2 x colp[3][16][128] + 2 mbarriers
-#define LN_CBUF_OFF (2 * LN_TILE_FLOATS * 4 + 2 * 3 * 16 * LN_TB * 4 + 64)
+// dynamic smem: LN_STAGES x 64 KB tile buffers + colp[3][16][128] + mbarriers (one per stage + "colp free").
+// Three stages keep two tiles (128 KB per SM, 19 MB chip-wide) in flight behind the one being evaluated: with two stages only
+// one 64 KB copy per SM is outstanding, which at the loaded HBM latency caps the kernel near 60 % of the copy bandwidth.
+#define LN_STAGES 3
+#define LN_COLP_OFF (LN_STAGES * LN_TILE_FLOATS * 4)
+#define LN_BAR_OFF (LN_COLP_OFF + 3 * 16 * LN_TB * 4)
+#define LN_CBUF_OFF (LN_BAR_OFF + 64)
 #define LN_SMEM (LN_CBUF_OFF + 2 * 2 * LN_TB * 16)       // + column coordinates (a, b) of the current and the next tile
 
 template <bool WANT_E, bool LOW_SOFT>
 __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* dbuf = (float*)smem;
-    float* colp = (float*)(smem + 2 * LN_TILE_FLOATS * 4);
-    uint64_t* bar = (uint64_t*)(smem + 2 * LN_TILE_FLOATS * 4 + 2 * 3 * 16 * LN_TB * 4);
+    float* colp = (float*)(smem + LN_COLP_OFF);
+    uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);         // [0, LN_STAGES): tile landed; [LN_STAGES]: colp drained by the reducer warps
     float4* cbuf = (float4*)(smem + LN_CBUF_OFF);       // [stage][a|b][128]
     if (a.done && *a.done) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -165,8 +189,8 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
     int* segI = a.seg_I + (size_t)blockIdx.x * a.maxseg;
     for (int s = tid; s < a.maxseg; s += LN_THREADS) segI[s] = -1;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[1])));
+        for (int q = 0; q < LN_STAGES; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[q])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar[LN_STAGES])), "r"(3 * LN_TB / 32));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -176,7 +200,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
                      ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(a.Dt + (size_t)(t - a.t0) * LN_TILE_FLOATS),
                        "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])) : "memory");
     };
-    if (tid == 0) { if (c0 < c1) issue(c0, 0); if (c0 + 1 < c1) issue(c0 + 1, 1); }
+    if (tid == 0 && a.dbg != 2) for (int q = 0; q < LN_STAGES; q++) if (c0 + q < c1) issue(c0 + q, q);
     // column coordinates of tile column Jn -> cbuf[stg] with cp.async (L2 latency hidden behind the previous tile's pairs)
     auto prefetch_cols = [&](int Jn, int stg) {
         if (tid < 2 * LN_TB) {
@@ -193,81 +217,92 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     int curI = -1, seg = -1;
-    float xi[8], yi[8], zi[8], fix[8], fiy[8], fiz[8];
-    float en = 0.f, ev = 0.f; double den = 0.0, dev = 0.0;
-    uint32_t phase[2] = {0, 0};
+    float2 xi[4], yi[4], zi[4], fix[4], fiy[4], fiz[4];          // row pairs (8w + 2rp, 8w + 2rp + 1)
+    float2 en = bc(0.f), ev = bc(0.f); double den = 0.0, dev = 0.0;
+    uint32_t phases = 0;           // bit q: parity to wait for on bar[q]
+    int stage = 0, cstage = 0;     // tile ring / column-coordinate double buffer
     const LnTerms tm = a.terms;
 
     auto flush_rows = [&]() {
         // reduce the 8 row accumulators over the 32 lanes (columns) of this warp
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            float vx = fix[r], vy = fiy[r], vz = fiz[r];
+            float vx = (r & 1) ? fix[r >> 1].y : fix[r >> 1].x, vy = (r & 1) ? fiy[r >> 1].y : fiy[r >> 1].x, vz = (r & 1) ? fiz[r >> 1].y : fiz[r >> 1].x;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { vx += __shfl_xor_sync(0xffffffffu, vx, o); vy += __shfl_xor_sync(0xffffffffu, vy, o); vz += __shfl_xor_sync(0xffffffffu, vz, o); }
             if (lane == r) a.rowpart[((size_t)blockIdx.x * a.maxseg + seg) * LN_TB + warp * 8 + r] = make_float4(vx, vy, vz, 0.f);
         }
-        den += (double)en; dev += (double)ev; en = 0.f; ev = 0.f;
+        den += (double)(en.x + en.y); dev += (double)(ev.x + ev.y); en = bc(0.f); ev = bc(0.f);
     };
 
     for (long long t = c0; t < c1; t++) {
-        const int stage = (int)((t - c0) & 1);
         if (I != curI) {
             if (curI >= 0) flush_rows();
             curI = I; seg++;
             if (tid == 0) segI[seg] = I;
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                int i = I * LN_TB + warp * 8 + r; if (i >= a.N) i = a.N - 1;
-                const float4 p = a.x[i], q = XB[i];
-                xi[r] = fmaf(lam, q.x, p.x); yi[r] = fmaf(lam, q.y, p.y); zi[r] = fmaf(lam, q.z, p.z); fix[r] = fiy[r] = fiz[r] = 0.f;
+            for (int rp = 0; rp < 4; rp++) {
+                int i0 = I * LN_TB + warp * 8 + 2 * rp, i1 = i0 + 1;
+                if (i0 >= a.N) i0 = a.N - 1;
+                if (i1 >= a.N) i1 = a.N - 1;
+                const float4 p0 = a.x[i0], q0 = XB[i0], p1 = a.x[i1], q1 = XB[i1];
+                xi[rp] = f2(fmaf(lam, q0.x, p0.x), fmaf(lam, q1.x, p1.x)); yi[rp] = f2(fmaf(lam, q0.y, p0.y), fmaf(lam, q1.y, p1.y));
+                zi[rp] = f2(fmaf(lam, q0.z, p0.z), fmaf(lam, q1.z, p1.z)); fix[rp] = fiy[rp] = fiz[rp] = bc(0.f);
             }
         }
-        if (t + 1 < c1) { int Jn = J + 1; if (Jn == (int)a.nT) Jn = I + 1; prefetch_cols(Jn, stage ^ 1); }
-        float xj[4], yj[4], zj[4], fjx[4] = {0.f, 0.f, 0.f, 0.f}, fjy[4] = {0.f, 0.f, 0.f, 0.f}, fjz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (t + 1 < c1) { int Jn = J + 1; if (Jn == (int)a.nT) Jn = I + 1; prefetch_cols(Jn, cstage ^ 1); }
+        float xj[4], yj[4], zj[4];
+        float2 gjx[4], gjy[4], gjz[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const float4 p = cbuf[(stage * 2) * LN_TB + c * 32 + lane], q = cbuf[(stage * 2 + 1) * LN_TB + c * 32 + lane];   // column 32c + lane
+            const float4 p = cbuf[(cstage * 2) * LN_TB + c * 32 + lane], q = cbuf[(cstage * 2 + 1) * LN_TB + c * 32 + lane];   // column 32c + lane
             xj[c] = fmaf(lam, q.x, p.x); yj[c] = fmaf(lam, q.y, p.y); zj[c] = fmaf(lam, q.z, p.z);
+            gjx[c] = gjy[c] = gjz[c] = bc(0.f);
         }
-        mbar_wait(&bar[stage], phase[stage]); phase[stage] ^= 1;
-        const float* D = dbuf + (size_t)stage * LN_TILE_FLOATS + (size_t)(warp * 8) * LN_TB + lane * 4;
+        if (a.dbg != 2) { mbar_wait(&bar[stage], (phases >> stage) & 1u); phases ^= 1u << stage; }
+        const float4* D4 = reinterpret_cast<const float4*>(dbuf + (size_t)stage * LN_TILE_FLOATS) + (warp * 8) * 32 + lane;   // see ln_tile_cell
         // padding beads (index >= N) exist only in the last tile row / column; their cells are -2 like the diagonal band's
         const bool near = J <= I + 1 || (J + 1) * LN_TB > a.N;
-        if (near) {
+        if (a.dbg == 1) {
+        } else if (near) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const float4 d4 = *reinterpret_cast<const float4*>(D + r * LN_TB);
-                pair_sym<WANT_E, LOW_SOFT, true>(tm, xi[r], yi[r], zi[r], xj[0], yj[0], zj[0], d4.x, fix[r], fiy[r], fiz[r], fjx[0], fjy[0], fjz[0], en, ev);
-                pair_sym<WANT_E, LOW_SOFT, true>(tm, xi[r], yi[r], zi[r], xj[1], yj[1], zj[1], d4.y, fix[r], fiy[r], fiz[r], fjx[1], fjy[1], fjz[1], en, ev);
-                pair_sym<WANT_E, LOW_SOFT, true>(tm, xi[r], yi[r], zi[r], xj[2], yj[2], zj[2], d4.z, fix[r], fiy[r], fiz[r], fjx[2], fjy[2], fjz[2], en, ev);
-                pair_sym<WANT_E, LOW_SOFT, true>(tm, xi[r], yi[r], zi[r], xj[3], yj[3], zj[3], d4.w, fix[r], fiy[r], fiz[r], fjx[3], fjy[3], fjz[3], en, ev);
+            for (int q = 0; q < 8; q++) {
+                const int rp = q >> 1, c = 2 * (q & 1);
+                const float4 d4 = D4[q * 32];
+                pair_sym2<WANT_E, LOW_SOFT, true>(tm, xi[rp], yi[rp], zi[rp], xj[c], yj[c], zj[c], f2(d4.x, d4.y), fix[rp], fiy[rp], fiz[rp], gjx[c], gjy[c], gjz[c], en, ev);
+                pair_sym2<WANT_E, LOW_SOFT, true>(tm, xi[rp], yi[rp], zi[rp], xj[c + 1], yj[c + 1], zj[c + 1], f2(d4.z, d4.w), fix[rp], fiy[rp], fiz[rp], gjx[c + 1], gjy[c + 1], gjz[c + 1], en, ev);
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const float4 d4 = *reinterpret_cast<const float4*>(D + r * LN_TB);
-                pair_sym<WANT_E, LOW_SOFT, false>(tm, xi[r], yi[r], zi[r], xj[0], yj[0], zj[0], d4.x, fix[r], fiy[r], fiz[r], fjx[0], fjy[0], fjz[0], en, ev);
-                pair_sym<WANT_E, LOW_SOFT, false>(tm, xi[r], yi[r], zi[r], xj[1], yj[1], zj[1], d4.y, fix[r], fiy[r], fiz[r], fjx[1], fjy[1], fjz[1], en, ev);
-                pair_sym<WANT_E, LOW_SOFT, false>(tm, xi[r], yi[r], zi[r], xj[2], yj[2], zj[2], d4.z, fix[r], fiy[r], fiz[r], fjx[2], fjy[2], fjz[2], en, ev);
-                pair_sym<WANT_E, LOW_SOFT, false>(tm, xi[r], yi[r], zi[r], xj[3], yj[3], zj[3], d4.w, fix[r], fiy[r], fiz[r], fjx[3], fjy[3], fjz[3], en, ev);
+            for (int q = 0; q < 8; q++) {
+                const int rp = q >> 1, c = 2 * (q & 1);
+                const float4 d4 = D4[q * 32];
+                pair_sym2<WANT_E, LOW_SOFT, false>(tm, xi[rp], yi[rp], zi[rp], xj[c], yj[c], zj[c], f2(d4.x, d4.y), fix[rp], fiy[rp], fiz[rp], gjx[c], gjy[c], gjz[c], en, ev);
+                pair_sym2<WANT_E, LOW_SOFT, false>(tm, xi[rp], yi[rp], zi[rp], xj[c + 1], yj[c + 1], zj[c + 1], f2(d4.z, d4.w), fix[rp], fiy[rp], fiz[rp], gjx[c + 1], gjy[c + 1], gjz[c + 1], en, ev);
             }
         }
-        // column partials: [comp][warp][128], this lane's 4 consecutive columns
-        float* cp = colp + (size_t)stage * 3 * 16 * LN_TB;
-        *reinterpret_cast<float4*>(cp + (0 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
-        *reinterpret_cast<float4*>(cp + (1 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
-        *reinterpret_cast<float4*>(cp + (2 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
+        float fjx[4], fjy[4], fjz[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { fjx[c] = -(gjx[c].x + gjx[c].y); fjy[c] = -(gjy[c].x + gjy[c].y); fjz[c] = -(gjz[c].x + gjz[c].y); }
+        // column partials: [comp][warp][128], this lane's 4 consecutive columns; the single buffer is free once the reducer
+        // warps of the previous tile have drained it (they arrived long ago: this wait does not block in practice)
+        if (t > c0) mbar_wait(&bar[LN_STAGES], (phases >> LN_STAGES) & 1u), phases ^= 1u << LN_STAGES;
+        *reinterpret_cast<float4*>(colp + (0 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
+        *reinterpret_cast<float4*>(colp + (1 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
+        *reinterpret_cast<float4*>(colp + (2 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                 // tile buffer `stage` is free, column partials are complete, next column coordinates have landed
-        if (tid == 0 && t + 2 < c1) issue(t + 2, stage);
+        if (tid == 0 && t + LN_STAGES < c1 && a.dbg != 2) issue(t + LN_STAGES, stage);
         if (tid < 3 * LN_TB) {
             const int comp = tid / LN_TB, col = tid % LN_TB;
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < 16; w++) s += cp[(comp * 16 + w) * LN_TB + col];
+            for (int w = 0; w < 16; w++) s += colp[(comp * 16 + w) * LN_TB + col];
             a.colpart[((size_t)(t - a.t0) * 3 + comp) * LN_TB + col] = s;
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar[LN_STAGES])) : "memory");
         }
+        stage = stage + 1 == LN_STAGES ? 0 : stage + 1; cstage ^= 1;
         J++; if (J == (int)a.nT) { I++; J = I; }
     }
     if (curI >= 0) flush_rows();
@@ -957,7 +992,8 @@ __global__ void __launch_bounds__(256) ln_build_tiles_kernel(const double* __res
     const double mean = *mean_p;
     float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
     for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
-        const int r = k / LN_TB, q = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + (q & 3) * 32 + (q >> 2);   // position q = 4*lane + c holds column 32*c + lane
+        int r, c; ln_tile_cell(k, r, c);
+        const int i = I * LN_TB + r, j = J * LN_TB + c;
         float v = -2.f;
         if (i < L && j < L && j > i) {
             const int sep = j - i;
@@ -978,7 +1014,8 @@ __global__ void __launch_bounds__(256) ln_tiles_from_tenths_kernel(const long lo
     int I, J; tile_coords(t, nT, I, J);
     float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
     for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
-        const int r = k / LN_TB, q = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + (q & 3) * 32 + (q >> 2);   // position q = 4*lane + c holds column 32*c + lane
+        int r, c; ln_tile_cell(k, r, c);
+        const int i = I * LN_TB + r, j = J * LN_TB + c;
         float v = -2.f;
         if (i < L && j < L && j > i) {
             const int sep = j - i;
@@ -1004,7 +1041,8 @@ __global__ void __launch_bounds__(256) ln_tiles_from_dense_kernel(const float* _
     int I, J; tile_coords(t, nT, I, J);
     float* out = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
     for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
-        const int r = k / LN_TB, q = k % LN_TB, i = I * LN_TB + r, j = J * LN_TB + (q & 3) * 32 + (q >> 2);   // position q = 4*lane + c holds column 32*c + lane
+        int r, c; ln_tile_cell(k, r, c);
+        const int i = I * LN_TB + r, j = J * LN_TB + c;
         out[k] = (i < N && j < N && j > i) ? T[(size_t)i * pitch + j] : -2.f;
     }
 }
@@ -1126,7 +1164,9 @@ static void ln_terms(const chr3d_sa_params& p, const chr3d_stage& s, LnTerms& t)
     double r = s.repel * p.vdw_rmin; t.R2 = (float)(r * r);
 }
 
-static void ln_launch_tiles(LnEngine& e, const LnTileArgs& a, bool want_e) {
+static void ln_launch_tiles(LnEngine& e, LnTileArgs a, bool want_e) {
+    static const int dbg = getenv("CHR3D_LN_DEBUG") ? atoi(getenv("CHR3D_LN_DEBUG")) : 0;
+    a.dbg = dbg;
     const bool soft = e.prm.noe_low_soft != 0;
     if (want_e) { if (soft) ln_tile_kernel<true, true><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); else ln_tile_kernel<true, false><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); }
     else { if (soft) ln_tile_kernel<false, true><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); else ln_tile_kernel<false, false><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); }

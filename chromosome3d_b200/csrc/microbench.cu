@@ -18,12 +18,35 @@ __global__ void __launch_bounds__(1024, 1) ffma_kernel(float* out, int iters, fl
     if (s == 12345.678f) out[0] = s;
 }
 
+// the same chain on the packed pipe (FFMA2, fma.rn.f32x2): two FMAs per lane per instruction
+__global__ void __launch_bounds__(1024, 1) ffma2_kernel(float* out, int iters, float a, float b) {
+    float2 x[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) x[q] = make_float2(threadIdx.x * 1e-3f + q, threadIdx.x * 2e-3f + q);
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) x[q] = __ffma2_rn(x[q], a2, b2);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s += x[q].x + x[q].y;
+    if (s == 12345.678f) out[0] = s;
+}
+
 }  // namespace chr3d
 
 using namespace chr3d;
 
 // Measured FP32 FMA throughput (TFLOP/s, FMA = 2 flop) of the whole chip; best of `reps` launches.
-CHR3D_API int chr3d_fp32_peak(int reps, double* tflops) {
+static int fp32_peak_impl(int reps, double* tflops, bool packed);
+CHR3D_API int chr3d_fp32_peak(int reps, double* tflops) { return fp32_peak_impl(reps, tflops, false); }
+// same measurement with packed FFMA2 instructions (the form ln_tile_kernel's pair term uses)
+CHR3D_API int chr3d_fp32_peak_packed(int reps, double* tflops) { return fp32_peak_impl(reps, tflops, true); }
+static int fp32_peak_impl(int reps, double* tflops, bool packed) {
     if (!tflops) { set_error("chr3d_fp32_peak: null output"); return CHR3D_ERR_ARG; }
     if (int rc = require_device()) return rc;
     int dev = 0, sms = 148;
@@ -35,11 +58,12 @@ CHR3D_API int chr3d_fp32_peak(int reps, double* tflops) {
     double best = 0.0;
     for (int r = 0; r < reps + 1; r++) {
         CHR3D_CUDA(cudaEventRecord(e0));
-        ffma_kernel<<<blocks, threads>>>(out.p, iters, 0.999f, 0.001f);
+        if (packed) ffma2_kernel<<<blocks, threads>>>(out.p, iters, 0.999f, 0.001f);
+        else ffma_kernel<<<blocks, threads>>>(out.p, iters, 0.999f, 0.001f);
         CHR3D_CUDA(cudaEventRecord(e1));
         CHR3D_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f; CHR3D_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads * (packed ? 2.0 : 1.0);
         if (r > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -413,6 +413,34 @@ __device__ __forceinline__ void pair_sym(const SaTerms& t, float xi, float yi, f
     fj[0] = fmaf(-coef, dx, fj[0]); fj[1] = fmaf(-coef, dy, fj[1]); fj[2] = fmaf(-coef, dz, fj[2]);
 }
 
+// The same pair term on Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2, PTX *.f32x2): one call evaluates the pairs
+// (row i, column j) and (row i, column j+4) — the two columns a lane holds side by side in a float4 of targets — in the
+// two halves of 64-bit register pairs; the row coordinates ride as broadcast operands.  Each half computes exactly the
+// scalar form's operations in the same order.  gj accumulates +coef*dx: the force on j is its negative.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+template <bool WANT_E, bool NEAR>
+__device__ __forceinline__ void pair_sym2(const SaTerms& t, float xi, float yi, float zi, const float2 xj, const float2 yj, const float2 zj, const float2 d,
+                                          float2* fi, float2* gj, float2& en, float2& ev) {
+    const float2 dx = __fadd2_rn(bc(xi), f2(-xj.x, -xj.y)), dy = __fadd2_rn(bc(yi), f2(-yj.x, -yj.y)), dz = __fadd2_rn(bc(zi), f2(-zj.x, -zj.y));
+    const float2 r2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, bc(1e-12f))));
+    const float2 rinv = f2(rsqrt_fast(r2.x), rsqrt_fast(r2.y));
+    float2 tr = __fadd2_rn(bc(t.R2), f2(-r2.x, -r2.y));
+    tr = f2(fmaxf(tr.x, 0.f), fmaxf(tr.y, 0.f));
+    if (NEAR) tr = f2(d.x > -1.5f ? tr.x : 0.f, d.y > -1.5f ? tr.y : 0.f);
+    const float2 delta = __ffma2_rn(r2, rinv, f2(-d.x, -d.y));                         // r - d
+    const float2 h = f2(fminf(delta.x, t.rsw), fminf(delta.y, t.rsw));
+    const float2 has = f2(d.x > 0.f ? 1.f : 0.f, d.y > 0.f ? 1.f : 0.f);
+    const float2 w2h = __fmul2_rn(__fmul2_rn(has, bc(t.wnC2m)), h);                    // -2 w C h
+    if (WANT_E) {
+        en = __ffma2_rn(__fmul2_rn(w2h, bc(-0.5f)), __ffma2_rn(delta, bc(2.f), f2(-h.x, -h.y)), en);   // w C h (2 delta - h)
+        ev = __ffma2_rn(__fmul2_rn(tr, bc(t.wv)), tr, ev);
+    }
+    const float2 coef = __ffma2_rn(bc(t.wv4), tr, __fmul2_rn(w2h, rinv));             // 4 w_vdw t - (dE_noe/dr)/r
+    fi[0] = __ffma2_rn(coef, dx, fi[0]); fi[1] = __ffma2_rn(coef, dy, fi[1]); fi[2] = __ffma2_rn(coef, dz, fi[2]);
+    gj[0] = __ffma2_rn(coef, dx, gj[0]); gj[1] = __ffma2_rn(coef, dy, gj[1]); gj[2] = __ffma2_rn(coef, dz, gj[2]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // energy + forces.  On return: c.f (owner), c.ebond (owner partial); if WANT_E the pair-energy
 // partials of every warp of the cluster are in eslots (pick them up with allreduce(.., true)).
@@ -440,38 +468,82 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevParams& prm, const DevSt
 #pragma unroll
             for (int q = 0; q < 8; q++) d[q] = __ldg(gp + q * 32);
         }
-        float xj[8], yj[8], zj[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) { const float4 t = ldx(c, 32 * J + cg4 + 4 * q); xj[q] = t.x; yj[q] = t.y; zj[q] = t.z; }
         float fi[4][3], fj[8][3];
+        if constexpr (!GENERAL) {
+            // packed pipe: the lane's columns as pairs (cg + 8p, cg + 8p + 4), p = 0..3 — adjacent components of its float4 targets
+            float2 xj2[4], yj2[4], zj2[4], gj2[4][3], fi2[4][3];
 #pragma unroll
-        for (int q = 0; q < 4; q++) fi[q][0] = fi[q][1] = fi[q][2] = 0.f;
+            for (int q = 0; q < 4; q++) {
+                const float4 t0 = ldx(c, 32 * J + cg4 + 8 * q), t1 = ldx(c, 32 * J + cg4 + 8 * q + 4);
+                xj2[q] = f2(t0.x, t1.x); yj2[q] = f2(t0.y, t1.y); zj2[q] = f2(t0.z, t1.z);
+                gj2[q][0] = gj2[q][1] = gj2[q][2] = bc(0.f);
+                fi2[q][0] = fi2[q][1] = fi2[q][2] = bc(0.f);
+            }
+            float2 en2 = bc(0.f), ev2 = bc(0.f);
+            if (J <= I + 1 || J == SGEO.nb - 1) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) fj[q][0] = fj[q][1] = fj[q][2] = 0.f;
-        if (J <= I + 1 || J == SGEO.nb - 1) {
+                for (int r = 0; r < 4; r++) {
+                    const float4 xi = ldx(c, 32 * I + rg + 8 * r);
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const float4 xi = ldx(c, 32 * I + rg + 8 * r);
+                    for (int hh = 0; hh < 2; hh++) {
+                        const float4 d4 = d[2 * r + hh];
+                        pair_sym2<WANT_E, true>(tm, xi.x, xi.y, xi.z, xj2[2 * hh], yj2[2 * hh], zj2[2 * hh], f2(d4.x, d4.y), fi2[r], gj2[2 * hh], en2, ev2);
+                        pair_sym2<WANT_E, true>(tm, xi.x, xi.y, xi.z, xj2[2 * hh + 1], yj2[2 * hh + 1], zj2[2 * hh + 1], f2(d4.z, d4.w), fi2[r], gj2[2 * hh + 1], en2, ev2);
+                    }
+                }
+            } else {
 #pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const float4 d4 = d[2 * r + hh];
-                    pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 0], yj[4 * hh + 0], zj[4 * hh + 0], d4.x, fi[r], fj[4 * hh + 0], en, ev);
-                    pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 1], yj[4 * hh + 1], zj[4 * hh + 1], d4.y, fi[r], fj[4 * hh + 1], en, ev);
-                    pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 2], yj[4 * hh + 2], zj[4 * hh + 2], d4.z, fi[r], fj[4 * hh + 2], en, ev);
-                    pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 3], yj[4 * hh + 3], zj[4 * hh + 3], d4.w, fi[r], fj[4 * hh + 3], en, ev);
+                for (int r = 0; r < 4; r++) {
+                    const float4 xi = ldx(c, 32 * I + rg + 8 * r);
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const float4 d4 = d[2 * r + hh];
+                        pair_sym2<WANT_E, false>(tm, xi.x, xi.y, xi.z, xj2[2 * hh], yj2[2 * hh], zj2[2 * hh], f2(d4.x, d4.y), fi2[r], gj2[2 * hh], en2, ev2);
+                        pair_sym2<WANT_E, false>(tm, xi.x, xi.y, xi.z, xj2[2 * hh + 1], yj2[2 * hh + 1], zj2[2 * hh + 1], f2(d4.z, d4.w), fi2[r], gj2[2 * hh + 1], en2, ev2);
+                    }
                 }
             }
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) fi[r][a] = fi2[r][a].x + fi2[r][a].y;
+#pragma unroll
+                for (int q = 0; q < 4; q++) { fj[2 * q][a] = -gj2[q][a].x; fj[2 * q + 1][a] = -gj2[q][a].y; }
+            }
+            if (WANT_E) { en += en2.x + en2.y; ev += ev2.x + ev2.y; }
         } else {
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const float4 xi = ldx(c, 32 * I + rg + 8 * r);
-#pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const float4 d4 = d[2 * r + hh];
-                    pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 0], yj[4 * hh + 0], zj[4 * hh + 0], d4.x, fi[r], fj[4 * hh + 0], en, ev);
-                    pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 1], yj[4 * hh + 1], zj[4 * hh + 1], d4.y, fi[r], fj[4 * hh + 1], en, ev);
-                    pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 2], yj[4 * hh + 2], zj[4 * hh + 2], d4.z, fi[r], fj[4 * hh + 2], en, ev);
-                    pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 3], yj[4 * hh + 3], zj[4 * hh + 3], d4.w, fi[r], fj[4 * hh + 3], en, ev);
+            float xj[8], yj[8], zj[8];
+    #pragma unroll
+            for (int q = 0; q < 8; q++) { const float4 t = ldx(c, 32 * J + cg4 + 4 * q); xj[q] = t.x; yj[q] = t.y; zj[q] = t.z; }
+    #pragma unroll
+            for (int q = 0; q < 4; q++) fi[q][0] = fi[q][1] = fi[q][2] = 0.f;
+    #pragma unroll
+            for (int q = 0; q < 8; q++) fj[q][0] = fj[q][1] = fj[q][2] = 0.f;
+            if (J <= I + 1 || J == SGEO.nb - 1) {
+    #pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const float4 xi = ldx(c, 32 * I + rg + 8 * r);
+    #pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const float4 d4 = d[2 * r + hh];
+                        pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 0], yj[4 * hh + 0], zj[4 * hh + 0], d4.x, fi[r], fj[4 * hh + 0], en, ev);
+                        pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 1], yj[4 * hh + 1], zj[4 * hh + 1], d4.y, fi[r], fj[4 * hh + 1], en, ev);
+                        pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 2], yj[4 * hh + 2], zj[4 * hh + 2], d4.z, fi[r], fj[4 * hh + 2], en, ev);
+                        pair_sym<WANT_E, GENERAL, true>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 3], yj[4 * hh + 3], zj[4 * hh + 3], d4.w, fi[r], fj[4 * hh + 3], en, ev);
+                    }
+                }
+            } else {
+    #pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const float4 xi = ldx(c, 32 * I + rg + 8 * r);
+    #pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const float4 d4 = d[2 * r + hh];
+                        pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 0], yj[4 * hh + 0], zj[4 * hh + 0], d4.x, fi[r], fj[4 * hh + 0], en, ev);
+                        pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 1], yj[4 * hh + 1], zj[4 * hh + 1], d4.y, fi[r], fj[4 * hh + 1], en, ev);
+                        pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 2], yj[4 * hh + 2], zj[4 * hh + 2], d4.z, fi[r], fj[4 * hh + 2], en, ev);
+                        pair_sym<WANT_E, GENERAL, false>(tm, xi.x, xi.y, xi.z, xj[4 * hh + 3], yj[4 * hh + 3], zj[4 * hh + 3], d4.w, fi[r], fj[4 * hh + 3], en, ev);
+                    }
                 }
             }
         }
@@ -966,6 +1038,14 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
 // ------------------------------------------------------------------------------------------------
 // host side: configuration choice and launch
 // ------------------------------------------------------------------------------------------------
+// kernel variant for a CTA size: the register cap follows from the thread count (one CTA per SM) — 168 registers up to
+// 12 warps (no spills in the pair loop), 128 up to 16, 96 up to 20
+typedef void (*SaKernelFn)(const TrajDesc*, DevParams, const DevStage*, int, int);
+static SaKernelFn sa_pick_kernel(bool general, int threads) {
+    if (threads <= 384) return general ? sa_kernel<true, 12> : sa_kernel<false, 12>;
+    if (threads <= 512) return general ? sa_kernel<true, 16> : sa_kernel<false, 16>;
+    return general ? sa_kernel<true, 20> : sa_kernel<false, 20>;
+}
 static size_t smem_fixed(int N, int C, int W, int m) {
     SaShape sh; sa_shape(N, C, W, m, SA_MAX_STAGES, 0, sh);
     SaLayout L; sa_layout(sh, L);
@@ -978,7 +1058,7 @@ static int max_active_clusters(int C, int threads, size_t smem) {
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
     int n = 0;
-    if ((threads > 512 ? cudaOccupancyMaxActiveClusters(&n, sa_kernel<false, 20>, &lc) : cudaOccupancyMaxActiveClusters(&n, sa_kernel<false, 16>, &lc)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, sa_pick_kernel(false, threads), &lc) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
@@ -1011,10 +1091,10 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int smem_hw = smem_max;
     if (getenv("CHR3D_SA_SMEM_CAP")) smem_max = std::min(smem_max, atoi(getenv("CHR3D_SA_SMEM_CAP")));   // development: force >1 CTA per SM
-    if (cudaFuncSetAttribute(sa_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_hw) != cudaSuccess) cudaGetLastError();
-    if (cudaFuncSetAttribute(sa_kernel<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_hw) != cudaSuccess) cudaGetLastError();
-    if (cudaFuncSetAttribute(sa_kernel<false, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
-    if (cudaFuncSetAttribute(sa_kernel<false, 20>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    for (int th : {384, 512, 640}) {
+        if (cudaFuncSetAttribute(sa_pick_kernel(false, th), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_hw) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncSetAttribute(sa_pick_kernel(false, th), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    }
     const int nb = (N + 31) / 32, ntiles = nb * (nb + 1) / 2;
     double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0};
     const int Cs[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};     // > 8: non-portable cluster sizes, two CTAs of different trajectories per SM
@@ -1059,8 +1139,7 @@ int sa_launch(const TrajDesc* d_traj, int n_traj, int Nmax, const DevParams& P, 
     (void)Nmax;
     if (nstages > SA_MAX_STAGES) { set_error("stage program has %d entries, the SA kernel keeps at most %d", nstages, SA_MAX_STAGES); return CHR3D_ERR_SIZE; }
     const bool general = P.general_noe || P.lo_clamp > -1e30f;
-    const bool wide = cfg.threads > 512;
-    auto kern = general ? (wide ? sa_kernel<true, 20> : sa_kernel<true, 16>) : (wide ? sa_kernel<false, 20> : sa_kernel<false, 16>);
+    SaKernelFn kern = sa_pick_kernel(general, cfg.threads);
     CHR3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     if (cfg.cluster > 8) CHR3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t lc = {};

@@ -155,6 +155,8 @@ int  chr3d_build_program(const chr3d_sa_params* p, chr3d_stage* out, int cap);
 /* Measurement aid: FP32 FMA throughput of the device in TFLOP/s (roofline denominator of the
  * FP32-bound small-N kernel).                                                              */
 int chr3d_fp32_peak(int reps, double* tflops);
+/* Same chain issued as packed FFMA2 (fma.rn.f32x2), the instruction form of the large-N pair term. */
+int chr3d_fp32_peak_packed(int reps, double* tflops);
 
 /* ------------------------- (1) IF -> restraints  C3D:110-206, 340-362 -------------------- */
 /* IF2dist_new: tenths[i*L+j] = the `%.1f` text of D as an integer number of tenths

@@ -9,6 +9,7 @@ from chromosome3d_b200 import api  # noqa: E402
 
 api.init(0)
 peaks = json.load(open("MEASURED_PEAKS.json")) if __import__("os").path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0}
+print(json.dumps({"fp32_peak_tflops": api.fp32_peak(3), "fp32_peak_packed_tflops": api.fp32_peak_packed(3)}), flush=True)
 for N in [int(a) for a in sys.argv[1:]] or [4985, 24925]:
     t0 = time.time()
     s = api.Single(N=N, alpha=1.1, synth_seed=20260001 + (N > 10000))
