@@ -164,7 +164,7 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 __host__ __device__ inline void sa_layout(const SaShape& s, SaLayout& L) {
     size_t o = SA_GEO_BYTES;
     L.prog = o;   o = align_up(o + sizeof(DevStage) * (size_t)s.nstages, 16);
-    L.mbar = o;   o = align_up(o + 16, 16);                            // two mbarriers: forces arrived, coordinates arrived
+    L.mbar = o;   o = align_up(o + 32, 16);                            // four mbarriers: forces arrived, coordinates arrived, all-reduce slots (two parities)
     L.ab = o;     o = align_up(o + sizeof(float4) * 4 * (size_t)(s.n32 + 1), 16);   // [parity][a|b][n32+1]
     L.part = o;   o = align_up(o + sizeof(float4) * (size_t)s.own_max * (s.nb + 1) * 32, 16);
     L.vec = o;    o = align_up(o + sizeof(float) * (size_t)s.nvec * 3 * s.rows_pad, 16);
@@ -227,7 +227,7 @@ struct Ctx {
     int par;
     // coordinates of every bead are x = a + lam*b, (a, b) double-buffered by parity `buf` (see dyn_after_eval)
     int buf; float lam;
-    unsigned phF, phX;               // parities of the two mbarriers
+    unsigned phF, phX, phR;          // parities of the mbarriers (phR: bit p = parity of MB_R + p)
     // owner state (valid when tid < rows_pad; row_ok when the thread owns a real bead)
     bool owner, row_ok; int row;
     float x[3], v[3], f[3];
@@ -284,6 +284,7 @@ __device__ __forceinline__ float4 ldx(const Ctx& c, int i) {
 // data that the consumer sent after completing the current one (see the header comment).
 #define MB_F 0
 #define MB_X 1
+#define MB_R 2          // MB_R + parity: scalars of an all-reduce have arrived
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, int rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
@@ -302,11 +303,20 @@ __device__ __forceinline__ void mbar_wait(const Ctx& c, int which, unsigned& par
     uint32_t done = 0;
     const long long t0 = clock64();
     while (!done) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (!done && clock64() - t0 > 20000000000ll) __trap();        // ~10 s: a peer died; fail instead of hanging the GPU
     }
     parity ^= 1u;
+}
+
+// (The wait is the default acquire at CTA scope, as for TMA-fed pipelines: st.async data and its complete_tx reach the
+// consumer's shared memory through the same path, and everything consumed after a wait lives in THIS CTA's shared memory.
+// A cluster-scope acquire would make ptxas append CCTL.IVALL — an L1 invalidation — to every wait: measured 20 % of all
+// stall samples of the kernel.)
+__device__ __forceinline__ void st_async8(uint32_t dst_cluster, uint32_t mbar_cluster, double v) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(dst_cluster), "l"(__double_as_longlong(v)), "r"(mbar_cluster) : "memory");
 }
 
 // Publish (a, b) of the owned bead to every CTA of the cluster (buffer of the other parity).
@@ -339,16 +349,15 @@ __device__ __forceinline__ void install_x(Ctx& c) { publish_x(c); await_coords(c
 // the same order, so all ranks take identical decisions afterwards.
 __device__ void allreduce(Ctx& c, int K, bool with_e) {
     __syncthreads();
+    const uint32_t bar = mbar_addr(c, MB_R + c.par);
     for (int k = c.warp; k < K; k += SGEO.W) {
         const float* col = S_P(c) + (size_t)k * SGEO.rows_pad;
         double s = 0;
         for (int t = c.lane; t < SGEO.rows_pad; t += 32) s += (double)col[t];
         s = warp_sum(s);
         if (SGEO.C > 1) {
-            if (c.lane < SGEO.C) {
-                double* remote = cg::this_cluster().map_shared_rank(S_SLOTS(c), c.lane);
-                remote[((size_t)c.par * SA_MAXC + c.rank) * SA_KTOT + k] = s;
-            }
+            if (c.lane < SGEO.C)      // slot (parity, this rank, k) of CTA `lane`; the bytes are credited to its mbarrier of this parity
+                st_async8(mapa_u32(smem_u32(S_SLOTS(c) + ((size_t)c.par * SA_MAXC + c.rank) * SA_KTOT + k), c.lane), mapa_u32(bar, c.lane), s);
         } else if (c.lane == 0) S_GSUM(c)[2 + k] = s;
     }
     if (with_e) {
@@ -361,7 +370,15 @@ __device__ void allreduce(Ctx& c, int K, bool with_e) {
         }
     }
     if (SGEO.C > 1) {
-        cg::this_cluster().sync();
+        // no cluster barrier: wait for the C*K scalars addressed to this CTA.  Consecutive all-reduces alternate between two
+        // mbarriers (and two slot sets), so scalars of the next one can never complete the current phase; a rank cannot be two
+        // all-reduces ahead, because the next one needs this rank's contribution.
+        if (c.tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(8 * SGEO.C * K)) : "memory");
+        {
+            unsigned ph = (c.phR >> c.par) & 1u;
+            mbar_wait(c, MB_R + c.par, ph);
+            c.phR ^= 1u << c.par;
+        }
         if (c.tid < K) {
             double s = 0;
             for (int r = 0; r < SGEO.C; r++) s += S_SLOTS(c)[((size_t)c.par * SA_MAXC + r) * SA_KTOT + c.tid];
@@ -908,10 +925,12 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
         __syncthreads();
     }
     c.Tt = (const float4*)STD.T;
-    c.phF = 0u; c.phX = 0u;
+    c.phF = 0u; c.phX = 0u; c.phR = 0u;
     if (c.tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr(c, MB_F)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr(c, MB_X)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr(c, MB_R)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr(c, MB_R + 1)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int ntiles = SGEO.nb * (SGEO.nb + 1) / 2;
@@ -1097,7 +1116,7 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
     }
     const int nb = (N + 31) / 32, ntiles = nb * (nb + 1) / 2;
     double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0};
-    const int Cs[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};     // > 8: non-portable cluster sizes, two CTAs of different trajectories per SM
+    const int Cs[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16};     // > 8: non-portable cluster sizes, two CTAs of different trajectories per SM
     for (int C : Cs) {
         if (force_c && C != force_c) continue;
         if (C > nb && C > 1) continue;
