@@ -319,6 +319,61 @@ def spearman_IF_pdb(IF, xyz, rng=3):
     return rho
 
 
+# ---------------------------------------------------------------------------------- SURVEY 8(f) "next" rows
+def reduce_model(xyz):
+    """Pair-averaged model of half the resolution (the shipped *_reduced.pdb files)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    out = np.zeros(((xyz.shape[0] + 1) // 2, 3))
+    _check(lib().chr3d_reduce_model(_d(xyz), xyz.shape[0], _d(out)))
+    return out
+
+
+def write_reduced_pdb(path, xyz):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    _check(lib().chr3d_write_reduced_pdb(str(path).encode(), _d(xyz), xyz.shape[0]))
+
+
+def model_similarity(xyz_a, xyz_b):
+    """(Spearman, RMSD) of output_models/similarity.txt between two models' pairwise-distance vectors."""
+    a = np.ascontiguousarray(xyz_a, dtype=np.float64)
+    b = np.ascontiguousarray(xyz_b, dtype=np.float64)
+    rho, rmsd = C.c_double(0), C.c_double(0)
+    _check(lib().chr3d_model_similarity(_d(a), a.shape[0], _d(b), b.shape[0], C.byref(rho), C.byref(rmsd)))
+    return rho.value, rmsd.value
+
+
+def read_if_text(path):
+    """input/<ID>.txt parsed as IF2dist_new does (C3D:116-129), by the library's threaded parser."""
+    L = C.c_int32(0)
+    _check(lib().chr3d_read_if_text(str(path).encode(), None, C.c_int64(0), C.byref(L)))
+    out = np.zeros((L.value, L.value))
+    _check(lib().chr3d_read_if_text(str(path).encode(), _d(out), C.c_int64(out.size), C.byref(L)))
+    return out
+
+
+def write_if_binary(path, IF, elem_bytes=8):
+    IF = np.ascontiguousarray(IF, dtype=np.float64)
+    _check(lib().chr3d_write_if_binary(str(path).encode(), _d(IF), IF.shape[0], elem_bytes))
+
+
+def read_if_binary(path):
+    L = C.c_int32(0)
+    _check(lib().chr3d_read_if_binary(str(path).encode(), None, C.c_int64(0), C.byref(L)))
+    out = np.zeros((L.value, L.value))
+    _check(lib().chr3d_read_if_binary(str(path).encode(), _d(out), C.c_int64(out.size), C.byref(L)))
+    return out
+
+
+def if_from_coo(bi, bj, v, L, base=0):
+    """Sparse (bin_i, bin_j, value) triplets -> dense symmetric IF matrix (scatter on the device)."""
+    bi = np.ascontiguousarray(bi, dtype=np.int32)
+    bj = np.ascontiguousarray(bj, dtype=np.int32)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros((L, L))
+    _check(lib().chr3d_if_from_coo(_i(bi), _i(bj), _d(v), C.c_int64(len(v)), L, base, _d(out)))
+    return out
+
+
 # ---------------------------------------------------------------------------------- one large structure
 def nccl_unique_id():
     """128-byte NCCL unique id (rank 0 creates it, the caller broadcasts it, e.g. over torch.distributed)."""

@@ -276,4 +276,80 @@ int dev_spearman(const double* d_IF, int L, const double* d_xyz, int n_models, i
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// model-vs-model similarity (the scorer behind output_models/similarity.txt):
+// Spearman rho between the upper-triangle distance vectors of two models, and the RMSE between them after
+// scaling b's distances by mean(da)/mean(db).  Distances are fp64 sqrt((dx^2 + dy^2) + dz^2) without FMA
+// contraction (the order a NumPy/Java scorer evaluates them in); ranks are exact (radix sort of the ordered
+// fp64 keys, average ranks for ties), rho comes from exact 128-bit integer moments.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_of(long long k, int n, int& i, int& j) {     // k-th pair (i < j) in row-major order
+    // row i starts at i*n - i(i+1)/2
+    double b = 2.0 * n - 1.0;
+    long long ii = (long long)floor((b - sqrt(b * b - 8.0 * (double)k)) * 0.5);
+    if (ii < 0) ii = 0;
+    while (ii > 0 && ii * n - ii * (ii + 1) / 2 > k) ii--;
+    while ((ii + 1) * n - (ii + 1) * (ii + 2) / 2 <= k) ii++;
+    i = (int)ii; j = (int)(k - (ii * n - ii * (ii + 1) / 2) + ii + 1);
+}
+__global__ void pdist_kernel(const double* __restrict__ x, int n, long long np, double* __restrict__ d, unsigned long long* __restrict__ keys) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= np) return;
+    int i, j; pair_of(k, n, i, j);
+    const double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+    const double v = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    d[k] = v; keys[k] = order_key(v);
+}
+// fixed-order sums: per-block partials of (sum da, sum db) or of sum (da - sc*db)^2
+__global__ void __launch_bounds__(256) sim_sums_kernel(const double* __restrict__ da, const double* __restrict__ db, long long np, const double* scale,
+                                                       double* __restrict__ part /* [blocks][2] */) {
+    double s0 = 0, s1 = 0;
+    const double sc = scale ? *scale : 0.0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
+        if (scale) { const double e = da[k] - sc * db[k]; s0 += e * e; } else { s0 += da[k]; s1 += db[k]; }
+    }
+    __shared__ double sh[2][256];
+    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = sh[0][0]; part[2 * blockIdx.x + 1] = sh[1][0]; }
+}
+__global__ void sim_finish_kernel(const double* part, int blocks, long long np, int stage, double* out /* [0] scale, [1] rmsd */) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double s0 = 0, s1 = 0;
+    for (int b = 0; b < blocks; b++) { s0 += part[2 * b]; s1 += part[2 * b + 1]; }
+    if (stage == 0) out[0] = (s0 / (double)np) / (s1 / (double)np); else out[1] = sqrt(s0 / (double)np);
+}
+int dev_model_similarity(const double* d_xa, const double* d_xb, int n, double* rho_host, double* rmsd_host, cudaStream_t s) {
+    const long long np = (long long)n * (n - 1) / 2;
+    if (np < 1) { *rho_host = nan(""); *rmsd_host = nan(""); return 0; }
+    if (np > 0x7fffffffLL) { set_error("model similarity: %lld pairs exceed the sort limit of this build", np); return CHR3D_ERR_SIZE; }
+    DevBuf<double> da, db, part, out; DevBuf<unsigned long long> keys, sorted, mom; DevBuf<long long> ra2, rb2; DevBuf<unsigned char> tmp;
+    const int blocks = 296;
+    CHR3D_CUDA(da.alloc((size_t)np)); CHR3D_CUDA(db.alloc((size_t)np)); CHR3D_CUDA(keys.alloc((size_t)np)); CHR3D_CUDA(sorted.alloc((size_t)np));
+    CHR3D_CUDA(ra2.alloc((size_t)np)); CHR3D_CUDA(rb2.alloc((size_t)np)); CHR3D_CUDA(part.alloc((size_t)blocks * 2)); CHR3D_CUDA(out.alloc(3));
+    CHR3D_CUDA(mom.alloc((size_t)blocks * 6));
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys.p, sorted.p, (int)np, 0, 64, s);
+    CHR3D_CUDA(tmp.alloc(tmp_bytes));
+    const unsigned g = (unsigned)((np + 255) / 256);
+    pdist_kernel<<<g, 256, 0, s>>>(d_xa, n, np, da.p, keys.p);
+    CHR3D_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, keys.p, sorted.p, (int)np, 0, 64, s));
+    rank2_kernel<<<g, 256, 0, s>>>(keys.p, sorted.p, np, ra2.p);
+    pdist_kernel<<<g, 256, 0, s>>>(d_xb, n, np, db.p, keys.p);
+    CHR3D_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, keys.p, sorted.p, (int)np, 0, 64, s));
+    rank2_kernel<<<g, 256, 0, s>>>(keys.p, sorted.p, np, rb2.p);
+    moments_kernel<<<blocks, 256, 0, s>>>(ra2.p, rb2.p, np, mom.p);
+    rho_kernel<<<1, 32, 0, s>>>(mom.p, blocks, out.p + 2);
+    sim_sums_kernel<<<blocks, 256, 0, s>>>(da.p, db.p, np, nullptr, part.p);
+    sim_finish_kernel<<<1, 32, 0, s>>>(part.p, blocks, np, 0, out.p);
+    sim_sums_kernel<<<blocks, 256, 0, s>>>(da.p, db.p, np, out.p, part.p);
+    sim_finish_kernel<<<1, 32, 0, s>>>(part.p, blocks, np, 1, out.p);
+    CHR3D_CUDA(cudaGetLastError());
+    double h[3];
+    CHR3D_CUDA(cudaMemcpyAsync(h, out.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    CHR3D_CUDA(cudaStreamSynchronize(s));
+    *rho_host = h[2]; *rmsd_host = h[1];
+    return 0;
+}
+
 }  // namespace chr3d

@@ -125,6 +125,7 @@ int dev_assess_rows(const double* d_xyz, int N, const int32_t* d_ri, const int32
                     int32_t* d_flag, double* d_dev, double* d_dist, cudaStream_t s);
 int dev_spearman(const double* d_IF, int L, const double* d_xyz, int n_models, int range, double* rho_host,
                  cudaStream_t s);
+int dev_model_similarity(const double* d_xa, const double* d_xb, int n, double* rho_host, double* rmsd_host, cudaStream_t s);
 
 }  // namespace chr3d
 

@@ -253,6 +253,24 @@ int chr3d_write_pdb(const char* path, const double* xyz, int32_t N, const double
 int chr3d_spearman(const double* IF, int32_t L, const double* xyz, int32_t n_models,
                    int32_t range, double* rho);
 
+/* ------------------------- 8(f) "next" rows: callers and formats either side of the path -------------------------
+ * The programs behind output_models "_reduced.pdb" files and similarity.txt are not in the reference tree; these entry points
+ * reproduce their shipped outputs (formats: SURVEY App. B.6).                                                           */
+/* bead k of the reduced model = mean of beads 2k, 2k+1 (a trailing unpaired bead is copied); out_xyz: ceil(N/2)*3        */
+int chr3d_reduce_model(const double* xyz, int32_t N, double* out_xyz);
+/* the "_reduced.pdb" dialect: empty first line, CRLF, chain B, "%.3f" with HALF_UP on the shortest decimal digits        */
+int chr3d_write_reduced_pdb(const char* path, const double* xyz, int32_t n);
+/* similarity.txt: Spearman of the upper-triangle distance vectors of two models (first min(n_a, n_b) beads) and the RMSE
+ * between them after scaling b's distances by mean(da)/mean(db)                                                          */
+int chr3d_model_similarity(const double* xyz_a, int32_t n_a, const double* xyz_b, int32_t n_b, double* spearman, double* rmsd);
+/* input/<ID>.txt as IF2dist_new parses it (C3D:116-129, 164-179); cap == 0: only *L is returned                           */
+int chr3d_read_if_text(const char* path, double* out, int64_t cap, int32_t* L);
+/* raw container for matrices beyond decimal text: "CHR3DIF1", int32 L, int32 elem_bytes (4|8), L*L little-endian values    */
+int chr3d_write_if_binary(const char* path, const double* IF, int32_t L, int32_t elem_bytes);
+int chr3d_read_if_binary(const char* path, double* out, int64_t cap, int32_t* L);
+/* sparse (bin_i, bin_j, value) triplets, base 0 or 1, -> dense symmetric L*L matrix (device scatter; repeats add up)        */
+int chr3d_if_from_coo(const int32_t* bi, const int32_t* bj, const double* v, int64_t nnz, int32_t L, int32_t base, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,3 +185,24 @@ def spearman(IF, xyz, rng=3):
     rho = np.zeros(xyz.shape[0])
     lib().orc_spearman(_d(IF), IF.shape[0], _d(xyz), xyz.shape[0], rng, _d(rho))
     return rho
+
+
+def reduce_model(xyz):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    out = np.zeros(((xyz.shape[0] + 1) // 2, 3))
+    lib().orc_reduce_model(_d(xyz), xyz.shape[0], _d(out))
+    return out
+
+
+def write_reduced_pdb(path, xyz):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    if lib().orc_write_reduced_pdb(str(path).encode(), _d(xyz), xyz.shape[0]) != 0:
+        raise OSError("orc_write_reduced_pdb: cannot write %s" % path)
+
+
+def model_similarity(xa, xb):
+    xa = np.ascontiguousarray(xa, dtype=np.float64)
+    xb = np.ascontiguousarray(xb, dtype=np.float64)
+    rho, rmsd = C.c_double(0), C.c_double(0)
+    lib().orc_model_similarity(_d(xa), xa.shape[0], _d(xb), xb.shape[0], C.byref(rho), C.byref(rmsd))
+    return rho.value, rmsd.value

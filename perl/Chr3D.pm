@@ -35,6 +35,12 @@ my %SIG = (    # name => [ret, args] in FFI::Platypus type names (pointers = opa
     chr3d_rank_models      => ['int',    ['opaque', 'sint32', 'opaque']],
     chr3d_write_pdb        => ['int',    ['string', 'opaque', 'sint32', 'opaque', 'opaque', 'sint32']],
     chr3d_spearman         => ['int',    ['opaque', 'sint32', 'opaque', 'sint32', 'sint32', 'opaque']],
+    chr3d_reduce_model     => ['int',    ['opaque', 'sint32', 'opaque']],
+    chr3d_write_reduced_pdb => ['int',   ['string', 'opaque', 'sint32']],
+    chr3d_model_similarity => ['int',    ['opaque', 'sint32', 'opaque', 'sint32', 'opaque', 'opaque']],
+    chr3d_read_if_text     => ['int',    ['string', 'opaque', 'sint64', 'opaque']],
+    chr3d_write_if_binary  => ['int',    ['string', 'opaque', 'sint32', 'sint32']],
+    chr3d_read_if_binary   => ['int',    ['string', 'opaque', 'sint64', 'opaque']],
 );
 
 sub _load {
@@ -116,21 +122,36 @@ sub write_rr   { _check(_c_chr3d_write_rr($_[0], ptr($_[1]), ptr($_[2]), ptr($_[
 sub write_tbl  { _check(_c_chr3d_write_tbl($_[0], ptr($_[1]), ptr($_[2]), ptr($_[3]), $_[4]), "chr3d_write_tbl"); }
 
 # build_models (C3D:254-289): anneal m models of one matrix.  Returns a hash of packed buffers.
+# One call for any number of (matrix, alpha) jobs: the library batches every trajectory of every job into one launch.
+# jobs: list of hashes { IF, L, alpha, K, min_sep, n_models, seed }; returns a list of result hashes.
+sub run_ensembles {
+    my ($jobs, $params) = @_;
+    _load();
+    my $p = $params // default_params();
+    my ($prog, $nst) = build_program($p);
+    my (@r, $jobbuf, $resbuf);
+    ($jobbuf, $resbuf) = ("", "");
+    for my $a (@$jobs) {
+        my ($L, $m) = ($a->{L}, $a->{n_models});
+        my %r = (xyz => _buf(8 * $m * $L * 3), energies => _buf(8 * 4 * $m), force_evals => _buf(8 * $m), hand => _buf(4 * $m),
+                 satisfied => _buf(4 * $m), sum_dev => _buf(8 * $m));
+        push @r, \%r;
+        # struct chr3d_job / chr3d_result (include/chr3d.h), x86-64 layout
+        $jobbuf .= pack("Q l l d d Q Q Q q l l Q Q", ptr($a->{IF}), $L, $a->{min_sep} // 5, $a->{alpha}, $a->{K} // 11, 0, 0, 0, 0, $m, 0, $a->{seed} // 0, 0);
+        $resbuf .= pack("Q Q Q Q Q Q q d", ptr($r{xyz}), ptr($r{energies}), ptr($r{force_evals}), ptr($r{hand}), ptr($r{satisfied}), ptr($r{sum_dev}), 0, 0.0);
+    }
+    _check(_c_chr3d_run_ensemble(ptr($jobbuf), scalar(@$jobs), ptr($p), ptr($prog), $nst, ptr($resbuf)), "chr3d_run_ensemble");
+    my $rsz = length($resbuf) / @$jobs;
+    for my $k (0 .. $#r) {
+        my @tail = unpack("Q6 q d", substr($resbuf, $k * $rsz, $rsz));
+        $r[$k]{n_restraints} = $tail[6]; $r[$k]{device_ms} = $tail[7];
+    }
+    return @r;
+}
 sub run_ensemble {
     my (%a) = @_;    # IF, L, alpha, K, min_sep, n_models, seed, params (opaque, optional)
-    _load();
-    my $p = $a{params} // default_params();
-    my ($prog, $nst) = build_program($p);
-    my ($L, $m) = ($a{L}, $a{n_models});
-    my %r = (xyz => _buf(8 * $m * $L * 3), energies => _buf(8 * 4 * $m), force_evals => _buf(8 * $m), hand => _buf(4 * $m),
-             satisfied => _buf(4 * $m), sum_dev => _buf(8 * $m));
-    # struct chr3d_job / chr3d_result (include/chr3d.h), x86-64 layout
-    my $job = pack("Q l l d d Q Q Q q l l Q Q", ptr($a{IF}), $L, $a{min_sep}, $a{alpha}, $a{K}, 0, 0, 0, 0, $m, 0, $a{seed} // 0, 0);
-    my $res = pack("Q Q Q Q Q Q q d", ptr($r{xyz}), ptr($r{energies}), ptr($r{force_evals}), ptr($r{hand}), ptr($r{satisfied}), ptr($r{sum_dev}), 0, 0.0);
-    _check(_c_chr3d_run_ensemble(ptr($job), 1, ptr($p), ptr($prog), $nst, ptr($res)), "chr3d_run_ensemble");
-    my @tail = unpack("Q6 q d", $res);
-    $r{n_restraints} = $tail[6]; $r{device_ms} = $tail[7];
-    return \%r;
+    my ($r) = run_ensembles([\%a], $a{params});
+    return $r;
 }
 sub assess_rows {
     my ($xyz_model, $N, $ri, $rj, $rd, $nr) = @_;
@@ -166,6 +187,47 @@ sub spearman {
     _check(_c_chr3d_spearman(ptr($IF), $L, ptr($xyz), $m, $range, ptr($rho)), "chr3d_spearman");
     return [unpack("d$m", $rho)];
 }
+
+# ---- SURVEY 8(f) "next" rows: cross-resolution tools and matrix containers ----------------------
+sub reduce_model {      # (packed xyz, N) -> (packed xyz of ceil(N/2) beads, n)
+    my ($xyz, $N) = @_;
+    _load();
+    my $m = int(($N + 1) / 2);
+    my $out = _buf(8 * 3 * $m);
+    _check(_c_chr3d_reduce_model(ptr($xyz), $N, ptr($out)), "chr3d_reduce_model");
+    return ($out, $m);
+}
+sub write_reduced_pdb { _load(); _check(_c_chr3d_write_reduced_pdb($_[0], ptr($_[1]), $_[2]), "chr3d_write_reduced_pdb"); }
+sub model_similarity {  # (xyz_a, n_a, xyz_b, n_b) -> (spearman, rmsd)
+    my ($xa, $na, $xb, $nb) = @_;
+    _load();
+    my ($rho, $rmsd) = (_buf(8), _buf(8));
+    _check(_c_chr3d_model_similarity(ptr($xa), $na, ptr($xb), $nb, ptr($rho), ptr($rmsd)), "chr3d_model_similarity");
+    return (unpack("d", $rho), unpack("d", $rmsd));
+}
+sub read_if_text {      # the library's threaded parser of input/<ID>.txt: (packed doubles, L)
+    my ($path) = @_;
+    _load();
+    my $Lb = _buf(4);
+    _check(_c_chr3d_read_if_text($path, 0, 0, ptr($Lb)), "chr3d_read_if_text");
+    my $L = unpack("l", $Lb);
+    my $buf = _buf(8 * $L * $L);
+    _check(_c_chr3d_read_if_text($path, ptr($buf), $L * $L, ptr($Lb)), "chr3d_read_if_text");
+    return ($buf, $L);
+}
+sub write_if_binary { _load(); _check(_c_chr3d_write_if_binary($_[0], ptr($_[1]), $_[2], $_[3] // 8), "chr3d_write_if_binary"); }
+sub read_if_binary {
+    my ($path) = @_;
+    _load();
+    my $Lb = _buf(4);
+    _check(_c_chr3d_read_if_binary($path, 0, 0, ptr($Lb)), "chr3d_read_if_binary");
+    my $L = unpack("l", $Lb);
+    my $buf = _buf(8 * $L * $L);
+    _check(_c_chr3d_read_if_binary($path, ptr($buf), $L * $L, ptr($Lb)), "chr3d_read_if_binary");
+    return ($buf, $L);
+}
+# shortest decimal text that reads back as the same double (what the similarity.txt writer printed)
+sub shortest { my $v = shift; for my $p (15, 16, 17) { my $s = sprintf("%.${p}g", $v); return $s if $s + 0 == $v; } return sprintf("%.17g", $v); }
 
 # IF matrix text -> (packed doubles, L).  L = token count of the first row (calc_len_IF, C3D:164-179); rows are split on
 # whitespace, which also eats the CR of the CRLF line ends (C3D:119-122).

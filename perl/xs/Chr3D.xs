@@ -209,3 +209,69 @@ chr3d_spearman(IF, L, xyz, n_models, range, rho)
     RETVAL = chr3d_spearman(P(const double*, IF), L, P(const double*, xyz), n_models, range, P(double*, rho));
   OUTPUT:
     RETVAL
+
+int
+chr3d_reduce_model(xyz, N, out_xyz)
+    UV xyz
+    int N
+    UV out_xyz
+  CODE:
+    RETVAL = chr3d_reduce_model(P(const double*, xyz), N, P(double*, out_xyz));
+  OUTPUT:
+    RETVAL
+
+int
+chr3d_write_reduced_pdb(path, xyz, n)
+    const char* path
+    UV xyz
+    int n
+  CODE:
+    RETVAL = chr3d_write_reduced_pdb(path, P(const double*, xyz), n);
+  OUTPUT:
+    RETVAL
+
+int
+chr3d_model_similarity(xyz_a, n_a, xyz_b, n_b, spearman, rmsd)
+    UV xyz_a
+    int n_a
+    UV xyz_b
+    int n_b
+    UV spearman
+    UV rmsd
+  CODE:
+    RETVAL = chr3d_model_similarity(P(const double*, xyz_a), n_a, P(const double*, xyz_b), n_b, P(double*, spearman), P(double*, rmsd));
+  OUTPUT:
+    RETVAL
+
+int
+chr3d_read_if_text(path, out, cap, L)
+    const char* path
+    UV out
+    IV cap
+    UV L
+  CODE:
+    RETVAL = chr3d_read_if_text(path, P(double*, out), (int64_t)cap, P(int32_t*, L));
+  OUTPUT:
+    RETVAL
+
+int
+chr3d_write_if_binary(path, IF, L, elem_bytes)
+    const char* path
+    UV IF
+    int L
+    int elem_bytes
+  CODE:
+    RETVAL = chr3d_write_if_binary(path, P(const double*, IF), L, elem_bytes);
+  OUTPUT:
+    RETVAL
+
+int
+chr3d_read_if_binary(path, out, cap, L)
+    const char* path
+    UV out
+    IV cap
+    UV L
+  CODE:
+    RETVAL = chr3d_read_if_binary(path, P(double*, out), (int64_t)cap, P(int32_t*, L));
+  OUTPUT:
+    RETVAL

@@ -110,3 +110,61 @@ def test_front_end_whole_run_layout_and_parity(tmp_path, golden_dir):
         v, f = ln.split("\t")
         assert v == "%.3f" % orc.spearman(IF, ds.read_ca_pdb(f))[0]
     assert [float(l.split("\t")[0]) for l in lines[1:]] == sorted((float(l.split("\t")[0]) for l in lines[1:]), reverse=True)
+
+
+# ------------------------------------------------------------------------------- SURVEY 8(f) rows through the Perl binding
+def test_perl_reduced_writer_and_text_loader_host_side(tmp_path):
+    """Host-only entry points through the Perl binding: the threaded text parser gives the same bytes as the Perl-side
+    parser, and the reduced-PDB writer reproduces a shipped file from (oracle-averaged) coordinates."""
+    src = os.path.join(ds.shipped_models_dir(), "chr21_500kb_rank04_a11.pdb")
+    red = orc.reduce_model(ds.read_ca_pdb(src))
+    red.tofile(tmp_path / "red.f64")
+    code = ('use Chr3D; my ($a, $L) = Chr3D::read_if_text($ARGV[0]); my ($b, $L2) = Chr3D::read_if_matrix($ARGV[0]);'
+            'open(my $f, "<:raw", $ARGV[1]) or die; local $/; my $x = <$f>; close $f;'
+            'Chr3D::write_reduced_pdb($ARGV[2], $x, length($x) / 24); print "$L $L2 ", ($a eq $b ? "same" : "diff"), "\\n";')
+    r = _perl(["-e", code, ds.input_path("chr22_1mb"), str(tmp_path / "red.f64"), str(tmp_path / "out.pdb")])
+    assert r.returncode == 0, r.stderr
+    L, L2, same = r.stdout.split()
+    assert L == L2 and same == "same"
+    assert open(tmp_path / "out.pdb", "rb").read() == open(src.replace(".pdb", "_reduced.pdb"), "rb").read()
+
+
+@pytest.mark.gpu
+def test_perl_similarity_tool_reproduces_shipped_block(tmp_path):
+    d = ds.shipped_models_dir()
+    r = _perl([os.path.join(PERL, "similarity_pdb.pl"), os.path.join(d, "chr21_1mb_rank07_a11.pdb"), os.path.join(d, "chr21_500kb_rank04_a11.pdb")])
+    assert r.returncode == 0, r.stderr
+    txt = open(os.path.join(d, "similarity.txt")).read().replace("\r", "")
+    m = re.search(r"chr21_500kb_rank04_a11\nSpearman correlation: (\S+)\nRMSD: (\S+)", txt)
+    lines = r.stdout.splitlines()
+    assert lines[0] == "chr21_500kb_rank04_a11"
+    assert abs(float(lines[1].split(": ")[1]) - float(m.group(1))) < 1e-12 and abs(float(lines[2].split(": ")[1]) - float(m.group(2))) < 1e-11
+    r = _perl([os.path.join(PERL, "similarity_pdb.pl"), "--reduce", os.path.join(d, "chr21_500kb_rank04_a11.pdb"), str(tmp_path / "r.pdb")])
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "r.pdb", "rb").read() == open(os.path.join(d, "chr21_500kb_rank04_a11_reduced.pdb"), "rb").read()
+
+
+@pytest.mark.gpu
+def test_alpha_sweep_driver(tmp_path):
+    """Three alphas x four models in one batched call; the selected file follows the shipped naming and layout and its
+    Spearman equals the oracle's on the written coordinates."""
+    out = tmp_path / "sweep"
+    r = _perl([os.path.join(PERL, "chromosome3D_sweep.pl"), "-i", ds.input_path("chr21_1mb"), "-o", str(out), "-m", "4", "--alphas", "0.5,1.1,1.5", "--keep-all"])
+    assert r.returncode == 0, r.stderr + r.stdout
+    rows = [l.split("\t") for l in open(out / "alpha_sweep.txt").read().splitlines() if not l.startswith("#")]
+    assert [row[0] for row in rows] == ["0.5", "1.1", "1.5"]
+    IF = ds.load_if_matrix(ds.input_path("chr21_1mb"))
+    for row in rows:
+        assert int(row[1]) == len(orc.if_to_restraints(IF, float(row[0]))[0])
+    sel = re.search(r"Selected\s+: (\S+)\.pdb", r.stdout).group(1)
+    assert re.fullmatch(r"chr21_1mb_rank\d\d_a(05|11|15)", sel)
+    kept = sorted(f for f in os.listdir(out) if re.fullmatch(r"chr21_1mb_rank\d\d_a\d\d\.pdb", f))
+    assert len(kept) == 3 and sel + ".pdb" in kept
+    xyz = ds.read_ca_pdb(str(out / (sel + ".pdb")))
+    best = min(float(row[3]) for row in rows)
+    assert "%.3f" % orc.spearman(IF, xyz, 3)[0] == "%.3f" % best
+    shipped = open(os.path.join(ds.shipped_models_dir(), "chr21_1mb_rank07_a11.pdb")).read().splitlines()
+    mine = open(out / (sel + ".pdb")).read().splitlines()
+    assert len(mine) == len(shipped) and [l[:30] for l in mine] == [l[:30] for l in shipped]        # same records, same columns
+    red = open(out / (sel + "_reduced.pdb"), "rb").read()
+    assert red.startswith(b"\r\nATOM      1   CA MET B1") and red.endswith(b"END\r\n") and red.count(b"ATOM") == 19
