@@ -443,7 +443,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         }
         tds.swap(sorted);
     }
-    if (e->groups.size() > 1) {
+    if (e->groups.size() > 1 && !getenv("CHR3D_SERIAL_GROUPS")) {      // CHR3D_SERIAL_GROUPS: development switch, one launch after the other
         e->gstreams.resize(e->groups.size()); e->gevents.resize(e->groups.size());
         for (size_t k = 0; k < e->groups.size(); k++) {
             CHR3D_CUDA(cudaStreamCreateWithFlags(&e->gstreams[k], cudaStreamNonBlocking));

@@ -1115,11 +1115,20 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
         if (cudaFuncSetAttribute(sa_pick_kernel(false, th), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
     }
     const int nb = (N + 31) / 32, ntiles = nb * (nb + 1) / 2;
+    // One CTA per SM, enforced by asking for more than half of the SM's shared memory.  CTAs of spin-waiting clusters that
+    // share an SM have hung intermittently on B200 (a peer never completes its force phase and the 10 s watchdog in mbar_wait
+    // traps): seen with 12 x 4-warp clusters in one launch and with concurrent launch groups of 4-warp CTAs; never with one
+    // CTA per SM.  Batches also run faster this way (all 45 inputs x 20 models: 193 ms against 235 ms), because the shapes
+    // the cost model then picks leave fewer, larger launch groups.  CHR3D_SA_MIN_SMEM=0 lifts the floor for experiments.
+    const size_t min_smem = getenv("CHR3D_SA_MIN_SMEM") ? (size_t)atol(getenv("CHR3D_SA_MIN_SMEM")) : (size_t)117 * 1024;
     double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0};
     const int Cs[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16};     // > 8: non-portable cluster sizes, two CTAs of different trajectories per SM
     for (int C : Cs) {
         if (force_c && C != force_c) continue;
         if (C > nb && C > 1) continue;
+        // Non-portable cluster sizes (> 8) only on request (CHR3D_SA_CLUSTER): with one CTA per SM (see min_smem) they cannot
+        // hold 20 trajectories in one wave, and they have far less test mileage than the portable sizes.
+        if (C > 8 && !force_c) continue;
         for (int W = 4; W <= SA_MAXW; W += 2) {
             if (force_w && W != force_w) continue;
             if (!force_w && (W & 3)) continue;
@@ -1131,18 +1140,22 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
             // resident targets when they fit, otherwise as many rounds as fit (the rest streams from L2)
             size_t want = fixed + (size_t)rounds * W * SA_TILE_FLOATS * sizeof(float);
             size_t smem = want <= (size_t)smem_max ? want : (size_t)smem_max;
+            smem = std::max(smem, std::min(min_smem, (size_t)smem_max));
             int res_rounds = (int)((smem - fixed) / ((size_t)W * SA_TILE_FLOATS * sizeof(float)));
+            if (res_rounds > rounds) res_rounds = rounds;
             int resident = max_active_clusters(C, 32 * W, smem);
             if (resident < 1 && smem > fixed) { smem = fixed; res_rounds = 0; resident = max_active_clusters(C, 32 * W, smem); }
             if (resident < 1) continue;
             const int waves = (n_traj + resident - 1) / resident;
-            // cost model per force evaluation (SM cycles), fitted to the B200 sweep of scripts/sa_sweep.sh:
-            // pair phase = tiles of the busiest scheduler x ~1150 issue slots, stretched when few warps hide latency;
-            // fixed part = owner phases, reductions, barriers (grows with the warps that meet at them)
+            // cost model per force evaluation (SM cycles), fitted to B200 measurements of the packed-math kernel
+            // (chr1_500kb: 6x12 warps 14.1k cycles, 3x12 23.0k, 3x8 23.1k, 2x12 29.2k per evaluation):
+            // pair phase = tiles of the busiest scheduler x ~1330 issue slots, stretched when few warps hide latency;
+            // fixed part = owner phases, reductions, exchanges (grows with the warps that meet at them)
             const double wps = W / 4.0;
-            const double tile_cycles = 1150.0 * (1.0 + 1.0 / wps) + (rounds > res_rounds ? 300.0 * (rounds - res_rounds) / rounds : 0.0);
+            const double spill = W > 16 ? 1.6 : (W > 12 ? 1.35 : 1.0);     // register cap of the wider variants: the pair loop spills
+            const double tile_cycles = spill * 1330.0 * (1.0 + 1.0 / wps) + (rounds > res_rounds ? 300.0 * (rounds - res_rounds) / rounds : 0.0);
             const double pair_cycles = tiles_per_scheduler(ntiles, C, W) * tile_cycles;
-            const double over = 9000.0 + 150.0 * W + (C > 1 ? 2500.0 : 0.0);
+            const double over = 3000.0 + 100.0 * W + (C > 1 ? 1000.0 : 0.0);
             const double cost = waves * (pair_cycles + over);
             if (cost < best) { best = cost; bc.cluster = C; bc.threads = 32 * W; bc.stage_targets = res_rounds; bc.smem = smem; }
         }

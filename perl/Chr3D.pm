@@ -176,9 +176,9 @@ sub rank_models {
     return [unpack("l$m", $o)];
 }
 sub write_pdb {
-    my ($path, $xyz_model, $N, $e4, $with_conect) = @_;
+    my ($path, $xyz_model, $N, $e4, $with_conect, $resnames) = @_;     # resnames: 3*N characters, default = the reference sequence (C3D:93-98)
     _load();
-    _check(_c_chr3d_write_pdb($path, ptr($xyz_model), $N, defined $e4 ? ptr($e4) : 0, 0, $with_conect ? 1 : 0), "chr3d_write_pdb");
+    _check(_c_chr3d_write_pdb($path, ptr($xyz_model), $N, defined $e4 ? ptr($e4) : 0, defined $resnames ? ptr($resnames) : 0, $with_conect ? 1 : 0), "chr3d_write_pdb");
 }
 sub spearman {
     my ($IF, $L, $xyz, $m, $range) = @_;

@@ -42,6 +42,7 @@ my $t0 = time;
 my @res = Chr3D::run_ensembles(\@jobs);
 printf "Annealed   : %d trajectories (%s, binding %s), device time %.1f ms\n", $m * @alpha, Chr3D::version(), Chr3D::backend(), $res[0]{device_ms};
 
+my $MET = "MET" x $L;      # the shipped rankNN_aXX.pdb files name every residue MET
 open(my $tab, ">", "$dir_out/alpha_sweep.txt") or die $!;
 print $tab "#alpha\trestraints\tbest_noe\tbest_srcc\tmedian_srcc\tpicked_model\tpicked_rank\n";
 my ($best, $xyz_bytes) = (undef, 8 * 3 * $L);
@@ -57,14 +58,14 @@ for my $ai (0 .. $#alpha) {
     printf $tab "%.1f\t%d\t%d\t%.3f\t%.3f\t%d\t%d\n", $alpha[$ai], $r->{n_restraints}, int($e[4 * $order[0] + 3]), $rho[$pick], $median, $pick + 1, $rank_of{$pick};
     if ($keep_all) {
         my $name = sprintf("%s_rank%02d_a%02d", $ID, $rank_of{$pick}, int($alpha[$ai] * 10 + 0.5));
-        Chr3D::write_pdb("$dir_out/$name.pdb", substr($r->{xyz}, $pick * $xyz_bytes, $xyz_bytes), $L, undef, 1);
+        Chr3D::write_pdb("$dir_out/$name.pdb", substr($r->{xyz}, $pick * $xyz_bytes, $xyz_bytes), $L, undef, 1, $MET);
     }
     $best = { a => $ai, k => $pick, rho => $rho[$pick], rank => $rank_of{$pick} } if !defined $best || $rho[$pick] < $best->{rho};
 }
 close $tab;
 my $name = sprintf("%s_rank%02d_a%02d", $ID, $best->{rank}, int($alpha[$best->{a}] * 10 + 0.5));
 my $xyz = substr($res[$best->{a}]{xyz}, $best->{k} * $xyz_bytes, $xyz_bytes);
-Chr3D::write_pdb("$dir_out/$name.pdb", $xyz, $L, undef, 1);
+Chr3D::write_pdb("$dir_out/$name.pdb", $xyz, $L, undef, 1, $MET);
 my ($red, $nred) = Chr3D::reduce_model($xyz, $L);
 Chr3D::write_reduced_pdb("$dir_out/${name}_reduced.pdb", $red, $nred);
 printf "Selected   : %s.pdb  (alpha %.1f, model %d, energy rank %d, SRCC %.3f)  [%d s]\n", $name, $alpha[$best->{a}], $best->{k} + 1, $best->{rank}, $best->{rho}, time - $t0;
