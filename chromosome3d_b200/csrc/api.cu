@@ -141,12 +141,16 @@ struct JobDev {
     DevBuf<int> hand, sat;
     DevBuf<int32_t> ri, rj; DevBuf<double> rd;
     SaLaunchCfg cfg;
+    // split run (see ensemble_create): the two hot-MD images of every model anneal side by side as trajectories of their own
+    // (launch shape cfg_img), a third trajectory resumes at PICK with the shape cfg
+    bool split = false; SaLaunchCfg cfg_img;
+    DevBuf<float> st_img; DevBuf<double> esaved; DevBuf<long long> nev_a, nev_b; DevBuf<int> hand_tmp;
     int traj0 = 0;
     chr3d_single* big = nullptr;      // structures beyond the cluster kernel's capacity run on the tile-streaming engine
     bool has_x0 = false;
     ~JobDev();
 };
-struct LaunchGroup { SaLaunchCfg cfg; int traj0, n_traj, Nmax; };
+struct LaunchGroup { SaLaunchCfg cfg; int traj0, n_traj, Nmax, phase; };
 
 JobDev::~JobDev() { if (big) chr3d_single_destroy(big); }
 
@@ -171,11 +175,11 @@ struct chr3d_ensemble {
     DevParams P;
     int nstages = 0, n_traj = 0, n_launches = 0;
     long long rows_total = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evmid = nullptr;
     std::vector<cudaStream_t> gstreams; std::vector<cudaEvent_t> gevents;
     bool ran = false;
     ~chr3d_ensemble() {
-        if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
+        if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (evmid) cudaEventDestroy(evmid);
         for (cudaEvent_t ev : gevents) if (ev) cudaEventDestroy(ev);
         for (cudaStream_t st : gstreams) if (st) cudaStreamDestroy(st);
     }
@@ -352,6 +356,17 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
     CHR3D_CUDA(cudaMemcpy(e->prog.p, hs.data(), sizeof(DevStage) * nstages, cudaMemcpyHostToDevice));
     std::vector<TrajDesc> tds;
     if (fbufs) { std::vector<DevBuf<float>> t(njobs); fbufs->swap(t); }
+    // The two images of a model (INIT(+1) .. SAVE, INIT(-1) .. PICK; C3D:1605-1727) do not interact before PICK.  When few
+    // trajectories share the GPU, running them side by side on smaller clusters beats running them one after the other on
+    // large ones (20 models of 455 beads: 2 x 7.2 us per pair of evaluations on 6-CTA clusters, 11.7 us on 3-CTA clusters).
+    int i_save = -1, i_pick = -1, n_init = 0, n_save = 0, n_pick = 0;
+    for (int k = 0; k < nstages; k++) {
+        if (program[k].op == CHR3D_OP_INIT) n_init++;
+        if (program[k].op == CHR3D_OP_SAVE) { n_save++; i_save = k; }
+        if (program[k].op == CHR3D_OP_PICK) { n_pick++; i_pick = k; }
+    }
+    const bool split_ok = !want_forces && !getenv("CHR3D_NO_SPLIT") && n_init == 2 && n_save == 1 && n_pick == 1 && program[0].op == CHR3D_OP_INIT &&
+                          i_save + 1 < i_pick && program[i_save + 1].op == CHR3D_OP_INIT;
     int total_traj = 0;                       // the launch shape of every job is chosen for the whole batch sharing the GPU
     for (int jn = 0; jn < njobs; jn++) total_traj += std::max(jobs[jn].n_models, 0);
     for (int jn = 0; jn < njobs; jn++) {
@@ -404,44 +419,69 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             e->jobs.push_back(std::move(jd));
             continue;
         }
-        jd->traj0 = (int)tds.size();          // (position in creation order; the launch order is decided below)
-        for (int m = 0; m < jb.n_models; m++) {
-            TrajDesc td; memset(&td, 0, sizeof td);
-            td.T = jd->Tt.p; td.x0 = jd->x0.p + (size_t)m * N * 3; td.x_out = jd->xout.p + (size_t)m * N * 3;
-            td.f_out = want_forces ? (*fbufs)[jn].p + (size_t)m * N * 3 : nullptr;
-            td.scratch = jd->scratch.p + (size_t)m * N * 6; td.e_out = jd->e.p + 4 * m; td.nevals_out = jd->nev.p + m;
-            td.hand_out = jd->hand.p + m; td.N = N; td.pitch = pitch; td.model = m; td.seed = jd->seed;
-            tds.push_back(td);
+        if (split_ok) {
+            SaLaunchCfg c2;
+            if (sa_choose_config(N, 2 * total_traj, e->P.m, &c2) == 0 && c2.cost < 1.9 * jd->cfg.cost) {
+                jd->split = true; jd->cfg_img = c2;
+                CHR3D_CUDA(jd->st_img.alloc(2 * nx)); CHR3D_CUDA(jd->esaved.alloc(jb.n_models)); CHR3D_CUDA(jd->nev_a.alloc(jb.n_models));
+                CHR3D_CUDA(jd->nev_b.alloc(jb.n_models)); CHR3D_CUDA(jd->hand_tmp.alloc(2 * (size_t)jb.n_models));
+            }
         }
         e->jobs.push_back(std::move(jd));
     }
-    // launch order: jobs grouped by launch shape, larger structures first inside a group (they finish last otherwise);
-    // one launch per group, groups run concurrently on their own streams
+    // Launch units: (job, phase).  Phase 1 holds whole trajectories of unsplit jobs and the two image trajectories of split
+    // jobs; phase 2 (after all of phase 1) holds the trajectories that resume at PICK.  Inside a phase units are grouped by
+    // launch shape, larger structures first (they finish last otherwise); one launch per group, groups of a phase run
+    // concurrently on their own streams.
     {
-        std::vector<int> order(e->jobs.size());
-        for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            const JobDev& x = *e->jobs[a]; const JobDev& y = *e->jobs[b];
+        struct Unit { int job, phase; SaLaunchCfg cfg; int L; std::vector<TrajDesc> t; };
+        std::vector<Unit> units;
+        for (size_t jn = 0; jn < e->jobs.size(); jn++) {
+            JobDev& jd = *e->jobs[jn];
+            if (jd.big) continue;
+            const int N = jd.L, pitch = target_pitch(N);
+            auto base = [&](int m) {
+                TrajDesc td; memset(&td, 0, sizeof td);
+                td.T = jd.Tt.p; td.x0 = jd.x0.p + (size_t)m * N * 3; td.x_out = jd.xout.p + (size_t)m * N * 3;
+                td.f_out = want_forces ? (*fbufs)[jn].p + (size_t)m * N * 3 : nullptr;
+                td.scratch = jd.scratch.p + (size_t)m * N * 6; td.e_out = jd.e.p + 4 * m; td.nevals_out = jd.nev.p + m;
+                td.hand_out = jd.hand.p + m; td.N = N; td.pitch = pitch; td.model = m; td.seed = jd.seed;
+                return td;
+            };
+            Unit u1; u1.job = (int)jn; u1.phase = 1; u1.L = N; u1.cfg = jd.split ? jd.cfg_img : jd.cfg;
+            Unit u2; u2.job = (int)jn; u2.phase = 2; u2.L = N; u2.cfg = jd.cfg;
+            for (int m = 0; m < jd.n_models; m++) {
+                if (!jd.split) { u1.t.push_back(base(m)); continue; }
+                float* st = jd.st_img.p + (size_t)m * N * 6;
+                TrajDesc a = base(m);          // image +1: INIT .. SAVE (x, v -> scratch, energy -> esaved)
+                a.k0 = 0; a.k1 = i_save + 1; a.x_out = a.scratch; a.esaved_out = jd.esaved.p + m; a.nevals_out = jd.nev_a.p + m; a.hand_out = jd.hand_tmp.p + 2 * m;
+                TrajDesc b = base(m);          // image -1: INIT .. last hot DYNAMICS (x, v -> st)
+                b.k0 = i_save + 1; b.k1 = i_pick; b.x_out = st; b.state_out = st; b.nevals_out = jd.nev_b.p + m; b.hand_out = jd.hand_tmp.p + 2 * m + 1;
+                TrajDesc c = base(m);          // PICK .. ENERGY, starting from image -1's end state
+                c.k0 = i_pick; c.k1 = nstages; c.state_in = st; c.resume_image = program[i_save + 1].flag; c.esaved_in = jd.esaved.p + m;
+                u1.t.push_back(a); u1.t.push_back(b); u2.t.push_back(c);
+            }
+            units.push_back(std::move(u1));
+            if (jd.split) units.push_back(std::move(u2));
+        }
+        std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) {
+            if (x.phase != y.phase) return x.phase < y.phase;
             if (x.cfg.cluster != y.cfg.cluster) return x.cfg.cluster > y.cfg.cluster;
             if (x.cfg.threads != y.cfg.threads) return x.cfg.threads > y.cfg.threads;
             return x.L > y.L;
         });
-        std::vector<TrajDesc> sorted; sorted.reserve(tds.size());
-        for (int jn : order) {
-            JobDev& jd = *e->jobs[jn];
-            if (jd.big) continue;
-            const int pos = (int)sorted.size();
-            for (int m = 0; m < jd.n_models; m++) sorted.push_back(tds[jd.traj0 + m]);
+        for (const Unit& u : units) {
+            const int pos = (int)tds.size();
+            tds.insert(tds.end(), u.t.begin(), u.t.end());
             if (!e->groups.empty()) {
                 LaunchGroup& g = e->groups.back();
-                if (g.cfg.cluster == jd.cfg.cluster && g.cfg.threads == jd.cfg.threads) {
-                    g.n_traj += jd.n_models; g.cfg.smem = std::max(g.cfg.smem, jd.cfg.smem); g.Nmax = std::max(g.Nmax, jd.L); continue;
+                if (g.phase == u.phase && g.cfg.cluster == u.cfg.cluster && g.cfg.threads == u.cfg.threads) {
+                    g.n_traj += (int)u.t.size(); g.cfg.smem = std::max(g.cfg.smem, u.cfg.smem); g.Nmax = std::max(g.Nmax, u.L); continue;
                 }
             }
-            LaunchGroup g; g.cfg = jd.cfg; g.traj0 = pos; g.n_traj = jd.n_models; g.Nmax = jd.L;
+            LaunchGroup g; g.cfg = u.cfg; g.traj0 = pos; g.n_traj = (int)u.t.size(); g.Nmax = u.L; g.phase = u.phase;
             e->groups.push_back(g);
         }
-        tds.swap(sorted);
     }
     if (e->groups.size() > 1 && !getenv("CHR3D_SERIAL_GROUPS")) {      // CHR3D_SERIAL_GROUPS: development switch, one launch after the other
         e->gstreams.resize(e->groups.size()); e->gevents.resize(e->groups.size());
@@ -449,6 +489,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             CHR3D_CUDA(cudaStreamCreateWithFlags(&e->gstreams[k], cudaStreamNonBlocking));
             CHR3D_CUDA(cudaEventCreateWithFlags(&e->gevents[k], cudaEventDisableTiming));
         }
+        CHR3D_CUDA(cudaEventCreateWithFlags(&e->evmid, cudaEventDisableTiming));
     }
     e->n_traj = (int)tds.size();
     CHR3D_CUDA(e->traj.alloc(std::max<size_t>(tds.size(), 1)));
@@ -470,10 +511,12 @@ CHR3D_API int chr3d_ensemble_run(chr3d_ensemble* e, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     e->n_launches = 0;
     CHR3D_CUDA(cudaEventRecord(e->ev0, s));
+    bool mid_recorded = false;
     for (size_t k = 0; k < e->groups.size(); k++) {
         const LaunchGroup& g = e->groups[k];
         cudaStream_t gs = e->gstreams.empty() ? s : e->gstreams[k];
-        if (gs != s) CHR3D_CUDA(cudaStreamWaitEvent(gs, e->ev0, 0));
+        if (g.phase == 2 && !mid_recorded && gs != s) { CHR3D_CUDA(cudaEventRecord(e->evmid, s)); mid_recorded = true; }   // s has joined every phase-1 group
+        if (gs != s) CHR3D_CUDA(cudaStreamWaitEvent(gs, g.phase == 2 ? e->evmid : e->ev0, 0));
         if (int rc = sa_launch(e->traj.p + g.traj0, g.n_traj, g.Nmax, e->P, e->prog.p, e->nstages, g.cfg, gs)) return rc;
         if (gs != s) { CHR3D_CUDA(cudaEventRecord(e->gevents[k], gs)); CHR3D_CUDA(cudaStreamWaitEvent(s, e->gevents[k], 0)); }
         e->n_launches++;
@@ -511,7 +554,15 @@ CHR3D_API int chr3d_ensemble_fetch(chr3d_ensemble* e, chr3d_result* results) {
         }
         if (r.xyz) CHR3D_CUDA(cudaMemcpy(r.xyz, jd.xyz_d.p, sizeof(double) * nx, cudaMemcpyDeviceToHost));
         if (r.energies) CHR3D_CUDA(cudaMemcpy(r.energies, jd.e.p, sizeof(double) * 4 * jd.n_models, cudaMemcpyDeviceToHost));
-        if (r.force_evals) CHR3D_CUDA(cudaMemcpy(r.force_evals, jd.nev.p, sizeof(long long) * jd.n_models, cudaMemcpyDeviceToHost));
+        if (r.force_evals) {
+            CHR3D_CUDA(cudaMemcpy(r.force_evals, jd.nev.p, sizeof(long long) * jd.n_models, cudaMemcpyDeviceToHost));
+            if (jd.split) {       // evaluations of the two image trajectories belong to the model as well
+                std::vector<long long> a(jd.n_models), b(jd.n_models);
+                CHR3D_CUDA(cudaMemcpy(a.data(), jd.nev_a.p, sizeof(long long) * jd.n_models, cudaMemcpyDeviceToHost));
+                CHR3D_CUDA(cudaMemcpy(b.data(), jd.nev_b.p, sizeof(long long) * jd.n_models, cudaMemcpyDeviceToHost));
+                for (int m = 0; m < jd.n_models; m++) r.force_evals[m] += a[m] + b[m];
+            }
+        }
         if (r.hand) CHR3D_CUDA(cudaMemcpy(r.hand, jd.hand.p, sizeof(int32_t) * jd.n_models, cudaMemcpyDeviceToHost));
         r.n_restraints = jd.nr; r.device_ms = ms;
         tr.lap("assess+d2h");

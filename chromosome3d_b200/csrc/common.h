@@ -107,8 +107,17 @@ struct TrajDesc {
     int*    hand_out;      // 1
     int     N, pitch, model, pad_;
     unsigned long long seed;
+    // stage range [k0, k1) of the program this trajectory executes (k1 == 0: the whole program).  The two hot-MD images of
+    // a model (C3D:1605-1708) are independent until PICK, so the host may run them as two trajectories side by side
+    // and let a third one resume at PICK:
+    int     k0, k1;
+    int     resume_image, pad2_;      // image sign of the state in state_in (the trajectory that resumes at PICK)
+    const float*  state_in;           // != nullptr: start from these 6N floats (x then v) instead of an INIT op
+    float*        state_out;          // != nullptr: x and v at the end of the range (6N floats)
+    const double* esaved_in;          // energy of the SAVE slot, for the resumed PICK
+    double*       esaved_out;         // != nullptr: the energy SAVE recorded
 };
-struct SaLaunchCfg { int cluster; int threads; int stage_targets; size_t smem; };   // stage_targets: resident tile rounds
+struct SaLaunchCfg { int cluster; int threads; int stage_targets; size_t smem; double cost; };   // stage_targets: resident tile rounds; cost: modelled cycles per force evaluation of the whole batch
 // dense [N][pitch] targets -> 32x32 tile-packed lane-major layout of the SA kernel
 int sa_pack_tiles(const float* d_T, int N, int pitch, float* d_Tt, cudaStream_t s);
 size_t sa_tiles_floats(int N);

@@ -42,7 +42,7 @@ namespace chr3d {
 #define SA_KTOT 64           // scalars per all-reduce (owner columns)
 #define SA_MAXW 20           // warps per CTA (kernel variants for <= 16 and <= 20 warps)
 #define SA_TILE_FLOATS 1024  // 32x32 micro-tile
-#define SA_GEO_BYTES 256     // SaGeo (first 128 bytes) and the trajectory descriptor (next 128) at the start of shared memory
+#define SA_GEO_BYTES 384     // SaGeo (first 128 bytes) and the trajectory descriptor (next 256) at the start of shared memory
 #define SA_MAX_STAGES 160    // stage-program entries kept in shared memory (the dgsa.inp program has 113)
 #define SA_MAXB (2 * CHR3D_LBFGS_MAX_M + 1)
 
@@ -207,6 +207,7 @@ struct SaGeo {
 };
 #define SGEO (*(const SaGeo*)sa_smem)
 #define STD (*(const TrajDesc*)(sa_smem + 128))
+static_assert(sizeof(SaGeo) <= 128 && sizeof(TrajDesc) <= SA_GEO_BYTES - 128, "SaGeo / TrajDesc outgrew their shared-memory slots");
 
 // Development aid (-DSA_TIMING): SM-clock cycles spent in the phases of a force evaluation, summed over all
 // evaluations, for the first owner warp and the last warp of cluster rank 0 of trajectory 0.
@@ -977,7 +978,15 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
 
     int cur_image = 1, hand = 1;
     double e_saved = 0.0;
-    for (int k = 0; k < nstages; k++) {
+    const int k_begin = STD.k1 > 0 ? STD.k0 : 0, k_end = STD.k1 > 0 ? STD.k1 : nstages;
+    if (STD.state_in) {            // resume: the other image's end state becomes the current one (as after its last DYNAMICS op)
+        if (c.row_ok) for (int q = 0; q < 3; q++) { c.x[q] = STD.state_in[3 * c.row + q]; c.v[q] = STD.state_in[3 * (SGEO.N + c.row) + q]; }
+        cur_image = STD.resume_image; hand = cur_image;
+        if (STD.esaved_in) e_saved = *STD.esaved_in;
+        csync(c);
+        install_x(c);
+    }
+    for (int k = k_begin; k < k_end; k++) {
         const DevStage& st = S_PROG(c)[k];
         OpState os;
         os.phase = 0; os.step = 0; os.cnt = 0; os.head = 0; os.it = 0; os.ls = 0; os.want_e = true; os.count = true;
@@ -1044,8 +1053,10 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
         }
     }
     if (c.row_ok) for (int q = 0; q < 3; q++) STD.x_out[3 * c.row + q] = c.x[q];
+    if (STD.state_out && c.row_ok) for (int q = 0; q < 3; q++) { STD.state_out[3 * c.row + q] = c.x[q]; STD.state_out[3 * (SGEO.N + c.row) + q] = c.v[q]; }
     if (c.rank == 0 && c.tid == 0) {
         *STD.nevals_out = c.nevals; *STD.hand_out = hand;
+        if (STD.esaved_out) *STD.esaved_out = e_saved;
     }
 #ifdef SA_TIMING
     if (c.tmark) for (int q = 0; q < 10; q++) sa_dbg[c.warp == 0 ? 0 : 1][q] = (unsigned long long)c.tacc[q];
@@ -1121,7 +1132,7 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
     // CTA per SM.  Batches also run faster this way (all 45 inputs x 20 models: 193 ms against 235 ms), because the shapes
     // the cost model then picks leave fewer, larger launch groups.  CHR3D_SA_MIN_SMEM=0 lifts the floor for experiments.
     const size_t min_smem = getenv("CHR3D_SA_MIN_SMEM") ? (size_t)atol(getenv("CHR3D_SA_MIN_SMEM")) : (size_t)117 * 1024;
-    double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0};
+    double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0, 0.0};
     const int Cs[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16};     // > 8: non-portable cluster sizes, two CTAs of different trajectories per SM
     for (int C : Cs) {
         if (force_c && C != force_c) continue;
@@ -1157,7 +1168,7 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
             const double pair_cycles = tiles_per_scheduler(ntiles, C, W) * tile_cycles;
             const double over = 3000.0 + 100.0 * W + (C > 1 ? 1000.0 : 0.0);
             const double cost = waves * (pair_cycles + over);
-            if (cost < best) { best = cost; bc.cluster = C; bc.threads = 32 * W; bc.stage_targets = res_rounds; bc.smem = smem; }
+            if (cost < best) { best = cost; bc.cluster = C; bc.threads = 32 * W; bc.stage_targets = res_rounds; bc.smem = smem; bc.cost = cost; }
         }
     }
     if (best >= 1e300) { set_error("no SA kernel configuration fits N=%d (use the single-structure engine)", N); return CHR3D_ERR_SIZE; }
