@@ -374,6 +374,19 @@ def if_from_coo(bi, bj, v, L, base=0):
     return out
 
 
+def dg_embed(ri, rj, rd, N, n_models=1, seed=0, p=None):
+    """DG stage of dgsa.inp (C3D:1470-1526) at bead level: starting coordinates (n_models, N, 3) by metric-matrix
+    embedding of the smoothed bounds; also returns the eigenvalues used and the number of triangle-inconsistent pairs.
+    Pass the coordinates as Job(x0=...) to anneal from them."""
+    ri, rj, rd = _list(ri, rj, rd)
+    p = p or default_params()
+    xyz = np.zeros((n_models, N, 3))
+    eig = np.zeros((n_models, 3))
+    bad = C.c_int64(0)
+    _check(lib().chr3d_dg_embed(_i(ri), _i(rj), _d(rd), C.c_int64(len(ri)), N, C.byref(p), n_models, C.c_uint64(seed), _d(xyz), _d(eig), C.byref(bad)))
+    return xyz, eig, bad.value
+
+
 # ---------------------------------------------------------------------------------- one large structure
 def nccl_unique_id():
     """128-byte NCCL unique id (rank 0 creates it, the caller broadcasts it, e.g. over torch.distributed)."""

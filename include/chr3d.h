@@ -271,6 +271,12 @@ int chr3d_read_if_binary(const char* path, double* out, int64_t cap, int32_t* L)
 /* sparse (bin_i, bin_j, value) triplets, base 0 or 1, -> dense symmetric L*L matrix (device scatter; repeats add up)        */
 int chr3d_if_from_coo(const int32_t* bi, const int32_t* bj, const double* v, int64_t nnz, int32_t L, int32_t base, double* out);
 
+/* DG stage of dgsa.inp (C3D:1470-1526) at bead level: bounds from the restraint table (0-based ri < rj), triangle smoothing,
+ * per-model trial distances, metric-matrix embedding (three largest positive eigenpairs).  xyz_out: n_models*N*3 starting
+ * coordinates — pass them as chr3d_job.x0; eig3_out (n_models*3) and n_inconsistent are optional diagnostics.  N <= 1600.   */
+int chr3d_dg_embed(const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr, int32_t N, const chr3d_sa_params* p,
+                   int32_t n_models, uint64_t seed, double* xyz_out, double* eig3_out, int64_t* n_inconsistent);
+
 #ifdef __cplusplus
 }
 #endif

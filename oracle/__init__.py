@@ -206,3 +206,19 @@ def model_similarity(xa, xb):
     rho, rmsd = C.c_double(0), C.c_double(0)
     lib().orc_model_similarity(_d(xa), xa.shape[0], _d(xb), xb.shape[0], C.byref(rho), C.byref(rmsd))
     return rho.value, rmsd.value
+
+
+def dg_bounds(N, ri, rj, rd, p):
+    ri, rj, rd = np.ascontiguousarray(ri, dtype=np.int32), np.ascontiguousarray(rj, dtype=np.int32), np.ascontiguousarray(rd, dtype=np.float64)
+    U, L = np.zeros((N, N)), np.zeros((N, N))
+    lib().orc_dg_bounds.restype = C.c_int64
+    bad = lib().orc_dg_bounds(N, _i(ri), _i(rj), _d(rd), C.c_int64(len(ri)), C.byref(p), _d(U), _d(L))
+    return U, L, bad
+
+
+def dg_embed(N, ri, rj, rd, p, seed, n_models):
+    U, L, bad = dg_bounds(N, ri, rj, rd, p)
+    xyz, eig = np.zeros((n_models, N, 3)), np.zeros((n_models, 3))
+    for m in range(n_models):
+        lib().orc_dg_embed_model(N, _d(U), _d(L), C.c_uint64(seed), m, _d(xyz[m]), _d(eig[m]))
+    return xyz, eig, bad

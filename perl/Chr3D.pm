@@ -35,6 +35,7 @@ my %SIG = (    # name => [ret, args] in FFI::Platypus type names (pointers = opa
     chr3d_rank_models      => ['int',    ['opaque', 'sint32', 'opaque']],
     chr3d_write_pdb        => ['int',    ['string', 'opaque', 'sint32', 'opaque', 'opaque', 'sint32']],
     chr3d_spearman         => ['int',    ['opaque', 'sint32', 'opaque', 'sint32', 'sint32', 'opaque']],
+    chr3d_dg_embed         => ['int',    ['opaque', 'opaque', 'opaque', 'sint64', 'sint32', 'opaque', 'sint32', 'uint64', 'opaque', 'opaque', 'opaque']],
     chr3d_reduce_model     => ['int',    ['opaque', 'sint32', 'opaque']],
     chr3d_write_reduced_pdb => ['int',   ['string', 'opaque', 'sint32']],
     chr3d_model_similarity => ['int',    ['opaque', 'sint32', 'opaque', 'sint32', 'opaque', 'opaque']],
@@ -137,7 +138,9 @@ sub run_ensembles {
                  satisfied => _buf(4 * $m), sum_dev => _buf(8 * $m));
         push @r, \%r;
         # struct chr3d_job / chr3d_result (include/chr3d.h), x86-64 layout
-        $jobbuf .= pack("Q l l d d Q Q Q q l l Q Q", ptr($a->{IF}), $L, $a->{min_sep} // 5, $a->{alpha}, $a->{K} // 11, 0, 0, 0, 0, $m, 0, $a->{seed} // 0, 0);
+        # x0 (optional): packed doubles n_models*L*3, e.g. from dg_embed(); the scalar must stay alive until the call returns
+        $jobbuf .= pack("Q l l d d Q Q Q q l l Q Q", ptr($a->{IF}), $L, $a->{min_sep} // 5, $a->{alpha}, $a->{K} // 11, 0, 0, 0, 0, $m, 0, $a->{seed} // 0,
+                        defined $a->{x0} ? ptr($a->{x0}) : 0);
         $resbuf .= pack("Q Q Q Q Q Q q d", ptr($r{xyz}), ptr($r{energies}), ptr($r{force_evals}), ptr($r{hand}), ptr($r{satisfied}), ptr($r{sum_dev}), 0, 0.0);
     }
     _check(_c_chr3d_run_ensemble(ptr($jobbuf), scalar(@$jobs), ptr($p), ptr($prog), $nst, ptr($resbuf)), "chr3d_run_ensemble");
@@ -188,7 +191,16 @@ sub spearman {
     return [unpack("d$m", $rho)];
 }
 
-# ---- SURVEY 8(f) "next" rows: cross-resolution tools and matrix containers ----------------------
+# ---- SURVEY 8(f) "next" rows: DG start, cross-resolution tools and matrix containers ------------
+# DG stage of dgsa.inp (C3D:1470-1526) at bead level: (packed xyz of n_models*N*3 doubles, inconsistent-pair count)
+sub dg_embed {
+    my ($ri, $rj, $rd, $nr, $N, $m, $seed, $params) = @_;
+    _load();
+    my $p = $params // default_params();
+    my ($xyz, $eig, $bad) = (_buf(8 * 3 * $N * $m), _buf(8 * 3 * $m), _buf(8));
+    _check(_c_chr3d_dg_embed(ptr($ri), ptr($rj), ptr($rd), $nr, $N, ptr($p), $m, $seed // 0, ptr($xyz), ptr($eig), ptr($bad)), "chr3d_dg_embed");
+    return ($xyz, unpack("q", $bad));
+}
 sub reduce_model {      # (packed xyz, N) -> (packed xyz of ceil(N/2) beads, n)
     my ($xyz, $N) = @_;
     _load();

@@ -22,13 +22,15 @@ use FindBin;
 use lib $FindBin::Bin;
 use Chr3D;
 
-my ($help, $dir_out, $KSCALING, $ALPHA, $mcount, $file_if, $seed, $device, $range);
+my ($help, $dir_out, $KSCALING, $ALPHA, $mcount, $file_if, $seed, $device, $range, $start);
 ($KSCALING, $ALPHA, $mcount) = (11, 0.5, 20);          # C3D:18-21
 my $min_sep  = 5;                                       # $SEPARATION, C3D:20
 my $DISTRELAX = 0.5;                                    # C3D:74
 Getopt::Long::Configure("no_auto_abbrev");
 GetOptions("h" => \$help, "o=s" => \$dir_out, "k=i" => \$KSCALING, "a=s" => \$ALPHA, "m=i" => \$mcount,
-           "i|if=s" => \$file_if, "seed=i" => \$seed, "device=i" => \$device) or usage("bad option");
+           "i|if=s" => \$file_if, "seed=i" => \$seed, "device=i" => \$device, "start=s" => \$start) or usage("bad option");
+$start //= "coil";
+usage("--start must be coil or dg") if $start ne "coil" && $start ne "dg";
 usage("") if $help;
 usage("-i <IF matrix> is required") if !defined $file_if;
 usage("-o <output directory> is required") if !defined $dir_out;
@@ -65,8 +67,13 @@ die "no restraints: nothing to fold\n" if $nr < 1;
 
 # ---- the DGSA run (replaces build_extended/build_models, C3D:234-289) --------------------------
 print "\n(B) Build models using libchr3d dgsa (" . Chr3D::version() . ", binding: " . Chr3D::backend() . ")..\n";
+my $x0;      # --start dg: the DG stage of dgsa.inp (C3D:1470-1526), metric-matrix embedding of the smoothed bounds
+if ($start eq "dg") {
+    ($x0, my $bad) = Chr3D::dg_embed($ri, $rj, $rd, $nr, $L, $mcount, $seed // 0);
+    print "DG start   : embedded $mcount models ($bad pairs with triangle-inconsistent bounds)\n";
+}
 my $res = Chr3D::run_ensemble(IF => $IF, L => $L, alpha => $ALPHA + 0, K => $KSCALING + 0, min_sep => $min_sep,
-                              n_models => $mcount, seed => $seed // 0);
+                              n_models => $mcount, seed => $seed // 0, x0 => $x0);
 my @energies = unpack("d" . (4 * $mcount), $res->{energies});
 my $xyz_bytes = 8 * 3 * $L;
 my @pdb;
@@ -146,6 +153,7 @@ Usage:  $0 -i <IF matrix> -o <output directory> [options]
   -m   number of models to build                           [20]
   -h   this message
   --seed <n>    annealing seed [82364]     --device <n>   CUDA device [0]
+  --start coil|dg   starting coordinates: seeded random coil [default] or distance-geometry embedding (the DG stage of dgsa.inp)
 EOT
     exit 1;
 }

@@ -275,3 +275,22 @@ chr3d_read_if_binary(path, out, cap, L)
     RETVAL = chr3d_read_if_binary(path, P(double*, out), (int64_t)cap, P(int32_t*, L));
   OUTPUT:
     RETVAL
+
+int
+chr3d_dg_embed(ri, rj, rd, nr, N, p, n_models, seed, xyz_out, eig3_out, n_inconsistent)
+    UV ri
+    UV rj
+    UV rd
+    IV nr
+    int N
+    UV p
+    int n_models
+    UV seed
+    UV xyz_out
+    UV eig3_out
+    UV n_inconsistent
+  CODE:
+    RETVAL = chr3d_dg_embed(P(const int32_t*, ri), P(const int32_t*, rj), P(const double*, rd), (int64_t)nr, N, P(const chr3d_sa_params*, p),
+                            n_models, (uint64_t)seed, P(double*, xyz_out), P(double*, eig3_out), P(int64_t*, n_inconsistent));
+  OUTPUT:
+    RETVAL

@@ -131,3 +131,70 @@ def test_gpu_coo_scatter(gpu_api):
     with pytest.raises(gpu_api.Chr3dError):
         gpu_api.if_from_coo([0], [L], [1.0], L)
     assert np.array_equal(gpu_api.if_from_coo([], [], [], 4), np.zeros((4, 4)))
+
+
+# ------------------------------------------------------------------------------------------ DG embedding (8(f) rank 1)
+def _exact_case():
+    X = ds.read_ca_pdb(os.path.join(ds.shipped_models_dir(), "chr21_1mb_rank07_a11.pdb"))
+    iu = np.triu_indices(len(X), 1)
+    return X, iu[0].astype(np.int32), iu[1].astype(np.int32), np.linalg.norm(X[iu[0]] - X[iu[1]], axis=1)
+
+
+def test_oracle_dg_recovers_a_consistent_structure():
+    """Metric data (all pair distances of a real model): no inconsistent pair, rank-3 metric matrix, every distance back to 1e-10;
+    the eigenvalues equal those of the double-centred squared-distance matrix."""
+    X, ri, rj, rd = _exact_case()
+    xyz, eig, bad = orc.dg_embed(len(X), ri, rj, rd, orc.default_params(), 7, 2)
+    assert bad == 0
+    D0 = np.linalg.norm(X[:, None] - X[None], axis=2)
+    for m in range(2):
+        D = np.linalg.norm(xyz[m][:, None] - xyz[m][None], axis=2)
+        assert np.abs(D - D0).max() < 1e-10
+    n = len(X)
+    J = np.eye(n) - 1.0 / n
+    w = np.linalg.eigvalsh(-0.5 * J @ (D0 ** 2) @ J)[::-1][:3]
+    assert np.allclose(eig[0], w, rtol=1e-10)
+
+
+def test_oracle_dg_on_hic_bounds():
+    """Hi-C targets are not metric: smoothing shortens upper bounds, the lower pass meets them; the embedded start already
+    correlates with the IF matrix far better than a random coil does."""
+    IF = ds.load_if_matrix(ds.input_path("chr21_500kb"))
+    N = IF.shape[0]
+    ri, rj, rd = orc.if_to_restraints(IF, 1.1)
+    p = orc.default_params()
+    U, L, bad = orc.dg_bounds(N, ri, rj, rd, p)
+    assert bad > 0 and np.all(L <= U + 1e-12) and np.allclose(U, U.T) and np.all(np.diag(U) == 0)
+    assert np.all(U[ri, rj] <= rd + 1e-12)                       # shortest paths never exceed the direct target
+    k = np.arange(N - 1)
+    assert np.all(U[k, k + 1] <= p.bond_r0 + 1e-12)
+    xyz, eig, _ = orc.dg_embed(N, ri, rj, rd, p, 82364, 1)
+    assert eig[0, 0] >= eig[0, 1] >= eig[0, 2] > 0
+    assert orc.spearman(IF, xyz[0], 3)[0] < orc.spearman(IF, orc.random_coil(N, 3.8, 82364, 0), 3)[0] - 0.1
+
+
+@pytest.mark.gpu
+def test_gpu_dg_embed_bit_identical_to_oracle(gpu_api):
+    X, ri, rj, rd = _exact_case()
+    xyz, eig, bad = gpu_api.dg_embed(ri, rj, rd, len(X), n_models=2, seed=7)
+    oxyz, oeig, obad = orc.dg_embed(len(X), ri, rj, rd, orc.default_params(), 7, 2)
+    assert bad == obad == 0 and np.array_equal(eig, oeig) and np.array_equal(xyz, oxyz)
+    for name, alpha in (("chr21_500kb", 1.1), ("chr22_1mb", 0.5), ("chr1_1mb", 1.1)):
+        IF = ds.load_if_matrix(ds.input_path(name))
+        ri, rj, rd = orc.if_to_restraints(IF, alpha)
+        xyz, eig, bad = gpu_api.dg_embed(ri, rj, rd, IF.shape[0], n_models=3, seed=82364)
+        oxyz, oeig, obad = orc.dg_embed(IF.shape[0], ri, rj, rd, orc.default_params(), 82364, 3)
+        assert bad == obad and np.array_equal(eig, oeig) and np.array_equal(xyz, oxyz), name
+
+
+@pytest.mark.gpu
+def test_gpu_annealing_from_dg_start(gpu_api):
+    """The embedded coordinates feed the annealer through Job.x0; the ensemble ends at least as well (IF-Spearman) as from coils."""
+    IF = ds.load_if_matrix(ds.input_path("chr21_500kb"))
+    N = IF.shape[0]
+    ri, rj, rd = gpu_api.if_to_restraints(IF, 1.1)
+    x0, _, _ = gpu_api.dg_embed(ri, rj, rd, N, n_models=6, seed=82364)
+    a = gpu_api.build_models([gpu_api.Job(IF=IF, alpha=1.1, n_models=6, seed=82364, x0=x0)])[0]
+    b = gpu_api.build_models([gpu_api.Job(IF=IF, alpha=1.1, n_models=6, seed=82364)])[0]
+    ra, rb = np.median(gpu_api.spearman_IF_pdb(IF, a.xyz, 3)), np.median(gpu_api.spearman_IF_pdb(IF, b.xyz, 3))
+    assert np.all(np.isfinite(a.energies)) and ra < rb + 0.02

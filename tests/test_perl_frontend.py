@@ -168,3 +168,16 @@ def test_alpha_sweep_driver(tmp_path):
     assert len(mine) == len(shipped) and [l[:30] for l in mine] == [l[:30] for l in shipped]        # same records, same columns
     red = open(out / (sel + "_reduced.pdb"), "rb").read()
     assert red.startswith(b"\r\nATOM      1   CA MET B1") and red.endswith(b"END\r\n") and red.count(b"ATOM") == 19
+
+
+@pytest.mark.gpu
+def test_front_end_dg_start(tmp_path):
+    """--start dg: the DG stage (C3D:1470-1526) supplies the starting coordinates; the run keeps the reference's layout."""
+    out = tmp_path / "dg"
+    r = _perl([os.path.join(PERL, "chromosome3D.pl"), "-i", ds.input_path("chr21_1mb"), "-o", str(out), "-m", "3", "--start", "dg"])
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert re.search(r"DG start\s+: embedded 3 models \(\d+ pairs", r.stdout)
+    assert all(os.path.exists(out / ("chr21_1mb_matrix_model%d.pdb" % k)) for k in (1, 2, 3))
+    IF = ds.load_if_matrix(ds.input_path("chr21_1mb"))
+    xyz = ds.read_ca_pdb(str(out / "chr21_1mb_matrix_model1.pdb"))
+    assert orc.spearman(IF, xyz, 3)[0] < -0.8
