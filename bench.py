@@ -438,12 +438,14 @@ def main():
                     "ms_per_step": e2e_ms_max, "sa_models_per_sec": models_all / (e2e_ms_max * 1e-3)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
-                         "traffic": prof.get("dram_bytes_per_launch"),
+                         "traffic": (prof.get("dram_bytes_per_launch") or 0) * max(int(info["launches"]), 1) or None,
                          "kernel": "sa_kernel (cluster-per-trajectory SA, 32x32 symmetric micro-tiles, targets resident in shared memory)",
-                         "algorithmic": "%d flop per restraint-pair evaluation x %.4g pair-evals per launch" % (FLOP_PER_PAIR_EVAL, pair_evals_step),
+                         "algorithmic": "%d flop per restraint-pair evaluation x %.4g pair-evals per step (%d sa_kernel launch(es) per step: with few "
+                                        "trajectories the two hot-MD images of a model run as one launch, the part from PICK on as a second; achieved and "
+                                        "traffic are sums over the launches of a step)" % (FLOP_PER_PAIR_EVAL, pair_evals_step, int(info["launches"])),
                          "peak_source": "FP32 FMA micro-benchmark run in this process (chr3d_fp32_peak); MEASURED_PEAKS.json (%s) has no FP32 entry: hbm %.0f GB/s" % (peak_src, peaks.get("hbm_gbs", 0)),
                          "note": "FP32-pipe roofline (targets live in shared memory, ~0 HBM traffic in steady state); with 20 trajectories of 3.7k "
-                                 "sequential force evaluations each the kernel is bound by per-evaluation latency (cluster barriers, owner phases), see DESIGN.md"},
+                                 "sequential force evaluations each the kernel is bound by per-evaluation latency (exchange waits, owner phases), see DESIGN.md"},
             "clocks": sampler.summary(), "wall_s": t_wall,
         }
         if not args.no_large_n and world == 1 and not args.profile:
