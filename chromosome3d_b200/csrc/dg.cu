@@ -50,6 +50,7 @@ __global__ void dg_fw_step_kernel(double* __restrict__ U, int N, int k) {
     const double v = U[(size_t)i * N + k] + U[(size_t)k * N + j];
     if (v < U[(size_t)i * N + j]) U[(size_t)i * N + j] = v;
 }
+// bad[0]: pairs whose lower bound had to be cut down to the upper one; bad[1]: pairs that keep some slack (L < U)
 __global__ void dg_lower_kernel(const double* __restrict__ U, const double* __restrict__ L0, double* __restrict__ L, int N, unsigned long long* __restrict__ bad) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= N || i == j) { if (j < N) L[(size_t)i * N + j] = 0.0; return; }
@@ -61,6 +62,7 @@ __global__ void dg_lower_kernel(const double* __restrict__ U, const double* __re
     }
     const double u = U[(size_t)i * N + j];
     if (l > u) { l = u; if (i < j) atomicAdd(bad, 1ull); }
+    if (l < u && i < j) atomicAdd(bad + 1, 1ull);
     L[(size_t)i * N + j] = l;
 }
 // squared trial distances of one model (symmetric)
@@ -173,8 +175,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_embed_kernel(const double* _
         if (tid == 0) {
             for (int a = 0; a < P; a++) for (int b = a + 1; b < P; b++) { const double m = 0.5 * (H[a * P + b] + H[b * P + a]); H[a * P + b] = H[b * P + a] = m; }
             dg_jacobi(H, Q, P);
+            // converged when the three largest Ritz values (the ones the embedding uses) have settled
+            double top[3] = {-1e300, -1e300, -1e300};
+            for (int c = 0; c < P; c++) { ritz[c] = H[c * P + c]; double v = ritz[c]; for (int q = 0; q < 3; q++) if (v > top[q]) { const double t = top[q]; top[q] = v; v = t; } }
             double chg = 0.0, mag = 0.0;
-            for (int c = 0; c < P; c++) { ritz[c] = H[c * P + c]; chg += fabs(ritz[c] - prev[c]); mag += fabs(ritz[c]); prev[c] = ritz[c]; }
+            for (int q = 0; q < 3 && q < P; q++) { chg += fabs(top[q] - prev[q]); mag += fabs(top[q]); prev[q] = top[q]; }
             if (it > 2 && chg <= 1e-13 * mag) stop = 1;
         }
         __syncthreads();
@@ -213,21 +218,22 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dg_embed_kernel(const double* _
 
 // bounds on the device; n_bad_host: pairs whose lower bound had to be cut down to the upper one (non-metric data)
 int dev_dg_bounds(int N, const int32_t* d_ri, const int32_t* d_rj, const double* d_rd, long long nr, const chr3d_sa_params& p,
-                  double* d_U, double* d_L, long long* n_bad_host, cudaStream_t s) {
+                  double* d_U, double* d_L, long long* n_bad_host, long long* n_slack_host, cudaStream_t s) {
     DevBuf<double> L0; DevBuf<unsigned long long> bad;
     const size_t nn = (size_t)N * N;
-    CHR3D_CUDA(L0.alloc(nn)); CHR3D_CUDA(bad.alloc(1));
-    CHR3D_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(unsigned long long), s));
+    CHR3D_CUDA(L0.alloc(nn)); CHR3D_CUDA(bad.alloc(2));
+    CHR3D_CUDA(cudaMemsetAsync(bad.p, 0, 2 * sizeof(unsigned long long), s));
     dg_init_bounds_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(d_U, L0.p, N, p.bond_r0, p.vdw_rmin * p.cool_rad_finl, p.vdw_min_sep);
     if (nr > 0) dg_scatter_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(d_U, L0.p, N, d_ri, d_rj, d_rd, nr);
     const dim3 grid((unsigned)((N + 127) / 128), (unsigned)N);
     for (int k = 0; k < N; k++) dg_fw_step_kernel<<<grid, 128, 0, s>>>(d_U, N, k);
     dg_lower_kernel<<<grid, 128, 0, s>>>(d_U, L0.p, d_L, N, bad.p);
     CHR3D_CUDA(cudaGetLastError());
-    unsigned long long h = 0;
-    CHR3D_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    unsigned long long h[2] = {0, 0};
+    CHR3D_CUDA(cudaMemcpyAsync(h, bad.p, sizeof h, cudaMemcpyDeviceToHost, s));
     CHR3D_CUDA(cudaStreamSynchronize(s));
-    if (n_bad_host) *n_bad_host = (long long)h;
+    if (n_bad_host) *n_bad_host = (long long)h[0];
+    if (n_slack_host) *n_slack_host = (long long)h[1];
     return 0;
 }
 // coordinates (n_models x N x 3, fp64, device) of the models first_model .. first_model + n_models - 1
@@ -278,9 +284,16 @@ CHR3D_API int chr3d_dg_embed(const int32_t* ri, const int32_t* rj, const double*
         CHR3D_CUDA(cudaMemcpy(dd.p, rd, sizeof(double) * (size_t)nr, cudaMemcpyHostToDevice));
     }
     CHR3D_CUDA(U.alloc(nn)); CHR3D_CUDA(L.alloc(nn)); CHR3D_CUDA(x.alloc((size_t)n_models * N * 3)); CHR3D_CUDA(e3.alloc((size_t)n_models * 3));
-    long long bad = 0;
-    if (int rc = dev_dg_bounds(N, di.p, dj.p, dd.p, nr, *p, U.p, L.p, &bad, 0)) return rc;
-    if (int rc = dev_dg_embed(N, U.p, L.p, seed ? seed : p->seed, 0, n_models, x.p, e3.p, 0)) return rc;
+    long long bad = 0, slack = 0;
+    if (int rc = dev_dg_bounds(N, di.p, dj.p, dd.p, nr, *p, U.p, L.p, &bad, &slack, 0)) return rc;
+    // no pair keeps any slack (the usual case for dense Hi-C tables: the smoothed bounds meet everywhere): every model draws the
+    // same distance matrix, so one embedding serves all of them (bit-identical to embedding each)
+    const int n_embed = slack == 0 ? 1 : n_models;
+    if (int rc = dev_dg_embed(N, U.p, L.p, seed ? seed : p->seed, 0, n_embed, x.p, e3.p, 0)) return rc;
+    for (int m = n_embed; m < n_models; m++) {
+        CHR3D_CUDA(cudaMemcpy(x.p + (size_t)m * N * 3, x.p, sizeof(double) * (size_t)N * 3, cudaMemcpyDeviceToDevice));
+        CHR3D_CUDA(cudaMemcpy(e3.p + (size_t)m * 3, e3.p, sizeof(double) * 3, cudaMemcpyDeviceToDevice));
+    }
     CHR3D_CUDA(cudaMemcpy(xyz_out, x.p, sizeof(double) * (size_t)n_models * N * 3, cudaMemcpyDeviceToHost));
     if (eig3_out) CHR3D_CUDA(cudaMemcpy(eig3_out, e3.p, sizeof(double) * (size_t)n_models * 3, cudaMemcpyDeviceToHost));
     if (n_inconsistent) *n_inconsistent = bad;
