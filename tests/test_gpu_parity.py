@@ -314,3 +314,22 @@ def test_seeded_random_coil_start_equals_oracle(gpu_api):
         for k in range(m):
             ref = orc.random_coil(N, 3.8, seed, k).astype(np.float32).astype(np.float64)
             assert np.array_equal(r.xyz[k], ref), (N, k)
+
+
+def test_images_side_by_side_equal_the_sequential_run(gpu_api, mats, monkeypatch):
+    """The host may run the two hot-MD images of a model as trajectories of their own and resume at PICK (api.cu,
+    ensemble_create).  With the launch shape pinned, that run must be bit-identical to the one-launch run: same Philox
+    streams, same reduction orders, same stage program."""
+    IF = mats["chr21_500kb"]
+    monkeypatch.setenv("CHR3D_SA_CLUSTER", "2")
+    monkeypatch.setenv("CHR3D_SA_WARPS", "8")
+    job = lambda: [gpu_api.Job(IF=IF, alpha=0.5, n_models=3, seed=11)]
+    e = gpu_api.Ensemble(job()); split_launches = e.info()["launches"]; e.close()
+    a = gpu_api.build_models(job())[0]
+    monkeypatch.setenv("CHR3D_NO_SPLIT", "1")
+    e = gpu_api.Ensemble(job()); one_launch = e.info()["launches"]; e.close()
+    b = gpu_api.build_models(job())[0]
+    assert split_launches == 2 and one_launch == 1
+    assert np.array_equal(a.xyz, b.xyz) and np.array_equal(a.energies, b.energies)
+    assert np.array_equal(a.force_evals, b.force_evals) and np.array_equal(a.hand, b.hand)
+    assert set(a.hand.tolist()) <= {1, -1}
