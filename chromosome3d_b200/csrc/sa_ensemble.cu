@@ -622,6 +622,12 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevParams& prm, const DevSt
     // this CTA's inputs of the force phase: nb+1 partial vectors (512 B) per owned block, and the energy partials of every warp
     if (c.tid == 0) mbar_expect(c, MB_F, (uint32_t)SGEO.nown * (uint32_t)(SGEO.nb + 1) * 512u + (WANT_E ? 16u * (uint32_t)SGEO.gwarps : 0u));
     mbar_wait(c, MB_F, c.phF);
+    // Every thread of the CTA must have seen this phase complete before any of them can move on: a parity wait only tells the
+    // current phase from the previous one.  Without this barrier a warp that is late to poll (its tiles need not feed this
+    // CTA's own beads, so nothing here waits for it) can find the mbarrier a full evaluation further — same parity again — and
+    // wait for a phase that needs its own, never-sent partial forces: a cluster-wide deadlock.  The same barrier covers MB_X
+    // (nobody can post the next coordinate phase before passing here).
+    __syncthreads();
     TSTAMP(c, 2);                                   // wait for the partial forces
     float gx = 0.f, gy = 0.f, gz = 0.f, eb = 0.f;
     if (c.row_ok) {
