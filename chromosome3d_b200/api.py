@@ -387,6 +387,27 @@ def dg_embed(ri, rj, rd, N, n_models=1, seed=0, p=None):
     return xyz, eig, bad.value
 
 
+def alpha_sweep(IF, alphas, n_models=20, K=11.0, seed=0, rng=3, p=None):
+    """The alpha sweep of perl/chromosome3D_sweep.pl: every (alpha, model) trajectory in ONE call,
+    models ranked per alpha like assess_dgsa (int(NOE energy), C3D:617, 802), scored by the IF-distance Spearman (SP:32-71);
+    returns per-alpha rows and the selected model (most negative Spearman) with its `rankNN_aXX` name stem."""
+    IF = np.ascontiguousarray(IF, dtype=np.float64)
+    jobs = [Job(IF=IF, alpha=a, K=K, n_models=n_models, seed=seed) for a in alphas]
+    res = build_models(jobs, p)
+    rows, best = [], None
+    for a, r in zip(alphas, res):
+        order = rank_models(r.energies)
+        rank_of = {int(m): k + 1 for k, m in enumerate(order)}
+        rho = spearman_IF_pdb(IF, r.xyz, rng)
+        pick = int(np.argmin(rho))
+        rows.append(dict(alpha=float(a), restraints=int(r.n_restraints), best_noe=int(r.energies[order[0], abi.E_NOE]),
+                         best_srcc=float(rho[pick]), median_srcc=float(np.median(rho)), picked_model=pick + 1, picked_rank=rank_of[pick]))
+        if best is None or rho[pick] < best["srcc"]:
+            best = dict(alpha=float(a), model=pick + 1, rank=rank_of[pick], srcc=float(rho[pick]), xyz=r.xyz[pick].copy(),
+                        stem="rank%02d_a%02d" % (rank_of[pick], int(a * 10 + 0.5)))
+    return rows, best
+
+
 # ---------------------------------------------------------------------------------- one large structure
 def nccl_unique_id():
     """128-byte NCCL unique id (rank 0 creates it, the caller broadcasts it, e.g. over torch.distributed)."""

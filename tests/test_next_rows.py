@@ -198,3 +198,15 @@ def test_gpu_annealing_from_dg_start(gpu_api):
     b = gpu_api.build_models([gpu_api.Job(IF=IF, alpha=1.1, n_models=6, seed=82364)])[0]
     ra, rb = np.median(gpu_api.spearman_IF_pdb(IF, a.xyz, 3)), np.median(gpu_api.spearman_IF_pdb(IF, b.xyz, 3))
     assert np.all(np.isfinite(a.energies)) and ra < rb + 0.02
+
+
+@pytest.mark.gpu
+def test_gpu_alpha_sweep_python_mirror(gpu_api):
+    IF = ds.load_if_matrix(ds.input_path("chr22_1mb"))
+    rows, best = gpu_api.alpha_sweep(IF, [0.4, 0.5, 0.6], n_models=3, seed=5)
+    assert [r["alpha"] for r in rows] == [0.4, 0.5, 0.6]
+    for r in rows:
+        assert r["restraints"] == len(orc.if_to_restraints(IF, r["alpha"])[0]) and 1 <= r["picked_rank"] <= 3
+    assert best["srcc"] == min(r["best_srcc"] for r in rows) and best["srcc"] < -0.7
+    assert re.fullmatch(r"rank0[123]_a0[456]", best["stem"])
+    assert "%.3f" % orc.spearman(IF, best["xyz"], 3)[0] == "%.3f" % best["srcc"]
