@@ -11,7 +11,7 @@
 //     Sentinels: -1 no restraint, -2 no restraint and no repel (|i-j| < vdw_min_sep, lower part of
 //     diagonal tiles, padding).
 //   * coordinates / forces / L-BFGS vectors: float4 arrays of N.
-// Force evaluation = ln_tile_kernel (persistent CTAs, contiguous tile ranges, double-buffered TMA,
+// Force evaluation = ln_tile_kernel (persistent CTAs, contiguous tile ranges, three-stage TMA ring,
 // symmetric tile evaluation: every unordered pair is evaluated once and its force goes to both beads)
 //   - a warp owns 8 rows of the tile, a lane the 4 columns {lane, lane+32, lane+64, lane+96} (stored as one float4 per row
 //     in the tile-packed layout, so target and coordinate reads are conflict-free): 32 pairs per thread per tile in registers;

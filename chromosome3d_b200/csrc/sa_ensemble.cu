@@ -19,9 +19,13 @@
 //   * NOE soft-square + repel are fused in the pair term, the bond term is added by the bead owner;
 //     energies and all other scalars are reduced in fp64 in a fixed order;
 //   * the whole stage program (pre-minimisation, hot MD, cooling, L-BFGS, C3D:1573-1829) runs
-//     inside the kernel.  An MD step costs two cluster barriers: one after the pair phase (forces
-//     complete) and one after the owners published a = x + dt*h*f, b = dt*v and their kinetic-energy
-//     partials, from which every CTA rebuilds x' = a + lambda*b for all beads itself.
+//     inside the kernel.  There is no cluster barrier on the per-evaluation path: partial forces, coordinates (published as
+//     a = x + dt*h*f, b = dt*v, from which every CTA rebuilds x' = a + lambda*b itself once the kinetic-energy partials are in)
+//     and the scalars of an all-reduce travel as st.async stores that credit an mbarrier of the receiving CTA, which waits only
+//     for ITS inputs;
+//   * the pair term runs on the packed fp32 pipe (FADD2 / FMUL2 / FFMA2): two columns per instruction;
+//   * the host may give a trajectory a stage range and a saved state to resume from, so that the two hot-MD images of a model
+//     run side by side (api.cu).
 //
 // L-BFGS is the vector-free formulation: all inner products of an iteration are reduced in one
 // exchange and the two-loop recursion runs on the (2m+1)x(2m+1) Gram matrix.
@@ -270,7 +274,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Coordinates.  Every CTA holds (a, b) of all beads; x = a + lam*b with the cluster-uniform scalar lam.
 // Publishing goes into the buffer of the other parity (readers of the current one may still be busy);
-// after the cluster barrier that follows every publish, flip() makes it current.
+// once the coordinate phase has completed (await_coords), flip() makes it current.
 __device__ __forceinline__ float4 ldx(const Ctx& c, int i) {
     const float4* A = S_AB(c) + (size_t)(2 * c.buf) * SGEO.n32p;
     const float4 a = A[i], b = A[SGEO.n32p + i];
@@ -465,7 +469,7 @@ __device__ __forceinline__ void pair_sym2(const SaTerms& t, float xi, float yi, 
 // ------------------------------------------------------------------------------------------------
 template <bool WANT_E, bool GENERAL>
 __device__ __forceinline__ void eval_t(Ctx& c, const DevParams& prm, const DevStage& st, bool count) {
-    const DevParams& p = prm;                       // precondition: coordinates installed (publish, cluster barrier, flip)
+    const DevParams& p = prm;                       // precondition: coordinates installed (publish, await_coords, flip)
     SaTerms tm;
     tm.wnC2m = -2.f * st.w_noe * p.C; tm.rsw = p.rsw; tm.wv = st.w_vdw; tm.wv4 = 4.f * st.w_vdw; tm.R2 = st.R2;
     tm.wn = st.w_noe; tm.C = p.C; tm.a = p.a; tm.b = p.b; tm.casym = p.casym; tm.low_soft = p.lo_clamp > -1e30f ? 1 : 0;
@@ -852,7 +856,7 @@ __device__ void dyn_begin(Ctx& c) {          // cmremove=true
     allreduce(c, 3, false);
     if (c.row_ok) for (int k = 0; k < 3; k++) c.v[k] -= (float)(S_GSUM(c)[2 + k] / SGEO.N);
 }
-// One cluster barrier per step besides the force barrier: owners publish a = x + dt*h*f, b = dt*v (v after
+// One exchange per step besides the force exchange: owners publish a = x + dt*h*f, b = dt*v (v after
 // the closing half kick) and their kinetic-energy partials; after the barrier every CTA knows the
 // temperature, hence lam, and x' = a + lam*b = x + dt*(lam*v + h*f) for all beads (read lazily by ldx).
 __device__ bool dyn_after_eval(Ctx& c, const DevParams& prm, const DevStage& st, OpState& os) {
