@@ -303,6 +303,13 @@ __device__ __forceinline__ uint32_t mbar_addr(const Ctx& c, int which) { return 
 __device__ __forceinline__ void mbar_expect(const Ctx& c, int which, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr(c, which)), "r"(bytes) : "memory");
 }
+#ifdef SA_HANGDIAG
+// Development aid (-DSA_HANGDIAG, scripts/hangdiag.sh): instead of trapping, the first wait that times out raises a global abort
+// flag; every CTA then records where it stands (rank, evaluation count, the barrier it waits on, the raw words of its four
+// mbarriers) and all waits return, so the kernel ends and the host can read the picture.
+__device__ int sa_abort;
+__device__ unsigned long long (*sa_diag)[8];       // 512 rows in pinned, mapped host memory: readable after the context has died
+#endif
 __device__ __forceinline__ void mbar_wait(const Ctx& c, int which, unsigned& parity) {
     const uint32_t bar = mbar_addr(c, which);
     uint32_t done = 0;
@@ -310,7 +317,26 @@ __device__ __forceinline__ void mbar_wait(const Ctx& c, int which, unsigned& par
     while (!done) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#ifdef SA_HANGDIAG
+        if (!done) {
+            if (clock64() - t0 > 1000000000ll) atomicExch(&sa_abort, 1);          // 0.5 s
+            if (*(volatile int*)&sa_abort) {
+                if (c.lane == 0 && blockIdx.x < 512 && atomicAdd((unsigned long long*)&sa_diag[blockIdx.x][7], 1ull) == 0ull) {
+                    const unsigned long long* mb = (const unsigned long long*)(sa_smem + SGEO.o_mbar);
+                    sa_diag[blockIdx.x][0] = ((unsigned long long)c.rank << 48) | ((unsigned long long)c.warp << 40) | ((unsigned long long)which << 32) | (unsigned long long)parity;
+                    sa_diag[blockIdx.x][1] = (unsigned long long)c.nevals;
+                    sa_diag[blockIdx.x][2] = ((unsigned long long)c.phF << 32) | ((unsigned long long)c.phX << 16) | (unsigned long long)c.phR;
+                    for (int q = 0; q < 4; q++) sa_diag[blockIdx.x][3 + q] = ((const volatile unsigned long long*)mb)[q];
+                    __threadfence_system();
+                }
+                const long long t1 = clock64();
+                while (clock64() - t1 < 400000000ll) { }          // 0.2 s for everybody to record, then stop the kernel for good
+                __trap();
+            }
+        }
+#else
         if (!done && clock64() - t0 > 20000000000ll) __trap();        // ~10 s: a peer died; fail instead of hanging the GPU
+#endif
     }
     parity ^= 1u;
 }
@@ -988,6 +1014,7 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
 
     int cur_image = 1, hand = 1;
     double e_saved = 0.0;
+    bool after_dyn = false;
     const int k_begin = STD.k1 > 0 ? STD.k0 : 0, k_end = STD.k1 > 0 ? STD.k1 : nstages;
     if (STD.state_in) {            // resume: the other image's end state becomes the current one (as after its last DYNAMICS op)
         if (c.row_ok) for (int q = 0; q < 3; q++) { c.x[q] = STD.state_in[3 * c.row + q]; c.v[q] = STD.state_in[3 * (SGEO.N + c.row) + q]; }
@@ -1002,6 +1029,13 @@ sa_kernel(const TrajDesc* __restrict__ traj, const __grid_constant__ DevParams p
         os.phase = 0; os.step = 0; os.cnt = 0; os.head = 0; os.it = 0; os.ls = 0; os.want_e = true; os.count = true;
         os.E = os.gg = os.gp = os.ts = os.ke = 0.0;
         bool more = false;
+        // A DYNAMICS op ends with a force evaluation and no exchange after it (the last step publishes nothing).  If the next
+        // op starts with an evaluation of its own (MINIMIZE, SAVE, PICK, ENERGY), a fast CTA could send the partial forces of
+        // that evaluation into the force phase a slow peer has not completed yet: the bytes would be credited to the wrong
+        // phase (deadlock, seen as intermittent hangs with co-resident CTAs) and the partial slots overwritten under the
+        // peer's gather.  A cluster barrier separates the two phases (twice per trajectory of the dgsa.inp program).
+        if (after_dyn && (st.op == CHR3D_OP_MINIMIZE || st.op == CHR3D_OP_SAVE || st.op == CHR3D_OP_PICK || st.op == CHR3D_OP_ENERGY)) csync(c);
+        if (st.op != CHR3D_OP_MAXWELL) after_dyn = st.op == CHR3D_OP_DYNAMICS;      // every other op ends with an exchange
         switch (st.op) {
         case CHR3D_OP_INIT:
             if (c.row_ok) {
@@ -1136,11 +1170,10 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
         if (cudaFuncSetAttribute(sa_pick_kernel(false, th), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
     }
     const int nb = (N + 31) / 32, ntiles = nb * (nb + 1) / 2;
-    // One CTA per SM, enforced by asking for more than half of the SM's shared memory.  CTAs of spin-waiting clusters that
-    // share an SM have hung intermittently on B200 (a peer never completes its force phase and the 10 s watchdog in mbar_wait
-    // traps): seen with 12 x 4-warp clusters in one launch and with concurrent launch groups of 4-warp CTAs; never with one
-    // CTA per SM.  Batches also run faster this way (all 45 inputs x 20 models: 193 ms against 235 ms), because the shapes
-    // the cost model then picks leave fewer, larger launch groups.  CHR3D_SA_MIN_SMEM=0 lifts the floor for experiments.
+    // One CTA per SM, enforced by asking for more than half of the SM's shared memory: batches run faster this way (all 45
+    // inputs x 20 models: 193 ms against 208 ms), because the shapes the cost model then picks leave fewer, larger launch
+    // groups.  (Co-resident CTAs used to hang intermittently; that was a phase race in the exchange protocol, fixed in
+    // sa_kernel — see "after_dyn" — and documented in DESIGN.md.)  CHR3D_SA_MIN_SMEM=0 lifts the floor.
     const size_t min_smem = getenv("CHR3D_SA_MIN_SMEM") ? (size_t)atol(getenv("CHR3D_SA_MIN_SMEM")) : (size_t)117 * 1024;
     double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0, 0.0};
     const int Cs[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16};     // > 8: non-portable cluster sizes, two CTAs of different trajectories per SM
@@ -1211,6 +1244,16 @@ int sa_launch(const TrajDesc* d_traj, int n_traj, int Nmax, const DevParams& P, 
 
 }  // namespace chr3d
 
+#ifdef SA_HANGDIAG
+extern "C" __attribute__((visibility("default"))) unsigned long long* chr3d_debug_sa_hang_init(void) {
+    unsigned long long* h = nullptr; void* d = nullptr;
+    if (cudaHostAlloc((void**)&h, sizeof(unsigned long long) * 4096, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(h, 0, sizeof(unsigned long long) * 4096);
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return nullptr;
+    if (cudaMemcpyToSymbol(chr3d::sa_diag, &d, sizeof d) != cudaSuccess) return nullptr;
+    return h;
+}
+#endif
 #ifdef SA_TIMING
 extern "C" __attribute__((visibility("default"))) int chr3d_debug_sa_timing(unsigned long long* out32) {
     return cudaMemcpyFromSymbol(out32, chr3d::sa_dbg, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -3;
