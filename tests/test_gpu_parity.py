@@ -333,3 +333,23 @@ def test_images_side_by_side_equal_the_sequential_run(gpu_api, mats, monkeypatch
     assert np.array_equal(a.xyz, b.xyz) and np.array_equal(a.energies, b.energies)
     assert np.array_equal(a.force_evals, b.force_evals) and np.array_equal(a.hand, b.hand)
     assert set(a.hand.tolist()) <= {1, -1}
+
+
+def test_co_resident_clusters_complete(gpu_api):
+    """Regression for a phase race in the cluster exchange ("Findings"): with several CTAs per SM the skew between
+    the CTAs of a cluster is large enough to expose any pair of exchange phases that lacks a separating dependency; the shape
+    4 CTAs x 4 warps with 120 trajectories used to hang 3 times out of 5.  Runs in child processes: a hang ends in a trap
+    that kills the CUDA context."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from chromosome3d_b200 import api, datasets as ds\n"
+            "api.init(0)\n"
+            "IF = ds.load_if_matrix(ds.input_path('chr9_1mb'))\n"
+            "p = api.default_params(); p.hot_step = p.cool_step = 60; p.pow_step = 20; p.premin_step = 5\n"
+            "r = api.build_models([api.Job(IF=IF, alpha=1.1, n_models=120, seed=82364)], p)[0]\n"
+            "print('ok', int(r.force_evals.min()))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CHR3D_SA_MIN_SMEM="0", CHR3D_NO_SPLIT="1", CHR3D_SA_CLUSTER="4", CHR3D_SA_WARPS="4")
+    for _ in range(4):
+        r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout.startswith("ok"), r.stderr[-400:]
