@@ -20,10 +20,10 @@ use FindBin;
 use lib $FindBin::Bin;
 use Chr3D;
 
-my ($help, $dir_out, $K, $m, $file_if, $seed, $device, $alphas, $range, $keep_all) = (0, undef, 11, 20, undef, 0, 0, "0.1:2.0:0.1", 3, 0);
+my ($help, $dir_out, $K, $m, $file_if, $seed, $device, $alphas, $range, $keep_all, $gpus, $part) = (0, undef, 11, 20, undef, 0, 0, "0.1:2.0:0.1", 3, 0, 1, undef);
 Getopt::Long::Configure("no_auto_abbrev");
 GetOptions("h" => \$help, "o=s" => \$dir_out, "k=i" => \$K, "m=i" => \$m, "i|if=s" => \$file_if, "seed=i" => \$seed, "device=i" => \$device,
-           "alphas=s" => \$alphas, "range=i" => \$range, "keep-all" => \$keep_all) or usage();
+           "alphas=s" => \$alphas, "range=i" => \$range, "keep-all" => \$keep_all, "gpus=i" => \$gpus, "part=i" => \$part) or usage();
 usage() if $help || !defined $file_if || !defined $dir_out || !-f $file_if || $m < 1;
 my @alpha;
 if ($alphas =~ /^([\d.]+):([\d.]+):([\d.]+)$/) { my $n = int(($2 - $1) / $3 + 0.5); @alpha = map { sprintf("%.1f", $1 + $3 * $_) + 0 } 0 .. $n; }
@@ -33,6 +33,46 @@ usage() if !@alpha;
 system("mkdir", "-p", $dir_out) == 0 or die "cannot create $dir_out\n";
 $dir_out = abs_path($dir_out); $file_if = abs_path($file_if);
 my $ID = basename($file_if, ".txt"); $ID =~ s/_matrix$//;
+
+# --gpus N: the alphas are dealt round-robin to N child processes, one per GPU (ensemble sharding, no collectives: the
+# reference's own parallelism is test.sh backgrounding independent runs, TS:4-12); the parent merges their tables and picks
+# the overall best model.
+if ($gpus > 1 && !defined $part) {
+    my @pids;
+    for my $g (0 .. $gpus - 1) {
+        my @mine = map { $alpha[$_] } grep { $_ % $gpus == $g } 0 .. $#alpha;
+        next if !@mine;
+        my $pid = fork(); die "fork: $!" if !defined $pid;
+        if ($pid == 0) {
+            my @cmd = ($^X, "-I", $FindBin::Bin, "$FindBin::Bin/" . basename($0), "-i", $file_if, "-o", $dir_out, "-k", $K, "-m", $m, "--seed", $seed,
+                       "--device", $g, "--alphas", join(",", @mine), "--range", $range, "--part", $g, ($keep_all ? ("--keep-all") : ()));
+            exec(@cmd) or die "exec: $!";
+        }
+        push @pids, $pid;
+    }
+    my $failed = 0;
+    for my $pid (@pids) { waitpid($pid, 0); $failed ||= $? != 0; }
+    die "a sweep worker failed\n" if $failed;
+    my (@rows, $best);
+    for my $g (0 .. $gpus - 1) {
+        next if !-f "$dir_out/alpha_sweep.part$g.txt";
+        open(my $fh, "<", "$dir_out/alpha_sweep.part$g.txt") or die $!;
+        while (my $l = <$fh>) { push @rows, $l if $l !~ /^#/; }
+        close $fh; unlink "$dir_out/alpha_sweep.part$g.txt";
+        open($fh, "<", "$dir_out/best.part$g.txt") or die $!;
+        my ($name, $rho) = split(/\t/, scalar <$fh>); chomp $rho; close $fh; unlink "$dir_out/best.part$g.txt";
+        $best = { name => $name, rho => $rho } if !defined $best || $rho < $best->{rho};
+    }
+    @rows = sort { (split(/\t/, $a))[0] <=> (split(/\t/, $b))[0] } @rows;
+    open(my $tab, ">", "$dir_out/alpha_sweep.txt") or die $!;
+    print $tab "#alpha\trestraints\tbest_noe\tbest_srcc\tmedian_srcc\tpicked_model\tpicked_rank\n", @rows;
+    close $tab;
+    if (!$keep_all) {       # only the overall winner stays
+        for my $f (glob("$dir_out/${ID}_rank*_a*.pdb")) { unlink $f if index($f, $best->{name}) < 0; }
+    }
+    printf "Selected   : %s.pdb  (SRCC %.3f, %d GPUs)\n", $best->{name}, $best->{rho}, $gpus;
+    exit 0;
+}
 Chr3D::init($device);
 my ($IF, $L) = Chr3D::read_if_text($file_if);
 print "Input      : $file_if (L = $L)\nAlphas     : @alpha\nModels     : $m per alpha, " . ($m * @alpha) . " trajectories in one call\n";
@@ -43,7 +83,7 @@ my @res = Chr3D::run_ensembles(\@jobs);
 printf "Annealed   : %d trajectories (%s, binding %s), device time %.1f ms\n", $m * @alpha, Chr3D::version(), Chr3D::backend(), $res[0]{device_ms};
 
 my $MET = "MET" x $L;      # the shipped rankNN_aXX.pdb files name every residue MET
-open(my $tab, ">", "$dir_out/alpha_sweep.txt") or die $!;
+open(my $tab, ">", defined $part ? "$dir_out/alpha_sweep.part$part.txt" : "$dir_out/alpha_sweep.txt") or die $!;
 print $tab "#alpha\trestraints\tbest_noe\tbest_srcc\tmedian_srcc\tpicked_model\tpicked_rank\n";
 my ($best, $xyz_bytes) = (undef, 8 * 3 * $L);
 for my $ai (0 .. $#alpha) {
@@ -68,12 +108,13 @@ my $xyz = substr($res[$best->{a}]{xyz}, $best->{k} * $xyz_bytes, $xyz_bytes);
 Chr3D::write_pdb("$dir_out/$name.pdb", $xyz, $L, undef, 1, $MET);
 my ($red, $nred) = Chr3D::reduce_model($xyz, $L);
 Chr3D::write_reduced_pdb("$dir_out/${name}_reduced.pdb", $red, $nred);
+if (defined $part) { open(my $bf, ">", "$dir_out/best.part$part.txt") or die $!; print $bf "$name\t$best->{rho}\n"; close $bf; }
 printf "Selected   : %s.pdb  (alpha %.1f, model %d, energy rank %d, SRCC %.3f)  [%d s]\n", $name, $alpha[$best->{a}], $best->{k} + 1, $best->{rank}, $best->{rho}, time - $t0;
 exit 0;
 
 sub usage {
     print <<"EOT";
-Usage: $0 -i <IF matrix> -o <output directory> [-k 11] [-m 20] [--alphas 0.1:2.0:0.1 | --alphas 0.5,1.1] [--range 3] [--keep-all]
+Usage: $0 -i <IF matrix> -o <output directory> [-k 11] [-m 20] [--alphas 0.1:2.0:0.1 | --alphas 0.5,1.1] [--range 3] [--keep-all] [--gpus N]
   sweeps alpha, anneals -m models per alpha in one GPU batch, selects the model with the best IF-distance Spearman and
   writes <ID>_rankNN_aXX.pdb, <ID>_rankNN_aXX_reduced.pdb and alpha_sweep.txt into the output directory
 EOT

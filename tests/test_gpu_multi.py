@@ -78,3 +78,32 @@ def test_sharded_single_structure_matches_one_gpu(tmp_path, p2p):
         assert o["rows"] == o["rows1"] and o["evals"] == o["evals1"], (name, o)
         assert np.allclose(o["e"], o["e1"], rtol=1e-5, atol=1e-6 * abs(o["e1"][0])), (name, o)
         assert o["dx"] < 1e-3, (name, o)
+
+
+def test_sweep_driver_shards_alphas_over_two_gpus(tmp_path):
+    """perl/chromosome3D_sweep.pl --gpus 2: alphas dealt to one child process per GPU, no communication; the merged table and
+    the selected model equal the one-GPU run (same seeds, same launch shapes per job)."""
+    import re
+    import shutil
+    from chromosome3d_b200 import api, datasets as ds
+    if api.device_count() < 2 or shutil.which("perl") is None:
+        pytest.skip("needs 2 GPUs and perl")
+    perl = os.path.join(ROOT, "perl")
+    outs = {}
+    for tag, extra in (("one", []), ("two", ["--gpus", "2"])):
+        out = tmp_path / tag
+        r = subprocess.run(["perl", "-I", perl, os.path.join(perl, "chromosome3D_sweep.pl"), "-i", ds.input_path("chr22_1mb"), "-o", str(out), "-m", "3",
+                            "--alphas", "0.4,0.5,0.6,0.7"] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout
+        outs[tag] = (open(out / "alpha_sweep.txt").read(), re.search(r"Selected\s+: (\S+)\.pdb", r.stdout).group(1), sorted(os.listdir(out)))
+    # the children anneal 6 trajectories per call instead of 12, so the launch shapes (hence the reduction orders) may differ:
+    # same alphas and restraint counts, statistically the same scores
+    rows = {t: [l.split("\t") for l in outs[t][0].splitlines() if not l.startswith("#")] for t in outs}
+    assert [r[0] for r in rows["one"]] == [r[0] for r in rows["two"]] == ["0.4", "0.5", "0.6", "0.7"]
+    assert [r[1] for r in rows["one"]] == [r[1] for r in rows["two"]]
+    for a, b in zip(rows["one"], rows["two"]):
+        assert abs(float(a[3]) - float(b[3])) < 0.05 and abs(float(a[4]) - float(b[4])) < 0.05
+    for t in outs:
+        sel, files = outs[t][1], outs[t][2]
+        assert re.fullmatch(r"chr22_1mb_rank0[123]_a0[4567]", sel)
+        assert files == ["alpha_sweep.txt", sel + ".pdb", sel + "_reduced.pdb"], files
