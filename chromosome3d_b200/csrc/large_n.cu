@@ -176,6 +176,7 @@ struct LnTileArgs {
 template <bool WANT_E, bool LOW_SOFT>
 __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic dependent launch: the previous kernel's results are complete from here on
     float* dbuf = (float*)smem;
     float* colp = (float*)(smem + LN_COLP_OFF);
     uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);         // [0, LN_STAGES): tile landed; [LN_STAGES]: colp drained by the reducer warps
@@ -586,6 +587,7 @@ __device__ void ln_min_decide(LnState* st, const double* G, const double* escal_
 }
 // applies the decision to the vectors
 __global__ void ln_min_update_kernel(LnVec v, const LnState* st) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int acc = st->accepted;
     if (acc == 0) return;
     const int m = v.m, cnt = st->cnt, head = st->head;
@@ -749,6 +751,7 @@ struct LnMdStepArgs {
 // computed at; v1 = lam*v + h*f_old is the velocity that led there; v2 = v1 + h*f closes the step.  Published for
 // the next step: a' = x + dt*h*f, b' = dt*v2; the last block turns the kinetic energy of v2 into lam'.
 __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArgs p) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int B = blockIdx.x, tid = threadIdx.x & (LN_TB - 1), grp = threadIdx.x >> 7, i = B * LN_TB + tid;
     const bool lead = grp == 0;
     __shared__ double sh[LN_TB];
@@ -825,6 +828,7 @@ struct LnMinStepArgs {
 // L-BFGS trial x = xb + t*p (t = *lam): forces, the 6m+6 inner products of (s, y, g') with the history, and in the
 // last block the line-search / history decision of ln_min_decide.  ln_min_update_kernel then applies it.
 __global__ void __launch_bounds__(LN_STEP_THREADS) ln_min_step_kernel(LnMinStepArgs p) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.st->done) { if (blockIdx.x == 0 && threadIdx.x == 0) p.st->accepted = 0; return; }   // later update launches are no-ops
     const int B = blockIdx.x, tid = threadIdx.x & (LN_TB - 1), grp = threadIdx.x >> 7, i = B * LN_TB + tid, lane = tid & 31, warp = tid >> 5;
     const bool lead = grp == 0;
@@ -1164,12 +1168,35 @@ static void ln_terms(const chr3d_sa_params& p, const chr3d_stage& s, LnTerms& t)
     double r = s.repel * p.vdw_rmin; t.R2 = (float)(r * r);
 }
 
+// Launch with programmatic stream serialization: the kernel is set up while its predecessor on the stream still runs and waits
+// at its griddepcontrol.wait until the predecessor has finished (nobody triggers early), which hides the launch latency between
+// the two kernels of a force evaluation — a sixth of the evaluation time of the L2-resident 50 kb structure.
+template <typename Kern, typename Arg>
+static cudaError_t ln_launch_pdl(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t s, const Arg& arg) {
+    static const bool off = getenv("CHR3D_LN_NO_PDL") != nullptr;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&lc, kern, arg);
+}
+template <typename Kern, typename A1, typename A2>
+static cudaError_t ln_launch_pdl2(Kern kern, unsigned grid, unsigned block, cudaStream_t s, const A1& a1, const A2& a2) {
+    static const bool off = getenv("CHR3D_LN_NO_PDL") != nullptr;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = 0; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&lc, kern, a1, a2);
+}
 static void ln_launch_tiles(LnEngine& e, LnTileArgs a, bool want_e) {
     static const int dbg = getenv("CHR3D_LN_DEBUG") ? atoi(getenv("CHR3D_LN_DEBUG")) : 0;
     a.dbg = dbg;
     const bool soft = e.prm.noe_low_soft != 0;
-    if (want_e) { if (soft) ln_tile_kernel<true, true><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); else ln_tile_kernel<true, false><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); }
-    else { if (soft) ln_tile_kernel<false, true><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); else ln_tile_kernel<false, false><<<e.ncta, LN_THREADS, LN_SMEM, e.stream>>>(a); }
+    if (want_e) { if (soft) ln_launch_pdl(ln_tile_kernel<true, true>, e.ncta, LN_THREADS, LN_SMEM, e.stream, a); else ln_launch_pdl(ln_tile_kernel<true, false>, e.ncta, LN_THREADS, LN_SMEM, e.stream, a); }
+    else { if (soft) ln_launch_pdl(ln_tile_kernel<false, true>, e.ncta, LN_THREADS, LN_SMEM, e.stream, a); else ln_launch_pdl(ln_tile_kernel<false, false>, e.ncta, LN_THREADS, LN_SMEM, e.stream, a); }
 }
 
 static LnGather ln_gather_args(LnEngine& e) {
@@ -1261,8 +1288,8 @@ static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
             ln_tiles(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf, &e.st.p->done, true);
             if (multi) if (int rc = ln_exchange(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf)) return rc;
             m.xc = e.xchg_next();
-            ln_min_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(m);
-            ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
+            ln_launch_pdl(ln_min_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, m);
+            ln_launch_pdl2(ln_min_update_kernel, vb, 256, e.stream, v, (const LnState*)e.st.p);
             e.n_launches += 2;
         }
         int done = 0;
@@ -1290,7 +1317,7 @@ static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
     if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
     p.a = e.vx.p; p.b = e.vx.p; p.lam = &e.st.p->zerof; p.a_next = e.va[0].p; p.b_next = e.vb[0].p; p.first = 1; p.want_e = 0;
     p.xc = e.xchg_next();
-    ln_md_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(p);
+    ln_launch_pdl(ln_md_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, p);
     e.n_launches++;
     int par = 0;
     for (int step = 0; step < s.nstep; step++) {
@@ -1299,7 +1326,7 @@ static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
         if (multi) if (int rc = ln_exchange(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf)) return rc;
         p.a = e.va[par].p; p.b = e.vb[par].p; p.lam = &e.st.p->lamf; p.a_next = e.va[par ^ 1].p; p.b_next = e.vb[par ^ 1].p; p.first = 0; p.want_e = want_e ? 1 : 0;
         p.xc = e.xchg_next();
-        ln_md_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(p);
+        ln_launch_pdl(ln_md_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, p);
         e.n_launches++;
         par ^= 1;
     }
