@@ -82,20 +82,6 @@ __global__ void assess_rows_kernel(const long long* __restrict__ mxyz, const int
     if (dist < (D0 - D1 - RELAX)) { vf = 1; dev = -(D0 - D1 - dist); }   // C3D:469-473
     flag[k] = vf; devv[k] = dev; distv[k] = dist;
 }
-// sequential fp64 sum per model in key order (one thread per model)
-__global__ void seq_rows_sum_kernel(const double* __restrict__ terms, long long per_model, int n_models, double* __restrict__ out) {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n_models) return;
-    const double* t = terms + (size_t)m * per_model;
-    double s = 0.0;
-    long long k = 0;
-    for (; k + 8 <= per_model; k += 8) {
-        double a0 = t[k], a1 = t[k + 1], a2 = t[k + 2], a3 = t[k + 3], a4 = t[k + 4], a5 = t[k + 5], a6 = t[k + 6], a7 = t[k + 7];
-        s += a0; s += a1; s += a2; s += a3; s += a4; s += a5; s += a6; s += a7;
-    }
-    for (; k < per_model; k++) s += t[k];
-    out[m] = s;
-}
 // large tables: fixed-shape tree sum (no Perl reference exists at that size)
 __global__ void block_sum_kernel(const double* __restrict__ terms, long long per_model, double* __restrict__ out) {
     int m = blockIdx.x;

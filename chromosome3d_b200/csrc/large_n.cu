@@ -437,55 +437,9 @@ struct LnVec {     // all float4[N]
 
 __device__ __forceinline__ float dot3(const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 
-// x = xb + t p  (trial point); skipped when the minimiser is done
-__global__ void ln_min_trial_kernel(LnVec v, const LnState* st) {
-    if (st->done) return;
-    const float t = (float)st->tstep;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
-        float4 b = v.xb[i], p = v.p[i];
-        v.x[i] = make_float4(fmaf(t, p.x, b.x), fmaf(t, p.y, b.y), fmaf(t, p.z, b.z), 0.f);
-    }
-}
-// per-block partial inner products of (s, y, g') with the basis; layout part[block][K]
+// layout of the inner products of (s, y, g') with the L-BFGS basis
 #define LDOT_L(l, w) (6 * (l) + (w))
 #define LDOT_X(m, w) (6 * (m) + (w))
-__global__ void __launch_bounds__(256) ln_min_dots_kernel(LnVec v, const LnState* st, double* part) {
-    const int m = v.m, K = 6 * m + 6, head = st->head;
-    __shared__ float sh[8][LN_KMAX];
-    float acc[LN_KMAX];
-#pragma unroll 1
-    for (int k = 0; k < K; k++) acc[k] = 0.f;
-    if (!st->done) {
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
-            float4 x = v.x[i], xb = v.xb[i], f = v.f[i], g = v.g[i];
-            float4 s = make_float4(x.x - xb.x, x.y - xb.y, x.z - xb.z, 0.f);
-            float4 gn = make_float4(-f.x, -f.y, -f.z, 0.f);
-            float4 y = make_float4(gn.x - g.x, gn.y - g.y, gn.z - g.z, 0.f);
-            for (int l = 0; l < m; l++) {
-                if (l == head) continue;
-                float4 sl = v.S[(size_t)l * v.N + i], yl = v.Y[(size_t)l * v.N + i];
-                acc[LDOT_L(l, 0)] += dot3(s, sl); acc[LDOT_L(l, 1)] += dot3(s, yl); acc[LDOT_L(l, 2)] += dot3(y, sl);
-                acc[LDOT_L(l, 3)] += dot3(y, yl); acc[LDOT_L(l, 4)] += dot3(gn, sl); acc[LDOT_L(l, 5)] += dot3(gn, yl);
-            }
-            acc[LDOT_X(m, 0)] += dot3(s, s); acc[LDOT_X(m, 1)] += dot3(s, y); acc[LDOT_X(m, 2)] += dot3(s, gn);
-            acc[LDOT_X(m, 3)] += dot3(y, y); acc[LDOT_X(m, 4)] += dot3(y, gn); acc[LDOT_X(m, 5)] += dot3(gn, gn);
-        }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-    for (int k = 0; k < K; k++) {
-        float s = acc[k];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) sh[warp][k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < K) {
-        double s = 0;
-        for (int w = 0; w < 8; w++) s += (double)sh[w][threadIdx.x];
-        part[(size_t)blockIdx.x * LN_KMAX + threadIdx.x] = s;
-    }
-}
-
 // vector-free L-BFGS direction on the Gram matrix (same recursion as sa_ensemble.cu)
 __device__ double ln_direction(double* B, double* delta, int m, int cnt, int head) {
     const int nb = 2 * m + 1, ig = 2 * m;
@@ -617,15 +571,6 @@ __global__ void ln_min_update_kernel(LnVec v, const LnState* st) {
 
 // ---- MD --------------------------------------------------------------------------------------
 struct LnMdCfg { float dt_akma, h; double dt_ps, temp, fbeta, kboltz, mass; int flag, N, nparts, count; };
-__global__ void ln_md_pre_kernel(LnVec v, const LnState* st, LnMdCfg c) {
-    const float lam = (float)st->lam;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.N; i += gridDim.x * blockDim.x) {
-        float4 vv = v.v[i], f = v.f[i], x = v.x[i];
-        vv.x = fmaf(c.h, f.x, lam * vv.x); vv.y = fmaf(c.h, f.y, lam * vv.y); vv.z = fmaf(c.h, f.z, lam * vv.z);
-        x.x = fmaf(c.dt_akma, vv.x, x.x); x.y = fmaf(c.dt_akma, vv.y, x.y); x.z = fmaf(c.dt_akma, vv.z, x.z);
-        v.v[i] = vv; v.x[i] = x;
-    }
-}
 // v += h f (skipped for the initial evaluation), kinetic-energy partials
 __global__ void __launch_bounds__(256) ln_md_post_kernel(LnVec v, LnMdCfg c, int kick, double* part) {
     float k2 = 0.f;

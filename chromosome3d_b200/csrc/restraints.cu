@@ -34,18 +34,6 @@ __global__ void pow_kernel(const double* __restrict__ IF, double* __restrict__ P
     for (; k < n; k += stride) P[k] = pow(IF[k], alpha);
 }
 
-// one thread, reference order (C3D:132-137)
-__global__ void seq_sum_kernel(const double* __restrict__ P, long long n, double* out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    double s = 0.0;
-    long long k = 0;
-    for (; k + 8 <= n; k += 8) {
-        double a0 = P[k], a1 = P[k + 1], a2 = P[k + 2], a3 = P[k + 3], a4 = P[k + 4], a5 = P[k + 5], a6 = P[k + 6], a7 = P[k + 7];
-        s += a0; s += a1; s += a2; s += a3; s += a4; s += a5; s += a6; s += a7;
-    }
-    for (; k < n; k++) s += P[k];
-    *out = s;
-}
 // large L: per-row sequential sums (one thread per row), then rows summed sequentially
 __global__ void row_sum_kernel(const double* __restrict__ P, int L, double* __restrict__ rows) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
