@@ -210,3 +210,40 @@ def test_gpu_alpha_sweep_python_mirror(gpu_api):
     assert best["srcc"] == min(r["best_srcc"] for r in rows) and best["srcc"] < -0.7
     assert re.fullmatch(r"rank0[123]_a0[456]", best["stem"])
     assert "%.3f" % orc.spearman(IF, best["xyz"], 3)[0] == "%.3f" % best["srcc"]
+
+
+# ------------------------------------------------------------------------------------------ small / degenerate inputs (CPU)
+def test_oracle_dg_tiny_chain_without_restraints():
+    """Three beads, bonds only: the bounds are (r0, r0, [repel floor, 2 r0]); three points always embed exactly."""
+    p = orc.default_params()
+    empty_i, empty_d = np.zeros(0, dtype=np.int32), np.zeros(0)
+    U, L, bad = orc.dg_bounds(3, empty_i, empty_i, empty_d, p)
+    assert bad == 0 and U[0, 1] == U[1, 2] == p.bond_r0 and U[0, 2] == 2 * p.bond_r0
+    assert L[0, 2] == pytest.approx(p.vdw_rmin * p.cool_rad_finl) and L[0, 1] == p.bond_r0
+    xyz, eig, _ = orc.dg_embed(3, empty_i, empty_i, empty_d, p, 3, 4)
+    for m in range(4):
+        d01, d12, d02 = (np.linalg.norm(xyz[m][a] - xyz[m][b]) for a, b in ((0, 1), (1, 2), (0, 2)))
+        assert d01 == pytest.approx(p.bond_r0, abs=1e-9) and d12 == pytest.approx(p.bond_r0, abs=1e-9)
+        assert L[0, 2] - 1e-9 <= d02 <= U[0, 2] + 1e-9
+    assert len({round(float(np.linalg.norm(x[0] - x[2])), 6) for x in xyz}) > 1        # the free distance differs between models
+
+
+def test_reduced_pdb_single_bead_and_pairs(tmp_path):
+    one = np.array([[1.2345, -0.0005, 10.0]])
+    api.write_reduced_pdb(tmp_path / "a.pdb", one)
+    assert open(tmp_path / "a.pdb", "rb").read() == b"\r\nATOM      1   CA MET B1          1.235  -0.001  10.000  0.20 10.00\r\nEND\r\n"
+    two = orc.reduce_model(np.array([[0.001, 0.0, 0.0], [0.002, 0.0, 0.0], [5.0, 5.0, 5.0]]))
+    assert two.shape == (2, 3) and two[0, 0] == 0.0015 and np.array_equal(two[1], [5.0, 5.0, 5.0])
+    orc.write_reduced_pdb(tmp_path / "b.pdb", two)
+    api.write_reduced_pdb(tmp_path / "c.pdb", two)
+    txt = open(tmp_path / "b.pdb", "rb").read()
+    assert txt == open(tmp_path / "c.pdb", "rb").read() and b"   0.002   0.000   0.000" in txt and txt.count(b"CONECT") == 1
+
+
+def test_text_loader_whitespace_variants(tmp_path):
+    p = tmp_path / "t.txt"
+    p.write_bytes(b"1\t2  3 \r\n  4 5\t6\r\n7 8 9")            # tabs, leading blanks, no newline at the end
+    assert np.array_equal(api.read_if_text(p), np.array([[1.0, 2, 3], [4, 5, 6], [7, 8, 9]]))
+    p.write_bytes(b"1 x\n2 3\n")
+    with pytest.raises(api.Chr3dError):
+        api.read_if_text(p)
