@@ -73,6 +73,9 @@ namespace chr3d {
 
 #define LN_TB 128
 #define LN_THREADS 512
+#ifndef LN_BOUND_THREADS
+#define LN_BOUND_THREADS LN_THREADS      // register cap of the tile kernel = 65536 / this (development: -DLN_BOUND_THREADS=640 ... probes the footprint)
+#endif
 #define LN_TILE_FLOATS (LN_TB * LN_TB)
 #define LN_MAXB (2 * CHR3D_LBFGS_MAX_M + 1)
 #define LN_KMAX 64
@@ -174,7 +177,7 @@ struct LnTileArgs {
 #define LN_SMEM (LN_CBUF_OFF + 2 * 2 * LN_TB * 16)       // + column coordinates (a, b) of the current and the next tile
 
 template <bool WANT_E, bool LOW_SOFT>
-__global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
+__global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic dependent launch: the previous kernel's results are complete from here on
     float* dbuf = (float*)smem;
@@ -252,45 +255,45 @@ __global__ void __launch_bounds__(LN_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
             }
         }
         if (t + 1 < c1) { int Jn = J + 1; if (Jn == (int)a.nT) Jn = I + 1; prefetch_cols(Jn, cstage ^ 1); }
-        float xj[4], yj[4], zj[4];
-        float2 gjx[4], gjy[4], gjz[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const float4 p = cbuf[(cstage * 2) * LN_TB + c * 32 + lane], q = cbuf[(cstage * 2 + 1) * LN_TB + c * 32 + lane];   // column 32c + lane
-            xj[c] = fmaf(lam, q.x, p.x); yj[c] = fmaf(lam, q.y, p.y); zj[c] = fmaf(lam, q.z, p.z);
-            gjx[c] = gjy[c] = gjz[c] = bc(0.f);
-        }
         if (a.dbg != 2) { mbar_wait(&bar[stage], (phases >> stage) & 1u); phases ^= 1u << stage; }
         const float4* D4 = reinterpret_cast<const float4*>(dbuf + (size_t)stage * LN_TILE_FLOATS) + (warp * 8) * 32 + lane;   // see ln_tile_cell
         // padding beads (index >= N) exist only in the last tile row / column; their cells are -2 like the diagonal band's
         const bool near = J <= I + 1 || (J + 1) * LN_TB > a.N;
-        if (a.dbg == 1) {
-        } else if (near) {
+        // the lane's four columns in two halves (columns 32*(2ch) + lane and 32*(2ch+1) + lane): only two columns' coordinates
+        // and force accumulators are live at a time, which is what keeps the pair loop inside the register budget
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int rp = q >> 1, c = 2 * (q & 1);
-                const float4 d4 = D4[q * 32];
-                pair_sym2<WANT_E, LOW_SOFT, true>(tm, xi[rp], yi[rp], zi[rp], xj[c], yj[c], zj[c], f2(d4.x, d4.y), fix[rp], fiy[rp], fiz[rp], gjx[c], gjy[c], gjz[c], en, ev);
-                pair_sym2<WANT_E, LOW_SOFT, true>(tm, xi[rp], yi[rp], zi[rp], xj[c + 1], yj[c + 1], zj[c + 1], f2(d4.z, d4.w), fix[rp], fiy[rp], fiz[rp], gjx[c + 1], gjy[c + 1], gjz[c + 1], en, ev);
-            }
-        } else {
+        for (int ch = 0; ch < 2; ch++) {
+            float xj[2], yj[2], zj[2];
+            float2 gjx[2], gjy[2], gjz[2];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int rp = q >> 1, c = 2 * (q & 1);
-                const float4 d4 = D4[q * 32];
-                pair_sym2<WANT_E, LOW_SOFT, false>(tm, xi[rp], yi[rp], zi[rp], xj[c], yj[c], zj[c], f2(d4.x, d4.y), fix[rp], fiy[rp], fiz[rp], gjx[c], gjy[c], gjz[c], en, ev);
-                pair_sym2<WANT_E, LOW_SOFT, false>(tm, xi[rp], yi[rp], zi[rp], xj[c + 1], yj[c + 1], zj[c + 1], f2(d4.z, d4.w), fix[rp], fiy[rp], fiz[rp], gjx[c + 1], gjy[c + 1], gjz[c + 1], en, ev);
+            for (int c = 0; c < 2; c++) {
+                const float4 p = cbuf[(cstage * 2) * LN_TB + (2 * ch + c) * 32 + lane], q = cbuf[(cstage * 2 + 1) * LN_TB + (2 * ch + c) * 32 + lane];
+                xj[c] = fmaf(lam, q.x, p.x); yj[c] = fmaf(lam, q.y, p.y); zj[c] = fmaf(lam, q.z, p.z);
+                gjx[c] = gjy[c] = gjz[c] = bc(0.f);
             }
+            if (a.dbg == 1) {
+            } else if (near) {
+#pragma unroll
+                for (int rp = 0; rp < 4; rp++) {
+                    const float4 d4 = D4[(2 * rp + ch) * 32];
+                    pair_sym2<WANT_E, LOW_SOFT, true>(tm, xi[rp], yi[rp], zi[rp], xj[0], yj[0], zj[0], f2(d4.x, d4.y), fix[rp], fiy[rp], fiz[rp], gjx[0], gjy[0], gjz[0], en, ev);
+                    pair_sym2<WANT_E, LOW_SOFT, true>(tm, xi[rp], yi[rp], zi[rp], xj[1], yj[1], zj[1], f2(d4.z, d4.w), fix[rp], fiy[rp], fiz[rp], gjx[1], gjy[1], gjz[1], en, ev);
+                }
+            } else {
+#pragma unroll
+                for (int rp = 0; rp < 4; rp++) {
+                    const float4 d4 = D4[(2 * rp + ch) * 32];
+                    pair_sym2<WANT_E, LOW_SOFT, false>(tm, xi[rp], yi[rp], zi[rp], xj[0], yj[0], zj[0], f2(d4.x, d4.y), fix[rp], fiy[rp], fiz[rp], gjx[0], gjy[0], gjz[0], en, ev);
+                    pair_sym2<WANT_E, LOW_SOFT, false>(tm, xi[rp], yi[rp], zi[rp], xj[1], yj[1], zj[1], f2(d4.z, d4.w), fix[rp], fiy[rp], fiz[rp], gjx[1], gjy[1], gjz[1], en, ev);
+                }
+            }
+            // column partials: [comp][warp][128], this lane's 4 consecutive positions; the single buffer is free once the reducer
+            // warps of the previous tile have drained it (they arrived long ago: this wait does not block in practice)
+            if (ch == 0 && t > c0) { mbar_wait(&bar[LN_STAGES], (phases >> LN_STAGES) & 1u); phases ^= 1u << LN_STAGES; }
+            *reinterpret_cast<float2*>(colp + (0 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjx[0].x + gjx[0].y), -(gjx[1].x + gjx[1].y));
+            *reinterpret_cast<float2*>(colp + (1 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjy[0].x + gjy[0].y), -(gjy[1].x + gjy[1].y));
+            *reinterpret_cast<float2*>(colp + (2 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjz[0].x + gjz[0].y), -(gjz[1].x + gjz[1].y));
         }
-        float fjx[4], fjy[4], fjz[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) { fjx[c] = -(gjx[c].x + gjx[c].y); fjy[c] = -(gjy[c].x + gjy[c].y); fjz[c] = -(gjz[c].x + gjz[c].y); }
-        // column partials: [comp][warp][128], this lane's 4 consecutive columns; the single buffer is free once the reducer
-        // warps of the previous tile have drained it (they arrived long ago: this wait does not block in practice)
-        if (t > c0) mbar_wait(&bar[LN_STAGES], (phases >> LN_STAGES) & 1u), phases ^= 1u << LN_STAGES;
-        *reinterpret_cast<float4*>(colp + (0 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
-        *reinterpret_cast<float4*>(colp + (1 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
-        *reinterpret_cast<float4*>(colp + (2 * 16 + warp) * LN_TB + lane * 4) = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                 // tile buffer `stage` is free, column partials are complete, next column coordinates have landed
         if (tid == 0 && t + LN_STAGES < c1 && a.dbg != 2) issue(t + LN_STAGES, stage);
