@@ -103,36 +103,49 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def cpu_baseline(workload, seconds_budget=25.0, threads=0, models=None):
-    """The fp64 oracle running the same schedule on the host cores, one model per thread."""
+def host_cores():
+    """Host cores this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1, so omp_get_max_threads() would
+    report 1 under torchrun: the CPU arm takes its thread count from the affinity mask instead and passes it explicitly
+    (orc_run_ensemble calls omp_set_num_threads)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline(workload, threads=0, models=None):
+    """The fp64 oracle running the same schedule on the host cores, one model per thread: the config's own ensemble
+    (20 models for configs[1]) dealt dynamically to `cores` threads."""
     import oracle as orc
     from chromosome3d_b200 import datasets as ds
-    name, alpha, _ = WORKLOADS[workload]
+    name, alpha, m = WORKLOADS[workload]
     IF = ds.load_if_matrix(ds.input_path(name))
     N = IF.shape[0]
     ri, rj, rd = orc.if_to_restraints(IF, alpha)
     p = orc.default_params()
     prog = orc.build_program(p)
-    cores = threads or orc.max_threads()
-    n_models = models or cores
+    cores = threads or host_cores()
+    # whole ensembles of the config's m models, as many as keep every core busy for whole rounds (m*k models, a multiple of cores)
+    import math
+    n_models = models or m * (cores // math.gcd(m, cores))
     t0 = time.time()
     res = orc.run_ensemble(N, ri, rj, rd, p, prog, 82364, n_models, 0, None, cores)
     dt = time.time() - t0
     pe = float(res["force_evals"].sum()) * len(ri)
     return {"value": pe / dt, "unit": "pair-evals/s", "cores": cores, "kind": "port",
-            "sample": "%d models of %s (one per thread, full dgsa schedule, %d force evals, %.1f s)" % (n_models, workload, int(res["force_evals"].sum()), dt),
+            "sample": "%d models of %s (= %d ensemble(s) of the config's %d models, one model per thread on %d threads, full dgsa schedule, %d force evals, %.1f s)"
+                      % (n_models, workload, max(1, n_models // m), m, cores, int(res["force_evals"].sum()), dt),
             "models_per_s": n_models / dt, "seconds": dt, "force_evals": int(res["force_evals"].sum())}
 
 
 def run_reference(args):
-    """--impl reference: the CPU path on this box's host cores (rank 0 only)."""
+    """--impl reference: the CPU path on this box's host cores (rank 0 only; the other ranks exit 0 without work)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     vals = []
-    for _ in range(args.warmup):
-        cpu_baseline(args.workload, models=max(1, (os.cpu_count() or 1) // 4))
-        break                                   # one short warm-up is enough for a CPU code
+    if args.warmup > 0:
+        cpu_baseline(args.workload, models=max(1, host_cores() // 4))      # one short warm-up is enough for a CPU code
     last = None
     t_all = time.time()
     for _ in range(args.steps):
@@ -142,17 +155,25 @@ def run_reference(args):
     pe = sum(v["value"] * v["seconds"] for v in vals)
     sec = sum(v["seconds"] for v in vals)
     value = pe / sec
-    name, alpha, m = WORKLOADS[args.workload]
-    line = {"metric": "restraint_pair_evals_per_sec", "value": value, "unit": "pair-evals/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "reference input matrix %s_matrix.txt, seeded random-coil starts" % name, "impl": "reference",
-            "config": {"workload": args.workload, "matrix": name, "alpha": alpha, "models_per_ensemble": m, "schedule": "dgsa.inp full (C3D:1573-1829)"},
-            "sa_models_per_sec": sum(v["models_per_s"] * v["seconds"] for v in vals) / sec,
-            "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]},
-            "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": wall,
-            "note": "CNS 1.3 is not in /root/reference and cannot be built offline; the fp64 CPU port of the same schedule stands in (BASELINE.md §3)"}
+    line = base_line(args, args.workload)
+    line.update({"value": value, "ms_per_step": 1e3 * sec / args.steps, "dtype": "f64", "impl": "reference",
+                 "sa_models_per_sec": sum(v["models_per_s"] * v["seconds"] for v in vals) / sec,
+                 "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+                 "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0, "wall_s": wall,
+                 "note": "CNS 1.3 is not in /root/reference and cannot be built offline; the fp64 CPU port of the same schedule stands in (BASELINE.md §3)"})
     print(json.dumps(line), flush=True)
+
+
+def base_line(args, workload):
+    """Keys both arms share (same `config` key set, so the driver's same_config check compares like with like)."""
+    name, alpha, m = WORKLOADS[workload]
+    return {"metric": "restraint_pair_evals_per_sec", "value": None, "unit": "pair-evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "reference input matrix %s_matrix.txt (real Hi-C IF), seeded random-coil starts" % name,
+            "config": {"workload": workload, "matrix": name, "alpha": alpha, "K": 11, "models_per_ensemble": m,
+                       "schedule": "dgsa.inp full (C3D:1573-1829)",
+                       "l2": "GPU arm: flushed between steps (512 MB write, outside the per-step events); CPU arm: not applicable"}}
 
 
 def large_n_probe(api, N=24925, seed=20260002, reps=10):
@@ -424,15 +445,23 @@ def main():
         pj = os.path.join(ROOT, "profiles", "sa_kernel_ncu_summary.json")
         if os.path.exists(pj):
             prof = json.load(open(pj))
-        line = {
-            "metric": "restraint_pair_evals_per_sec", "value": value, "unit": "pair-evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": kernel_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "reference input matrices (real Hi-C IF): %s, seeded random-coil starts" % name,
-            "config": {"workload": args.workload, "matrix": name, "beads": N, "alpha": alpha, "K": 11,
-                       "restraint_rows": int(sum(r.n_restraints for r in all_res)), "jobs_per_rank": len(jobs),
-                       "models_per_ensemble": m, "ensembles": world * len(jobs), "sa_launches_per_step": info["launches"], "schedule": "dgsa.inp full (C3D:1573-1829)" if not args.profile else "PROFILE (shortened)",
+        if args.workload in WORKLOADS:
+            line = base_line(args, args.workload)           # same config keys/values as the --impl reference arm
+        else:
+            line = {"metric": "restraint_pair_evals_per_sec", "value": None, "unit": "pair-evals/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                    "data": "reference input matrices (real Hi-C IF): %s, seeded random-coil starts" % name,
+                    "config": {"workload": args.workload, "matrix": name, "alpha": alpha, "K": 11, "models_per_ensemble": m,
+                               "schedule": "dgsa.inp full (C3D:1573-1829)",
+                               "l2": "flushed between steps (512 MB write, outside the per-step events)"}}
+        if args.profile:
+            line["config"]["schedule"] = "PROFILE (shortened)"
+        line.update({
+            "value": value, "n_gpus": world, "ms_per_step": kernel_ms_max,
+            "detail": {"beads": N, "restraint_rows": int(sum(r.n_restraints for r in all_res)), "jobs_per_rank": len(jobs),
+                       "ensembles": world * len(jobs), "sa_launches_per_step": info["launches"],
                        "force_evals_per_model": float(res.force_evals.mean()), "cluster_size": info["cluster"], "threads_per_cta": info["threads"],
-                       "l2": "flushed between steps (512 MB write, outside the per-step events)", "parallelism": "ensemble shards, no collectives"},
+                       "parallelism": "ensemble shards, no collectives"},
             "sa_models_per_sec": models_all / (kernel_ms_max * 1e-3),
             "e2e": {"value": e2e_pe_all / (e2e_ms_max * 1e-3), "unit": "pair-evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max, "sa_models_per_sec": models_all / (e2e_ms_max * 1e-3)},
@@ -447,7 +476,7 @@ def main():
                          "note": "FP32-pipe roofline (targets live in shared memory, ~0 HBM traffic in steady state); with 20 trajectories of 3.7k "
                                  "sequential force evaluations each the kernel is bound by per-evaluation latency (exchange waits, owner phases), see DESIGN.md"},
             "clocks": sampler.summary(), "wall_s": t_wall,
-        }
+        })
         if not args.no_large_n and world == 1 and not args.profile:
             try:
                 line["large_n_probe"] = large_n_probe(api)
