@@ -176,49 +176,31 @@ def base_line(args, workload):
                        "l2": "GPU arm: flushed between steps (512 MB write, outside the per-step events); CPU arm: not applicable"}}
 
 
-def large_n_probe(api, N=24925, seed=20260002, reps=10):
-    """Force-evaluation throughput of the tile-streaming kernel on the synthetic 10 kb matrix (BASELINE configs[4]
-    shape), one GPU: the HBM-bound kernel of the path.  Device-timed inside chr3d_single_eval_bench."""
-    s = api.Single(N=N, alpha=1.1, synth_seed=seed)
-    try:
-        info = s.info()
-        rows = s.fetch()["restraint_rows"]
-        tile_ms, eval_ms = s.eval_bench(reps=reps, want_energy=False)
-        peaks, src = measured_peaks()
-        gbs = rows * BYTES_PER_PAIR_EVAL / (tile_ms * 1e-3) / 1e9
-        return {"beads": N, "restraint_rows": int(rows), "tile_kernel_ms": tile_ms, "force_eval_ms": eval_ms,
-                "pair_evals_per_sec": rows / (eval_ms * 1e-3), "launches": 3 * (reps + 2) + (reps + 3),
-                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                             "traffic": info["target_bytes"] + 32 * N, "kernel": "ln_tile_kernel",
-                             "algorithmic": "4 B per restraint-pair evaluation x %d rows per launch" % rows,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % src}}
-    finally:
-        s.close()
-
-
-def run_single(args, torch, dist, api, rank, world, local):
-    """One large structure (configs[3]/[4]); with N>1 GPUs the tile list is sharded (strong scaling) and every
-    force evaluation ends in one NCCL all-reduce of the forces."""
-    N, alpha, sseed = SINGLE_WORKLOADS[args.workload]
+def single_structure(args, torch, dist, api, rank, world, local, workload, steps, warmup, with_e2e):
+    """One large structure (BASELINE.json configs[3] / configs[4]) annealed through the full schedule.  With N > 1 GPUs the
+    tile list is sharded over the ranks (strong scaling: total work fixed) and the partial forces are exchanged inside the
+    persistent kernel over NVLink peer memory.  Returns the block on rank 0 (None elsewhere)."""
+    N, alpha, sseed = SINGLE_WORKLOADS[workload]
     p = api.default_params()
     if args.profile:
         p.hot_step, p.cool_step, p.pow_step, p.pow_cycl, p.premin_step, p.images = 16, 80, 10, 1, 5, 1
+    nccl_path = world > 1 and os.environ.get("CHR3D_NO_P2P") == "1"
     nccl_id = None
-    if world > 1:
+    if nccl_path:
         box = [api.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         nccl_id = box[0]
     stream = torch.cuda.current_stream()
     single = api.Single(N=N, alpha=alpha, synth_seed=sseed, seed=82364, p=p, rank=rank, world=world, nccl_id=nccl_id)
     info = single.info()
-    exchange = "none"
+    exchange = "none (one GPU)"
     if world > 1:
-        exchange = "nccl all-reduce"
-        if os.environ.get("CHR3D_NO_P2P") != "1":
+        exchange = "NCCL all-reduce per evaluation (multi-launch baseline path)"
+        if not nccl_path:
             hs = [None] * world
             dist.all_gather_object(hs, single.comm_handle())
             single.comm_connect(hs)
-            exchange = "fused peer-memory exchange in the step kernel (NVLink remote stores + epoch flags)"
+            exchange = "fused into the persistent kernel: remote stores + epoch flags over NVLink peer memory, every rank integrates all beads"
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
     def barrier():
@@ -234,24 +216,28 @@ def run_single(args, torch, dist, api, rank, world, local):
         e1.record(stream)
         return e0, e1
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_step()
     barrier()
+    single.profile()                                     # reset the phase clock
     sampler = ClockSampler(local)
     sampler.start()
     t0 = time.time()
-    evs = [one_step() for _ in range(args.steps)]
+    evs = [one_step() for _ in range(steps)]
     barrier()
     wall = time.time() - t0
     sampler.stop_flag = True
     sampler.join(timeout=2)
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
     res = single.fetch()
+    assert single.comm_error() == 0, "peer exchange failed"
+    prof = single.profile()
     tile_ms, eval_ms = single.eval_bench(reps=10, want_energy=False, stream=stream.cuda_stream)
+    assert single.comm_error() == 0, "peer exchange failed"
     rows_rank = float(res["restraint_rows"])
     # e2e: host IF matrix (pinned) -> create (H2D, target derivation) -> run -> fetch (D2H), world == 1 only
     e2e = None
-    if world == 1:
+    if world == 1 and with_e2e:
         try:
             IF_np = api.synthetic_if(N, sseed)                      # the host buffer a caller would hold (outside the timed region)
             IF = torch.from_numpy(IF_np).pin_memory().numpy()
@@ -271,39 +257,61 @@ def run_single(args, torch, dist, api, rank, world, local):
                    "ms_per_step": ms[-1]}
         except Exception as ex:
             e2e = {"value": None, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)}
-    t = torch.tensor([step_ms, tile_ms, eval_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([step_ms, tile_ms, eval_ms] + [prof[k] / max(steps, 1) for k in ("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms")],
+                     dtype=torch.float64, device="cuda")
     w = torch.tensor([rows_rank], dtype=torch.float64, device="cuda")
+    wmax = w.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    step_ms_max, tile_ms_max, eval_ms_max = t.tolist()
-    rows_all = w.item()
-    if rank == 0:
-        peaks, peak_src = measured_peaks()
-        evals = float(res["force_evals"])
-        gbs = rows_rank * BYTES_PER_PAIR_EVAL / (tile_ms * 1e-3) / 1e9
-        line = {"metric": "restraint_pair_evals_per_sec", "value": evals * rows_all / (step_ms_max * 1e-3), "unit": "pair-evals/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic IF matrix (SURVEY 8(d) generator, Philox seed %d), seeded random-coil start" % sseed,
-                "config": {"workload": args.workload, "beads": N, "alpha": alpha, "K": 11, "restraint_rows": int(rows_all), "models": 1,
-                           "schedule": "dgsa.inp full (C3D:1573-1829)" if not args.profile else "PROFILE (shortened)", "force_evals_per_model": evals,
-                           "tiles": info["n_tiles"], "tiles_rank0": info["tiles_this_rank"], "target_bytes_rank0": info["target_bytes"],
-                           "l2": "flushed between steps (512 MB write); targets exceed L2 at this size" if N > 8000 else "flushed between steps (512 MB write); the 51 MB of targets are re-read from L2 inside a step",
-                           "parallelism": ("tile-range shards; force exchange per evaluation: " + exchange) if world > 1 else "single GPU"},
-                "sa_models_per_sec": 1.0 / (step_ms_max * 1e-3),
-                "force_eval_ms": eval_ms_max, "tile_kernel_ms": tile_ms_max,
-                "e2e": e2e if e2e is not None else {"value": None, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                                                    "note": "e2e is measured at N=1 only"},
-                "gpu_launches": int(res["launches"]) * (args.steps + args.warmup),
-                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                             "traffic": info["target_bytes"] + 32 * N, "kernel": "ln_tile_kernel (TMA-fed 128x128 target tiles, symmetric pair evaluation)",
-                             "algorithmic": "4 B per restraint-pair evaluation x %d rows per launch (rank 0)" % int(rows_rank),
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % peak_src,
-                             "note": "achieved = algorithmic bytes / average ln_tile_kernel duration, CUDA events around back-to-back launches (chr3d_single_eval_bench)"},
-                "clocks": sampler.summary(), "wall_s": wall}
-        print(json.dumps(line), flush=True)
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+    step_ms_max, tile_ms_max, eval_ms_max, ph_tile, ph_b1, ph_step, ph_b2, ph_upd = t.tolist()
+    rows_all, rows_max = w.item(), wmax.item()
     single.close()
+    del flush
+    if rank != 0:
+        return None
+    peaks, peak_src = measured_peaks()
+    evals = float(res["force_evals"])
+    # per-rank roofline of the dominant kernel: the slowest rank's stand-alone tile kernel over the largest shard
+    gbs = rows_max * BYTES_PER_PAIR_EVAL / (tile_ms_max * 1e-3) / 1e9
+    # the same inside the persistent kernel: tile phases of CTA 0 (max over ranks) per evaluation
+    tile_phase_ms = ph_tile / max(evals, 1.0)
+    gbs_in = rows_max * BYTES_PER_PAIR_EVAL / (tile_phase_ms * 1e-3) / 1e9 if tile_phase_ms > 0 else None
+    return {"workload": workload, "n_gpus": world, "scaling": "strong", "beads": N, "alpha": alpha, "K": 11, "restraint_rows": int(rows_all),
+            "schedule": "dgsa.inp full (C3D:1573-1829)" if not args.profile else "PROFILE (shortened)",
+            "steps": steps, "warmup": warmup, "ms_per_step": step_ms_max, "sa_models_per_sec": 1.0 / (step_ms_max * 1e-3),
+            "value": evals * rows_all / (step_ms_max * 1e-3), "unit": "pair-evals/s", "force_evals_per_model": evals,
+            "force_eval_ms": eval_ms_max, "tile_kernel_ms": tile_ms_max,
+            "phases_ms_per_step": {"tile": ph_tile, "barrier1": ph_b1, "gather_exchange_integrate": ph_step, "barrier2_decide": ph_b2, "lbfgs_update": ph_upd,
+                                   "note": "phase clock of the persistent kernel (CTA 0 of each rank, max over ranks), per step"},
+            "tiles": info["n_tiles"], "tiles_rank0": info["tiles_this_rank"], "target_bytes_rank0": info["target_bytes"], "launches_per_step": int(res["launches"]),
+            "l2": "flushed between steps (512 MB write); targets exceed L2 at this size" if N > 8000 else "flushed between steps (512 MB write); the 51 MB of targets are re-read from L2 inside a step",
+            "parallelism": ("tile-range shards over %d ranks; force exchange per evaluation: %s" % (world, exchange)) if world > 1 else "single GPU",
+            "e2e": e2e if e2e is not None else {"value": None, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                "note": "e2e of the single structure is measured at N=1 with --workload " + workload},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "achieved_in_persistent_kernel": gbs_in, "frac_in_persistent_kernel": (gbs_in / peaks["hbm_gbs"]) if gbs_in else None,
+                         "traffic": None, "traffic_note": "not measured in this run; ncu of the same kernel: profiles/ (dram bytes per launch = algorithmic bytes + 1 %)",
+                         "kernel": "ln_tile_kernel / tile phase of ln_persist_kernel (TMA-fed 128x128 target tiles, symmetric pair evaluation)",
+                         "algorithmic": "4 B per restraint-pair evaluation x %d rows per launch (largest shard)" % int(rows_max),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % peak_src,
+                         "note": "achieved = algorithmic bytes / average ln_tile_kernel duration, CUDA events around back-to-back launches (chr3d_single_eval_bench), slowest rank"},
+            "clocks": sampler.summary(), "wall_s": wall}
+
+
+def run_single(args, torch, dist, api, rank, world, local):
+    blk = single_structure(args, torch, dist, api, rank, world, local, args.workload, args.steps, args.warmup, True)
+    if rank == 0:
+        line = {"metric": "restraint_pair_evals_per_sec", "value": blk["value"], "unit": "pair-evals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic IF matrix (SURVEY 8(d) generator, Philox seed %d), seeded random-coil start" % SINGLE_WORKLOADS[args.workload][2],
+                "config": {k: blk[k] for k in ("workload", "beads", "alpha", "K", "restraint_rows", "schedule", "force_evals_per_model", "tiles", "tiles_rank0",
+                                               "target_bytes_rank0", "l2", "parallelism")},
+                "sa_models_per_sec": blk["sa_models_per_sec"], "force_eval_ms": blk["force_eval_ms"], "tile_kernel_ms": blk["tile_kernel_ms"],
+                "phases_ms_per_step": blk["phases_ms_per_step"], "e2e": blk["e2e"], "gpu_launches": blk["launches_per_step"] * (args.steps + args.warmup),
+                "roofline": blk["roofline"], "clocks": blk["clocks"], "wall_s": blk["wall_s"]}
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -314,7 +322,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="chr1_500kb_a1.1_m20", choices=sorted(WORKLOADS) + sorted(BATCH_WORKLOADS) + sorted(SINGLE_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-large-n", action="store_true", help="skip the large-N kernel probe appended to the default line")
+    ap.add_argument("--no-large-n", action="store_true", help="skip the single_structure block (synthetic 10 kb chr1 at this GPU count) appended to the default line")
     ap.add_argument("--profile", action="store_true", help="short schedule for ncu captures (not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -468,6 +476,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
                          "traffic": (prof.get("dram_bytes_per_launch") or 0) * max(int(info["launches"]), 1) or None,
+                         "traffic_source": "static: ncu dram__bytes_read+write per sa_kernel launch from profiles/sa_kernel_ncu_summary.json x launches per step; not measured in this run",
                          "kernel": "sa_kernel (cluster-per-trajectory SA, 32x32 symmetric micro-tiles, targets resident in shared memory)",
                          "algorithmic": "%d flop per restraint-pair evaluation x %.4g pair-evals per step (%d sa_kernel launch(es) per step: with few "
                                         "trajectories the two hot-MD images of a model run as one launch, the part from PICK on as a second; achieved and "
@@ -477,19 +486,26 @@ def main():
                                  "sequential force evaluations each the kernel is bound by per-evaluation latency (exchange waits, owner phases), see DESIGN.md"},
             "clocks": sampler.summary(), "wall_s": t_wall,
         })
-        if not args.no_large_n and world == 1 and not args.profile:
-            try:
-                line["large_n_probe"] = large_n_probe(api)
-                line["gpu_launches"] += line["large_n_probe"].pop("launches")
-            except Exception as ex:
-                line["large_n_probe"] = {"error": repr(ex)}
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload).items() if k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as ex:     # the oracle is only the reported baseline
                 line["cpu_baseline"] = {"value": None, "unit": "pair-evals/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
-        print(json.dumps(line), flush=True)
     ens.close()
+    del flush
+    # the north-star single structure (BASELINE.json configs[4]: synthetic 10 kb chr1, 24,925 beads) at this GPU count: tile-range
+    # shards over the ranks, strong scaling.  Every rank takes part; rank 0 attaches the block to the line.
+    blk = None
+    if not args.no_large_n and not args.profile:
+        try:
+            blk = single_structure(args, torch, dist, api, rank, world, local, "synth_10kb_single", 2, 1, False)
+        except Exception as ex:
+            blk = {"error": repr(ex)}
+    if rank == 0:
+        if blk is not None:
+            line["single_structure"] = blk
+            line["gpu_launches"] += int(blk.get("launches_per_step", 0)) * 3
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -480,6 +480,18 @@ class Single:
         return dict(xyz=xyz, forces=f, energies=e, force_evals=nev.value, hand=hand.value, device_ms=ms.value, launches=nl.value,
                     restraint_rows=npairs.value)
 
+    def profile(self):
+        """Phase clock of the persistent kernel since the last call (ms, CTA 0 of this rank): tile, barrier1, step, barrier2, update."""
+        a = (C.c_double * 5)()
+        _check(lib().chr3d_single_profile(self._h, a))
+        return dict(zip(("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms"), [float(v) for v in a]))
+
+    def targets(self):
+        """Test aid: this rank's targets as a dense N*N fp32 matrix (NaN outside the rank's tiles)."""
+        out = np.zeros((self.N, self.N), dtype=np.float32)
+        _check(lib().chr3d_single_targets(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
     def info(self):
         nt, mine, tb = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         ctas = C.c_int32(0)
@@ -496,3 +508,14 @@ class Single:
             self.close()
         except Exception:
             pass
+
+
+def group_connect(singles):
+    """Virtual ranks: the Single objects (rank g of world n, same process, same device) become one launch group."""
+    arr = (C.c_void_p * len(singles))(*[s._h.value for s in singles])
+    _check(lib().chr3d_single_group_connect(arr, len(singles)))
+
+
+def group_run(singles, stream=None):
+    arr = (C.c_void_p * len(singles))(*[s._h.value for s in singles])
+    _check(lib().chr3d_single_group_run(arr, len(singles), C.c_void_p(stream or 0)))

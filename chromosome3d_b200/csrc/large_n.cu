@@ -160,10 +160,9 @@ struct LnTileArgs {
     const int* done;          // may be nullptr; *done != 0: the minimiser has finished, skip the evaluation
     float* colpart;           // [(t - t0)][3][128]
     float4* rowpart;          // [cta][maxseg][128]
-    int* seg_I;               // [cta][maxseg] tile row of each segment (-1 unused)
     double* epart;            // [cta][2]
     int maxseg;
-    int dbg;                  // development probe (CHR3D_LN_DEBUG): 1 = stream tiles without the pair term, 2 = pair term without tile traffic
+    int dbg;                  // development probe (-DCHR3D_DEV + CHR3D_LN_DEBUG): 1 = stream tiles without the pair term, 2 = pair term without tile traffic
     LnTerms terms;
 };
 
@@ -171,94 +170,140 @@ struct LnTileArgs {
 // Three stages keep two tiles (128 KB per SM, 19 MB chip-wide) in flight behind the one being evaluated: with two stages only
 // one 64 KB copy per SM is outstanding, which at the loaded HBM latency caps the kernel near 60 % of the copy bandwidth.
 #define LN_STAGES 3
-#define LN_COLP_OFF (LN_STAGES * LN_TILE_FLOATS * 4)
-#define LN_BAR_OFF (LN_COLP_OFF + 3 * 16 * LN_TB * 4)
-#define LN_CBUF_OFF (LN_BAR_OFF + 64)
-#define LN_SMEM (LN_CBUF_OFF + 2 * 2 * LN_TB * 16)       // + column coordinates (a, b) of the current and the next tile
+#define LN_BAR_OFF (LN_STAGES * LN_TILE_FLOATS * 4)       // mbarriers (one per stage + "colp free")
+#define LN_RING_OFF (LN_BAR_OFF + 32)                    // LnRing: the pipeline state that survives from one evaluation to the next
+#define LN_COLP_OFF (LN_BAR_OFF + 64)                    // colp[3][16][128]
+#define LN_CBUF_OFF (LN_COLP_OFF + 3 * 16 * LN_TB * 4)   // column coordinates (a, b) of the current and the next tile
+#define LN_SMEM (LN_CBUF_OFF + 2 * 2 * LN_TB * 16)
+#define LN_SCRATCH_BYTES (LN_SMEM - LN_COLP_OFF)         // colp + cbuf: free between two tile phases (scratch of the step phases)
 
+#ifdef CHR3D_DEV
+#define LN_DBG(a) ((a).dbg)
+#else
+#define LN_DBG(a) 0
+#endif
+
+// Everything the tile phase of one CTA needs, in SHARED memory: the pair loop wants the whole register budget, so nothing of
+// this is carried in registers — it is read where it is used (there is no L1 behind 229 KB of shared memory: a spill in the
+// pair loop would be an L2 round trip, a shared-memory read is not).
+//
+// Ring state: a CTA's n tiles are walked as a periodic sequence — position g (counted over all evaluations of a launch) is
+// tile g % n of the range, stage g % LN_STAGES.  After position g has been evaluated the copy of position g + LN_STAGES is
+// issued, so at the end of an evaluation the first tiles of the next one are already in flight (the targets do not depend on
+// the coordinates): a persistent kernel pays the pipeline prologue once per launch, not once per evaluation.
+struct LnTileRun {
+    const float* Dt;          // first tile of this CTA
+    float* colpart;           // column partials of this CTA's tiles: [k][3][128]
+    float4* rowpart;          // row partials of this CTA's segments: [seg][128]
+    double* epart;            // [2]
+    const float4* X; const float4* XB; float lam;      // coordinates X + lam * XB
+    int n, I0, J0, nT, N;     // tiles, tile coordinates of the first one
+    int more, dbg;            // more: another evaluation follows in this launch (keep the ring running across the boundary)
+    LnTerms terms;
+    unsigned int phases, pending; int stage, cstage;   // phases bit q: parity to wait for on bar[q]; pending: stages with a copy outstanding
+};
+#define LN_RUN(field) (((volatile LnTileRun*)run)->field)
+
+__device__ __forceinline__ void ln_ring_issue(LnTileRun* run, unsigned char* smem, int k, int stage) {      // one elected thread: 64 KB bulk copy of the CTA's tile k
+    float* dbuf = (float*)smem; uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar[stage])), "r"(LN_TILE_FLOATS * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(LN_RUN(Dt) + (size_t)k * LN_TILE_FLOATS),
+                   "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])) : "memory");
+    LN_RUN(pending) = LN_RUN(pending) | (1u << stage);
+}
+// once per launch (all threads; run->Dt, n, dbg are set): mbarriers, ring state, the first LN_STAGES copies.
+// periodic: the ring runs across evaluations (persistent kernel); otherwise only tiles of one evaluation are issued.
+__device__ __forceinline__ void ln_ring_init(LnTileRun* run, unsigned char* smem, bool periodic) {
+    uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < LN_STAGES; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[q])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar[LN_STAGES])), "r"(3 * LN_TB / 32));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        run->phases = 0; run->pending = 0; run->stage = 0; run->cstage = 0;
+        const int n = run->n;
+        if (n > 0 && run->dbg != 2) for (int q = 0; q < LN_STAGES; q++) if (periodic || q < n) ln_ring_issue(run, smem, q % n, q);
+    }
+    __syncthreads();
+}
+// before the kernel exits (all threads): wait for the copies still in flight
+__device__ __forceinline__ void ln_ring_drain(LnTileRun* run, unsigned char* smem) {
+    uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);
+    __syncthreads();
+    if (threadIdx.x == 0) for (int q = 0; q < LN_STAGES; q++) if (run->pending >> q & 1u) mbar_wait(&bar[q], (run->phases >> q) & 1u);
+    __syncthreads();
+}
+
+// One force evaluation of this CTA's tile range at the coordinates X + lam * XB (all in *run).
 template <bool WANT_E, bool LOW_SOFT>
-__global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic dependent launch: the previous kernel's results are complete from here on
+__device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* smem) {
+#ifdef CHR3D_DEV
+    const int dbg = run->dbg;
+#else
+    constexpr int dbg = 0;
+#endif
     float* dbuf = (float*)smem;
     float* colp = (float*)(smem + LN_COLP_OFF);
     uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);         // [0, LN_STAGES): tile landed; [LN_STAGES]: colp drained by the reducer warps
     float4* cbuf = (float4*)(smem + LN_CBUF_OFF);       // [stage][a|b][128]
-    if (a.done && *a.done) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float lam = a.xb2 ? *a.lam : 0.f;
-    const float4* __restrict__ XB = a.xb2 ? a.xb2 : a.x;
-    const long long ntl = a.t1 - a.t0;
-    const long long c0 = a.t0 + (ntl * blockIdx.x) / gridDim.x, c1 = a.t0 + (ntl * (blockIdx.x + 1)) / gridDim.x;
-    int* segI = a.seg_I + (size_t)blockIdx.x * a.maxseg;
-    for (int s = tid; s < a.maxseg; s += LN_THREADS) segI[s] = -1;
-    if (tid == 0) {
-        for (int q = 0; q < LN_STAGES; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[q])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar[LN_STAGES])), "r"(3 * LN_TB / 32));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](long long t, int stage) {      // one elected thread: 64 KB bulk copy of tile t
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar[stage])), "r"(LN_TILE_FLOATS * 4) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(a.Dt + (size_t)(t - a.t0) * LN_TILE_FLOATS),
-                       "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])) : "memory");
-    };
-    if (tid == 0 && a.dbg != 2) for (int q = 0; q < LN_STAGES; q++) if (c0 + q < c1) issue(c0 + q, q);
+    const int n = run->n;
+    const LnTerms tm = run->terms;
+    const float lam = run->lam;
     // column coordinates of tile column Jn -> cbuf[stg] with cp.async (L2 latency hidden behind the previous tile's pairs)
     auto prefetch_cols = [&](int Jn, int stg) {
         if (tid < 2 * LN_TB) {
-            const int col = tid & (LN_TB - 1), which = tid >> 7;
-            int j = Jn * LN_TB + col; if (j >= a.N) j = a.N - 1;
-            const float4* src = (which ? XB : a.x) + j;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr(cbuf + (stg * 2 + which) * LN_TB + col)), "l"(src) : "memory");
+            const int col = tid & (LN_TB - 1), which = tid >> 7, N = LN_RUN(N);
+            int j = Jn * LN_TB + col; if (j >= N) j = N - 1;
+            const float4* src = (which ? LN_RUN(XB) : LN_RUN(X)) + j;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(cbuf + (stg * 2 + which) * LN_TB + col)), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    int I = 0, J = 0;
-    if (c0 < c1) { tile_coords(c0, a.nT, I, J); prefetch_cols(J, 0); }
+    uint32_t phases = run->phases;                           // bit q: parity to wait for on bar[q]
+    int stage = run->stage, cstage = run->cstage;            // tile ring / column-coordinate double buffer
+    int I = run->I0, J = run->J0;
+    if (n > 0) prefetch_cols(J, cstage);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    int curI = -1, seg = -1;
+    int seg = -1;
+    bool newrow = true;
     float2 xi[4], yi[4], zi[4], fix[4], fiy[4], fiz[4];          // row pairs (8w + 2rp, 8w + 2rp + 1)
-    float2 en = bc(0.f), ev = bc(0.f); double den = 0.0, dev = 0.0;
-    uint32_t phases = 0;           // bit q: parity to wait for on bar[q]
-    int stage = 0, cstage = 0;     // tile ring / column-coordinate double buffer
-    const LnTerms tm = a.terms;
+    float2 en = bc(0.f), ev = bc(0.f);
 
     auto flush_rows = [&]() {
         // reduce the 8 row accumulators over the 32 lanes (columns) of this warp
+        float4* rp_out = LN_RUN(rowpart) + (size_t)seg * LN_TB + warp * 8;
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             float vx = (r & 1) ? fix[r >> 1].y : fix[r >> 1].x, vy = (r & 1) ? fiy[r >> 1].y : fiy[r >> 1].x, vz = (r & 1) ? fiz[r >> 1].y : fiz[r >> 1].x;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { vx += __shfl_xor_sync(0xffffffffu, vx, o); vy += __shfl_xor_sync(0xffffffffu, vy, o); vz += __shfl_xor_sync(0xffffffffu, vz, o); }
-            if (lane == r) a.rowpart[((size_t)blockIdx.x * a.maxseg + seg) * LN_TB + warp * 8 + r] = make_float4(vx, vy, vz, 0.f);
+            if (lane == r) rp_out[r] = make_float4(vx, vy, vz, 0.f);
         }
-        den += (double)(en.x + en.y); dev += (double)(ev.x + ev.y); en = bc(0.f); ev = bc(0.f);
     };
 
-    for (long long t = c0; t < c1; t++) {
-        if (I != curI) {
-            if (curI >= 0) flush_rows();
-            curI = I; seg++;
-            if (tid == 0) segI[seg] = I;
+    for (int k = 0; k < n; k++) {
+        if (newrow) {
+            newrow = false; seg++;
+            const float4* X = LN_RUN(X); const float4* XB = LN_RUN(XB); const int N = LN_RUN(N);
 #pragma unroll
             for (int rp = 0; rp < 4; rp++) {
                 int i0 = I * LN_TB + warp * 8 + 2 * rp, i1 = i0 + 1;
-                if (i0 >= a.N) i0 = a.N - 1;
-                if (i1 >= a.N) i1 = a.N - 1;
-                const float4 p0 = a.x[i0], q0 = XB[i0], p1 = a.x[i1], q1 = XB[i1];
+                if (i0 >= N) i0 = N - 1;
+                if (i1 >= N) i1 = N - 1;
+                const float4 p0 = __ldcg(X + i0), q0 = __ldcg(XB + i0), p1 = __ldcg(X + i1), q1 = __ldcg(XB + i1);
                 xi[rp] = f2(fmaf(lam, q0.x, p0.x), fmaf(lam, q1.x, p1.x)); yi[rp] = f2(fmaf(lam, q0.y, p0.y), fmaf(lam, q1.y, p1.y));
                 zi[rp] = f2(fmaf(lam, q0.z, p0.z), fmaf(lam, q1.z, p1.z)); fix[rp] = fiy[rp] = fiz[rp] = bc(0.f);
             }
         }
-        if (t + 1 < c1) { int Jn = J + 1; if (Jn == (int)a.nT) Jn = I + 1; prefetch_cols(Jn, cstage ^ 1); }
-        if (a.dbg != 2) { mbar_wait(&bar[stage], (phases >> stage) & 1u); phases ^= 1u << stage; }
+        const int nT = LN_RUN(nT);
+        if (k + 1 < n) { int Jn = J + 1; if (Jn == nT) Jn = I + 1; prefetch_cols(Jn, cstage ^ 1); }
+        if (dbg != 2) { mbar_wait(&bar[stage], (phases >> stage) & 1u); phases ^= 1u << stage; }
         const float4* D4 = reinterpret_cast<const float4*>(dbuf + (size_t)stage * LN_TILE_FLOATS) + (warp * 8) * 32 + lane;   // see ln_tile_cell
         // padding beads (index >= N) exist only in the last tile row / column; their cells are -2 like the diagonal band's
-        const bool near = J <= I + 1 || (J + 1) * LN_TB > a.N;
+        const bool near = J <= I + 1 || (J + 1) * LN_TB > LN_RUN(N);
         // the lane's four columns in two halves (columns 32*(2ch) + lane and 32*(2ch+1) + lane): only two columns' coordinates
         // and force accumulators are live at a time, which is what keeps the pair loop inside the register budget
 #pragma unroll
@@ -271,7 +316,7 @@ __global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs
                 xj[c] = fmaf(lam, q.x, p.x); yj[c] = fmaf(lam, q.y, p.y); zj[c] = fmaf(lam, q.z, p.z);
                 gjx[c] = gjy[c] = gjz[c] = bc(0.f);
             }
-            if (a.dbg == 1) {
+            if (dbg == 1) {
             } else if (near) {
 #pragma unroll
                 for (int rp = 0; rp < 4; rp++) {
@@ -289,37 +334,79 @@ __global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs
             }
             // column partials: [comp][warp][128], this lane's 4 consecutive positions; the single buffer is free once the reducer
             // warps of the previous tile have drained it (they arrived long ago: this wait does not block in practice)
-            if (ch == 0 && t > c0) { mbar_wait(&bar[LN_STAGES], (phases >> LN_STAGES) & 1u); phases ^= 1u << LN_STAGES; }
+            if (ch == 0 && k > 0) { mbar_wait(&bar[LN_STAGES], (phases >> LN_STAGES) & 1u); phases ^= 1u << LN_STAGES; }
             *reinterpret_cast<float2*>(colp + (0 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjx[0].x + gjx[0].y), -(gjx[1].x + gjx[1].y));
             *reinterpret_cast<float2*>(colp + (1 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjy[0].x + gjy[0].y), -(gjy[1].x + gjy[1].y));
             *reinterpret_cast<float2*>(colp + (2 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjz[0].x + gjz[0].y), -(gjz[1].x + gjz[1].y));
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                 // tile buffer `stage` is free, column partials are complete, next column coordinates have landed
-        if (tid == 0 && t + LN_STAGES < c1 && a.dbg != 2) issue(t + LN_STAGES, stage);
+        if (tid == 0 && dbg != 2) {      // next position of the periodic tile sequence that wants this stage
+            LN_RUN(pending) = LN_RUN(pending) & ~(1u << stage);
+            const int nx = k + LN_STAGES;
+            if (nx < n) ln_ring_issue(run, smem, nx, stage);
+            else if (LN_RUN(more)) ln_ring_issue(run, smem, nx % n, stage);
+        }
         if (tid < 3 * LN_TB) {
             const int comp = tid / LN_TB, col = tid % LN_TB;
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < 16; w++) s += colp[(comp * 16 + w) * LN_TB + col];
-            a.colpart[((size_t)(t - a.t0) * 3 + comp) * LN_TB + col] = s;
+            LN_RUN(colpart)[((size_t)k * 3 + comp) * LN_TB + col] = s;
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar[LN_STAGES])) : "memory");
         }
         stage = stage + 1 == LN_STAGES ? 0 : stage + 1; cstage ^= 1;
-        J++; if (J == (int)a.nT) { I++; J = I; }
+        J++;
+        if (J == nT) { I++; J = I; newrow = true; }
+        if (newrow || k + 1 == n) flush_rows();
     }
-    if (curI >= 0) flush_rows();
-    // block energy
-    __shared__ double esh[2][16];
-    for (int o = 16; o > 0; o >>= 1) { den += __shfl_xor_sync(0xffffffffu, den, o); dev += __shfl_xor_sync(0xffffffffu, dev, o); }
-    if (lane == 0) { esh[0][warp] = den; esh[1][warp] = dev; }
+    // the last tile's reducer arrivals complete a phase nobody waited for: consume it, so that the next evaluation starts clean
+    if (n > 0) { mbar_wait(&bar[LN_STAGES], (phases >> LN_STAGES) & 1u); phases ^= 1u << LN_STAGES; }
+    // block energy (the column-partial buffer is free now)
+    if (WANT_E) {
+        double den = (double)(en.x + en.y), dev = (double)(ev.x + ev.y);
+        double* esh = reinterpret_cast<double*>(colp);
+        for (int o = 16; o > 0; o >>= 1) { den += __shfl_xor_sync(0xffffffffu, den, o); dev += __shfl_xor_sync(0xffffffffu, dev, o); }
+        __syncthreads();
+        if (lane == 0) { esh[warp] = den; esh[16 + warp] = dev; }
+        __syncthreads();
+        if (tid == 0) {
+            double s0 = 0, s1 = 0;
+            for (int w = 0; w < 16; w++) { s0 += esh[w]; s1 += esh[16 + w]; }
+            double* ep = LN_RUN(epart); ep[0] = s0; ep[1] = s1;
+        }
+    }
     __syncthreads();
-    if (tid == 0) {
-        double s0 = 0, s1 = 0;
-        for (int w = 0; w < 16; w++) { s0 += esh[0][w]; s1 += esh[1][w]; }
-        a.epart[blockIdx.x * 2] = s0; a.epart[blockIdx.x * 2 + 1] = s1;
+    if (tid == 0) { run->phases = phases; run->stage = stage; run->cstage = cstage; }
+    __syncthreads();
+}
+
+// fills the static part of a CTA's LnTileRun (one thread)
+__device__ __forceinline__ void ln_run_setup(LnTileRun* run, const float* Dt, long long t0, long long t1, long long nT, int N, float* colpart, float4* rowpart, double* epart,
+                                             int maxseg, int cta, int ncta) {
+    const long long ntl = t1 - t0;
+    const long long c0 = t0 + (ntl * cta) / ncta, c1 = t0 + (ntl * (cta + 1)) / ncta;
+    run->Dt = Dt + (size_t)(c0 - t0) * LN_TILE_FLOATS; run->colpart = colpart + (size_t)(c0 - t0) * 3 * LN_TB;
+    run->rowpart = rowpart + (size_t)cta * maxseg * LN_TB; run->epart = epart + 2 * cta;
+    run->n = (int)(c1 - c0); run->nT = (int)nT; run->N = N;
+    int I = 0, J = 0; if (c1 > c0) tile_coords(c0, nT, I, J);
+    run->I0 = I; run->J0 = J;
+}
+
+template <bool WANT_E, bool LOW_SOFT>
+__global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ LnTileRun run;
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic dependent launch: the previous kernel's results are complete from here on
+    if (a.done && *a.done) return;
+    if (threadIdx.x == 0) {
+        ln_run_setup(&run, a.Dt, a.t0, a.t1, a.nT, a.N, a.colpart, a.rowpart, a.epart, a.maxseg, blockIdx.x, gridDim.x);
+        run.X = a.x; run.XB = a.xb2 ? a.xb2 : a.x; run.lam = a.xb2 ? *a.lam : 0.f; run.more = 0; run.dbg = LN_DBG(a); run.terms = a.terms;
     }
+    __syncthreads();
+    ln_ring_init(&run, smem, false);
+    ln_tile_phase<WANT_E, LOW_SOFT>(&run, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,7 +517,9 @@ struct LnState {
     int cnt, head, it, ls, done, accepted, keep, have_E, hand, cur_image, nsteps, fresh;
     long long nevals;
     float lamf, tstepf, zerof, pad_;      // device scalars read by the tile kernel: x = a + lamf*b (MD), x = xb + tstepf*p (L-BFGS)
-    unsigned int counter, pad2_;          // "last block done" counter of the fused step kernels
+    unsigned int counter, epoch;          // "last block done" counter of the legacy step kernels; evaluation counter of the peer exchange
+    double eloc[2];                       // pair energies of this rank (persistent kernel)
+    unsigned long long tprof[8];          // phase clock of the persistent kernel (ns, CTA 0): tile, barrier 1, step, barrier 2, update
 };
 
 struct LnVec {     // all float4[N]
@@ -624,22 +713,21 @@ __device__ __forceinline__ bool ln_last_block(unsigned int* counter, int nblk) {
 }
 
 
-// ---- force exchange over NVLink peer memory, fused into the step kernels ------------------------------------
+// ---- force exchange over NVLink peer memory, fused into the persistent kernel (ln_persist.cuh) --------------------
 // Every rank owns a communication buffer (cudaMalloc + CUDA IPC) that its peers map:
 //   recv [2 parities][world][N + 1] float4   slot g = partial forces of rank g (no bond term)
 //   flags[world][nblk] u32                   flags[g][B] = epoch of the newest block-B partial of rank g that has landed here
 //   es   [2][world][2] double, eflag[world]  pair energies of rank g, and their epoch
-// Block B of the step kernel gathers this rank's partial force on its 128 beads, PUSHES it into slot `rank` of every
+// The CTA that handles bead block B gathers this rank's partial force on its 128 beads, PUSHES it into slot `rank` of every
 // rank's recv (remote stores, fire-and-forget), fences, pushes the epoch into every rank's flags, then waits until
-// the block-B flags of all ranks show the epoch and sums the world slots locally in rank order (identical on every
+// the block-B flags of all contributing ranks show the epoch and sums their slots locally in rank order (identical on every
 // rank, so the redundant integration stays bit-identical).  Parity double-buffering makes overwriting safe: a rank
 // cannot run two evaluations ahead of a peer, because each evaluation needs that peer's current flags.
 #define LN_MAXWORLD 8
 struct LnXchg {
     int world, rank, nblk, n4;                 // n4 = N + 1
     float4* recv[LN_MAXWORLD]; unsigned int* flags[LN_MAXWORLD]; double* es[LN_MAXWORLD]; unsigned int* eflag[LN_MAXWORLD];
-    unsigned int epoch; int parity;
-    int* err;                                  // set when a wait times out (a peer died): the host reports it
+    int* err;                                  // host-visible word, set when a wait times out (a peer died): the host reports it
 };
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     unsigned int v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -647,47 +735,9 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ bool ln_wait_flag(const unsigned int* p, unsigned int epoch, int* err) {
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(p) - epoch) < 0) {
-        if (clock64() - t0 > 4000000000ll) { *err = 1; return false; }          // ~2 s: give up instead of hanging the GPU
-    }
-    return true;
-}
-// all threads of the block call; (fx, fy, fz) of the lead threads: this rank's partial in, total over ranks out
-__device__ __forceinline__ void ln_exchange_forces(const LnXchg& x, int B, int tid, bool lead, int i, int N, float& fx, float& fy, float& fz) {
-    const size_t slot = ((size_t)x.parity * x.world + x.rank) * x.n4;
-    if (lead && i < N) {
-        const float4 v = make_float4(fx, fy, fz, 0.f);
-        for (int g = 0; g < x.world; g++) x.recv[g][slot + i] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < x.world) st_release_sys(x.flags[threadIdx.x] + (size_t)x.rank * x.nblk + B, x.epoch);
-    if (threadIdx.x < x.world) ln_wait_flag(x.flags[x.rank] + (size_t)threadIdx.x * x.nblk + B, x.epoch, x.err);
-    __syncthreads();
-    if (lead && i < N) {
-        fx = fy = fz = 0.f;
-        const float4* R = x.recv[x.rank] + (size_t)x.parity * x.world * x.n4 + i;
-        for (int g = 0; g < x.world; g++) { const float4 v = __ldcg(R + (size_t)g * x.n4); fx += v.x; fy += v.y; fz += v.z; }
-    }
-}
-// one thread (of the last block): pair energies of this rank in, totals over ranks out
-__device__ __forceinline__ void ln_exchange_energies(const LnXchg& x, double& e0, double& e1) {
-    for (int g = 0; g < x.world; g++) { double* d = x.es[g] + ((size_t)x.parity * x.world + x.rank) * 2; d[0] = e0; d[1] = e1; }
-    __threadfence_system();
-    for (int g = 0; g < x.world; g++) st_release_sys(x.eflag[g] + x.rank, x.epoch);
-    e0 = e1 = 0.0;
-    for (int g = 0; g < x.world; g++) {
-        if (!ln_wait_flag(x.eflag[x.rank] + g, x.epoch, x.err)) return;
-        const double* d = x.es[x.rank] + ((size_t)x.parity * x.world + g) * 2;
-        e0 += __ldcg(d); e1 += __ldcg(d + 1);
-    }
-}
 
 struct LnMdStepArgs {
     LnGather g; const float4* fsum;     // fsum != nullptr: total forces (bond included) already in fsum (NCCL path)
-    LnXchg xc;                          // xc.world > 1: fused peer-memory exchange
     const float4* a; const float4* b; const float* lam;     // coordinates of the evaluation just done: a + lam*b
     float4 *x, *v, *f, *a_next, *b_next;
     LnEnergySrc es;
@@ -708,7 +758,6 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArg
     if (p.fsum) { if (lead && i < p.N) { const float4 t = p.fsum[i]; fx = t.x; fy = t.y; fz = t.z; } }
     else {
         ln_gather(p.g, B, tid, grp, fx, fy, fz);
-        if (p.xc.world > 1) ln_exchange_forces(p.xc, B, tid, lead, i, p.N, fx, fy, fz);
         if (lead && i < p.N) ln_bond(p.a, p.b, lam, i, p.N, p.w_bond, p.r0, fx, fy, fz, eb);
     }
     if (lead && i < p.N) {
@@ -757,7 +806,6 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArg
             if (p.es.escal) { e0 = p.es.escal[0]; e1 = p.es.escal[1]; e2 = p.es.escal[2]; }
             else {
                 e0 = red[2][0]; e1 = red[3][0];
-                if (p.xc.world > 1) ln_exchange_energies(p.xc, e0, e1);
             }
             st->Enoe = e0; st->Evdw = e1; st->Ebond = e2; st->E = e0 + e1 + e2;
         }
@@ -766,7 +814,7 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArg
 }
 
 struct LnMinStepArgs {
-    LnGather g; const float4* fsum; LnXchg xc;
+    LnGather g; const float4* fsum;
     LnVec v; const float* lam; int init;         // init: evaluation at the starting point (x = v.x, nothing pending)
     LnEnergySrc es;
     LnState* st; double* blockpart; int nblk;
@@ -790,7 +838,6 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_min_step_kernel(LnMinStepA
     if (p.fsum) { if (lead && i < N) { const float4 t = p.fsum[i]; fx = t.x; fy = t.y; fz = t.z; } }
     else {
         ln_gather(p.g, B, tid, grp, fx, fy, fz);
-        if (p.xc.world > 1) ln_exchange_forces(p.xc, B, tid, lead, i, N, fx, fy, fz);
         if (lead && i < N) ln_bond(A, p.v.p, lam, i, N, p.w_bond, p.r0, fx, fy, fz, eb);
     }
     float acc[LN_KMAX];
@@ -840,13 +887,14 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_min_step_kernel(LnMinStepA
         if (p.es.escal) { e3[0] = p.es.escal[0]; e3[1] = p.es.escal[1]; e3[2] = p.es.escal[2]; }
         else {
             for (int q = 0; q < p.es.ncta; q++) { e3[0] += p.es.epart[2 * q]; e3[1] += p.es.epart[2 * q + 1]; }
-            if (p.xc.world > 1) ln_exchange_energies(p.xc, e3[0], e3[1]);
         }
         ln_min_decide(p.st, G, e3, p.cfg, p.init);
         p.st->tstepf = (float)p.st->tstep;
         p.st->counter = 0;
     }
 }
+
+#include "ln_persist.cuh"
 
 // sums of a float4 array (COM velocity / geometric centre): partials then subtraction
 __global__ void __launch_bounds__(256) ln_sum3_kernel(const float4* a, int N, double* part) {
@@ -1020,63 +1068,82 @@ __global__ void ln_synth_if_kernel(double* __restrict__ IF, int N, unsigned long
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
+struct LnEngine;
+// the engines one persistent launch serves: one (the normal case: one process per GPU), or the virtual ranks of a test group
+struct LnGroup { std::vector<LnEngine*> es; DevBuf<LnCtx> ctxs; int grid = 0; bool dirty = true; };
+
 struct LnEngine {
-    int N = 0, nT = 0, rank = 0, world = 1, m = 5, ncta = 0, maxseg = 0, nblk = 0, nparts = 0;
+    int N = 0, nT = 0, rank = 0, world = 1, m = 5, ncta = 0, maxseg = 0, nblk = 0, nparts = 0, sms = 148;
     long long n_tiles = 0, t0 = 0, t1 = 0, pairs_total = 0;
     DevBuf<float> Dt, colpart, x0; DevBuf<float4> rowpart, vx, vxb, vg, vp, vv, vf, vS, vY, sx, sv, va[2], vb[2], vfr;
-    DevBuf<int> seg_I, rs_off, rs_idx; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st;
+    DevBuf<int> rs_off, rs_idx; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st; DevBuf<unsigned int> bar;
     chr3d_sa_params prm; unsigned long long seed = 0; int model = 0;     // model: Philox stream of the coil / Maxwell draws
     cudaStream_t stream = nullptr;
     long long n_launches = 0;
 #ifdef CHR3D_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
-    // peer-memory exchange (world > 1): this rank's buffer, the mapped peer buffers, the evaluation counter
-    void* xbuf = nullptr; size_t xbytes = 0; void* peer[LN_MAXWORLD] = {nullptr}; bool p2p = false; unsigned int epoch = 0;
-    DevBuf<int> xerr;
+    // peer-memory exchange (world > 1): this rank's buffer, the mapped peer buffers
+    void* xbuf = nullptr; size_t xbytes = 0; void* peer[LN_MAXWORLD] = {nullptr}; bool p2p = false, peers_local = false;
+    int* xerr = nullptr;                       // pinned host word the kernel writes before it traps on a wait that cannot complete
+    bool legacy = false;                       // multi-launch evaluation (NCCL all-reduce between ranks): the baseline path
+    LnGroup self; LnGroup* group = nullptr;    // group: the launch group this engine currently belongs to (&self unless virtual ranks)
     static size_t up16(size_t v) { return (v + 15) / 16 * 16; }
     size_t x_off_flags() const { return sizeof(float4) * 2 * (size_t)world * (N + 1); }
     size_t x_off_es() const { return x_off_flags() + up16(sizeof(unsigned int) * (size_t)world * nblk); }
     size_t x_off_eflag() const { return x_off_es() + sizeof(double) * 2 * 2 * (size_t)world; }
     size_t x_total() const { return x_off_eflag() + up16(sizeof(unsigned int) * (size_t)world); }
-    LnXchg xchg_next() {            // descriptor of the next evaluation's exchange
-        LnXchg x; memset(&x, 0, sizeof x);
-        x.world = p2p ? world : 1; x.rank = rank; x.nblk = nblk; x.n4 = N + 1;
-        if (p2p) {
-            epoch++;
-            x.epoch = epoch; x.parity = (int)(epoch & 1u); x.err = xerr.p;
-            for (int g = 0; g < world; g++) {
-                char* base = (char*)peer[g];
-                x.recv[g] = (float4*)base; x.flags[g] = (unsigned int*)(base + x_off_flags());
-                x.es[g] = (double*)(base + x_off_es()); x.eflag[g] = (unsigned int*)(base + x_off_eflag());
-            }
-        }
-        return x;
-    }
     LnVec vec() { LnVec v; v.x = vx.p; v.xb = vxb.p; v.g = vg.p; v.p = vp.p; v.v = vv.p; v.f = vf.p; v.S = vS.p; v.Y = vY.p; v.N = N; v.m = m; return v; }
+    bool persistent() const { return !legacy && (world == 1 || p2p); }
 };
+
+// tile range -> CTA ranges: row-partial slots, the static CSR list "which (CTA, segment) row partials belong to tile row B"
+// (mirrors the walk of ln_tile_phase)
+static int ln_plan(LnEngine& e, int ncta) {
+    const long long ntl = e.t1 - e.t0;
+    e.ncta = (int)std::max<long long>(1, std::min<long long>(ncta, std::max<long long>(ntl, 1)));
+    // a CTA's contiguous tile range of length len touches at most len/(shortest row) + 2 tile rows
+    long long per = (ntl + e.ncta - 1) / e.ncta;
+    e.maxseg = (int)std::min<long long>(e.nT, per + 2);
+    CHR3D_CUDA(e.rowpart.alloc((size_t)e.ncta * e.maxseg * LN_TB));
+    CHR3D_CUDA(e.epart.alloc((size_t)e.ncta * 2));
+    CHR3D_CUDA(cudaMemset(e.epart.p, 0, sizeof(double) * 2 * e.ncta));
+    std::vector<std::vector<int>> rows(e.nT);
+    for (int c = 0; c < e.ncta; c++) {
+        const long long c0 = e.t0 + (ntl * c) / e.ncta, c1 = e.t0 + (ntl * (c + 1)) / e.ncta;
+        int curI = -1, seg = -1;
+        for (long long t = c0; t < c1; t++) {
+            int I, J; tile_coords(t, e.nT, I, J);
+            if (I != curI) { curI = I; seg++; rows[I].push_back(c * e.maxseg + seg); }
+        }
+    }
+    std::vector<int> off(e.nT + 1, 0), idx;
+    for (int B = 0; B < e.nT; B++) { off[B + 1] = off[B] + (int)rows[B].size(); idx.insert(idx.end(), rows[B].begin(), rows[B].end()); }
+    CHR3D_CUDA(e.rs_off.alloc(off.size())); CHR3D_CUDA(e.rs_idx.alloc(std::max<size_t>(idx.size(), 1)));
+    CHR3D_CUDA(cudaMemcpy(e.rs_off.p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+    if (!idx.empty()) CHR3D_CUDA(cudaMemcpy(e.rs_idx.p, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+    if (e.group) e.group->dirty = true;
+    return 0;
+}
 
 static int ln_alloc(LnEngine& e) {
     const int N = e.N;
     e.nT = (N + LN_TB - 1) / LN_TB; e.nblk = e.nT;
     e.n_tiles = (long long)e.nT * (e.nT + 1) / 2;
     e.t0 = e.n_tiles * e.rank / e.world; e.t1 = e.n_tiles * (e.rank + 1) / e.world;
-    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&e.sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ntl = e.t1 - e.t0;
-    e.ncta = (int)std::max<long long>(1, std::min<long long>(sms, ntl));
-    // a CTA's contiguous tile range of length len touches at most len/(shortest row) + 2 tile rows
-    long long per = (ntl + e.ncta - 1) / e.ncta;
-    e.maxseg = (int)std::min<long long>(e.nT, per + 2);
     e.nparts = std::min(64, std::max(1, (N + 255) / 256));
+    e.self.es.assign(1, &e); e.group = &e.self;
     CHR3D_CUDA(e.Dt.alloc((size_t)std::max<long long>(ntl, 1) * LN_TILE_FLOATS));
     CHR3D_CUDA(e.colpart.alloc((size_t)std::max<long long>(ntl, 1) * 3 * LN_TB));
-    CHR3D_CUDA(e.rowpart.alloc((size_t)e.ncta * e.maxseg * LN_TB));
-    CHR3D_CUDA(e.seg_I.alloc((size_t)e.ncta * e.maxseg));
-    CHR3D_CUDA(e.epart.alloc((size_t)e.ncta * 2));
+    if (int rc = ln_plan(e, e.sms)) return rc;
     CHR3D_CUDA(e.escal.alloc((size_t)3 + e.nblk));
     CHR3D_CUDA(e.part.alloc((size_t)e.nparts * LN_KMAX));
     CHR3D_CUDA(e.st.alloc(1));
     CHR3D_CUDA(cudaMemset(e.st.p, 0, sizeof(LnState)));
+    CHR3D_CUDA(e.bar.alloc(64));
+    CHR3D_CUDA(cudaMemset(e.bar.p, 0, sizeof(unsigned int) * 64));
     const size_t n4 = (size_t)N + 1;
     CHR3D_CUDA(e.vx.alloc(n4)); CHR3D_CUDA(e.vxb.alloc(n4)); CHR3D_CUDA(e.vg.alloc(n4)); CHR3D_CUDA(e.vp.alloc(n4));
     CHR3D_CUDA(e.vv.alloc(n4)); CHR3D_CUDA(e.vf.alloc(n4)); CHR3D_CUDA(e.sx.alloc(n4)); CHR3D_CUDA(e.sv.alloc(n4));
@@ -1086,26 +1153,13 @@ static int ln_alloc(LnEngine& e) {
     CHR3D_CUDA(e.vfr.alloc(n4)); CHR3D_CUDA(e.blockpart.alloc((size_t)e.nblk * LN_KMAX));
     CHR3D_CUDA(cudaMemset(e.vf.p, 0, sizeof(float4) * n4));
     CHR3D_CUDA(cudaMemset(e.vp.p, 0, sizeof(float4) * n4));
-    {   // static CSR list: which (CTA, segment) row partials belong to tile row B (mirrors the walk of ln_tile_kernel)
-        std::vector<std::vector<int>> rows(e.nT);
-        for (int c = 0; c < e.ncta; c++) {
-            const long long c0 = e.t0 + (ntl * c) / e.ncta, c1 = e.t0 + (ntl * (c + 1)) / e.ncta;
-            int curI = -1, seg = -1;
-            for (long long t = c0; t < c1; t++) {
-                int I, J; tile_coords(t, e.nT, I, J);
-                if (I != curI) { curI = I; seg++; rows[I].push_back(c * e.maxseg + seg); }
-            }
-        }
-        std::vector<int> off(e.nT + 1, 0), idx;
-        for (int B = 0; B < e.nT; B++) { off[B + 1] = off[B] + (int)rows[B].size(); idx.insert(idx.end(), rows[B].begin(), rows[B].end()); }
-        CHR3D_CUDA(e.rs_off.alloc(off.size())); CHR3D_CUDA(e.rs_idx.alloc(std::max<size_t>(idx.size(), 1)));
-        CHR3D_CUDA(cudaMemcpy(e.rs_off.p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
-        if (!idx.empty()) CHR3D_CUDA(cudaMemcpy(e.rs_idx.p, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
-    }
+    CHR3D_CUDA(cudaMallocHost((void**)&e.xerr, sizeof(int))); *e.xerr = 0;
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    CHR3D_CUDA(cudaFuncSetAttribute(ln_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    CHR3D_CUDA(cudaFuncSetAttribute(ln_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
     return 0;
 }
 
@@ -1115,33 +1169,93 @@ static void ln_terms(const chr3d_sa_params& p, const chr3d_stage& s, LnTerms& t)
     t.wv = (float)s.w_vdw; t.wv4 = 4.f * (float)s.w_vdw;
     double r = s.repel * p.vdw_rmin; t.R2 = (float)(r * r);
 }
+static int ln_dbg() {
+#ifdef CHR3D_DEV
+    static const int dbg = getenv("CHR3D_LN_DEBUG") ? atoi(getenv("CHR3D_LN_DEBUG")) : 0;
+    return dbg;
+#else
+    return 0;
+#endif
+}
 
-// Launch with programmatic stream serialization: the kernel is set up while its predecessor on the stream still runs and waits
-// at its griddepcontrol.wait until the predecessor has finished (nobody triggers early), which hides the launch latency between
-// the two kernels of a force evaluation — a sixth of the evaluation time of the L2-resident 50 kb structure.
+// ---- the persistent path: one cooperative launch per op ---------------------------------------------------------------
+static void ln_fill_ctx(LnEngine& e, int cta0, LnCtx& c) {
+    memset(&c, 0, sizeof c);
+    c.Dt = e.Dt.p; c.t0 = e.t0; c.t1 = e.t1; c.nT = e.nT; c.N = e.N; c.nblk = e.nblk; c.maxseg = e.maxseg; c.cta0 = cta0; c.ncta = e.ncta;
+    c.colpart = e.colpart.p; c.rowpart = e.rowpart.p; c.epart = e.epart.p; c.rs_off = e.rs_off.p; c.rs_idx = e.rs_idx.p;
+    tile_coords(e.t0, e.nT, c.gI0, c.gJ0);
+    if (e.t1 >= e.n_tiles) { c.gI1 = e.nT; c.gJ1 = e.nT; } else tile_coords(e.t1, e.nT, c.gI1, c.gJ1);
+    c.v = e.vec(); for (int q = 0; q < 2; q++) { c.va[q] = e.va[q].p; c.vb[q] = e.vb[q].p; }
+    c.st = e.st.p; c.blockpart = e.blockpart.p; c.bar = e.bar.p;
+    LnXchg& x = c.xc;
+    x.world = e.p2p ? e.world : 1; x.rank = e.rank; x.nblk = e.nblk; x.n4 = e.N + 1; x.err = e.xerr;
+    for (int g = 0; g < e.world && g < LN_MAXWORLD; g++) {
+        int I, J; tile_coords(e.n_tiles * g / e.world, e.nT, I, J); c.bmin[g] = I;
+        if (e.p2p) {
+            char* base = (char*)e.peer[g];
+            x.recv[g] = (float4*)base; x.flags[g] = (unsigned int*)(base + e.x_off_flags());
+            x.es[g] = (double*)(base + e.x_off_es()); x.eflag[g] = (unsigned int*)(base + e.x_off_eflag());
+        }
+    }
+}
+static int ln_group_sync(LnGroup& g) {        // (re)build the device copy of the rank contexts
+    if (!g.dirty) return 0;
+    std::vector<LnCtx> h(g.es.size());
+    int cta0 = 0;
+    for (size_t k = 0; k < g.es.size(); k++) { ln_fill_ctx(*g.es[k], cta0, h[k]); cta0 += g.es[k]->ncta; }
+    g.grid = cta0;
+    CHR3D_CUDA(g.ctxs.alloc(h.size()));
+    CHR3D_CUDA(cudaMemcpy(g.ctxs.p, h.data(), sizeof(LnCtx) * h.size(), cudaMemcpyHostToDevice));
+    g.dirty = false;
+    return 0;
+}
+static int ln_launch_persist(LnGroup& g, LnOp& op, cudaStream_t stream) {
+    if (int rc = ln_group_sync(g)) return rc;
+    LnEngine& e0 = *g.es[0];
+    op.dbg = ln_dbg();
+    const LnCtx* ctxs = g.ctxs.p; int nvr = (int)g.es.size();
+    void* args[3] = {(void*)&ctxs, (void*)&nvr, (void*)&op};
+    const void* fn = e0.prm.noe_low_soft ? (const void*)ln_persist_kernel<true> : (const void*)ln_persist_kernel<false>;
+    // cooperative: all CTAs are co-resident (they wait on one another at the grid barriers and on the peers' flags)
+    CHR3D_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)g.grid), dim3(LN_P_THREADS), args, (size_t)LN_SMEM, stream));
+    for (LnEngine* e : g.es) e->n_launches++;
+    return 0;
+}
+static void ln_op_common(LnEngine& e, const chr3d_stage& s, LnOp& op) {
+    memset(&op, 0, sizeof op);
+    ln_terms(e.prm, s, op.terms); op.w_bond = (float)s.w_bond; op.r0 = (float)e.prm.bond_r0; op.count_eval = 1;
+}
+static void ln_md_cfg(LnEngine& e, const chr3d_stage& s, LnMdCfg& c) {
+    c.dt_akma = (float)(s.dt / CHR3D_TIMFAC); c.h = (float)(0.5 * (s.dt / CHR3D_TIMFAC) / e.prm.mass); c.dt_ps = s.dt; c.temp = s.temp;
+    c.fbeta = e.prm.fbeta; c.kboltz = CHR3D_KBOLTZ; c.mass = e.prm.mass; c.flag = s.flag; c.N = e.N; c.nparts = e.nparts; c.count = 1;
+}
+static void ln_min_cfg(LnEngine& e, const chr3d_stage& s, LnMinCfg& c) {
+    c.m = e.m; c.max_ls = e.prm.lbfgs_max_ls; c.nstep = s.nstep; c.nparts = e.nparts; c.c1 = e.prm.lbfgs_c1; c.gtol = e.prm.lbfgs_gtol;
+    c.ftol = e.prm.lbfgs_ftol; c.drop = s.drop; c.N = e.N;
+}
+
+// Launch with programmatic stream serialization (legacy multi-launch path): the kernel is set up while its predecessor on the
+// stream still runs and waits at its griddepcontrol.wait until the predecessor has finished (nobody triggers early).
 template <typename Kern, typename Arg>
 static cudaError_t ln_launch_pdl(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t s, const Arg& arg) {
-    static const bool off = getenv("CHR3D_LN_NO_PDL") != nullptr;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = smem; lc.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = off ? 0 : 1;
+    lc.attrs = at; lc.numAttrs = 1;
     return cudaLaunchKernelEx(&lc, kern, arg);
 }
 template <typename Kern, typename A1, typename A2>
 static cudaError_t ln_launch_pdl2(Kern kern, unsigned grid, unsigned block, cudaStream_t s, const A1& a1, const A2& a2) {
-    static const bool off = getenv("CHR3D_LN_NO_PDL") != nullptr;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = 0; lc.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = off ? 0 : 1;
+    lc.attrs = at; lc.numAttrs = 1;
     return cudaLaunchKernelEx(&lc, kern, a1, a2);
 }
 static void ln_launch_tiles(LnEngine& e, LnTileArgs a, bool want_e) {
-    static const int dbg = getenv("CHR3D_LN_DEBUG") ? atoi(getenv("CHR3D_LN_DEBUG")) : 0;
-    a.dbg = dbg;
+    a.dbg = ln_dbg();
     const bool soft = e.prm.noe_low_soft != 0;
     if (want_e) { if (soft) ln_launch_pdl(ln_tile_kernel<true, true>, e.ncta, LN_THREADS, LN_SMEM, e.stream, a); else ln_launch_pdl(ln_tile_kernel<true, false>, e.ncta, LN_THREADS, LN_SMEM, e.stream, a); }
     else { if (soft) ln_launch_pdl(ln_tile_kernel<false, true>, e.ncta, LN_THREADS, LN_SMEM, e.stream, a); else ln_launch_pdl(ln_tile_kernel<false, false>, e.ncta, LN_THREADS, LN_SMEM, e.stream, a); }
@@ -1154,10 +1268,11 @@ static LnGather ln_gather_args(LnEngine& e) {
 // pair tiles at the coordinates x + lam*xb2 (xb2 == nullptr: plain x)
 static void ln_tiles(LnEngine& e, const chr3d_stage& s, const float4* x, const float4* xb2, const float* lam, const int* done, bool want_e) {
     LnTileArgs a; a.Dt = e.Dt.p; a.t0 = e.t0; a.t1 = e.t1; a.nT = e.nT; a.N = e.N; a.x = x; a.xb2 = xb2; a.lam = lam; a.done = done;
-    a.colpart = e.colpart.p; a.rowpart = e.rowpart.p; a.seg_I = e.seg_I.p; a.epart = e.epart.p; a.maxseg = e.maxseg; ln_terms(e.prm, s, a.terms);
+    a.colpart = e.colpart.p; a.rowpart = e.rowpart.p; a.epart = e.epart.p; a.maxseg = e.maxseg; ln_terms(e.prm, s, a.terms);
     ln_launch_tiles(e, a, want_e);
     e.n_launches++;
 }
+// ---- legacy multi-launch path (the NCCL baseline between ranks) ---------------------------------------------------------
 // several ranks: reduce this rank's partial forces (+ bond on rank 0) into vfr, sum vfr and the three energies over the
 // ranks with NCCL; afterwards every rank holds the total force in vfr and the totals in escal[0..2]
 static int ln_exchange(LnEngine& e, const chr3d_stage& s, const float4* x, const float4* xb2, const float* lam) {
@@ -1178,8 +1293,8 @@ static int ln_exchange(LnEngine& e, const chr3d_stage& s, const float4* x, const
     CHR3D_CUDA(cudaGetLastError());
     return 0;
 }
-// one energy + force evaluation at explicit coordinates e.vx, forces into e.vf, totals in escal[0..2] (SAVE / PICK / ENERGY / bench)
-static int ln_eval(LnEngine& e, const chr3d_stage& s, bool want_e = true) {
+// one energy + force evaluation at explicit coordinates e.vx, forces into e.vf, totals in escal[0..2]
+static int ln_eval_legacy(LnEngine& e, const chr3d_stage& s, bool want_e = true) {
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, want_e);
     LnReduceArgs r; r.g = ln_gather_args(e); r.epart = e.epart.p; r.N = e.N; r.ncta = e.ncta; r.add_bond = e.rank == 0 ? 1 : 0;
     r.x = e.vx.p; r.xb2 = nullptr; r.lam = nullptr; r.f = e.vf.p; r.escal = e.escal.p; r.w_bond = (float)s.w_bond; r.r0 = (float)e.prm.bond_r0;
@@ -1206,28 +1321,21 @@ static int ln_poll_done(LnEngine& e, int* done) {
     return 0;
 }
 
-// L-BFGS: per trial three launches (tiles at xb + t*p, ln_min_step_kernel, ln_min_update_kernel); the host only polls
+// L-BFGS, legacy: per trial three launches (tiles at xb + t*p, ln_min_step_kernel, ln_min_update_kernel); the host polls
 // the `done` flag every 32 trials, launches after `done` return immediately
-static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
+static int ln_minimize_legacy(LnEngine& e, const chr3d_stage& s) {
     const int vb = std::min(296, (e.N + 255) / 256);
     LnVec v = e.vec();
-    const bool multi = e.world > 1 && !e.p2p;       // NCCL path; with p2p the exchange is fused into the step kernel
-    LnMinCfg c; c.m = e.m; c.max_ls = e.prm.lbfgs_max_ls; c.nstep = s.nstep; c.nparts = e.nparts; c.c1 = e.prm.lbfgs_c1; c.gtol = e.prm.lbfgs_gtol;
-    c.ftol = e.prm.lbfgs_ftol; c.drop = s.drop; c.N = e.N;
+    const bool multi = e.world > 1;
+    LnMinCfg c; ln_min_cfg(e, s, c);
     LnMinStepArgs m; m.g = ln_gather_args(e); m.fsum = multi ? e.vfr.p : nullptr; m.v = v; m.lam = &e.st.p->tstepf; m.init = 1;
     m.es.epart = e.epart.p; m.es.ncta = e.ncta; m.es.escal = multi ? e.escal.p : nullptr; m.st = e.st.p; m.blockpart = e.blockpart.p; m.nblk = e.nblk;
     m.w_bond = (float)s.w_bond; m.r0 = (float)e.prm.bond_r0; m.cfg = c;
-    ln_state_reset_kernel<<<1, 32, 0, e.stream>>>(e.st.p, 0);
-    ln_copy_xb_kernel<<<vb, 256, 0, e.stream>>>(v);
-    // g := 0 so that the initial "y" is -f and g.g comes out of the same inner products; p := 0 keeps x + 0*p finite
-    CHR3D_CUDA(cudaMemsetAsync(e.vg.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
-    CHR3D_CUDA(cudaMemsetAsync(e.vp.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, true);
     if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
-    m.xc = e.xchg_next();
     ln_min_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(m);
     ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
-    e.n_launches += 6;
+    e.n_launches += 2;
     m.init = 0;
     const long long max_trials = (long long)s.nstep * (e.prm.lbfgs_max_ls + 2) + 2;
     const int poll_every = 32;
@@ -1235,7 +1343,6 @@ static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
         for (int k = 0; k < poll_every; k++, trial++) {
             ln_tiles(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf, &e.st.p->done, true);
             if (multi) if (int rc = ln_exchange(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf)) return rc;
-            m.xc = e.xchg_next();
             ln_launch_pdl(ln_min_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, m);
             ln_launch_pdl2(ln_min_update_kernel, vb, 256, e.stream, v, (const LnState*)e.st.p);
             e.n_launches += 2;
@@ -1247,16 +1354,10 @@ static int ln_minimize(LnEngine& e, const chr3d_stage& s) {
     CHR3D_CUDA(cudaGetLastError());
     return 0;
 }
-
-// Verlet MD: per step two launches (tiles at a + lam*b, ln_md_step_kernel); (a, b) double-buffered by parity
-static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
-    const int vb = std::min(296, (e.N + 255) / 256);
-    const bool multi = e.world > 1 && !e.p2p;
-    LnMdCfg c; c.dt_akma = (float)(s.dt / CHR3D_TIMFAC); c.h = (float)(0.5 * (s.dt / CHR3D_TIMFAC) / e.prm.mass); c.dt_ps = s.dt; c.temp = s.temp;
-    c.fbeta = e.prm.fbeta; c.kboltz = CHR3D_KBOLTZ; c.mass = e.prm.mass; c.flag = s.flag; c.N = e.N; c.nparts = e.nparts; c.count = 1;
-    ln_sum3_kernel<<<e.nparts, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p);             // cmremove
-    ln_sub_mean_kernel<<<vb, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p, e.nparts);
-    e.n_launches += 2;
+// Verlet MD, legacy: per step two launches (tiles at a + lam*b, ln_md_step_kernel); (a, b) double-buffered by parity
+static int ln_dynamics_legacy(LnEngine& e, const chr3d_stage& s) {
+    const bool multi = e.world > 1;
+    LnMdCfg c; ln_md_cfg(e, s, c);
     LnMdStepArgs p; p.g = ln_gather_args(e); p.fsum = multi ? e.vfr.p : nullptr; p.x = e.vx.p; p.v = e.vv.p; p.f = e.vf.p;
     p.es.epart = e.epart.p; p.es.ncta = e.ncta; p.es.escal = multi ? e.escal.p : nullptr; p.st = e.st.p; p.blockpart = e.blockpart.p; p.nblk = e.nblk; p.N = e.N;
     p.w_bond = (float)s.w_bond; p.r0 = (float)e.prm.bond_r0; p.h = c.h; p.dt_akma = c.dt_akma; p.md = c;
@@ -1264,7 +1365,6 @@ static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, false);
     if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
     p.a = e.vx.p; p.b = e.vx.p; p.lam = &e.st.p->zerof; p.a_next = e.va[0].p; p.b_next = e.vb[0].p; p.first = 1; p.want_e = 0;
-    p.xc = e.xchg_next();
     ln_launch_pdl(ln_md_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, p);
     e.n_launches++;
     int par = 0;
@@ -1273,7 +1373,6 @@ static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
         ln_tiles(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf, nullptr, want_e);
         if (multi) if (int rc = ln_exchange(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf)) return rc;
         p.a = e.va[par].p; p.b = e.vb[par].p; p.lam = &e.st.p->lamf; p.a_next = e.va[par ^ 1].p; p.b_next = e.vb[par ^ 1].p; p.first = 0; p.want_e = want_e ? 1 : 0;
-        p.xc = e.xchg_next();
         ln_launch_pdl(ln_md_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, p);
         e.n_launches++;
         par ^= 1;
@@ -1281,9 +1380,8 @@ static int ln_dynamics(LnEngine& e, const chr3d_stage& s) {
     CHR3D_CUDA(cudaGetLastError());
     return 0;
 }
-
-static int ln_energy_only(LnEngine& e, const chr3d_stage& s, bool count) {
-    if (int rc = ln_eval(e, s)) return rc;
+static int ln_energy_only_legacy(LnEngine& e, const chr3d_stage& s, bool count) {
+    if (int rc = ln_eval_legacy(e, s)) return rc;
     LnMdCfg c; memset(&c, 0, sizeof c); c.mass = e.prm.mass; c.kboltz = CHR3D_KBOLTZ; c.N = e.N; c.nparts = e.nparts; c.flag = 0; c.temp = 0; c.count = count ? 1 : 0;
     LnVec v = e.vec();
     ln_md_post_kernel<<<e.nparts, 256, 0, e.stream>>>(v, c, 0, e.part.p);
@@ -1292,39 +1390,93 @@ static int ln_energy_only(LnEngine& e, const chr3d_stage& s, bool count) {
     return 0;
 }
 
-static int ln_run_program(LnEngine& e, const chr3d_stage* prog, int nst) {
-    const int vb = std::min(296, (e.N + 255) / 256);
-    LnVec v = e.vec();
-    ln_state_reset_kernel<<<1, 32, 0, e.stream>>>(e.st.p, 1);
+// ---- ops on a launch group ---------------------------------------------------------------------------------------------
+static int ln_minimize(LnGroup& g, const chr3d_stage& s) {
+    for (LnEngine* ep : g.es) {
+        LnEngine& e = *ep;
+        const int vb = std::min(296, (e.N + 255) / 256);
+        LnVec v = e.vec();
+        ln_state_reset_kernel<<<1, 32, 0, e.stream>>>(e.st.p, 0);
+        ln_copy_xb_kernel<<<vb, 256, 0, e.stream>>>(v);
+        // g := 0 so that the initial "y" is -f and g.g comes out of the same inner products; p := 0 keeps x + 0*p finite
+        CHR3D_CUDA(cudaMemsetAsync(e.vg.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
+        CHR3D_CUDA(cudaMemsetAsync(e.vp.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
+        e.n_launches += 4;
+    }
+    LnEngine& e0 = *g.es[0];
+    if (!e0.persistent()) return ln_minimize_legacy(e0, s);
+    LnOp op; ln_op_common(e0, s, op); op.kind = LN_OP_MIN; ln_min_cfg(e0, s, op.min);
+    op.max_trials = (long long)s.nstep * (e0.prm.lbfgs_max_ls + 2) + 2;
+    return ln_launch_persist(g, op, e0.stream);          // leaves its loop on the device once the minimiser is done
+}
+static int ln_dynamics(LnGroup& g, const chr3d_stage& s) {
+    for (LnEngine* ep : g.es) {
+        LnEngine& e = *ep;
+        const int vb = std::min(296, (e.N + 255) / 256);
+        ln_sum3_kernel<<<e.nparts, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p);             // cmremove
+        ln_sub_mean_kernel<<<vb, 256, 0, e.stream>>>(e.vv.p, e.N, e.part.p, e.nparts);
+        e.n_launches += 2;
+    }
+    LnEngine& e0 = *g.es[0];
+    if (!e0.persistent()) return ln_dynamics_legacy(e0, s);
+    LnOp op; ln_op_common(e0, s, op); op.kind = LN_OP_MD; op.nstep = s.nstep; ln_md_cfg(e0, s, op.md);
+    return ln_launch_persist(g, op, e0.stream);
+}
+static int ln_energy_only(LnGroup& g, const chr3d_stage& s, bool count) {
+    LnEngine& e0 = *g.es[0];
+    if (!e0.persistent()) return ln_energy_only_legacy(e0, s, count);
+    LnOp op; ln_op_common(e0, s, op); op.kind = LN_OP_EVAL; op.count_eval = count ? 1 : 0;
+    return ln_launch_persist(g, op, e0.stream);
+}
+
+static int ln_run_program(LnGroup& g, const chr3d_stage* prog, int nst) {
+    for (LnEngine* ep : g.es) { ln_state_reset_kernel<<<1, 32, 0, ep->stream>>>(ep->st.p, 1); }
     for (int k = 0; k < nst; k++) {
         const chr3d_stage& s = prog[k];
         switch (s.op) {
-        case CHR3D_OP_INIT:
-            ln_init_kernel<<<vb, 256, 0, e.stream>>>(v, e.x0.p, s.flag);
-            ln_set_image_kernel<<<1, 32, 0, e.stream>>>(e.st.p, s.flag);
-            break;
-        case CHR3D_OP_MINIMIZE: if (int rc = ln_minimize(e, s)) return rc; break;
-        case CHR3D_OP_MAXWELL:
-            ln_maxwell_kernel<<<vb, 256, 0, e.stream>>>(v, e.seed, 0x100000u + (uint32_t)k, (uint32_t)e.model, sqrt(CHR3D_KBOLTZ * s.temp / e.prm.mass));
-            break;
-        case CHR3D_OP_DYNAMICS: if (int rc = ln_dynamics(e, s)) return rc; break;
-        case CHR3D_OP_SAVE:
-            if (int rc = ln_energy_only(e, s, true)) return rc;
-            ln_save_kernel<<<vb, 256, 0, e.stream>>>(v, e.sx.p, e.sv.p, e.st.p);
-            break;
-        case CHR3D_OP_PICK:
-            if (int rc = ln_energy_only(e, s, true)) return rc;
-            ln_pick_kernel<<<vb, 256, 0, e.stream>>>(v, e.sx.p, e.sv.p, e.st.p);
-            ln_pick_state_kernel<<<1, 32, 0, e.stream>>>(e.st.p);
-            break;
-        case CHR3D_OP_CENTER:
-            ln_sum3_kernel<<<e.nparts, 256, 0, e.stream>>>(e.vx.p, e.N, e.part.p);
-            ln_sub_mean_kernel<<<vb, 256, 0, e.stream>>>(e.vx.p, e.N, e.part.p, e.nparts);
-            break;
-        case CHR3D_OP_ENERGY: if (int rc = ln_energy_only(e, s, false)) return rc; break;
+        case CHR3D_OP_MINIMIZE: if (int rc = ln_minimize(g, s)) return rc; break;
+        case CHR3D_OP_DYNAMICS: if (int rc = ln_dynamics(g, s)) return rc; break;
+        case CHR3D_OP_SAVE: case CHR3D_OP_PICK: if (int rc = ln_energy_only(g, s, true)) return rc; break;
+        case CHR3D_OP_ENERGY: if (int rc = ln_energy_only(g, s, false)) return rc; break;
         default: break;
         }
+        for (LnEngine* ep : g.es) {
+            LnEngine& e = *ep;
+            const int vb = std::min(296, (e.N + 255) / 256);
+            LnVec v = e.vec();
+            switch (s.op) {
+            case CHR3D_OP_INIT:
+                ln_init_kernel<<<vb, 256, 0, e.stream>>>(v, e.x0.p, s.flag);
+                ln_set_image_kernel<<<1, 32, 0, e.stream>>>(e.st.p, s.flag);
+                break;
+            case CHR3D_OP_MAXWELL:
+                ln_maxwell_kernel<<<vb, 256, 0, e.stream>>>(v, e.seed, 0x100000u + (uint32_t)k, (uint32_t)e.model, sqrt(CHR3D_KBOLTZ * s.temp / e.prm.mass));
+                break;
+            case CHR3D_OP_SAVE:
+                ln_save_kernel<<<vb, 256, 0, e.stream>>>(v, e.sx.p, e.sv.p, e.st.p);
+                break;
+            case CHR3D_OP_PICK:
+                ln_pick_kernel<<<vb, 256, 0, e.stream>>>(v, e.sx.p, e.sv.p, e.st.p);
+                ln_pick_state_kernel<<<1, 32, 0, e.stream>>>(e.st.p);
+                break;
+            case CHR3D_OP_CENTER:
+                ln_sum3_kernel<<<e.nparts, 256, 0, e.stream>>>(e.vx.p, e.N, e.part.p);
+                ln_sub_mean_kernel<<<vb, 256, 0, e.stream>>>(e.vx.p, e.N, e.part.p, e.nparts);
+                break;
+            default: break;
+            }
+        }
         CHR3D_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// a wait inside the persistent kernel gave up (a peer died or stalled): report it instead of returning stale results
+static int ln_check_comm(LnEngine& e, const char* where) {
+    if (e.xerr && *e.xerr) {
+        set_error("%s: the persistent kernel gave up waiting (%s, code %d): a peer rank died or stalled; the results are invalid", where,
+                  *e.xerr == 1 ? "peer flag" : "grid barrier", *e.xerr);
+        return CHR3D_ERR_CUDA;
     }
     return 0;
 }
@@ -1333,7 +1485,7 @@ static int ln_run_program(LnEngine& e, const chr3d_stage* prog, int nst) {
 
 using namespace chr3d;
 
-struct chr3d_single { LnEngine e; cudaEvent_t ev0 = nullptr, ev1 = nullptr; std::vector<chr3d_stage> prog; };
+struct chr3d_single { LnEngine e; cudaEvent_t ev0 = nullptr, ev1 = nullptr; std::vector<chr3d_stage> prog; LnGroup vgroup; };
 
 // job: IF (host, N*N) or synthetic (IF == NULL, synth_seed != 0); x0 optional.
 CHR3D_API int chr3d_single_create(const double* IF, int32_t N, double alpha, double K, int32_t min_sep, uint64_t synth_seed,
@@ -1347,26 +1499,29 @@ CHR3D_API int chr3d_single_create(const double* IF, int32_t N, double alpha, dou
     e.N = N; e.rank = rank; e.world = world; e.prm = *p; e.seed = seed ? seed : p->seed;
     e.m = std::max(1, std::min((int)p->lbfgs_m, CHR3D_LBFGS_MAX_M));
     h->prog.assign(program, program + nstages);
+    {
+        const long long nT = (N + LN_TB - 1) / LN_TB, n_tiles = nT * (nT + 1) / 2;
+        if (world > LN_MAXWORLD || world > n_tiles) { set_error("chr3d_single_create: world %d exceeds %d ranks or the %lld tiles of the structure", world, LN_MAXWORLD, n_tiles); return CHR3D_ERR_ARG; }
+    }
     if (world > 1) {
-#ifdef CHR3D_WITH_NCCL
-        // nccl_id == NULL: shard without a communicator — forces/energies stay this rank's partial sums and the caller
-        // reduces them (used to check the partition on one GPU; chr3d_single_run refuses to integrate in that mode)
+        // nccl_id == NULL: no NCCL communicator — the ranks exchange over peer memory once chr3d_single_comm_connect (or
+        // chr3d_single_group_connect) has run; until then forces/energies stay this rank's partial sums and
+        // chr3d_single_run refuses to integrate
         if (nccl_id) {
+#ifdef CHR3D_WITH_NCCL
             if (!nccl_api().ok) { set_error("libnccl.so.2 could not be loaded"); return CHR3D_ERR_ARG; }
             ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
             if (ncclCommInitRank(&e.comm, world, id, rank) != ncclSuccess) { set_error("ncclCommInitRank failed"); return CHR3D_ERR_CUDA; }
-        }
 #else
-        set_error("libchr3d was built without NCCL"); return CHR3D_ERR_ARG;
+            set_error("libchr3d was built without NCCL"); return CHR3D_ERR_ARG;
 #endif
+        }
     }
     if (int rc = ln_alloc(e)) return rc;
     if (world > 1) {
-        if (world > LN_MAXWORLD) { set_error("chr3d_single_create: world %d exceeds %d", world, LN_MAXWORLD); return CHR3D_ERR_ARG; }
         e.xbytes = e.x_total();
         CHR3D_CUDA(cudaMalloc(&e.xbuf, e.xbytes));           // plain cudaMalloc: exportable through CUDA IPC
         CHR3D_CUDA(cudaMemset(e.xbuf, 0, e.xbytes));
-        CHR3D_CUDA(e.xerr.alloc(1)); CHR3D_CUDA(cudaMemset(e.xerr.p, 0, sizeof(int)));
     }
     {   // targets
         DevBuf<double> dIF, rows, mean; DevBuf<long long> dT;
@@ -1435,25 +1590,68 @@ int chr3d_single_run_model(chr3d_single* h, int model, const float* d_x0, void* 
     e.stream = (cudaStream_t)stream; e.model = model;
     if (d_x0) CHR3D_CUDA(cudaMemcpyAsync(e.x0.p, d_x0, sizeof(float) * 3 * (size_t)e.N, cudaMemcpyDeviceToDevice, e.stream));
     else { if (int rc = dev_random_coil(e.x0.p, e.N, 1, model, e.prm.bond_r0, e.seed, e.stream)) return rc; }
-    if (int rc = ln_run_program(e, h->prog.data(), (int)h->prog.size())) return rc;
+    if (int rc = ln_run_program(e.self, h->prog.data(), (int)h->prog.size())) return rc;
     ln_pack_result_kernel<<<std::min(296, (e.N + 255) / 256), 256, 0, e.stream>>>(e.vx.p, e.N, e.st.p, d_xout, d_e4, d_nevals, d_hand);
     CHR3D_CUDA(cudaGetLastError());
     return 0;
 }
 
+static bool ln_integrates(const std::vector<chr3d_stage>& prog) {
+    for (const chr3d_stage& s : prog) if (s.op == CHR3D_OP_MINIMIZE || s.op == CHR3D_OP_DYNAMICS) return true;
+    return false;
+}
+
 CHR3D_API int chr3d_single_run(chr3d_single* h, void* stream) {
     if (!h) { set_error("chr3d_single_run: null handle"); return CHR3D_ERR_ARG; }
+    LnEngine& e = h->e;
+    if (e.group != &e.self) { set_error("chr3d_single_run: this structure is a virtual rank of a group (use chr3d_single_group_run)"); return CHR3D_ERR_ARG; }
+    bool connected = e.world == 1 || e.p2p;
 #ifdef CHR3D_WITH_NCCL
-    if (h->e.world > 1 && !h->e.comm) {
-        bool integrates = false;
-        for (const chr3d_stage& s : h->prog) if (s.op == CHR3D_OP_MINIMIZE || s.op == CHR3D_OP_DYNAMICS) integrates = true;
-        if (integrates) { set_error("chr3d_single_run: a sharded structure without a communicator can only evaluate (INIT/ENERGY)"); return CHR3D_ERR_ARG; }
-    }
+    if (e.comm) connected = true;
 #endif
-    h->e.stream = (cudaStream_t)stream; h->e.n_launches = 0;
-    CHR3D_CUDA(cudaEventRecord(h->ev0, h->e.stream));
-    if (int rc = ln_run_program(h->e, h->prog.data(), (int)h->prog.size())) return rc;
-    CHR3D_CUDA(cudaEventRecord(h->ev1, h->e.stream));
+    if (!connected && ln_integrates(h->prog)) {
+        set_error("chr3d_single_run: a sharded structure without a communicator or a peer connection can only evaluate (INIT/ENERGY)"); return CHR3D_ERR_ARG;
+    }
+    e.legacy = e.world > 1 && !e.p2p;
+#ifdef CHR3D_DEV
+    if (getenv("CHR3D_LN_LEGACY")) e.legacy = true;
+#endif
+    if (e.legacy && e.world > 1 && !connected) {     // partial sums of a shard on one GPU (tests of the partition)
+        e.legacy = true;
+    }
+    e.stream = (cudaStream_t)stream; e.n_launches = 0;
+    CHR3D_CUDA(cudaEventRecord(h->ev0, e.stream));
+    if (int rc = ln_run_program(e.self, h->prog.data(), (int)h->prog.size())) return rc;
+    CHR3D_CUDA(cudaEventRecord(h->ev1, e.stream));
+    return 0;
+}
+
+// Virtual ranks: `n` structures created in THIS process on THIS device with rank g of world n become one launch group — the
+// persistent kernel hosts all of them in one cooperative grid (SMs / n CTAs each) and their "peer" buffers are plain device
+// pointers.  This is the multi-rank protocol (tile-range shards, peer exchange, redundant integration) on a single GPU.
+CHR3D_API int chr3d_single_group_connect(chr3d_single** hs, int32_t n) {
+    if (!hs || n < 1 || n > LN_MAXWORLD) { set_error("chr3d_single_group_connect: bad arguments"); return CHR3D_ERR_ARG; }
+    for (int g = 0; g < n; g++) if (!hs[g] || hs[g]->e.world != n || hs[g]->e.rank != g || (n > 1 && !hs[g]->e.xbuf)) { set_error("chr3d_single_group_connect: handle %d is not rank %d of %d", g, g, n); return CHR3D_ERR_ARG; }
+    LnGroup& grp = hs[0]->vgroup;
+    grp.es.clear(); grp.dirty = true;
+    const int each = std::max(1, hs[0]->e.sms / n);
+    for (int g = 0; g < n; g++) {
+        LnEngine& e = hs[g]->e;
+        for (int q = 0; q < n; q++) e.peer[q] = hs[q]->e.xbuf;
+        e.p2p = n > 1; e.peers_local = true; e.legacy = false;
+        e.group = &grp;
+        if (int rc = ln_plan(e, each)) return rc;
+        grp.es.push_back(&e);
+    }
+    return 0;
+}
+CHR3D_API int chr3d_single_group_run(chr3d_single** hs, int32_t n, void* stream) {
+    if (!hs || n < 1 || !hs[0] || (int)hs[0]->vgroup.es.size() != n) { set_error("chr3d_single_group_run: the handles are not a connected group"); return CHR3D_ERR_ARG; }
+    for (int g = 0; g < n; g++) { hs[g]->e.stream = (cudaStream_t)stream; hs[g]->e.n_launches = 0; }
+    CHR3D_CUDA(cudaEventRecord(hs[0]->ev0, (cudaStream_t)stream));
+    if (int rc = ln_run_program(hs[0]->vgroup, hs[0]->prog.data(), (int)hs[0]->prog.size())) return rc;
+    CHR3D_CUDA(cudaEventRecord(hs[0]->ev1, (cudaStream_t)stream));
+    for (int g = 1; g < n; g++) { CHR3D_CUDA(cudaEventRecord(hs[g]->ev0, (cudaStream_t)stream)); CHR3D_CUDA(cudaEventRecord(hs[g]->ev1, (cudaStream_t)stream)); }
     return 0;
 }
 
@@ -1461,12 +1659,17 @@ CHR3D_API int chr3d_single_run(chr3d_single* h, void* stream) {
 CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t reps, int32_t want_energy, double* tile_ms, double* eval_ms) {
     if (!h || reps < 1) { set_error("chr3d_single_eval_bench: bad arguments"); return CHR3D_ERR_ARG; }
     LnEngine& e = h->e; e.stream = (cudaStream_t)stream;
+    if (e.group != &e.self) { set_error("chr3d_single_eval_bench: not available for virtual ranks"); return CHR3D_ERR_ARG; }
+    e.legacy = e.world > 1 && !e.p2p;
+#ifdef CHR3D_DEV
+    if (getenv("CHR3D_LN_LEGACY")) e.legacy = true;
+#endif
     LnVec v = e.vec();
     ln_init_kernel<<<std::min(296, (e.N + 255) / 256), 256, 0, e.stream>>>(v, e.x0.p, 1);
     chr3d_stage s = h->prog.back();
     cudaEvent_t a, b; CHR3D_CUDA(cudaEventCreate(&a)); CHR3D_CUDA(cudaEventCreate(&b));
     LnTileArgs ta; ta.Dt = e.Dt.p; ta.t0 = e.t0; ta.t1 = e.t1; ta.nT = e.nT; ta.N = e.N; ta.x = e.vx.p; ta.xb2 = nullptr; ta.lam = nullptr; ta.done = nullptr;
-    ta.colpart = e.colpart.p; ta.rowpart = e.rowpart.p; ta.seg_I = e.seg_I.p; ta.epart = e.epart.p; ta.maxseg = e.maxseg; ln_terms(e.prm, s, ta.terms);
+    ta.colpart = e.colpart.p; ta.rowpart = e.rowpart.p; ta.epart = e.epart.p; ta.maxseg = e.maxseg; ln_terms(e.prm, s, ta.terms);
     for (int w = 0; w < 3; w++) ln_launch_tiles(e, ta, want_energy != 0);
     CHR3D_CUDA(cudaEventRecord(a, e.stream));
     for (int r = 0; r < reps; r++) ln_launch_tiles(e, ta, want_energy != 0);
@@ -1477,24 +1680,27 @@ CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t rep
     // a whole force evaluation as the integrator issues it: `reps` MD steps with dt = 0 (the state does not move)
     chr3d_stage md = s; md.op = CHR3D_OP_DYNAMICS; md.dt = 0.0; md.temp = 0.0; md.flag = 0; md.nstep = 2;
     CHR3D_CUDA(cudaMemsetAsync(e.vv.p, 0, sizeof(float4) * (size_t)(e.N + 1), e.stream));
-    if (int rc = ln_dynamics(e, md)) return rc;
+    if (int rc = ln_dynamics(e.self, md)) return rc;
     md.nstep = reps;
     CHR3D_CUDA(cudaEventRecord(a, e.stream));
-    if (int rc = ln_dynamics(e, md)) return rc;
+    if (int rc = ln_dynamics(e.self, md)) return rc;
     CHR3D_CUDA(cudaEventRecord(b, e.stream));
     CHR3D_CUDA(cudaEventSynchronize(b));
     CHR3D_CUDA(cudaEventElapsedTime(&ms, a, b));
-    ms = ms * reps / (reps + 1);                 // the stage's starting-point evaluation is one more
-    if (eval_ms) *eval_ms = ms / reps;
+    if (eval_ms) *eval_ms = ms / (reps + 1);     // the stage's starting-point evaluation is one more
     cudaEventDestroy(a); cudaEventDestroy(b);
-    return 0;
+    return ln_check_comm(e, "chr3d_single_eval_bench");
 }
 
 CHR3D_API int chr3d_single_fetch(chr3d_single* h, double* xyz, double* energies4, double* forces, int64_t* force_evals, int32_t* hand,
                                  double* device_ms, int64_t* n_launches, int64_t* restraint_pairs) {
     if (!h) { set_error("chr3d_single_fetch: null handle"); return CHR3D_ERR_ARG; }
     LnEngine& e = h->e;
-    CHR3D_CUDA(cudaStreamSynchronize(e.stream));
+    {
+        const cudaError_t se = cudaStreamSynchronize(e.stream);
+        if (int rc = ln_check_comm(e, "chr3d_single_fetch")) return rc;
+        CHR3D_CUDA(se);
+    }
     LnState st;
     CHR3D_CUDA(cudaMemcpy(&st, e.st.p, sizeof st, cudaMemcpyDeviceToHost));
     std::vector<float4> buf((size_t)e.N);
@@ -1515,12 +1721,52 @@ CHR3D_API int chr3d_single_fetch(chr3d_single* h, double* xyz, double* energies4
     return 0;
 }
 
+// Phase clock of the persistent kernel since the last call (milliseconds, as seen by CTA 0 of this rank): tile phases, first grid
+// barrier (+ energy publication), step phases (gather, peer exchange, integration), second barrier (+ decisions), L-BFGS update +
+// third barrier.  Reading resets the clock.
+CHR3D_API int chr3d_single_profile(chr3d_single* h, double* ms5) {
+    if (!h || !ms5) { set_error("chr3d_single_profile: bad arguments"); return CHR3D_ERR_ARG; }
+    LnEngine& e = h->e;
+    CHR3D_CUDA(cudaStreamSynchronize(e.stream));
+    unsigned long long t[8];
+    CHR3D_CUDA(cudaMemcpy(t, &e.st.p->tprof[0], sizeof t, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 5; q++) ms5[q] = 1e-6 * (double)t[q];
+    CHR3D_CUDA(cudaMemset(&e.st.p->tprof[0], 0, sizeof t));
+    return 0;
+}
+
 CHR3D_API int chr3d_single_info(const chr3d_single* h, int64_t* n_tiles, int64_t* tiles_this_rank, int32_t* ctas, int64_t* target_bytes) {
     if (!h) { set_error("chr3d_single_info: null handle"); return CHR3D_ERR_ARG; }
     if (n_tiles) *n_tiles = h->e.n_tiles;
     if (tiles_this_rank) *tiles_this_rank = h->e.t1 - h->e.t0;
     if (ctas) *ctas = h->e.ncta;
     if (target_bytes) *target_bytes = (h->e.t1 - h->e.t0) * (long long)LN_TILE_FLOATS * 4;
+    return 0;
+}
+
+// Test aid: this rank's targets as a dense row-major N*N fp32 matrix (cells outside the rank's tiles: NaN; the lower triangle
+// mirrors the upper one).  Sentinels as stored: -1 no restraint, -2 no restraint and no repel.
+__global__ void __launch_bounds__(256) ln_tiles_to_dense_kernel(const float* __restrict__ Dt, int N, long long t0, long long t1, long long nT, float* __restrict__ T) {
+    const long long t = t0 + blockIdx.x;
+    if (t >= t1) return;
+    int I, J; tile_coords(t, nT, I, J);
+    const float* in = Dt + (size_t)(t - t0) * LN_TILE_FLOATS;
+    for (int k = threadIdx.x; k < LN_TILE_FLOATS; k += blockDim.x) {
+        int r, c; ln_tile_cell(k, r, c);
+        const int i = I * LN_TB + r, j = J * LN_TB + c;
+        if (i < N && j < N && j > i) { T[(size_t)i * N + j] = in[k]; T[(size_t)j * N + i] = in[k]; }
+    }
+}
+CHR3D_API int chr3d_single_targets(chr3d_single* h, float* out) {
+    if (!h || !out) { set_error("chr3d_single_targets: bad arguments"); return CHR3D_ERR_ARG; }
+    LnEngine& e = h->e;
+    const size_t n2 = (size_t)e.N * e.N;
+    DevBuf<float> d; CHR3D_CUDA(d.alloc(n2));
+    CHR3D_CUDA(cudaMemset(d.p, 0xff, sizeof(float) * n2));          // NaN
+    const long long ntl = e.t1 - e.t0;
+    if (ntl > 0) ln_tiles_to_dense_kernel<<<(unsigned)ntl, 256>>>(e.Dt.p, e.N, e.t0, e.t1, e.nT, d.p);
+    CHR3D_CUDA(cudaGetLastError());
+    CHR3D_CUDA(cudaMemcpy(out, d.p, sizeof(float) * n2, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1532,8 +1778,9 @@ CHR3D_API int chr3d_single_destroy(chr3d_single* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     cudaDeviceSynchronize();
-    for (int g = 0; g < h->e.world && g < LN_MAXWORLD; g++) if (h->e.peer[g] && g != h->e.rank) cudaIpcCloseMemHandle(h->e.peer[g]);
+    if (!h->e.peers_local) for (int g = 0; g < h->e.world && g < LN_MAXWORLD; g++) if (h->e.peer[g] && g != h->e.rank) cudaIpcCloseMemHandle(h->e.peer[g]);
     if (h->e.xbuf) cudaFree(h->e.xbuf);
+    if (h->e.xerr) cudaFreeHost(h->e.xerr);
     cudaGetLastError();
     delete h;
     return 0;
@@ -1542,7 +1789,7 @@ CHR3D_API int chr3d_single_destroy(chr3d_single* h) {
 // Peer-memory exchange set-up (world > 1): every rank exports the IPC handle of its communication buffer
 // (64 bytes), the caller gathers the handles of all ranks in rank order (e.g. torch.distributed.all_gather_object)
 // and hands them to chr3d_single_comm_connect on every rank.  After that the force exchange of every evaluation
-// is fused into the step kernels (remote stores + flags over NVLink); without it the engine uses NCCL all-reduce.
+// is fused into the persistent kernel (remote stores + flags over NVLink); without it the engine uses NCCL all-reduce.
 CHR3D_API int chr3d_single_comm_handle(chr3d_single* h, void* out64) {
     if (!h || !out64 || !h->e.xbuf) { set_error("chr3d_single_comm_handle: no communication buffer (world == 1?)"); return CHR3D_ERR_ARG; }
     cudaIpcMemHandle_t mh;
@@ -1559,13 +1806,12 @@ CHR3D_API int chr3d_single_comm_connect(chr3d_single* h, const void* handles, in
         cudaIpcMemHandle_t mh; memcpy(&mh, (const char*)handles + 64 * (size_t)g, 64);
         CHR3D_CUDA(cudaIpcOpenMemHandle(&e.peer[g], mh, cudaIpcMemLazyEnablePeerAccess));
     }
-    e.p2p = true;
+    e.p2p = true; e.self.dirty = true;
     return 0;
 }
 CHR3D_API int chr3d_single_comm_error(chr3d_single* h, int32_t* err) {
     if (!h || !err) { set_error("chr3d_single_comm_error: bad arguments"); return CHR3D_ERR_ARG; }
-    *err = 0;
-    if (h->e.xerr.p) CHR3D_CUDA(cudaMemcpy(err, h->e.xerr.p, sizeof(int), cudaMemcpyDeviceToHost));
+    *err = h->e.xerr ? *h->e.xerr : 0;
     return 0;
 }
 

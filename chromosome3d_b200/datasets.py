@@ -15,11 +15,25 @@ _CACHE = os.path.join(_DATA, "_cache")
 
 
 def _unpack(archive, marker):
+    """Unpacks once, atomically: several processes (the ranks of a torchrun launch) may call this at the same time on a fresh
+    checkout, so the archive is extracted into a private temporary directory and renamed into place; a rank that loses the
+    rename race discards its copy.  Nobody ever sees a half-extracted directory."""
     dst = os.path.join(_CACHE, marker)
     if not os.path.isdir(dst):
+        import shutil
+        import tempfile
         os.makedirs(_CACHE, exist_ok=True)
-        with tarfile.open(os.path.join(_DATA, archive), "r:xz") as tf:
-            tf.extractall(_CACHE)
+        tmp = tempfile.mkdtemp(prefix=".unpack_", dir=_CACHE)
+        try:
+            with tarfile.open(os.path.join(_DATA, archive), "r:xz") as tf:
+                tf.extractall(tmp)
+            try:
+                os.rename(os.path.join(tmp, marker), dst)
+            except OSError:
+                if not os.path.isdir(dst):
+                    raise
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
     return dst
 
 

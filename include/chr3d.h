@@ -201,9 +201,13 @@ int chr3d_ensemble_destroy(chr3d_ensemble* e);
 /* The same dgsa.inp run (C3D:254-289, protocol C3D:1573-1829) for one structure of thousands of
  * beads, far beyond the reference's 663-bead cap (C3D:93-94).  The upper triangle of the target
  * matrix lives in HBM as 128x128 fp32 tiles; rank `rank` of `world` owns a contiguous range of
- * the tile list (balanced by pair count) and only derives/stores that part.  One process per
- * GPU; with world > 1 every force evaluation ends in one NCCL all-reduce of the N float4 forces
- * over NVLink (chr3d_nccl_unique_id() on rank 0, broadcast by the caller, e.g. torch.distributed).
+ * the tile list (row blocks balanced by pair count) and only derives/stores that part.  One process
+ * per GPU.  Every DYNAMICS / MINIMIZE / ENERGY op of the stage program is ONE persistent cooperative
+ * kernel per rank that runs all force evaluations of the op (tile pipeline, grid barriers, integrator
+ * or L-BFGS decisions on the device); with world > 1 the partial forces are exchanged inside that
+ * kernel over NVLink peer memory (chr3d_single_comm_handle / _connect).  Without a peer connection
+ * the ranks fall back to the multi-launch path with one NCCL all-reduce per evaluation
+ * (chr3d_nccl_unique_id() on rank 0, broadcast by the caller): the baseline, not the product path.
  *   IF        : host N*N row-major, or NULL with synth_seed != 0 (synthetic IF generated on the
  *               device; parsing 25k^2 decimals is not part of the hot path)
  *   x0        : optional N*3 start coordinates, NULL = seeded random coil                     */
@@ -215,7 +219,8 @@ int chr3d_single_create(const double* IF, int32_t N, double alpha, double K, int
                         chr3d_single** out);
 int chr3d_single_run(chr3d_single* h, void* stream);
 /* Measurement aid: `reps` force evaluations at the start coordinates, device-timed.
- * tile_ms = the pair-tile kernel alone, eval_ms = the whole evaluation (+reduction, +all-reduce). */
+ * tile_ms = the stand-alone pair-tile kernel, eval_ms = a whole evaluation as the integrator runs it
+ * (inside the persistent kernel: tile phase, barriers, gather, peer exchange, integration).      */
 int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t reps, int32_t want_energy,
                             double* tile_ms, double* eval_ms);
 int chr3d_single_fetch(chr3d_single* h, double* xyz, double* energies4, double* forces,
@@ -223,14 +228,27 @@ int chr3d_single_fetch(chr3d_single* h, double* xyz, double* energies4, double* 
                        int64_t* n_launches, int64_t* restraint_pairs);
 int chr3d_single_info(const chr3d_single* h, int64_t* n_tiles, int64_t* tiles_this_rank,
                       int32_t* ctas, int64_t* target_bytes);
+/* Phase clock of the persistent kernel since the last call, milliseconds as seen by CTA 0 of this rank:
+ * [0] tile phases, [1] first grid barrier (+ energy publication), [2] step phases (gather, peer exchange,
+ * integration), [3] second barrier (+ decisions), [4] L-BFGS update + third barrier.  Reading resets it. */
+int chr3d_single_profile(chr3d_single* h, double* ms5);
+/* Test aid: this rank's targets as a dense row-major N*N fp32 matrix (cells of other ranks' tiles and the
+ * diagonal: NaN; sentinels as stored: -1 no restraint, -2 no restraint and no repel).                  */
+int chr3d_single_targets(chr3d_single* h, float* out);
 int chr3d_single_destroy(chr3d_single* h);
 int chr3d_nccl_unique_id(void* out128);
 /* Fused peer-memory force exchange (world > 1): export this rank's 64-byte CUDA IPC handle, gather the handles of
- * all ranks in rank order, connect.  Afterwards the per-evaluation exchange runs inside the step kernels over
- * NVLink (remote stores + epoch flags) instead of NCCL.  chr3d_single_comm_error reports a peer time-out.     */
+ * all ranks in rank order, connect.  Afterwards the per-evaluation exchange runs inside the persistent kernel over
+ * NVLink (remote stores + epoch flags).  A wait that cannot complete (a peer died) makes the kernel give up after
+ * ~20 s; chr3d_single_fetch / _eval_bench then return CHR3D_ERR_CUDA and chr3d_single_comm_error reports the code. */
 int chr3d_single_comm_handle(chr3d_single* h, void* out64);
 int chr3d_single_comm_connect(chr3d_single* h, const void* handles /* world*64 bytes */, int32_t world);
 int chr3d_single_comm_error(chr3d_single* h, int32_t* err);
+/* Virtual ranks: `n` structures created in this process on this device as rank g of world n become ONE launch
+ * group — the persistent kernel hosts all of them in one cooperative grid (SMs/n CTAs each), their "peer" buffers
+ * are plain device pointers.  The multi-rank protocol on a single GPU (used by the parity tests).               */
+int chr3d_single_group_connect(chr3d_single** hs, int32_t n);
+int chr3d_single_group_run(chr3d_single** hs, int32_t n, void* stream);
 /* Synthetic IF matrix of SURVEY 8(d) (N*N doubles, generated on the device, copied back).     */
 int chr3d_synthetic_if(int32_t N, uint64_t seed, double* out);
 

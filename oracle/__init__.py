@@ -107,6 +107,30 @@ def energy_forces(xyz, ri, rj, rd, p, st, want_forces=True):
     return e, f
 
 
+def large_check(IF, alpha, p, st, K=11.0, min_sep=5, gpu_targets=None, x=None, want_forces=True, threads=0):
+    """Large structures: cell-by-cell check of the GPU's dense fp32 target matrix and fp64 energies/forces straight from the IF matrix."""
+    IF = np.ascontiguousarray(IF, dtype=np.float64)
+    N = IF.shape[0]
+    bad, rows, worst = C.c_int64(0), C.c_int64(0), C.c_double(0)
+    e = np.zeros(4)
+    f = np.zeros((N, 3)) if (x is not None and want_forces) else None
+    if x is not None:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+    if gpu_targets is not None:
+        gpu_targets = np.ascontiguousarray(gpu_targets, dtype=np.float32)
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except Exception:
+            threads = os.cpu_count() or 1
+    rc = lib().orc_large_check(_d(IF), N, C.c_double(alpha), C.c_double(K), int(min_sep), C.byref(p), C.byref(st),
+                               gpu_targets.ctypes.data_as(C.POINTER(C.c_float)) if gpu_targets is not None else None,
+                               C.byref(bad), C.byref(worst), C.byref(rows), _d(x) if x is not None else None, _d(e),
+                               _d(f) if f is not None else None, int(threads))
+    assert rc == 0
+    return dict(mismatches=bad.value, max_diff=worst.value, rows=rows.value, energies=e, forces=f)
+
+
 def energy_forces_bench(x, ri, rj, rd, p, st, reps, threads):
     x = np.ascontiguousarray(x, dtype=np.float64)
     e = C.c_double(0)
