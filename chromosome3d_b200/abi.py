@@ -27,6 +27,7 @@ class SaParams(C.Structure):
         ("premin_step", C.c_int32), ("images", C.c_int32), ("lbfgs_m", C.c_int32),
         ("lbfgs_max_ls", C.c_int32), ("lbfgs_c1", C.c_double), ("lbfgs_gtol", C.c_double), ("lbfgs_ftol", C.c_double),
         ("pow_drop", C.c_double), ("seed", C.c_uint64),
+        ("angle_d2", C.c_double), ("angle_k", C.c_double),
     ]
 
     def copy(self):

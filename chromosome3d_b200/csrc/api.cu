@@ -23,7 +23,7 @@ static int g_device = -1;
 struct Trace {
     bool on; double t0; const char* what;
     static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
-    explicit Trace(const char* w) : what(w) { static int en = getenv("CHR3D_TRACE") ? 1 : 0; on = en; if (on) t0 = now(); }
+    explicit Trace(const char* w) : what(w) { static int en = dev_getenv("CHR3D_TRACE") ? 1 : 0; on = en; if (on) t0 = now(); }
     void lap(const char* tag) { if (on) { cudaDeviceSynchronize(); double t = now(); fprintf(stderr, "[chr3d] %s/%s %.3f ms\n", what, tag, 1e3 * (t - t0)); t0 = t; } }
 };
 int require_device() {
@@ -215,6 +215,13 @@ CHR3D_API void chr3d_default_params(chr3d_sa_params* p) {
     p->pow_step = 15000; p->pow_cycl = 10; p->premin_step = 100; p->images = 2;
     p->lbfgs_m = 5; p->lbfgs_max_ls = 20; p->lbfgs_c1 = 1e-4; p->lbfgs_gtol = 1e-3; p->lbfgs_ftol = 1e-7; p->pow_drop = 10.0;
     p->seed = 82364;
+    p->angle_d2 = 0.0; p->angle_k = 0.0;       // the CA(i)-CA(i+2) lower bound is off by default
+}
+CHR3D_API void chr3d_abi_sizes(int32_t* sa_params, int32_t* stage, int32_t* job, int32_t* result) {
+    if (sa_params) *sa_params = (int32_t)sizeof(chr3d_sa_params);
+    if (stage) *stage = (int32_t)sizeof(chr3d_stage);
+    if (job) *job = (int32_t)sizeof(chr3d_job);
+    if (result) *result = (int32_t)sizeof(chr3d_result);
 }
 
 // The dgsa.inp protocol body as a stage program (C3D:1573-1829).
@@ -365,7 +372,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
         if (program[k].op == CHR3D_OP_SAVE) { n_save++; i_save = k; }
         if (program[k].op == CHR3D_OP_PICK) { n_pick++; i_pick = k; }
     }
-    const bool split_ok = !want_forces && !getenv("CHR3D_NO_SPLIT") && n_init == 2 && n_save == 1 && n_pick == 1 && program[0].op == CHR3D_OP_INIT &&
+    const bool split_ok = !want_forces && !dev_getenv("CHR3D_NO_SPLIT") && n_init == 2 && n_save == 1 && n_pick == 1 && program[0].op == CHR3D_OP_INIT &&
                           i_save + 1 < i_pick && program[i_save + 1].op == CHR3D_OP_INIT;
     int total_traj = 0;                       // the launch shape of every job is chosen for the whole batch sharing the GPU
     for (int jn = 0; jn < njobs; jn++) total_traj += std::max(jobs[jn].n_models, 0);
@@ -483,7 +490,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             e->groups.push_back(g);
         }
     }
-    if (e->groups.size() > 1 && !getenv("CHR3D_SERIAL_GROUPS")) {      // CHR3D_SERIAL_GROUPS: development switch, one launch after the other
+    if (e->groups.size() > 1 && !dev_getenv("CHR3D_SERIAL_GROUPS")) {      // CHR3D_SERIAL_GROUPS: development switch, one launch after the other
         e->gstreams.resize(e->groups.size()); e->gevents.resize(e->groups.size());
         for (size_t k = 0; k < e->groups.size(); k++) {
             CHR3D_CUDA(cudaStreamCreateWithFlags(&e->gstreams[k], cudaStreamNonBlocking));

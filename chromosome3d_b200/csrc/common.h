@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../include/chr3d.h"
@@ -14,6 +15,14 @@
 #define CHR3D_KBOLTZ 1.987191e-3
 
 namespace chr3d {
+
+// Development switches (launch shapes, probes, traces) are read from the environment only in a -DCHR3D_DEV build
+// (`make DEV=1`); the release library ignores them, so a stray variable cannot change what a benchmark measures.
+#ifdef CHR3D_DEV
+static inline const char* dev_getenv(const char* name) { return getenv(name); }
+#else
+static inline const char* dev_getenv(const char*) { return nullptr; }
+#endif
 
 void set_error(const char* fmt, ...);
 int  require_device();                 // 0 or CHR3D_ERR_NO_DEVICE, sets the error text

@@ -1170,12 +1170,8 @@ static void ln_terms(const chr3d_sa_params& p, const chr3d_stage& s, LnTerms& t)
     double r = s.repel * p.vdw_rmin; t.R2 = (float)(r * r);
 }
 static int ln_dbg() {
-#ifdef CHR3D_DEV
-    static const int dbg = getenv("CHR3D_LN_DEBUG") ? atoi(getenv("CHR3D_LN_DEBUG")) : 0;
+    static const int dbg = dev_getenv("CHR3D_LN_DEBUG") ? atoi(dev_getenv("CHR3D_LN_DEBUG")) : 0;
     return dbg;
-#else
-    return 0;
-#endif
 }
 
 // ---- the persistent path: one cooperative launch per op ---------------------------------------------------------------
@@ -1613,9 +1609,7 @@ CHR3D_API int chr3d_single_run(chr3d_single* h, void* stream) {
         set_error("chr3d_single_run: a sharded structure without a communicator or a peer connection can only evaluate (INIT/ENERGY)"); return CHR3D_ERR_ARG;
     }
     e.legacy = e.world > 1 && !e.p2p;
-#ifdef CHR3D_DEV
-    if (getenv("CHR3D_LN_LEGACY")) e.legacy = true;
-#endif
+    if (dev_getenv("CHR3D_LN_LEGACY")) e.legacy = true;
     if (e.legacy && e.world > 1 && !connected) {     // partial sums of a shard on one GPU (tests of the partition)
         e.legacy = true;
     }
@@ -1661,9 +1655,7 @@ CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t rep
     LnEngine& e = h->e; e.stream = (cudaStream_t)stream;
     if (e.group != &e.self) { set_error("chr3d_single_eval_bench: not available for virtual ranks"); return CHR3D_ERR_ARG; }
     e.legacy = e.world > 1 && !e.p2p;
-#ifdef CHR3D_DEV
-    if (getenv("CHR3D_LN_LEGACY")) e.legacy = true;
-#endif
+    if (dev_getenv("CHR3D_LN_LEGACY")) e.legacy = true;
     LnVec v = e.vec();
     ln_init_kernel<<<std::min(296, (e.N + 255) / 256), 256, 0, e.stream>>>(v, e.x0.p, 1);
     chr3d_stage s = h->prog.back();

@@ -1154,8 +1154,8 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
     static std::map<std::tuple<int, int, int, int>, SaLaunchCfg> cache;
     int dev = 0, smem_max = 227 * 1024;
     cudaGetDevice(&dev);
-    const int force_c = getenv("CHR3D_SA_CLUSTER") ? atoi(getenv("CHR3D_SA_CLUSTER")) : 0;
-    const int force_w = getenv("CHR3D_SA_WARPS") ? atoi(getenv("CHR3D_SA_WARPS")) : 0;
+    const int force_c = dev_getenv("CHR3D_SA_CLUSTER") ? atoi(dev_getenv("CHR3D_SA_CLUSTER")) : 0;
+    const int force_w = dev_getenv("CHR3D_SA_WARPS") ? atoi(dev_getenv("CHR3D_SA_WARPS")) : 0;
     const auto key = std::make_tuple(dev, N, n_traj, m);
     {
         std::lock_guard<std::mutex> g(mu);
@@ -1164,7 +1164,7 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
     }
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int smem_hw = smem_max;
-    if (getenv("CHR3D_SA_SMEM_CAP")) smem_max = std::min(smem_max, atoi(getenv("CHR3D_SA_SMEM_CAP")));   // development: force >1 CTA per SM
+    if (dev_getenv("CHR3D_SA_SMEM_CAP")) smem_max = std::min(smem_max, atoi(dev_getenv("CHR3D_SA_SMEM_CAP")));   // development: force >1 CTA per SM
     for (int th : {384, 512, 640}) {
         if (cudaFuncSetAttribute(sa_pick_kernel(false, th), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_hw) != cudaSuccess) cudaGetLastError();
         if (cudaFuncSetAttribute(sa_pick_kernel(false, th), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
@@ -1174,7 +1174,7 @@ int sa_choose_config(int N, int n_traj, int m, SaLaunchCfg* cfg) {
     // inputs x 20 models: 193 ms against 208 ms), because the shapes the cost model then picks leave fewer, larger launch
     // groups.  (Co-resident CTAs used to hang intermittently; that was a phase race in the exchange protocol, fixed in
     // sa_kernel — see "after_dyn" — and documented in DESIGN.md.)  CHR3D_SA_MIN_SMEM=0 lifts the floor.
-    const size_t min_smem = getenv("CHR3D_SA_MIN_SMEM") ? (size_t)atol(getenv("CHR3D_SA_MIN_SMEM")) : (size_t)117 * 1024;
+    const size_t min_smem = dev_getenv("CHR3D_SA_MIN_SMEM") ? (size_t)atol(dev_getenv("CHR3D_SA_MIN_SMEM")) : (size_t)117 * 1024;
     double best = 1e300; SaLaunchCfg bc = {1, 128, 0, 0, 0.0};
     const int Cs[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16};     // > 8: non-portable cluster sizes, two CTAs of different trajectories per SM
     for (int C : Cs) {

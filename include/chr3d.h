@@ -75,6 +75,11 @@ typedef struct chr3d_sa_params {
     double  lbfgs_ftol;     /* stop when a quasi-Newton step lowers E by <= ftol*max(|E|,1)  */
     double  pow_drop;       /* drop=10.0 expected first-step energy decrease       C3D:1802 */
     uint64_t seed;          /* md.seed 82364                                        C3D:980 */
+    /* Stand-in for the terms the bead model drops (CNS adds `angl`, then `impr dihe`, C3D:1641, 1643):
+     * a soft lower bound on the CA(i)-CA(i+2) distance, E = w* . angle_k . max(0, angle_d2 - r)^2, scaled by the
+     * stage's `weights *` factor like the bond term and reported with it (REMARK bon).  Default off (angle_d2 = 0).  */
+    double  angle_d2;       /* A; 0 = off                                                    */
+    double  angle_k;        /* kcal/mol/A^2                                                  */
 } chr3d_sa_params;
 
 #define CHR3D_LBFGS_MAX_M 8
@@ -149,6 +154,8 @@ int  chr3d_init(int device);          /* bind this host thread/process to a CUDA
 int  chr3d_shutdown(void);
 
 void chr3d_default_params(chr3d_sa_params* p);
+/* sizeof of the ABI structs as this build of the library sees them: a binding checks its own layout against these */
+void chr3d_abi_sizes(int32_t* sa_params, int32_t* stage, int32_t* job, int32_t* result);
 /* Writes the stage program for `p`; returns the number of stages (or <0).  cap==0: size query. */
 int  chr3d_build_program(const chr3d_sa_params* p, chr3d_stage* out, int cap);
 

@@ -86,8 +86,8 @@ sub version      { _load(); return _c_chr3d_version(); }
 sub device_count { _load(); return _c_chr3d_device_count(); }
 sub init         { _load(); _check(_c_chr3d_init($_[0] // 0), "chr3d_init"); }
 
-# chr3d_sa_params is kept as an opaque 224-byte buffer; the few fields the front end sets are patched by offset.
-use constant PARAMS_BYTES => 224;
+# chr3d_sa_params is kept as an opaque 240-byte buffer; the few fields the front end sets are patched by offset.
+use constant PARAMS_BYTES => 240;
 use constant STAGE_BYTES  => 72;
 sub default_params { _load(); my $p = _buf(PARAMS_BYTES); _c_chr3d_default_params(ptr($p)); return $p; }
 sub build_program {
