@@ -28,7 +28,10 @@ def test_struct_layouts_match_header():
     which includes the same header)."""
     p, po = api.default_params(), orc.default_params()
     assert bytes(p) == bytes(po)
-    assert C.sizeof(abi.Stage) == 72 and C.sizeof(abi.SaParams) == 224
+    assert C.sizeof(abi.Stage) == 72 and C.sizeof(abi.SaParams) == 240
+    sizes = [C.c_int32(0) for _ in range(4)]
+    api.lib().chr3d_abi_sizes(*[C.byref(v) for v in sizes])        # what the library itself was compiled with
+    assert [v.value for v in sizes] == [C.sizeof(abi.SaParams), C.sizeof(abi.Stage), C.sizeof(abi.Job), C.sizeof(abi.Result)]
 
 
 def test_stage_program_equals_oracle_program():
