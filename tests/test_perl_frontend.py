@@ -33,7 +33,7 @@ def test_binding_loads_and_host_entry_points_work():
     r = _perl(["-e", code])
     assert r.returncode == 0, r.stderr
     backend, n, plen, *order = r.stdout.split()
-    assert backend in ("XS", "FFI::Platypus") and int(n) == 113 and int(plen) == 224
+    assert backend in ("XS", "FFI::Platypus") and int(n) == 113 and int(plen) == 240
     assert [int(o) for o in order] == [3, 2, 4, 0, 1]            # int() truncation + index tie-break (C3D:617, 823)
 
 
