@@ -486,6 +486,16 @@ class Single:
         _check(lib().chr3d_single_profile(self._h, a))
         return dict(zip(("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms"), [float(v) for v in a]))
 
+    def profile_ctas(self):
+        """Per-CTA tile counts (all, near, rows started) and tile-phase milliseconds of the persistent kernel since the last call."""
+        cap = 1024
+        n = C.c_int32(0)
+        t, nn, r = (C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_int32 * cap)()
+        ms = (C.c_double * cap)()
+        _check(lib().chr3d_single_profile_ctas(self._h, cap, C.byref(n), t, nn, r, ms))
+        k = min(n.value, cap)
+        return dict(tiles=np.array(t[:k]), near=np.array(nn[:k]), rows=np.array(r[:k]), tile_ms=np.array(ms[:k]))
+
     def targets(self):
         """Test aid: this rank's targets as a dense N*N fp32 matrix (NaN outside the rank's tiles)."""
         out = np.zeros((self.N, self.N), dtype=np.float32)

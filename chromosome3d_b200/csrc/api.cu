@@ -60,6 +60,7 @@ void make_dev_params(const chr3d_sa_params& p, DevParams& d) {
     d.fbeta = (float)p.fbeta; d.kboltz = (float)CHR3D_KBOLTZ;
     d.m = std::max(1, std::min((int)p.lbfgs_m, CHR3D_LBFGS_MAX_M)); d.max_ls = p.lbfgs_max_ls;
     d.c1 = (float)p.lbfgs_c1; d.gtol = (float)p.lbfgs_gtol; d.ftol = (float)p.lbfgs_ftol;
+    d.ang_d2 = (p.angle_d2 > 0 && p.bond_k > 0 && p.angle_k > 0) ? (float)p.angle_d2 : 0.f; d.ang_ratio = d.ang_d2 > 0.f ? (float)(p.angle_k / p.bond_k) : 0.f;
 }
 void make_dev_stage(const chr3d_sa_params& p, const chr3d_stage& s, DevStage& d) {
     memset(&d, 0, sizeof d);

@@ -68,6 +68,7 @@ struct DevParams {
     int   m, max_ls;
     float c1, gtol, ftol;
     int   general_noe;             // b != 0: use the exact piecewise formula
+    float ang_d2, ang_ratio;       // CA(i)-CA(i+2) lower bound (0 = off), angle_k / bond_k
 };
 struct DevStage {
     int   op, nstep, flag, pad_;

@@ -81,6 +81,9 @@ namespace chr3d {
 #define LN_KMAX 64
 
 struct LnTerms { float wnC, wnC2m, lo, rsw, wv, wv4, R2; };
+// the O(N) terms added by the bead's owner: harmonic bond (i, i+1) and, when d2 > 0, the soft lower bound on the CA(i)-CA(i+2)
+// distance that stands in for CNS's angle term (C3D:1641; chr3d_sa_params.angle_d2 / angle_k), same `weights *` factor
+struct LnBonded { float w_bond, r0, w_ang, d2; };
 
 // one symmetric pair: accumulates the force on i (fi) and on j (fj) and, if WANT_E, the energies.
 // r^2 carries a 1e-12 floor folded into the FMA chain (coincident beads), as the oracle's max(r^2, 1e-12).
@@ -161,6 +164,7 @@ struct LnTileArgs {
     float* colpart;           // [(t - t0)][3][128]
     float4* rowpart;          // [cta][maxseg][128]
     double* epart;            // [cta][2]
+    const long long* cstart;  // [ctas + 1] first tile of every CTA (cost-balanced partition of [t0, t1), ln_plan)
     int maxseg;
     int dbg;                  // development probe (-DCHR3D_DEV + CHR3D_LN_DEBUG): 1 = stream tiles without the pair term, 2 = pair term without tile traffic
     LnTerms terms;
@@ -383,10 +387,9 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
 }
 
 // fills the static part of a CTA's LnTileRun (one thread)
-__device__ __forceinline__ void ln_run_setup(LnTileRun* run, const float* Dt, long long t0, long long t1, long long nT, int N, float* colpart, float4* rowpart, double* epart,
-                                             int maxseg, int cta, int ncta) {
-    const long long ntl = t1 - t0;
-    const long long c0 = t0 + (ntl * cta) / ncta, c1 = t0 + (ntl * (cta + 1)) / ncta;
+__device__ __forceinline__ void ln_run_setup(LnTileRun* run, const float* Dt, long long t0, const long long* cstart, long long nT, int N, float* colpart, float4* rowpart, double* epart,
+                                             int maxseg, int cta) {
+    const long long c0 = cstart[cta], c1 = cstart[cta + 1];
     run->Dt = Dt + (size_t)(c0 - t0) * LN_TILE_FLOATS; run->colpart = colpart + (size_t)(c0 - t0) * 3 * LN_TB;
     run->rowpart = rowpart + (size_t)cta * maxseg * LN_TB; run->epart = epart + 2 * cta;
     run->n = (int)(c1 - c0); run->nT = (int)nT; run->N = N;
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs
     asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic dependent launch: the previous kernel's results are complete from here on
     if (a.done && *a.done) return;
     if (threadIdx.x == 0) {
-        ln_run_setup(&run, a.Dt, a.t0, a.t1, a.nT, a.N, a.colpart, a.rowpart, a.epart, a.maxseg, blockIdx.x, gridDim.x);
+        ln_run_setup(&run, a.Dt, a.t0, a.cstart, a.nT, a.N, a.colpart, a.rowpart, a.epart, a.maxseg, blockIdx.x);
         run.X = a.x; run.XB = a.xb2 ? a.xb2 : a.x; run.lam = a.xb2 ? *a.lam : 0.f; run.more = 0; run.dbg = LN_DBG(a); run.terms = a.terms;
     }
     __syncthreads();
@@ -458,18 +461,35 @@ __device__ __forceinline__ float4 ln_ldx(const float4* a, const float4* b, float
     const float4 p = a[i], q = b[i];
     return make_float4(fmaf(lam, q.x, p.x), fmaf(lam, q.y, p.y), fmaf(lam, q.z, p.z), 0.f);
 }
-__device__ __forceinline__ void ln_bond(const float4* a, const float4* b, float lam, int i, int N, float w_bond, float r0,
-                                        float& fx, float& fy, float& fz, float& eb) {
-    const float4 xi = ln_ldx(a, b, lam, i);
+// bond (+ angle stand-in) terms of bead i at coordinates a + lam*b; LD: how a float4 is loaded (plain, or around L1)
+template <typename LD>
+__device__ __forceinline__ void ln_bonded(LD ld, const float4* a, const float4* b, float lam, int i, int N, const LnBonded& bd,
+                                          float& fx, float& fy, float& fz, float& eb) {
+    const float4 pi = ld(a + i), qi = ld(b + i);
+    const float xi = fmaf(lam, qi.x, pi.x), yi = fmaf(lam, qi.y, pi.y), zi = fmaf(lam, qi.z, pi.z);
     for (int s = -1; s <= 1; s += 2) {
         const int nb = i + s; if (nb < 0 || nb >= N) continue;
-        const float4 xn = ln_ldx(a, b, lam, nb);
-        const float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
-        const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f), rinv = ln_rsqrt(r2), r = r2 * rinv, u = r - r0;
-        const float g = 2.f * w_bond * u * rinv;
+        const float4 pn = ld(a + nb), qn = ld(b + nb);
+        const float dx = xi - fmaf(lam, qn.x, pn.x), dy = yi - fmaf(lam, qn.y, pn.y), dz = zi - fmaf(lam, qn.z, pn.z);
+        const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f), rinv = ln_rsqrt(r2), r = r2 * rinv, u = r - bd.r0;
+        const float g = 2.f * bd.w_bond * u * rinv;
         fx -= g * dx; fy -= g * dy; fz -= g * dz;
-        if (s == 1) eb = w_bond * u * u;
+        if (s == 1) eb = bd.w_bond * u * u;
     }
+    if (bd.w_ang > 0.f) for (int s = -2; s <= 2; s += 4) {
+        const int nb = i + s; if (nb < 0 || nb >= N) continue;
+        const float4 pn = ld(a + nb), qn = ld(b + nb);
+        const float dx = xi - fmaf(lam, qn.x, pn.x), dy = yi - fmaf(lam, qn.y, pn.y), dz = zi - fmaf(lam, qn.z, pn.z);
+        const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f), rinv = ln_rsqrt(r2), r = r2 * rinv, u = fmaxf(bd.d2 - r, 0.f);
+        const float g = -2.f * bd.w_ang * u * rinv;          // dE/dr / r of w (d2 - r)^2
+        fx -= g * dx; fy -= g * dy; fz -= g * dz;
+        if (s == 2) eb += bd.w_ang * u * u;
+    }
+}
+struct LnLdPlain { __device__ __forceinline__ float4 operator()(const float4* p) const { return *p; } };
+struct LnLdCg { __device__ __forceinline__ float4 operator()(const float4* p) const { return __ldcg(p); } };
+__device__ __forceinline__ void ln_bond(const float4* a, const float4* b, float lam, int i, int N, const LnBonded& bd, float& fx, float& fy, float& fz, float& eb) {
+    ln_bonded(LnLdPlain(), a, b, lam, i, N, bd, fx, fy, fz, eb);
 }
 __device__ __forceinline__ double ln_block_sum(double v, double* sh, int tid, bool lead) {   // sum over the LN_TB lead threads; every thread of the block calls
     __syncthreads();
@@ -485,14 +505,14 @@ struct LnReduceArgs {
     const float4* x; const float4* xb2; const float* lam;     // coordinates x + lam*xb2 (xb2 may be nullptr)
     float4* f;                           // f has N + 1 entries; entry N is unused padding
     double* escal;                       // [3] e_noe, e_vdw, e_bond of this rank
-    float w_bond, r0;
+    LnBonded bd;
 };
 __global__ void __launch_bounds__(LN_STEP_THREADS) ln_reduce_kernel(LnReduceArgs a) {
     const int B = blockIdx.x, tid = threadIdx.x & (LN_TB - 1), grp = threadIdx.x >> 7, i = B * LN_TB + tid;
     const bool lead = grp == 0;
     float fx, fy, fz, eb = 0.f;
     ln_gather(a.g, B, tid, grp, fx, fy, fz);
-    if (lead && a.add_bond && i < a.N) ln_bond(a.x, a.xb2 ? a.xb2 : a.x, a.xb2 ? *a.lam : 0.f, i, a.N, a.w_bond, a.r0, fx, fy, fz, eb);
+    if (lead && a.add_bond && i < a.N) ln_bond(a.x, a.xb2 ? a.xb2 : a.x, a.xb2 ? *a.lam : 0.f, i, a.N, a.bd, fx, fy, fz, eb);
     if (lead && i < a.N) a.f[i] = make_float4(fx, fy, fz, 0.f);
     __shared__ double sh[LN_TB];
     const double ebs = ln_block_sum((double)eb, sh, tid, lead);
@@ -742,7 +762,7 @@ struct LnMdStepArgs {
     float4 *x, *v, *f, *a_next, *b_next;
     LnEnergySrc es;
     LnState* st; double* blockpart; int nblk, N;
-    float w_bond, r0, h, dt_akma; int first, want_e;
+    LnBonded bd; float h, dt_akma; int first, want_e;
     LnMdCfg md;
 };
 // Verlet step (definition of the oracle's sim_dynamics):  x = a + lam*b are the coordinates the forces were just
@@ -758,7 +778,7 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_md_step_kernel(LnMdStepArg
     if (p.fsum) { if (lead && i < p.N) { const float4 t = p.fsum[i]; fx = t.x; fy = t.y; fz = t.z; } }
     else {
         ln_gather(p.g, B, tid, grp, fx, fy, fz);
-        if (lead && i < p.N) ln_bond(p.a, p.b, lam, i, p.N, p.w_bond, p.r0, fx, fy, fz, eb);
+        if (lead && i < p.N) ln_bond(p.a, p.b, lam, i, p.N, p.bd, fx, fy, fz, eb);
     }
     if (lead && i < p.N) {
         const float4 xi = ln_ldx(p.a, p.b, lam, i);
@@ -818,7 +838,7 @@ struct LnMinStepArgs {
     LnVec v; const float* lam; int init;         // init: evaluation at the starting point (x = v.x, nothing pending)
     LnEnergySrc es;
     LnState* st; double* blockpart; int nblk;
-    float w_bond, r0;
+    LnBonded bd;
     LnMinCfg cfg;
 };
 // L-BFGS trial x = xb + t*p (t = *lam): forces, the 6m+6 inner products of (s, y, g') with the history, and in the
@@ -838,7 +858,7 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_min_step_kernel(LnMinStepA
     if (p.fsum) { if (lead && i < N) { const float4 t = p.fsum[i]; fx = t.x; fy = t.y; fz = t.z; } }
     else {
         ln_gather(p.g, B, tid, grp, fx, fy, fz);
-        if (lead && i < N) ln_bond(A, p.v.p, lam, i, N, p.w_bond, p.r0, fx, fy, fz, eb);
+        if (lead && i < N) ln_bond(A, p.v.p, lam, i, N, p.bd, fx, fy, fz, eb);
     }
     float acc[LN_KMAX];
 #pragma unroll 1
@@ -1074,9 +1094,10 @@ struct LnGroup { std::vector<LnEngine*> es; DevBuf<LnCtx> ctxs; int grid = 0; bo
 
 struct LnEngine {
     int N = 0, nT = 0, rank = 0, world = 1, m = 5, ncta = 0, maxseg = 0, nblk = 0, nparts = 0, sms = 148;
-    long long n_tiles = 0, t0 = 0, t1 = 0, pairs_total = 0;
+    long long n_tiles = 0, t0 = 0, t1 = 0, pairs_total = 0; std::vector<long long> rank_cut;
     DevBuf<float> Dt, colpart, x0; DevBuf<float4> rowpart, vx, vxb, vg, vp, vv, vf, vS, vY, sx, sv, va[2], vb[2], vfr;
-    DevBuf<int> rs_off, rs_idx; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st; DevBuf<unsigned int> bar;
+    DevBuf<int> rs_off, rs_idx, blk_off, blk_idx; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st; DevBuf<unsigned int> bar;
+    DevBuf<long long> cstart; DevBuf<unsigned long long> cta_ns; std::vector<long long> h_cstart;
     chr3d_sa_params prm; unsigned long long seed = 0; int model = 0;     // model: Philox stream of the coil / Maxwell draws
     cudaStream_t stream = nullptr;
     long long n_launches = 0;
@@ -1097,31 +1118,90 @@ struct LnEngine {
     bool persistent() const { return !legacy && (world == 1 || p2p); }
 };
 
-// tile range -> CTA ranges: row-partial slots, the static CSR list "which (CTA, segment) row partials belong to tile row B"
-// (mirrors the walk of ln_tile_phase)
+// Cost model of the tile walk, in units of one far tile: a tile that touches the diagonal band or the padded last column takes
+// the slower path (sentinel selects), and every tile row a CTA starts costs a flush of the row accumulators plus the exposed
+// latency of the row-coordinate loads.  Fitted to per-CTA phase times on B200 (scripts/ln_cta_fit.py over chr3d_single_profile_ctas:
+// near/far = 0.99 .. 1.05, row/far = 0.79 .. 0.93 at N = 24,925 / 4,985; an equal-count split leaves the CTAs of the short bottom
+// rows 12 % behind, this one brings max/mean of the per-CTA times to 1.015).
+#define LN_COST_NEAR 1.0
+#define LN_COST_ROW 0.9
+static inline double ln_tile_cost(int I, int J, int nT, int N) {
+    const bool near = J <= I + 1 || (long long)(J + 1) * LN_TB > N;
+    return (near ? LN_COST_NEAR : 1.0) + (J == I ? LN_COST_ROW : 0.0);
+}
+// cuts the tile range [lo, hi) into `parts` contiguous pieces of equal modelled cost (every piece non-empty when hi - lo >= parts)
+static std::vector<long long> ln_cost_split(long long lo, long long hi, int parts, int nT, int N) {
+    std::vector<long long> cut(parts + 1, hi);
+    cut[0] = lo;
+    if (hi <= lo) return cut;
+    double total = 0.0;
+    { int I, J; tile_coords(lo, nT, I, J);
+      for (long long t = lo; t < hi; t++) { total += ln_tile_cost(I, J, nT, N); if (++J == nT) { I++; J = I; } } }
+    int I, J; tile_coords(lo, nT, I, J);
+    double acc = 0.0; int k = 1;
+    for (long long t = lo; t < hi && k < parts; t++) {
+        acc += ln_tile_cost(I, J, nT, N);
+        if (++J == nT) { I++; J = I; }
+        // piece k-1 ends after tile t once its share is reached; leave at least one tile for each remaining piece
+        while (k < parts && (acc >= total * k / parts || hi - (t + 1) <= parts - k)) { cut[k] = std::max(t + 1, cut[k - 1] + 1); k++; }
+    }
+    for (int q = 1; q <= parts; q++) cut[q] = std::min(hi, std::max(cut[q], cut[q - 1] + (q < parts ? 1 : 0)));
+    cut[parts] = hi;
+    return cut;
+}
+
+// tile range -> CTA ranges (cost-balanced): row-partial slots, the static CSR list "which (CTA, segment) row partials belong to
+// tile row B" (mirrors the walk of ln_tile_phase), and the bead blocks every CTA gathers / integrates (balanced by gather length)
 static int ln_plan(LnEngine& e, int ncta) {
     const long long ntl = e.t1 - e.t0;
     e.ncta = (int)std::max<long long>(1, std::min<long long>(ncta, std::max<long long>(ntl, 1)));
-    // a CTA's contiguous tile range of length len touches at most len/(shortest row) + 2 tile rows
-    long long per = (ntl + e.ncta - 1) / e.ncta;
-    e.maxseg = (int)std::min<long long>(e.nT, per + 2);
+    e.h_cstart = ln_cost_split(e.t0, e.t1, e.ncta, e.nT, e.N);
+    std::vector<std::vector<int>> rows(e.nT);
+    int maxseg = 1;
+    for (int pass = 0; pass < 2; pass++) {         // pass 0: segments per CTA -> maxseg; pass 1: the list
+        for (int c = 0; c < e.ncta; c++) {
+            int curI = -1, seg = -1;
+            for (long long t = e.h_cstart[c]; t < e.h_cstart[c + 1]; t++) {
+                int I, J; tile_coords(t, e.nT, I, J);
+                if (I != curI) { curI = I; seg++; if (pass) rows[I].push_back(c * e.maxseg + seg); }
+            }
+            if (!pass) maxseg = std::max(maxseg, seg + 1);
+        }
+        if (!pass) e.maxseg = maxseg;
+    }
     CHR3D_CUDA(e.rowpart.alloc((size_t)e.ncta * e.maxseg * LN_TB));
     CHR3D_CUDA(e.epart.alloc((size_t)e.ncta * 2));
     CHR3D_CUDA(cudaMemset(e.epart.p, 0, sizeof(double) * 2 * e.ncta));
-    std::vector<std::vector<int>> rows(e.nT);
-    for (int c = 0; c < e.ncta; c++) {
-        const long long c0 = e.t0 + (ntl * c) / e.ncta, c1 = e.t0 + (ntl * (c + 1)) / e.ncta;
-        int curI = -1, seg = -1;
-        for (long long t = c0; t < c1; t++) {
-            int I, J; tile_coords(t, e.nT, I, J);
-            if (I != curI) { curI = I; seg++; rows[I].push_back(c * e.maxseg + seg); }
-        }
-    }
+    CHR3D_CUDA(e.cstart.alloc(e.h_cstart.size()));
+    CHR3D_CUDA(cudaMemcpy(e.cstart.p, e.h_cstart.data(), sizeof(long long) * e.h_cstart.size(), cudaMemcpyHostToDevice));
+    CHR3D_CUDA(e.cta_ns.alloc(e.ncta));
+    CHR3D_CUDA(cudaMemset(e.cta_ns.p, 0, sizeof(unsigned long long) * e.ncta));
     std::vector<int> off(e.nT + 1, 0), idx;
     for (int B = 0; B < e.nT; B++) { off[B + 1] = off[B] + (int)rows[B].size(); idx.insert(idx.end(), rows[B].begin(), rows[B].end()); }
     CHR3D_CUDA(e.rs_off.alloc(off.size())); CHR3D_CUDA(e.rs_idx.alloc(std::max<size_t>(idx.size(), 1)));
     CHR3D_CUDA(cudaMemcpy(e.rs_off.p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
     if (!idx.empty()) CHR3D_CUDA(cudaMemcpy(e.rs_idx.p, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+    {   // bead blocks -> CTAs, longest gather first onto the least loaded CTA (LPT); cost = owned tiles of the block's column + row partials + a constant
+        int I0, J0, I1, J1; tile_coords(e.t0, e.nT, I0, J0);
+        if (e.t1 >= e.n_tiles) { I1 = e.nT; J1 = e.nT; } else tile_coords(e.t1, e.nT, I1, J1);
+        std::vector<std::pair<int, int>> cost(e.nblk);
+        for (int B = 0; B < e.nblk; B++) {
+            int lo = (B >= J0) ? I0 : I0 + 1, hi = (B < J1) ? I1 + 1 : I1;
+            hi = std::min(hi, B + 1);
+            cost[B] = std::make_pair(std::max(0, hi - lo) + (int)rows[B].size() + 8, B);
+        }
+        std::sort(cost.begin(), cost.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+        std::vector<std::vector<int>> mine(e.ncta); std::vector<long long> load(e.ncta, 0);
+        for (auto& cb : cost) {
+            int best = 0; for (int c = 1; c < e.ncta; c++) if (load[c] < load[best]) best = c;
+            mine[best].push_back(cb.second); load[best] += cb.first;
+        }
+        std::vector<int> boff(e.ncta + 1, 0), bidx;
+        for (int c = 0; c < e.ncta; c++) { std::sort(mine[c].begin(), mine[c].end()); boff[c + 1] = boff[c] + (int)mine[c].size(); bidx.insert(bidx.end(), mine[c].begin(), mine[c].end()); }
+        CHR3D_CUDA(e.blk_off.alloc(boff.size())); CHR3D_CUDA(e.blk_idx.alloc(std::max<size_t>(bidx.size(), 1)));
+        CHR3D_CUDA(cudaMemcpy(e.blk_off.p, boff.data(), sizeof(int) * boff.size(), cudaMemcpyHostToDevice));
+        if (!bidx.empty()) CHR3D_CUDA(cudaMemcpy(e.blk_idx.p, bidx.data(), sizeof(int) * bidx.size(), cudaMemcpyHostToDevice));
+    }
     if (e.group) e.group->dirty = true;
     return 0;
 }
@@ -1130,7 +1210,10 @@ static int ln_alloc(LnEngine& e) {
     const int N = e.N;
     e.nT = (N + LN_TB - 1) / LN_TB; e.nblk = e.nT;
     e.n_tiles = (long long)e.nT * (e.nT + 1) / 2;
-    e.t0 = e.n_tiles * e.rank / e.world; e.t1 = e.n_tiles * (e.rank + 1) / e.world;
+    {   // rank boundaries: contiguous tile ranges of equal modelled cost (every rank derives the same cuts)
+        std::vector<long long> cut = ln_cost_split(0, e.n_tiles, e.world, e.nT, e.N);
+        e.t0 = cut[e.rank]; e.t1 = cut[e.rank + 1]; e.rank_cut = cut;
+    }
     int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&e.sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ntl = e.t1 - e.t0;
     e.nparts = std::min(64, std::max(1, (N + 255) / 256));
@@ -1169,6 +1252,11 @@ static void ln_terms(const chr3d_sa_params& p, const chr3d_stage& s, LnTerms& t)
     t.wv = (float)s.w_vdw; t.wv4 = 4.f * (float)s.w_vdw;
     double r = s.repel * p.vdw_rmin; t.R2 = (float)(r * r);
 }
+static LnBonded ln_bonded_terms(const chr3d_sa_params& p, const chr3d_stage& s) {
+    LnBonded b; b.w_bond = (float)s.w_bond; b.r0 = (float)p.bond_r0; b.d2 = (float)p.angle_d2;
+    b.w_ang = (p.angle_d2 > 0 && p.bond_k > 0) ? (float)(s.w_bond * (p.angle_k / p.bond_k)) : 0.f;
+    return b;
+}
 static int ln_dbg() {
     static const int dbg = dev_getenv("CHR3D_LN_DEBUG") ? atoi(dev_getenv("CHR3D_LN_DEBUG")) : 0;
     return dbg;
@@ -1179,6 +1267,7 @@ static void ln_fill_ctx(LnEngine& e, int cta0, LnCtx& c) {
     memset(&c, 0, sizeof c);
     c.Dt = e.Dt.p; c.t0 = e.t0; c.t1 = e.t1; c.nT = e.nT; c.N = e.N; c.nblk = e.nblk; c.maxseg = e.maxseg; c.cta0 = cta0; c.ncta = e.ncta;
     c.colpart = e.colpart.p; c.rowpart = e.rowpart.p; c.epart = e.epart.p; c.rs_off = e.rs_off.p; c.rs_idx = e.rs_idx.p;
+    c.cstart = e.cstart.p; c.blk_off = e.blk_off.p; c.blk_idx = e.blk_idx.p; c.cta_ns = e.cta_ns.p;
     tile_coords(e.t0, e.nT, c.gI0, c.gJ0);
     if (e.t1 >= e.n_tiles) { c.gI1 = e.nT; c.gJ1 = e.nT; } else tile_coords(e.t1, e.nT, c.gI1, c.gJ1);
     c.v = e.vec(); for (int q = 0; q < 2; q++) { c.va[q] = e.va[q].p; c.vb[q] = e.vb[q].p; }
@@ -1186,7 +1275,7 @@ static void ln_fill_ctx(LnEngine& e, int cta0, LnCtx& c) {
     LnXchg& x = c.xc;
     x.world = e.p2p ? e.world : 1; x.rank = e.rank; x.nblk = e.nblk; x.n4 = e.N + 1; x.err = e.xerr;
     for (int g = 0; g < e.world && g < LN_MAXWORLD; g++) {
-        int I, J; tile_coords(e.n_tiles * g / e.world, e.nT, I, J); c.bmin[g] = I;
+        int I, J; tile_coords(e.rank_cut[g], e.nT, I, J); c.bmin[g] = I;
         if (e.p2p) {
             char* base = (char*)e.peer[g];
             x.recv[g] = (float4*)base; x.flags[g] = (unsigned int*)(base + e.x_off_flags());
@@ -1219,7 +1308,7 @@ static int ln_launch_persist(LnGroup& g, LnOp& op, cudaStream_t stream) {
 }
 static void ln_op_common(LnEngine& e, const chr3d_stage& s, LnOp& op) {
     memset(&op, 0, sizeof op);
-    ln_terms(e.prm, s, op.terms); op.w_bond = (float)s.w_bond; op.r0 = (float)e.prm.bond_r0; op.count_eval = 1;
+    ln_terms(e.prm, s, op.terms); op.bd = ln_bonded_terms(e.prm, s); op.count_eval = 1;
 }
 static void ln_md_cfg(LnEngine& e, const chr3d_stage& s, LnMdCfg& c) {
     c.dt_akma = (float)(s.dt / CHR3D_TIMFAC); c.h = (float)(0.5 * (s.dt / CHR3D_TIMFAC) / e.prm.mass); c.dt_ps = s.dt; c.temp = s.temp;
@@ -1264,7 +1353,7 @@ static LnGather ln_gather_args(LnEngine& e) {
 // pair tiles at the coordinates x + lam*xb2 (xb2 == nullptr: plain x)
 static void ln_tiles(LnEngine& e, const chr3d_stage& s, const float4* x, const float4* xb2, const float* lam, const int* done, bool want_e) {
     LnTileArgs a; a.Dt = e.Dt.p; a.t0 = e.t0; a.t1 = e.t1; a.nT = e.nT; a.N = e.N; a.x = x; a.xb2 = xb2; a.lam = lam; a.done = done;
-    a.colpart = e.colpart.p; a.rowpart = e.rowpart.p; a.epart = e.epart.p; a.maxseg = e.maxseg; ln_terms(e.prm, s, a.terms);
+    a.colpart = e.colpart.p; a.rowpart = e.rowpart.p; a.epart = e.epart.p; a.cstart = e.cstart.p; a.maxseg = e.maxseg; ln_terms(e.prm, s, a.terms);
     ln_launch_tiles(e, a, want_e);
     e.n_launches++;
 }
@@ -1273,7 +1362,7 @@ static void ln_tiles(LnEngine& e, const chr3d_stage& s, const float4* x, const f
 // ranks with NCCL; afterwards every rank holds the total force in vfr and the totals in escal[0..2]
 static int ln_exchange(LnEngine& e, const chr3d_stage& s, const float4* x, const float4* xb2, const float* lam) {
     LnReduceArgs r; r.g = ln_gather_args(e); r.epart = e.epart.p; r.N = e.N; r.ncta = e.ncta; r.add_bond = e.rank == 0 ? 1 : 0;
-    r.x = x; r.xb2 = xb2; r.lam = lam; r.f = e.vfr.p; r.escal = e.escal.p; r.w_bond = (float)s.w_bond; r.r0 = (float)e.prm.bond_r0;
+    r.x = x; r.xb2 = xb2; r.lam = lam; r.f = e.vfr.p; r.escal = e.escal.p; r.bd = ln_bonded_terms(e.prm, s);
     ln_reduce_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(r);
     ln_energy_kernel<<<1, 32, 0, e.stream>>>(e.epart.p, e.ncta, e.escal.p, e.nblk);
     e.n_launches += 2;
@@ -1293,7 +1382,7 @@ static int ln_exchange(LnEngine& e, const chr3d_stage& s, const float4* x, const
 static int ln_eval_legacy(LnEngine& e, const chr3d_stage& s, bool want_e = true) {
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, want_e);
     LnReduceArgs r; r.g = ln_gather_args(e); r.epart = e.epart.p; r.N = e.N; r.ncta = e.ncta; r.add_bond = e.rank == 0 ? 1 : 0;
-    r.x = e.vx.p; r.xb2 = nullptr; r.lam = nullptr; r.f = e.vf.p; r.escal = e.escal.p; r.w_bond = (float)s.w_bond; r.r0 = (float)e.prm.bond_r0;
+    r.x = e.vx.p; r.xb2 = nullptr; r.lam = nullptr; r.f = e.vf.p; r.escal = e.escal.p; r.bd = ln_bonded_terms(e.prm, s);
     ln_reduce_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(r);
     ln_energy_kernel<<<1, 32, 0, e.stream>>>(e.epart.p, e.ncta, e.escal.p, e.nblk);
     e.n_launches += 2;
@@ -1326,7 +1415,7 @@ static int ln_minimize_legacy(LnEngine& e, const chr3d_stage& s) {
     LnMinCfg c; ln_min_cfg(e, s, c);
     LnMinStepArgs m; m.g = ln_gather_args(e); m.fsum = multi ? e.vfr.p : nullptr; m.v = v; m.lam = &e.st.p->tstepf; m.init = 1;
     m.es.epart = e.epart.p; m.es.ncta = e.ncta; m.es.escal = multi ? e.escal.p : nullptr; m.st = e.st.p; m.blockpart = e.blockpart.p; m.nblk = e.nblk;
-    m.w_bond = (float)s.w_bond; m.r0 = (float)e.prm.bond_r0; m.cfg = c;
+    m.bd = ln_bonded_terms(e.prm, s); m.cfg = c;
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, true);
     if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
     ln_min_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(m);
@@ -1356,7 +1445,7 @@ static int ln_dynamics_legacy(LnEngine& e, const chr3d_stage& s) {
     LnMdCfg c; ln_md_cfg(e, s, c);
     LnMdStepArgs p; p.g = ln_gather_args(e); p.fsum = multi ? e.vfr.p : nullptr; p.x = e.vx.p; p.v = e.vv.p; p.f = e.vf.p;
     p.es.epart = e.epart.p; p.es.ncta = e.ncta; p.es.escal = multi ? e.escal.p : nullptr; p.st = e.st.p; p.blockpart = e.blockpart.p; p.nblk = e.nblk; p.N = e.N;
-    p.w_bond = (float)s.w_bond; p.r0 = (float)e.prm.bond_r0; p.h = c.h; p.dt_akma = c.dt_akma; p.md = c;
+    p.bd = ln_bonded_terms(e.prm, s); p.h = c.h; p.dt_akma = c.dt_akma; p.md = c;
     // evaluation at the starting point: explicit x, nothing pending
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, false);
     if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
@@ -1661,7 +1750,7 @@ CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t rep
     chr3d_stage s = h->prog.back();
     cudaEvent_t a, b; CHR3D_CUDA(cudaEventCreate(&a)); CHR3D_CUDA(cudaEventCreate(&b));
     LnTileArgs ta; ta.Dt = e.Dt.p; ta.t0 = e.t0; ta.t1 = e.t1; ta.nT = e.nT; ta.N = e.N; ta.x = e.vx.p; ta.xb2 = nullptr; ta.lam = nullptr; ta.done = nullptr;
-    ta.colpart = e.colpart.p; ta.rowpart = e.rowpart.p; ta.epart = e.epart.p; ta.maxseg = e.maxseg; ln_terms(e.prm, s, ta.terms);
+    ta.colpart = e.colpart.p; ta.rowpart = e.rowpart.p; ta.epart = e.epart.p; ta.cstart = e.cstart.p; ta.maxseg = e.maxseg; ln_terms(e.prm, s, ta.terms);
     for (int w = 0; w < 3; w++) ln_launch_tiles(e, ta, want_energy != 0);
     CHR3D_CUDA(cudaEventRecord(a, e.stream));
     for (int r = 0; r < reps; r++) ln_launch_tiles(e, ta, want_energy != 0);
@@ -1724,6 +1813,28 @@ CHR3D_API int chr3d_single_profile(chr3d_single* h, double* ms5) {
     CHR3D_CUDA(cudaMemcpy(t, &e.st.p->tprof[0], sizeof t, cudaMemcpyDeviceToHost));
     for (int q = 0; q < 5; q++) ms5[q] = 1e-6 * (double)t[q];
     CHR3D_CUDA(cudaMemset(&e.st.p->tprof[0], 0, sizeof t));
+    return 0;
+}
+
+// Per-CTA view of the tile walk: tiles, "near" tiles (slow path), tile rows started, and the time every CTA spent in tile phases
+// of the persistent kernel since the last call (ms; reading resets it).  Arrays of `cap` entries; *n = CTAs of this rank.
+CHR3D_API int chr3d_single_profile_ctas(chr3d_single* h, int32_t cap, int32_t* n, int32_t* tiles, int32_t* near_tiles, int32_t* rows, double* tile_ms) {
+    if (!h || !n) { set_error("chr3d_single_profile_ctas: bad arguments"); return CHR3D_ERR_ARG; }
+    LnEngine& e = h->e;
+    *n = e.ncta;
+    CHR3D_CUDA(cudaStreamSynchronize(e.stream));
+    std::vector<unsigned long long> ns(e.ncta);
+    CHR3D_CUDA(cudaMemcpy(ns.data(), e.cta_ns.p, sizeof(unsigned long long) * e.ncta, cudaMemcpyDeviceToHost));
+    CHR3D_CUDA(cudaMemset(e.cta_ns.p, 0, sizeof(unsigned long long) * e.ncta));
+    for (int c = 0; c < e.ncta && c < cap; c++) {
+        int nt = 0, nn = 0, nr = 0, curI = -1;
+        for (long long t = e.h_cstart[c]; t < e.h_cstart[c + 1]; t++) {
+            int I, J; tile_coords(t, e.nT, I, J);
+            nt++; if (J <= I + 1 || (long long)(J + 1) * LN_TB > e.N) nn++;
+            if (I != curI) { curI = I; nr++; }
+        }
+        if (tiles) tiles[c] = nt; if (near_tiles) near_tiles[c] = nn; if (rows) rows[c] = nr; if (tile_ms) tile_ms[c] = 1e-6 * (double)ns[c];
+    }
     return 0;
 }
 

@@ -28,6 +28,9 @@ struct LnCtx {                              // one (virtual) rank
     const float* Dt; long long t0, t1, nT; int N, nblk, maxseg, cta0, ncta;
     float* colpart; float4* rowpart; double* epart;
     const int* rs_off; const int* rs_idx;
+    const long long* cstart;                // [ncta + 1] first tile of every CTA (cost-balanced, ln_plan)
+    const int* blk_off; const int* blk_idx; // bead blocks of every CTA (balanced by gather length)
+    unsigned long long* cta_ns;             // [ncta] time spent in tile phases (ns)
     int gI0, gJ0, gI1, gJ1;                 // tile coordinates of t0 and t1: the owned tiles of a column are a contiguous row range
     LnVec v; float4* va[2]; float4* vb[2];
     LnState* st; double* blockpart;
@@ -36,12 +39,15 @@ struct LnCtx {                              // one (virtual) rank
 };
 struct LnOp {
     int kind, nstep, count_eval, dbg;
-    LnTerms terms; float w_bond, r0;
+    LnTerms terms; LnBonded bd;
     LnMdCfg md; LnMinCfg min; long long max_trials;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+    unsigned int v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -66,14 +72,19 @@ __device__ __forceinline__ void ln_wait_flag_sys(const unsigned int* p, unsigned
 __device__ __forceinline__ bool ln_bar_arrive(const LnCtx& c, unsigned int gen, int* s_flag) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int old = atomicAdd(c.bar, 1u);
+        // release: everything this CTA wrote (ordered before by the barrier above) is visible to whoever acquires the counter;
+        // acquire: the last arriver sees every other CTA's writes.  (An acquire at gpu scope also invalidates this SM's L1.)
+        unsigned int old;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(c.bar) : "memory");
         const int last = old == (unsigned)c.ncta - 1u;
         if (!last) {
-            const long long t0 = clock64();
-            while (ld_acquire_gpu(c.bar + 32) == gen) if (clock64() - t0 > LN_WAIT_LIMIT) ln_fail(c.xc.err, 2);
+            // poll with relaxed loads (an acquire load drags an L1 invalidation behind every poll), acquire once at the end
+            if (ld_relaxed_gpu(c.bar + 32) == gen) {
+                const long long t0 = clock64();
+                while (ld_relaxed_gpu(c.bar + 32) == gen) if (clock64() - t0 > LN_WAIT_LIMIT) ln_fail(c.xc.err, 2);
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
-        __threadfence();                     // (invalidates this SM's L1: plain loads after the barrier see the other CTAs' writes)
         *s_flag = last;
     }
     __syncthreads();
@@ -81,7 +92,7 @@ __device__ __forceinline__ bool ln_bar_arrive(const LnCtx& c, unsigned int gen, 
 }
 __device__ __forceinline__ void ln_bar_release(const LnCtx& c, unsigned int gen) {      // the last arriver, after its serial section
     __syncthreads();
-    if (threadIdx.x == 0) { *c.bar = 0u; __threadfence(); st_release_gpu(c.bar + 32, gen + 1u); }
+    if (threadIdx.x == 0) { *c.bar = 0u; st_release_gpu(c.bar + 32, gen + 1u); }     // (the release orders the counter reset before the new generation)
 }
 
 // ---- scratch in the dynamic shared memory: the column-partial buffer of the tile phase is free between tile phases ------
@@ -106,18 +117,19 @@ __device__ __forceinline__ void ln_gather4(const LnCtx& c, int B, LnScratch* sc,
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
         const float4* base = reinterpret_cast<const float4*>(c.colpart) + q;
         int I = lo + grp;
+#define LN_GLD(u, k) const float4 u = __ldcg(base + (size_t)(tile_index(I + (k) * LN_P_GGRP, B, c.nT) - c.t0) * 96)
+#define LN_GADD(a, u) a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w
+        for (; I + 7 * LN_P_GGRP < hi; I += 8 * LN_P_GGRP) {       // eight independent 16-byte loads in flight per thread
+            LN_GLD(u0, 0); LN_GLD(u1, 1); LN_GLD(u2, 2); LN_GLD(u3, 3); LN_GLD(u4, 4); LN_GLD(u5, 5); LN_GLD(u6, 6); LN_GLD(u7, 7);
+            LN_GADD(a0, u0); LN_GADD(a1, u1); LN_GADD(a2, u2); LN_GADD(a3, u3); LN_GADD(a0, u4); LN_GADD(a1, u5); LN_GADD(a2, u6); LN_GADD(a3, u7);
+        }
         for (; I + 3 * LN_P_GGRP < hi; I += 4 * LN_P_GGRP) {
-            const float4 u0 = __ldcg(base + (size_t)(tile_index(I, B, c.nT) - c.t0) * 96);
-            const float4 u1 = __ldcg(base + (size_t)(tile_index(I + LN_P_GGRP, B, c.nT) - c.t0) * 96);
-            const float4 u2 = __ldcg(base + (size_t)(tile_index(I + 2 * LN_P_GGRP, B, c.nT) - c.t0) * 96);
-            const float4 u3 = __ldcg(base + (size_t)(tile_index(I + 3 * LN_P_GGRP, B, c.nT) - c.t0) * 96);
-            a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w; a1.x += u1.x; a1.y += u1.y; a1.z += u1.z; a1.w += u1.w;
-            a2.x += u2.x; a2.y += u2.y; a2.z += u2.z; a2.w += u2.w; a3.x += u3.x; a3.y += u3.y; a3.z += u3.z; a3.w += u3.w;
+            LN_GLD(u0, 0); LN_GLD(u1, 1); LN_GLD(u2, 2); LN_GLD(u3, 3);
+            LN_GADD(a0, u0); LN_GADD(a1, u1); LN_GADD(a2, u2); LN_GADD(a3, u3);
         }
-        for (; I < hi; I += LN_P_GGRP) {
-            const float4 u0 = __ldcg(base + (size_t)(tile_index(I, B, c.nT) - c.t0) * 96);
-            a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
-        }
+        for (; I < hi; I += LN_P_GGRP) { LN_GLD(u0, 0); LN_GADD(a0, u0); }
+#undef LN_GLD
+#undef LN_GADD
         a0.x = (a0.x + a1.x) + (a2.x + a3.x); a0.y = (a0.y + a1.y) + (a2.y + a3.y); a0.z = (a0.z + a1.z) + (a2.z + a3.z); a0.w = (a0.w + a1.w) + (a2.w + a3.w);
         *reinterpret_cast<float4*>(&sc->gred[grp][q * 4]) = a0;
     }
@@ -143,7 +155,7 @@ __device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch
     const int tid = threadIdx.x, cta = blockIdx.x - c.cta0;
     const LnXchg& x = c.xc;
     if (x.world <= 1) {
-        for (int B = cta; B < c.nblk; B += c.ncta) {
+        for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
             float fx, fy, fz;
             ln_gather4(c, B, sc, fx, fy, fz);
             emit(B, B * LN_TB + tid, fx, fy, fz);
@@ -153,7 +165,7 @@ __device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch
     const int parity = (int)(epoch & 1u);
     const size_t slot = ((size_t)parity * x.world + x.rank) * x.n4;
     // push: this rank's partial of every block it contributes to -> slot `rank` of every rank (self included)
-    for (int B = cta; B < c.nblk; B += c.ncta) {
+    for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
         if (B < c.bmin[x.rank]) continue;
         float fx, fy, fz;
         ln_gather4(c, B, sc, fx, fy, fz);
@@ -165,10 +177,10 @@ __device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch
     }
     __threadfence_system();
     __syncthreads();
-    for (int B = cta; B < c.nblk; B += c.ncta)
+    for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++)
         if (B >= c.bmin[x.rank] && tid < x.world) st_release_sys(x.flags[tid] + (size_t)x.rank * x.nblk + B, epoch);
     // wait for the contributors of each block, add their slots in rank order
-    for (int B = cta; B < c.nblk; B += c.ncta) {
+    for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
         if (tid < x.world && B >= c.bmin[tid]) ln_wait_flag_sys(x.flags[x.rank] + (size_t)tid * x.nblk + B, epoch, x.err);
         __syncthreads();
         const int i = B * LN_TB + tid;
@@ -199,18 +211,8 @@ __device__ __forceinline__ float4 ln_ldx_cg(const float4* a, const float4* b, fl
     const float4 p = __ldcg(a + i), q = __ldcg(b + i);
     return make_float4(fmaf(lam, q.x, p.x), fmaf(lam, q.y, p.y), fmaf(lam, q.z, p.z), 0.f);
 }
-__device__ __forceinline__ void ln_bond_cg(const float4* a, const float4* b, float lam, int i, int N, float w_bond, float r0,
-                                           float& fx, float& fy, float& fz, float& eb) {
-    const float4 xi = ln_ldx_cg(a, b, lam, i);
-    for (int s = -1; s <= 1; s += 2) {
-        const int nb = i + s; if (nb < 0 || nb >= N) continue;
-        const float4 xn = ln_ldx_cg(a, b, lam, nb);
-        const float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
-        const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f), rinv = ln_rsqrt(r2), r = r2 * rinv, u = r - r0;
-        const float g = 2.f * w_bond * u * rinv;
-        fx -= g * dx; fy -= g * dy; fz -= g * dz;
-        if (s == 1) eb = w_bond * u * u;
-    }
+__device__ __forceinline__ void ln_bond_cg(const float4* a, const float4* b, float lam, int i, int N, const LnBonded& bd, float& fx, float& fy, float& fz, float& eb) {
+    ln_bonded(LnLdCg(), a, b, lam, i, N, bd, fx, fy, fz, eb);
 }
 
 // pair energies of this rank (sum of the per-CTA partials of the tile phase, fixed order) -> every rank; called by all threads
@@ -257,7 +259,7 @@ __device__ __noinline__ void ln_step_md(const LnCtx& c, const LnOp& op, LnScratc
     ln_forces_of_my_blocks(c, sc, epoch, [&](int B, int i, float fx, float fy, float fz) {
         float eb = 0.f, k2 = 0.f;
         if (tid < LN_TB && i < c.N) {
-            ln_bond_cg(A, Bv, lam, i, c.N, op.w_bond, op.r0, fx, fy, fz, eb);
+            ln_bond_cg(A, Bv, lam, i, c.N, op.bd, fx, fy, fz, eb);
             const float4 xi = ln_ldx_cg(A, Bv, lam, i);
             float4 vv = c.v.v[i];
             if (!first) {
@@ -313,7 +315,7 @@ __device__ __noinline__ void ln_step_min(const LnCtx& c, const LnOp& op, LnScrat
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f), y = s, gn = s;
             const bool live = i < N;
             if (live) {
-                ln_bond_cg(A, v.p, lam, i, N, op.w_bond, op.r0, fx, fy, fz, eb);
+                ln_bond_cg(A, v.p, lam, i, N, op.bd, fx, fy, fz, eb);
                 const float4 x = ln_ldx_cg(A, v.p, lam, i), xb = v.xb[i], g = v.g[i];
                 s = make_float4(x.x - xb.x, x.y - xb.y, x.z - xb.z, 0.f);
                 gn = make_float4(-fx, -fy, -fz, 0.f);
@@ -375,7 +377,7 @@ __device__ __noinline__ void ln_update_min(const LnCtx& c) {
     float dl[2 * CHR3D_LBFGS_MAX_M + 1];
 #pragma unroll
     for (int l = 0; l < 2 * CHR3D_LBFGS_MAX_M + 1; l++) dl[l] = l < 2 * m + 1 ? (float)__ldcg(&st->delta[l]) : 0.f;
-    for (int B = cta; B < c.nblk; B += c.ncta) {
+    for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
         const int i = B * LN_TB + tid;
         if (i >= v.N) continue;
         if (acc == 4) { v.x[i] = v.xb[i]; continue; }
@@ -407,7 +409,7 @@ __device__ __noinline__ void ln_step_eval(const LnCtx& c, const LnOp& op, LnScra
     ln_forces_of_my_blocks(c, sc, epoch, [&](int B, int i, float fx, float fy, float fz) {
         float eb = 0.f;
         if (tid < LN_TB && i < c.N) {
-            ln_bond_cg(c.v.x, c.v.x, 0.f, i, c.N, op.w_bond, op.r0, fx, fy, fz, eb);
+            ln_bond_cg(c.v.x, c.v.x, 0.f, i, c.N, op.bd, fx, fy, fz, eb);
             c.v.f[i] = make_float4(fx, fy, fz, 0.f);
         }
         const double ebb = ln_lead_sum((double)eb, sc->dsum);
@@ -434,7 +436,7 @@ __device__ __noinline__ void ln_decide_eval(const LnCtx& c, const LnOp& op, LnSc
 // budget (there is no L1 behind 229 KB of shared memory, a spill in the pair loop is an L2 round trip).
 // tacc: phase clock of CTA 0 of a rank (ns, accumulated into LnState::tprof): 0 tile phase, 1 first barrier (+ energy
 // publication), 2 step phase (gather, exchange, integration), 3 second barrier (+ decisions), 4 L-BFGS update + third barrier
-struct LnLoop { int step, par, stop; unsigned int gen, epoch; unsigned long long tlast, tacc[5]; };
+struct LnLoop { int step, par, stop; unsigned int gen, epoch; unsigned long long tlast, tacc[5], t0tile, ttile; };
 __device__ __forceinline__ void ln_tprof(volatile LnLoop* L, int slot, bool timing) {
     if (timing) { const unsigned long long t = ln_globaltimer(); L->tacc[slot] += t - L->tlast; L->tlast = t; }
 }
@@ -524,13 +526,13 @@ __global__ void __launch_bounds__(LN_P_THREADS, 1) ln_persist_kernel(const LnCtx
     LnScratch* sc = reinterpret_cast<LnScratch*>(smem + LN_COLP_OFF);
     const bool timing = blockIdx.x == c.cta0 && threadIdx.x == 0;
     if (threadIdx.x == 0) {
-        ln_run_setup(&run, c.Dt, c.t0, c.t1, c.nT, c.N, c.colpart, c.rowpart, c.epart, c.maxseg, blockIdx.x - c.cta0, c.ncta);
+        ln_run_setup(&run, c.Dt, c.t0, c.cstart, c.nT, c.N, c.colpart, c.rowpart, c.epart, c.maxseg, blockIdx.x - c.cta0);
         run.terms = op.terms; run.dbg = op.dbg;
         Ls.step = -1; Ls.par = 0; Ls.stop = 0;
         Ls.gen = ld_acquire_gpu(c.bar + 32);             // stable between launches
         Ls.epoch = c.st->epoch;
         for (int q = 0; q < 5; q++) Ls.tacc[q] = 0;
-        Ls.tlast = ln_globaltimer();
+        Ls.tlast = ln_globaltimer(); Ls.ttile = 0;
     }
     __syncthreads();
     ln_ring_init(&run, smem, true);
@@ -539,14 +541,18 @@ __global__ void __launch_bounds__(LN_P_THREADS, 1) ln_persist_kernel(const LnCtx
         // every evaluation but the last one without energies
         while (L->step < 0 || L->step < sop.nstep - 1) {
             if (threadIdx.x == 0) ln_md_setup(c, sop, L, &run);
+            if (threadIdx.x == 0) L->t0tile = ln_globaltimer();
             __syncthreads();
             ln_tile_phase<false, LOW_SOFT>(&run, smem);
+            if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
             ln_md_rest(c, sop, sc, L, &s_flag, timing);
         }
         if (sop.nstep > 0) {
             if (threadIdx.x == 0) ln_md_setup(c, sop, L, &run);
+            if (threadIdx.x == 0) L->t0tile = ln_globaltimer();
             __syncthreads();
             ln_tile_phase<true, LOW_SOFT>(&run, smem);
+            if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
             ln_md_rest(c, sop, sc, L, &s_flag, timing);
         }
     } else if (op.kind == LN_OP_MIN) {
@@ -556,16 +562,21 @@ __global__ void __launch_bounds__(LN_P_THREADS, 1) ln_persist_kernel(const LnCtx
                 run.X = init ? c.v.x : c.v.xb; run.XB = init ? c.v.x : c.v.p;
                 run.lam = init ? 0.f : __ldcg(&c.st->tstepf); run.more = 1;
             }
+            if (threadIdx.x == 0) L->t0tile = ln_globaltimer();
             __syncthreads();
             ln_tile_phase<true, LOW_SOFT>(&run, smem);
+            if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
             ln_min_rest(c, sop, sc, L, &s_flag, timing);
         }
     } else {
         if (threadIdx.x == 0) { run.X = c.v.x; run.XB = c.v.x; run.lam = 0.f; run.more = 0; }
+        if (threadIdx.x == 0) L->t0tile = ln_globaltimer();
         __syncthreads();
         ln_tile_phase<true, LOW_SOFT>(&run, smem);
+        if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
         ln_eval_rest(c, sop, sc, L, &s_flag, timing);
     }
     ln_ring_drain(&run, smem);
+    if (threadIdx.x == 0) c.cta_ns[blockIdx.x - c.cta0] += L->ttile;
     if (timing) { c.st->epoch = L->epoch; for (int q = 0; q < 5; q++) c.st->tprof[q] += L->tacc[q]; }
 }

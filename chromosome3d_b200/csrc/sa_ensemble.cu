@@ -681,6 +681,20 @@ __device__ __forceinline__ void eval_t(Ctx& c, const DevParams& prm, const DevSt
             gx -= g * dx; gy -= g * dy; gz -= g * dz;
             if (s == 1) eb = st.w_bond * u * u;
         }
+        if (p.ang_d2 > 0.f) {                       // soft lower bound on CA(i)-CA(i+2): the stand-in for CNS's angle term (C3D:1641)
+            const float w_ang = st.w_bond * p.ang_ratio;
+            for (int s = -2; s <= 2; s += 4) {
+                const int nbr = c.row + s;
+                if (nbr < 0 || nbr >= SGEO.N) continue;
+                const float4 xn = ldx(c, nbr);
+                const float dx = xi.x - xn.x, dy = xi.y - xn.y, dz = xi.z - xn.z;
+                const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f);
+                const float rinv = rsqrtf(r2), r = r2 * rinv, u = fmaxf(p.ang_d2 - r, 0.f);
+                const float g = -2.f * w_ang * u * rinv;
+                gx -= g * dx; gy -= g * dy; gz -= g * dz;
+                if (s == 2) eb += w_ang * u * u;
+            }
+        }
     }
     c.f[0] = gx; c.f[1] = gy; c.f[2] = gz; c.ebond = eb;
     if (count) c.nevals++;

@@ -239,6 +239,11 @@ int chr3d_single_info(const chr3d_single* h, int64_t* n_tiles, int64_t* tiles_th
  * [0] tile phases, [1] first grid barrier (+ energy publication), [2] step phases (gather, peer exchange,
  * integration), [3] second barrier (+ decisions), [4] L-BFGS update + third barrier.  Reading resets it. */
 int chr3d_single_profile(chr3d_single* h, double* ms5);
+/* Per-CTA view of the tile walk (arrays of `cap` entries, *n = CTAs of this rank): tiles, tiles on the slow "near" path, tile
+ * rows started, and the milliseconds every CTA spent in tile phases of the persistent kernel since the last call (reset by
+ * reading).  This is the data the cost model of the tile partition is fitted to.                                        */
+int chr3d_single_profile_ctas(chr3d_single* h, int32_t cap, int32_t* n, int32_t* tiles, int32_t* near_tiles, int32_t* rows,
+                              double* tile_ms);
 /* Test aid: this rank's targets as a dense row-major N*N fp32 matrix (cells of other ranks' tiles and the
  * diagonal: NaN; sentinels as stored: -1 no restraint, -2 no restraint and no repel).                  */
 int chr3d_single_targets(chr3d_single* h, float* out);

@@ -73,3 +73,39 @@ def test_mirror_image_pick_keeps_the_lower_energy_image(gpu_api, engine, long_fi
     assert np.abs(xyz - o["xyz"]).max() < 1e-2
     # image -1 starts from the mirrored coil: its x coordinates keep the mirrored sign pattern
     assert np.sign(np.sum(xyz[:, 0] * x0[:, 0])) == want
+
+
+@pytest.mark.parametrize("name,alpha", [("chr21_1mb", 0.5), ("chr1_500kb", 0.5)])
+def test_angle_stand_in_term_matches_fp64(gpu_api, name, alpha):
+    """The CA(i)-CA(i+2) soft lower bound (chr3d_sa_params.angle_d2 / angle_k, the stand-in for CNS's angle term, C3D:1641) in
+    both engines against the fp64 oracle: energies (reported with the bonded term) and forces within 1e-5, on a coil compact
+    enough that the term is active for many beads."""
+    IF = ds.load_if_matrix(ds.input_path(name))
+    N = IF.shape[0]
+    ri, rj, rd = orc.if_to_restraints(IF, alpha)
+    p = gpu_api.default_params()
+    p.angle_d2, p.angle_k = 6.0, 500.0
+    w = abi.stage(abi.OP_ENERGY, w_noe=10, w_bond=1000, w_vdw=4.0, repel=0.85)
+    x = orc.random_coil(N, 2.6, 21, 0).astype(np.float32).astype(np.float64)
+    eo, fo = orc.energy_forces(x, ri, rj, rd, p, w)
+    p0 = gpu_api.default_params()
+    e0, _ = orc.energy_forces(x, ri, rj, rd, p0, w)
+    assert eo[0, 1] > 1.05 * e0[0, 1]                                       # the term contributes
+    e, f = gpu_api.energy_forces(x, ri, rj, rd, p, w)                       # cluster engine
+    assert np.allclose(e[0], eo[0], rtol=1e-5, atol=1e-5 * abs(eo[0, 0]))
+    assert np.abs(f[0] - fo[0]).max() <= 1e-5 * np.abs(fo).max()
+    prog = abi.stage_array([abi.stage(abi.OP_INIT, flag=1), w])
+    s = gpu_api.Single(IF=IF, alpha=alpha, x0=x, p=p, program=prog)        # tile engine
+    s.run()
+    r = s.fetch()
+    s.close()
+    assert np.allclose(r["energies"], eo[0], rtol=1e-5, atol=1e-5 * abs(eo[0, 0]))
+    assert np.abs(r["forces"] - fo[0]).max() <= 1e-5 * np.abs(fo).max()
+    # and a short trajectory with the term on tracks the oracle
+    ww = dict(w_noe=2.0, w_bond=200.0, w_vdw=0.01, repel=0.9)
+    prog = abi.stage_array([abi.stage(abi.OP_INIT, flag=1), abi.stage(abi.OP_MAXWELL, temp=300.0),
+                            abi.stage(abi.OP_DYNAMICS, nstep=10, flag=abi.COUPLE_TCOUP, dt=0.003, temp=2000.0, **ww), abi.stage(abi.OP_ENERGY, **ww)])
+    r = gpu_api.build_models([gpu_api.Job(restraints=(ri, rj, rd), N=N, n_models=1, seed=9, x0=x[None])], p, prog)[0]
+    o = orc.run_model(N, ri, rj, rd, p, prog, 9, 0, x)
+    assert np.abs(r.xyz[0] - o["xyz"]).max() < 1e-4
+    assert np.allclose(r.energies[0], o["energies"], rtol=1e-5, atol=1e-5 * o["energies"][0])
