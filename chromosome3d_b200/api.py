@@ -482,9 +482,9 @@ class Single:
 
     def profile(self):
         """Phase clock of the persistent kernel since the last call (ms, CTA 0 of this rank): tile, barrier1, step, barrier2, update."""
-        a = (C.c_double * 5)()
+        a = (C.c_double * 8)()
         _check(lib().chr3d_single_profile(self._h, a))
-        return dict(zip(("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms"), [float(v) for v in a]))
+        return dict(zip(("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms", "gather_push_ms", "peer_wait_ms"), [float(v) for v in a[:7]]))
 
     def profile_ctas(self):
         """Per-CTA tile counts (all, near, rows started) and tile-phase milliseconds of the persistent kernel since the last call."""

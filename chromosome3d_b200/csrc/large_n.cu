@@ -165,7 +165,7 @@ struct LnTileArgs {
     float4* rowpart;          // [cta][maxseg][128]
     double* epart;            // [cta][2]
     const long long* cstart;  // [ctas + 1] first tile of every CTA (cost-balanced partition of [t0, t1), ln_plan)
-    int maxseg;
+    int maxseg, stream_l2;
     int dbg;                  // development probe (-DCHR3D_DEV + CHR3D_LN_DEBUG): 1 = stream tiles without the pair term, 2 = pair term without tile traffic
     LnTerms terms;
 };
@@ -203,6 +203,8 @@ struct LnTileRun {
     const float4* X; const float4* XB; float lam;      // coordinates X + lam * XB
     int n, I0, J0, nT, N;     // tiles, tile coordinates of the first one
     int more, dbg;            // more: another evaluation follows in this launch (keep the ring running across the boundary)
+    int stream_l2;            // 1: the targets of this rank exceed what L2 can keep between evaluations -> the TMA copies carry an
+                              // evict-first L2 policy, so that the stream does not push the partial forces and the vectors out of L2
     LnTerms terms;
     unsigned int phases, pending; int stage, cstage;   // phases bit q: parity to wait for on bar[q]; pending: stages with a copy outstanding
 };
@@ -211,9 +213,17 @@ struct LnTileRun {
 __device__ __forceinline__ void ln_ring_issue(LnTileRun* run, unsigned char* smem, int k, int stage) {      // one elected thread: 64 KB bulk copy of the CTA's tile k
     float* dbuf = (float*)smem; uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar[stage])), "r"(LN_TILE_FLOATS * 4) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(LN_RUN(Dt) + (size_t)k * LN_TILE_FLOATS),
-                   "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])) : "memory");
+    if (LN_RUN(stream_l2)) {
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(LN_RUN(Dt) + (size_t)k * LN_TILE_FLOATS),
+                       "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])), "l"(pol) : "memory");
+    } else {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(LN_RUN(Dt) + (size_t)k * LN_TILE_FLOATS),
+                       "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])) : "memory");
+    }
     LN_RUN(pending) = LN_RUN(pending) | (1u << stage);
 }
 // once per launch (all threads; run->Dt, n, dbg are set): mbarriers, ring state, the first LN_STAGES copies.
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs
     if (a.done && *a.done) return;
     if (threadIdx.x == 0) {
         ln_run_setup(&run, a.Dt, a.t0, a.cstart, a.nT, a.N, a.colpart, a.rowpart, a.epart, a.maxseg, blockIdx.x);
-        run.X = a.x; run.XB = a.xb2 ? a.xb2 : a.x; run.lam = a.xb2 ? *a.lam : 0.f; run.more = 0; run.dbg = LN_DBG(a); run.terms = a.terms;
+        run.X = a.x; run.XB = a.xb2 ? a.xb2 : a.x; run.lam = a.xb2 ? *a.lam : 0.f; run.more = 0; run.dbg = LN_DBG(a); run.terms = a.terms; run.stream_l2 = a.stream_l2;
     }
     __syncthreads();
     ln_ring_init(&run, smem, false);
@@ -735,18 +745,19 @@ __device__ __forceinline__ bool ln_last_block(unsigned int* counter, int nblk) {
 
 // ---- force exchange over NVLink peer memory, fused into the persistent kernel (ln_persist.cuh) --------------------
 // Every rank owns a communication buffer (cudaMalloc + CUDA IPC) that its peers map:
-//   recv [2 parities][world][N + 1] float4   slot g = partial forces of rank g (no bond term)
-//   flags[world][nblk] u32                   flags[g][B] = epoch of the newest block-B partial of rank g that has landed here
-//   es   [2][world][2] double, eflag[world]  pair energies of rank g, and their epoch
-// The CTA that handles bead block B gathers this rank's partial force on its 128 beads, PUSHES it into slot `rank` of every
-// rank's recv (remote stores, fire-and-forget), fences, pushes the epoch into every rank's flags, then waits until
-// the block-B flags of all contributing ranks show the epoch and sums their slots locally in rank order (identical on every
-// rank, so the redundant integration stays bit-identical).  Parity double-buffering makes overwriting safe: a rank
-// cannot run two evaluations ahead of a peer, because each evaluation needs that peer's current flags.
+//   recv [2 parities][world][N + 1] float4   slot g = partial forces of rank g (no bond term); .w carries the EPOCH of the
+//                                            evaluation the value belongs to
+//   es   [2 parities][world][2] {double, epoch}   pair energies of rank g
+// The CTA that handles bead block B gathers this rank's partial force on its 128 beads and PUSHES it into slot `rank` of every
+// rank's recv as 16-byte remote stores (fire-and-forget: no fence, no separate flag — a 16-byte aligned store arrives as one
+// piece, so the epoch in .w says that x, y, z next to it are the new ones; the same assumption NCCL's LL/LL128 protocols make
+// on NVLink).  The receiver polls the slots of the contributing ranks until they show the current epoch and adds them in rank
+// order (identical on every rank, so the redundant integration stays bit-identical).  Parity double-buffering makes overwriting
+// safe: a rank cannot run two evaluations ahead of a peer, because each evaluation needs that peer's current data.
 #define LN_MAXWORLD 8
 struct LnXchg {
     int world, rank, nblk, n4;                 // n4 = N + 1
-    float4* recv[LN_MAXWORLD]; unsigned int* flags[LN_MAXWORLD]; double* es[LN_MAXWORLD]; unsigned int* eflag[LN_MAXWORLD];
+    float4* recv[LN_MAXWORLD]; double2* es[LN_MAXWORLD];      // es element: {value, epoch (as the bits of the second double)}
     int* err;                                  // host-visible word, set when a wait times out (a peer died): the host reports it
 };
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -1093,7 +1104,7 @@ struct LnEngine;
 struct LnGroup { std::vector<LnEngine*> es; DevBuf<LnCtx> ctxs; int grid = 0; bool dirty = true; };
 
 struct LnEngine {
-    int N = 0, nT = 0, rank = 0, world = 1, m = 5, ncta = 0, maxseg = 0, nblk = 0, nparts = 0, sms = 148;
+    int N = 0, nT = 0, rank = 0, world = 1, m = 5, ncta = 0, maxseg = 0, nblk = 0, nparts = 0, sms = 148, stream_l2 = 0;
     long long n_tiles = 0, t0 = 0, t1 = 0, pairs_total = 0; std::vector<long long> rank_cut;
     DevBuf<float> Dt, colpart, x0; DevBuf<float4> rowpart, vx, vxb, vg, vp, vv, vf, vS, vY, sx, sv, va[2], vb[2], vfr;
     DevBuf<int> rs_off, rs_idx, blk_off, blk_idx; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st; DevBuf<unsigned int> bar;
@@ -1110,10 +1121,8 @@ struct LnEngine {
     bool legacy = false;                       // multi-launch evaluation (NCCL all-reduce between ranks): the baseline path
     LnGroup self; LnGroup* group = nullptr;    // group: the launch group this engine currently belongs to (&self unless virtual ranks)
     static size_t up16(size_t v) { return (v + 15) / 16 * 16; }
-    size_t x_off_flags() const { return sizeof(float4) * 2 * (size_t)world * (N + 1); }
-    size_t x_off_es() const { return x_off_flags() + up16(sizeof(unsigned int) * (size_t)world * nblk); }
-    size_t x_off_eflag() const { return x_off_es() + sizeof(double) * 2 * 2 * (size_t)world; }
-    size_t x_total() const { return x_off_eflag() + up16(sizeof(unsigned int) * (size_t)world); }
+    size_t x_off_es() const { return sizeof(float4) * 2 * (size_t)world * (N + 1); }
+    size_t x_total() const { return x_off_es() + sizeof(double2) * 2 * 2 * (size_t)world; }
     LnVec vec() { LnVec v; v.x = vx.p; v.xb = vxb.p; v.g = vg.p; v.p = vp.p; v.v = vv.p; v.f = vf.p; v.S = vS.p; v.Y = vY.p; v.N = N; v.m = m; return v; }
     bool persistent() const { return !legacy && (world == 1 || p2p); }
 };
@@ -1216,6 +1225,10 @@ static int ln_alloc(LnEngine& e) {
     }
     int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&e.sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ntl = e.t1 - e.t0;
+    {   // targets that cannot stay in L2 from one evaluation to the next are streamed with an evict-first policy
+        int l2 = 0; cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+        e.stream_l2 = (double)ntl * LN_TILE_FLOATS * 4 > 0.6 * (double)l2 ? 1 : 0;
+    }
     e.nparts = std::min(64, std::max(1, (N + 255) / 256));
     e.self.es.assign(1, &e); e.group = &e.self;
     CHR3D_CUDA(e.Dt.alloc((size_t)std::max<long long>(ntl, 1) * LN_TILE_FLOATS));
@@ -1267,7 +1280,7 @@ static void ln_fill_ctx(LnEngine& e, int cta0, LnCtx& c) {
     memset(&c, 0, sizeof c);
     c.Dt = e.Dt.p; c.t0 = e.t0; c.t1 = e.t1; c.nT = e.nT; c.N = e.N; c.nblk = e.nblk; c.maxseg = e.maxseg; c.cta0 = cta0; c.ncta = e.ncta;
     c.colpart = e.colpart.p; c.rowpart = e.rowpart.p; c.epart = e.epart.p; c.rs_off = e.rs_off.p; c.rs_idx = e.rs_idx.p;
-    c.cstart = e.cstart.p; c.blk_off = e.blk_off.p; c.blk_idx = e.blk_idx.p; c.cta_ns = e.cta_ns.p;
+    c.stream_l2 = e.stream_l2; c.cstart = e.cstart.p; c.blk_off = e.blk_off.p; c.blk_idx = e.blk_idx.p; c.cta_ns = e.cta_ns.p;
     tile_coords(e.t0, e.nT, c.gI0, c.gJ0);
     if (e.t1 >= e.n_tiles) { c.gI1 = e.nT; c.gJ1 = e.nT; } else tile_coords(e.t1, e.nT, c.gI1, c.gJ1);
     c.v = e.vec(); for (int q = 0; q < 2; q++) { c.va[q] = e.va[q].p; c.vb[q] = e.vb[q].p; }
@@ -1278,8 +1291,7 @@ static void ln_fill_ctx(LnEngine& e, int cta0, LnCtx& c) {
         int I, J; tile_coords(e.rank_cut[g], e.nT, I, J); c.bmin[g] = I;
         if (e.p2p) {
             char* base = (char*)e.peer[g];
-            x.recv[g] = (float4*)base; x.flags[g] = (unsigned int*)(base + e.x_off_flags());
-            x.es[g] = (double*)(base + e.x_off_es()); x.eflag[g] = (unsigned int*)(base + e.x_off_eflag());
+            x.recv[g] = (float4*)base; x.es[g] = (double2*)(base + e.x_off_es());
         }
     }
 }
@@ -1353,7 +1365,7 @@ static LnGather ln_gather_args(LnEngine& e) {
 // pair tiles at the coordinates x + lam*xb2 (xb2 == nullptr: plain x)
 static void ln_tiles(LnEngine& e, const chr3d_stage& s, const float4* x, const float4* xb2, const float* lam, const int* done, bool want_e) {
     LnTileArgs a; a.Dt = e.Dt.p; a.t0 = e.t0; a.t1 = e.t1; a.nT = e.nT; a.N = e.N; a.x = x; a.xb2 = xb2; a.lam = lam; a.done = done;
-    a.colpart = e.colpart.p; a.rowpart = e.rowpart.p; a.epart = e.epart.p; a.cstart = e.cstart.p; a.maxseg = e.maxseg; ln_terms(e.prm, s, a.terms);
+    a.colpart = e.colpart.p; a.rowpart = e.rowpart.p; a.epart = e.epart.p; a.cstart = e.cstart.p; a.maxseg = e.maxseg; a.stream_l2 = e.stream_l2; ln_terms(e.prm, s, a.terms);
     ln_launch_tiles(e, a, want_e);
     e.n_launches++;
 }
@@ -1750,7 +1762,7 @@ CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t rep
     chr3d_stage s = h->prog.back();
     cudaEvent_t a, b; CHR3D_CUDA(cudaEventCreate(&a)); CHR3D_CUDA(cudaEventCreate(&b));
     LnTileArgs ta; ta.Dt = e.Dt.p; ta.t0 = e.t0; ta.t1 = e.t1; ta.nT = e.nT; ta.N = e.N; ta.x = e.vx.p; ta.xb2 = nullptr; ta.lam = nullptr; ta.done = nullptr;
-    ta.colpart = e.colpart.p; ta.rowpart = e.rowpart.p; ta.epart = e.epart.p; ta.cstart = e.cstart.p; ta.maxseg = e.maxseg; ln_terms(e.prm, s, ta.terms);
+    ta.colpart = e.colpart.p; ta.rowpart = e.rowpart.p; ta.epart = e.epart.p; ta.cstart = e.cstart.p; ta.maxseg = e.maxseg; ta.stream_l2 = e.stream_l2; ln_terms(e.prm, s, ta.terms);
     for (int w = 0; w < 3; w++) ln_launch_tiles(e, ta, want_energy != 0);
     CHR3D_CUDA(cudaEventRecord(a, e.stream));
     for (int r = 0; r < reps; r++) ln_launch_tiles(e, ta, want_energy != 0);
@@ -1802,16 +1814,18 @@ CHR3D_API int chr3d_single_fetch(chr3d_single* h, double* xyz, double* energies4
     return 0;
 }
 
-// Phase clock of the persistent kernel since the last call (milliseconds, as seen by CTA 0 of this rank): tile phases, first grid
-// barrier (+ energy publication), step phases (gather, peer exchange, integration), second barrier (+ decisions), L-BFGS update +
-// third barrier.  Reading resets the clock.
-CHR3D_API int chr3d_single_profile(chr3d_single* h, double* ms5) {
+// Phase clock of the persistent kernel since the last call (milliseconds, as seen by CTA 0 of this rank), 8 entries: [0] tile
+// phases, [1] first grid barrier (+ energy publication), [2] step phases (one rank: gather + integration; several ranks: summation
+// + integration), [3] second barrier (+ decisions), [4] L-BFGS update + third barrier, [5] gather + push to the peers, [6] wait for
+// the peers' partial forces, [7] unused.  Reading resets the clock.
+CHR3D_API int chr3d_single_profile(chr3d_single* h, double* ms8) {
+    double* ms5 = ms8;
     if (!h || !ms5) { set_error("chr3d_single_profile: bad arguments"); return CHR3D_ERR_ARG; }
     LnEngine& e = h->e;
     CHR3D_CUDA(cudaStreamSynchronize(e.stream));
     unsigned long long t[8];
     CHR3D_CUDA(cudaMemcpy(t, &e.st.p->tprof[0], sizeof t, cudaMemcpyDeviceToHost));
-    for (int q = 0; q < 5; q++) ms5[q] = 1e-6 * (double)t[q];
+    for (int q = 0; q < 8; q++) ms5[q] = 1e-6 * (double)t[q];
     CHR3D_CUDA(cudaMemset(&e.st.p->tprof[0], 0, sizeof t));
     return 0;
 }

@@ -25,7 +25,7 @@
 enum { LN_OP_MD = 1, LN_OP_MIN = 2, LN_OP_EVAL = 3 };
 
 struct LnCtx {                              // one (virtual) rank
-    const float* Dt; long long t0, t1, nT; int N, nblk, maxseg, cta0, ncta;
+    const float* Dt; long long t0, t1, nT; int N, nblk, maxseg, cta0, ncta, stream_l2;
     float* colpart; float4* rowpart; double* epart;
     const int* rs_off; const int* rs_idx;
     const long long* cstart;                // [ncta + 1] first tile of every CTA (cost-balanced, ln_plan)
@@ -51,6 +51,19 @@ __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
 }
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// 16-byte pieces of the peer exchange: one store / one load each (the epoch travels inside the piece)
+__device__ __forceinline__ void st_v4_sys(float4* p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_v4_sys(const float4* p) {
+    float4 v; asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_d2_sys(double2* p, double a, double b) {
+    asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ double2 ld_d2_sys(const double2* p) {
+    double2 v; asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ unsigned long long ln_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // A wait that can never complete (a peer died, a protocol bug) must not hang the GPU: after ~20 s the reason goes to the
@@ -95,6 +108,15 @@ __device__ __forceinline__ void ln_bar_release(const LnCtx& c, unsigned int gen)
     if (threadIdx.x == 0) { *c.bar = 0u; st_release_gpu(c.bar + 32, gen + 1u); }     // (the release orders the counter reset before the new generation)
 }
 
+// Loop state lives in shared memory, not in registers: the tile phase is inlined into the kernel and needs the whole register
+// budget (there is no L1 behind 229 KB of shared memory, a spill in the pair loop is an L2 round trip).
+// tacc: phase clock of CTA 0 of a rank (ns, accumulated into LnState::tprof): 0 tile phase, 1 first barrier (+ energy
+// publication), 2 step phase (one rank: gather + integration; several ranks: summation + integration only), 3 second barrier
+// (+ decisions), 4 L-BFGS update + third barrier, 5 gather + push to the peers, 6 wait for the peers' partial forces
+struct LnLoop { int step, par, stop; unsigned int gen, epoch; unsigned long long tlast, tacc[8], t0tile, ttile; };
+__device__ __forceinline__ void ln_tprof(volatile LnLoop* L, int slot, bool timing) {
+    if (timing) { const unsigned long long t = ln_globaltimer(); L->tacc[slot] += t - L->tlast; L->tlast = t; }
+}
 // ---- scratch in the dynamic shared memory: the column-partial buffer of the tile phase is free between tile phases ------
 struct LnScratch {
     union {
@@ -119,7 +141,13 @@ __device__ __forceinline__ void ln_gather4(const LnCtx& c, int B, LnScratch* sc,
         int I = lo + grp;
 #define LN_GLD(u, k) const float4 u = __ldcg(base + (size_t)(tile_index(I + (k) * LN_P_GGRP, B, c.nT) - c.t0) * 96)
 #define LN_GADD(a, u) a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w
-        for (; I + 7 * LN_P_GGRP < hi; I += 8 * LN_P_GGRP) {       // eight independent 16-byte loads in flight per thread
+        for (; I + 15 * LN_P_GGRP < hi; I += 16 * LN_P_GGRP) {     // sixteen independent 16-byte loads in flight per thread: the gather is
+            LN_GLD(u0, 0); LN_GLD(u1, 1); LN_GLD(u2, 2); LN_GLD(u3, 3); LN_GLD(u4, 4); LN_GLD(u5, 5); LN_GLD(u6, 6); LN_GLD(u7, 7);     // bound by dependent round trips to L2
+            LN_GLD(u8, 8); LN_GLD(u9, 9); LN_GLD(u10, 10); LN_GLD(u11, 11); LN_GLD(u12, 12); LN_GLD(u13, 13); LN_GLD(u14, 14); LN_GLD(u15, 15);
+            LN_GADD(a0, u0); LN_GADD(a1, u1); LN_GADD(a2, u2); LN_GADD(a3, u3); LN_GADD(a0, u4); LN_GADD(a1, u5); LN_GADD(a2, u6); LN_GADD(a3, u7);
+            LN_GADD(a0, u8); LN_GADD(a1, u9); LN_GADD(a2, u10); LN_GADD(a3, u11); LN_GADD(a0, u12); LN_GADD(a1, u13); LN_GADD(a2, u14); LN_GADD(a3, u15);
+        }
+        for (; I + 7 * LN_P_GGRP < hi; I += 8 * LN_P_GGRP) {
             LN_GLD(u0, 0); LN_GLD(u1, 1); LN_GLD(u2, 2); LN_GLD(u3, 3); LN_GLD(u4, 4); LN_GLD(u5, 5); LN_GLD(u6, 6); LN_GLD(u7, 7);
             LN_GADD(a0, u0); LN_GADD(a1, u1); LN_GADD(a2, u2); LN_GADD(a3, u3); LN_GADD(a0, u4); LN_GADD(a1, u5); LN_GADD(a2, u6); LN_GADD(a3, u7);
         }
@@ -151,7 +179,7 @@ __device__ __forceinline__ void ln_gather4(const LnCtx& c, int B, LnScratch* sc,
 // 128 lead threads of every block (i = bead index, may be >= N) with all threads of the CTA participating (block-wide
 // reductions inside emit are allowed).
 template <typename Emit>
-__device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch* sc, unsigned int epoch, Emit emit) {
+__device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch* sc, unsigned int epoch, volatile LnLoop* L, bool timing, Emit emit) {
     const int tid = threadIdx.x, cta = blockIdx.x - c.cta0;
     const LnXchg& x = c.xc;
     if (x.world <= 1) {
@@ -164,31 +192,34 @@ __device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch
     }
     const int parity = (int)(epoch & 1u);
     const size_t slot = ((size_t)parity * x.world + x.rank) * x.n4;
-    // push: this rank's partial of every block it contributes to -> slot `rank` of every rank (self included)
+    // push: this rank's partial of every block it contributes to -> slot `rank` of every rank (self included), the epoch in .w
     for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
         if (B < c.bmin[x.rank]) continue;
         float fx, fy, fz;
         ln_gather4(c, B, sc, fx, fy, fz);
         const int i = B * LN_TB + tid;
         if (tid < LN_TB && i < c.N) {
-            const float4 v = make_float4(fx, fy, fz, 0.f);
-            for (int g = 0; g < x.world; g++) x.recv[g][slot + i] = v;
+            const float4 v = make_float4(fx, fy, fz, __uint_as_float(epoch));
+            for (int g = 0; g < x.world; g++) st_v4_sys(x.recv[g] + slot + i, v);
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++)
-        if (B >= c.bmin[x.rank] && tid < x.world) st_release_sys(x.flags[tid] + (size_t)x.rank * x.nblk + B, epoch);
-    // wait for the contributors of each block, add their slots in rank order
+    ln_tprof(L, 5, timing);
+    // poll the slots of the contributors of each block until they carry this epoch, add them in rank order
     for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
-        if (tid < x.world && B >= c.bmin[tid]) ln_wait_flag_sys(x.flags[x.rank] + (size_t)tid * x.nblk + B, epoch, x.err);
-        __syncthreads();
         const int i = B * LN_TB + tid;
         float fx = 0.f, fy = 0.f, fz = 0.f;
         if (tid < LN_TB && i < c.N) {
             const float4* R = x.recv[x.rank] + (size_t)parity * x.world * x.n4 + i;
-            for (int g = 0; g < x.world; g++) if (B >= c.bmin[g]) { const float4 v = __ldcg(R + (size_t)g * x.n4); fx += v.x; fy += v.y; fz += v.z; }
+            for (int g = 0; g < x.world; g++) if (B >= c.bmin[g]) {
+                float4 v = ld_v4_sys(R + (size_t)g * x.n4);
+                if (__float_as_uint(v.w) != epoch) {
+                    const long long t0 = clock64();
+                    do { v = ld_v4_sys(R + (size_t)g * x.n4); if (clock64() - t0 > LN_WAIT_LIMIT) ln_fail(x.err, 1); } while (__float_as_uint(v.w) != epoch);
+                }
+                fx += v.x; fy += v.y; fz += v.z;
+            }
         }
+        if (bk + 1 == c.blk_off[cta + 1]) ln_tprof(L, 6, timing);
         emit(B, i, fx, fy, fz);
     }
 }
@@ -230,9 +261,11 @@ __device__ __forceinline__ void ln_energy_publish(const LnCtx& c, LnScratch* sc,
         c.st->eloc[0] = red[0]; c.st->eloc[1] = red[LN_P_THREADS];
         if (x.world > 1) {
             const int parity = (int)(epoch & 1u);
-            for (int g = 0; g < x.world; g++) { double* d = x.es[g] + ((size_t)parity * x.world + x.rank) * 2; d[0] = red[0]; d[1] = red[LN_P_THREADS]; }
-            __threadfence_system();
-            for (int g = 0; g < x.world; g++) st_release_sys(x.eflag[g] + x.rank, epoch);
+            const double ep = __longlong_as_double((long long)epoch);
+            for (int g = 0; g < x.world; g++) {
+                double2* d = x.es[g] + ((size_t)parity * x.world + x.rank) * 2;
+                st_d2_sys(d, red[0], ep); st_d2_sys(d + 1, red[LN_P_THREADS], ep);
+            }
         }
     }
     __syncthreads();
@@ -244,19 +277,25 @@ __device__ __forceinline__ void ln_energy_collect(const LnCtx& c, unsigned int e
     const int parity = (int)(epoch & 1u);
     e0 = e1 = 0.0;
     for (int g = 0; g < x.world; g++) {
-        ln_wait_flag_sys(x.eflag[x.rank] + g, epoch, x.err);
-        const double* d = x.es[x.rank] + ((size_t)parity * x.world + g) * 2;
-        e0 += __ldcg(d); e1 += __ldcg(d + 1);
+        const double2* d = x.es[x.rank] + ((size_t)parity * x.world + g) * 2;
+        for (int q = 0; q < 2; q++) {
+            double2 v = ld_d2_sys(d + q);
+            if (__double_as_longlong(v.y) != (long long)epoch) {
+                const long long t0 = clock64();
+                do { v = ld_d2_sys(d + q); if (clock64() - t0 > LN_WAIT_LIMIT) ln_fail(x.err, 1); } while (__double_as_longlong(v.y) != (long long)epoch);
+            }
+            if (q == 0) e0 += v.x; else e1 += v.x;
+        }
     }
 }
 
 // ---- the step phases ----------------------------------------------------------------------------------------------------
 // Verlet step (definition of the oracle's sim_dynamics, see ln_md_step_kernel)
 __device__ __noinline__ void ln_step_md(const LnCtx& c, const LnOp& op, LnScratch* sc, const float4* A, const float4* Bv, float lam, int first,
-                                        float4* a_next, float4* b_next, unsigned int epoch) {
+                                        float4* a_next, float4* b_next, unsigned int epoch, volatile LnLoop* L, bool timing) {
     const int tid = threadIdx.x;
     const float h = op.md.h, dt = op.md.dt_akma, dth = dt * h;
-    ln_forces_of_my_blocks(c, sc, epoch, [&](int B, int i, float fx, float fy, float fz) {
+    ln_forces_of_my_blocks(c, sc, epoch, L, timing, [&](int B, int i, float fx, float fy, float fz) {
         float eb = 0.f, k2 = 0.f;
         if (tid < LN_TB && i < c.N) {
             ln_bond_cg(A, Bv, lam, i, c.N, op.bd, fx, fy, fz, eb);
@@ -303,13 +342,13 @@ __device__ __noinline__ void ln_decide_md(const LnCtx& c, const LnOp& op, LnScra
 }
 
 // L-BFGS trial x = xb + t*p (see ln_min_step_kernel): forces, the 6m+6 inner products of (s, y, g') with the history
-__device__ __noinline__ void ln_step_min(const LnCtx& c, const LnOp& op, LnScratch* sc, float lam, int init, unsigned int epoch) {
+__device__ __noinline__ void ln_step_min(const LnCtx& c, const LnOp& op, LnScratch* sc, float lam, int init, unsigned int epoch, volatile LnLoop* L, bool timing) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const LnVec& v = c.v;
     const int m = v.m, K = 6 * m + 6, N = v.N;
     const int head = __ldcg(&c.st->head);
     const float4* A = init ? v.x : v.xb;
-    ln_forces_of_my_blocks(c, sc, epoch, [&](int B, int i, float fx, float fy, float fz) {
+    ln_forces_of_my_blocks(c, sc, epoch, L, timing, [&](int B, int i, float fx, float fy, float fz) {
         float eb = 0.f;
         if (tid < LN_TB) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f), y = s, gn = s;
@@ -404,9 +443,9 @@ __device__ __noinline__ void ln_update_min(const LnCtx& c) {
 }
 
 // energies + forces at explicit coordinates (SAVE / PICK / ENERGY ops)
-__device__ __noinline__ void ln_step_eval(const LnCtx& c, const LnOp& op, LnScratch* sc, unsigned int epoch) {
+__device__ __noinline__ void ln_step_eval(const LnCtx& c, const LnOp& op, LnScratch* sc, unsigned int epoch, volatile LnLoop* L, bool timing) {
     const int tid = threadIdx.x;
-    ln_forces_of_my_blocks(c, sc, epoch, [&](int B, int i, float fx, float fy, float fz) {
+    ln_forces_of_my_blocks(c, sc, epoch, L, timing, [&](int B, int i, float fx, float fy, float fz) {
         float eb = 0.f;
         if (tid < LN_TB && i < c.N) {
             ln_bond_cg(c.v.x, c.v.x, 0.f, i, c.N, op.bd, fx, fy, fz, eb);
@@ -432,14 +471,6 @@ __device__ __noinline__ void ln_decide_eval(const LnCtx& c, const LnOp& op, LnSc
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
-// Loop state lives in shared memory, not in registers: the tile phase is inlined into the kernel and needs the whole register
-// budget (there is no L1 behind 229 KB of shared memory, a spill in the pair loop is an L2 round trip).
-// tacc: phase clock of CTA 0 of a rank (ns, accumulated into LnState::tprof): 0 tile phase, 1 first barrier (+ energy
-// publication), 2 step phase (gather, exchange, integration), 3 second barrier (+ decisions), 4 L-BFGS update + third barrier
-struct LnLoop { int step, par, stop; unsigned int gen, epoch; unsigned long long tlast, tacc[5], t0tile, ttile; };
-__device__ __forceinline__ void ln_tprof(volatile LnLoop* L, int slot, bool timing) {
-    if (timing) { const unsigned long long t = ln_globaltimer(); L->tacc[slot] += t - L->tlast; L->tlast = t; }
-}
 // grid barrier; `serial` runs in the last arriver (all its threads) before the others are released
 template <typename Serial>
 __device__ __forceinline__ void ln_barrier(const LnCtx& c, volatile LnLoop* L, int* s_flag, Serial serial) {
@@ -462,7 +493,7 @@ __device__ __noinline__ void ln_md_rest(const LnCtx& c, const LnOp& op, LnScratc
     {
         const float4* A = first ? c.v.x : c.va[par]; const float4* Bv = first ? c.v.x : c.vb[par];
         const float lam = first ? 0.f : __ldcg(&c.st->lamf);
-        ln_step_md(c, op, sc, A, Bv, lam, first, first ? c.va[0] : c.va[par ^ 1], first ? c.vb[0] : c.vb[par ^ 1], epoch);
+        ln_step_md(c, op, sc, A, Bv, lam, first, first ? c.va[0] : c.va[par ^ 1], first ? c.vb[0] : c.vb[par ^ 1], epoch, L, timing);
     }
     ln_tprof(L, 2, timing);
     ln_barrier(c, L, s_flag, [&]() { ln_decide_md(c, op, sc, want_e, epoch); });
@@ -476,7 +507,7 @@ __device__ __noinline__ void ln_min_rest(const LnCtx& c, const LnOp& op, LnScrat
     const unsigned int epoch = L->epoch + 1u;
     ln_barrier(c, L, s_flag, [&]() { ln_energy_publish(c, sc, epoch); });
     ln_tprof(L, 1, timing);
-    ln_step_min(c, op, sc, init ? 0.f : __ldcg(&c.st->tstepf), init, epoch);
+    ln_step_min(c, op, sc, init ? 0.f : __ldcg(&c.st->tstepf), init, epoch, L, timing);
     ln_tprof(L, 2, timing);
     ln_barrier(c, L, s_flag, [&]() { ln_decide_min(c, op, sc, init, epoch); });
     ln_tprof(L, 3, timing);
@@ -491,7 +522,7 @@ __device__ __noinline__ void ln_eval_rest(const LnCtx& c, const LnOp& op, LnScra
     const unsigned int epoch = L->epoch + 1u;
     ln_barrier(c, L, s_flag, [&]() { ln_energy_publish(c, sc, epoch); });
     ln_tprof(L, 1, timing);
-    ln_step_eval(c, op, sc, epoch);
+    ln_step_eval(c, op, sc, epoch, L, timing);
     ln_tprof(L, 2, timing);
     ln_barrier(c, L, s_flag, [&]() { ln_decide_eval(c, op, sc, epoch); });
     if (threadIdx.x == 0) L->epoch = epoch;
@@ -527,11 +558,11 @@ __global__ void __launch_bounds__(LN_P_THREADS, 1) ln_persist_kernel(const LnCtx
     const bool timing = blockIdx.x == c.cta0 && threadIdx.x == 0;
     if (threadIdx.x == 0) {
         ln_run_setup(&run, c.Dt, c.t0, c.cstart, c.nT, c.N, c.colpart, c.rowpart, c.epart, c.maxseg, blockIdx.x - c.cta0);
-        run.terms = op.terms; run.dbg = op.dbg;
+        run.terms = op.terms; run.dbg = op.dbg; run.stream_l2 = c.stream_l2;
         Ls.step = -1; Ls.par = 0; Ls.stop = 0;
         Ls.gen = ld_acquire_gpu(c.bar + 32);             // stable between launches
         Ls.epoch = c.st->epoch;
-        for (int q = 0; q < 5; q++) Ls.tacc[q] = 0;
+        for (int q = 0; q < 8; q++) Ls.tacc[q] = 0;
         Ls.tlast = ln_globaltimer(); Ls.ttile = 0;
     }
     __syncthreads();
@@ -578,5 +609,5 @@ __global__ void __launch_bounds__(LN_P_THREADS, 1) ln_persist_kernel(const LnCtx
     }
     ln_ring_drain(&run, smem);
     if (threadIdx.x == 0) c.cta_ns[blockIdx.x - c.cta0] += L->ttile;
-    if (timing) { c.st->epoch = L->epoch; for (int q = 0; q < 5; q++) c.st->tprof[q] += L->tacc[q]; }
+    if (timing) { c.st->epoch = L->epoch; for (int q = 0; q < 8; q++) c.st->tprof[q] += L->tacc[q]; }
 }

@@ -109,7 +109,7 @@ Chr3D::write_pdb("$dir_out/$name.pdb", $xyz, $L, undef, 1, $MET);
 my ($red, $nred) = Chr3D::reduce_model($xyz, $L);
 Chr3D::write_reduced_pdb("$dir_out/${name}_reduced.pdb", $red, $nred);
 if (defined $part) { open(my $bf, ">", "$dir_out/best.part$part.txt") or die $!; print $bf "$name\t$best->{rho}\n"; close $bf; }
-printf "Selected   : %s.pdb  (alpha %.1f, model %d, energy rank %d, SRCC %.3f)  [%d s]\n", $name, $alpha[$best->{a}], $best->{k} + 1, $best->{rank}, $best->{rho}, time - $t0;
+printf "%s : %s.pdb  (alpha %.1f, model %d, energy rank %d, SRCC %.3f)  [%d s]\n", (defined $part ? "Part $part best" : "Selected  "), $name, $alpha[$best->{a}], $best->{k} + 1, $best->{rank}, $best->{rho}, time - $t0;
 exit 0;
 
 sub usage {

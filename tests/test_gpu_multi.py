@@ -95,7 +95,7 @@ def test_sweep_driver_shards_alphas_over_two_gpus(tmp_path):
         r = subprocess.run(["perl", "-I", perl, os.path.join(perl, "chromosome3D_sweep.pl"), "-i", ds.input_path("chr22_1mb"), "-o", str(out), "-m", "3",
                             "--alphas", "0.4,0.5,0.6,0.7"] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
         assert r.returncode == 0, r.stderr + r.stdout
-        outs[tag] = (open(out / "alpha_sweep.txt").read(), re.search(r"Selected\s+: (\S+)\.pdb", r.stdout).group(1), sorted(os.listdir(out)))
+        outs[tag] = (open(out / "alpha_sweep.txt").read(), re.findall(r"Selected\s+: (\S+)\.pdb", r.stdout)[-1], sorted(os.listdir(out)))
     # the children anneal 6 trajectories per call instead of 12, so the launch shapes (hence the reduction orders) may differ:
     # same alphas and restraint counts, statistically the same scores
     rows = {t: [l.split("\t") for l in outs[t][0].splitlines() if not l.startswith("#")] for t in outs}
