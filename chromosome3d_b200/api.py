@@ -19,7 +19,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchr3d.so")
+LIB_PATH = os.environ.get("CHR3D_LIBRARY") or os.path.join(_HERE, "libchr3d.so")     # CHR3D_LIBRARY: another build of the same library (kernel variants)
 _lib = None
 
 _dp = C.POINTER(C.c_double)

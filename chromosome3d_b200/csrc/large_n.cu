@@ -145,12 +145,21 @@ __host__ __device__ inline void ln_tile_cell(int k, int& r, int& c) {
     c = 32 * (2 * (q & 1) + (e >> 1)) + l;
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// A wait that cannot complete is a bug in the pipeline protocol: trap after ~10 s instead of hanging the GPU.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
     uint32_t done = 0;
     while (!done) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 20000000000ll) __trap();
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    if (!done) mbar_wait_slow(smem_addr(bar), parity);
 }
 
 struct LnTileArgs {
@@ -206,24 +215,21 @@ struct LnTileRun {
     int stream_l2;            // 1: the targets of this rank exceed what L2 can keep between evaluations -> the TMA copies carry an
                               // evict-first L2 policy, so that the stream does not push the partial forces and the vectors out of L2
     LnTerms terms;
-    unsigned int phases, pending; int stage, cstage;   // phases bit q: parity to wait for on bar[q]; pending: stages with a copy outstanding
+    unsigned long long l2pol; // L2 cache policy of the TMA copies (created once per launch from stream_l2)
+    unsigned int pending;     // stages with a copy outstanding
+    unsigned int pos;         // position of the next tile in the periodic sequence (tiles consumed since the launch started)
+    // bookkeeping of the walk, per tile, written one tile ahead by thread 0 and read by everybody at the top of the tile
+    // (double-buffered by tile parity; the per-tile __syncthreads orders the two): nothing of it is carried in registers
+    struct Step { int I, J, Jn, stage, tpar, cpar, near, newrow, seg, last; } step[2];
 };
 #define LN_RUN(field) (((volatile LnTileRun*)run)->field)
 
 __device__ __forceinline__ void ln_ring_issue(LnTileRun* run, unsigned char* smem, int k, int stage) {      // one elected thread: 64 KB bulk copy of the CTA's tile k
     float* dbuf = (float*)smem; uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar[stage])), "r"(LN_TILE_FLOATS * 4) : "memory");
-    if (LN_RUN(stream_l2)) {
-        uint64_t pol;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                     ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(LN_RUN(Dt) + (size_t)k * LN_TILE_FLOATS),
-                       "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])), "l"(pol) : "memory");
-    } else {
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(LN_RUN(Dt) + (size_t)k * LN_TILE_FLOATS),
-                       "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])) : "memory");
-    }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_addr(dbuf + (size_t)stage * LN_TILE_FLOATS)), "l"(LN_RUN(Dt) + (size_t)k * LN_TILE_FLOATS),
+                   "r"(LN_TILE_FLOATS * 4), "r"(smem_addr(&bar[stage])), "l"(LN_RUN(l2pol)) : "memory");
     LN_RUN(pending) = LN_RUN(pending) | (1u << stage);
 }
 // once per launch (all threads; run->Dt, n, dbg are set): mbarriers, ring state, the first LN_STAGES copies.
@@ -234,7 +240,17 @@ __device__ __forceinline__ void ln_ring_init(LnTileRun* run, unsigned char* smem
         for (int q = 0; q < LN_STAGES; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[q])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar[LN_STAGES])), "r"(3 * LN_TB / 32));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        run->phases = 0; run->pending = 0; run->stage = 0; run->cstage = 0;
+        run->pending = 0; run->pos = 0;
+        {
+            unsigned long long pol;
+#ifdef LN_NO_L2HINT
+            if (false) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#else
+            if (run->stream_l2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+            else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+            run->l2pol = pol;
+        }
         const int n = run->n;
         if (n > 0 && run->dbg != 2) for (int q = 0; q < LN_STAGES; q++) if (periodic || q < n) ln_ring_issue(run, smem, q % n, q);
     }
@@ -244,13 +260,19 @@ __device__ __forceinline__ void ln_ring_init(LnTileRun* run, unsigned char* smem
 __device__ __forceinline__ void ln_ring_drain(LnTileRun* run, unsigned char* smem) {
     uint64_t* bar = (uint64_t*)(smem + LN_BAR_OFF);
     __syncthreads();
-    if (threadIdx.x == 0) for (int q = 0; q < LN_STAGES; q++) if (run->pending >> q & 1u) mbar_wait(&bar[q], (run->phases >> q) & 1u);
+    // stage q is consumed next at the first position >= pos that maps to it; its parity there is (position / LN_STAGES) & 1
+    if (threadIdx.x == 0) for (int q = 0; q < LN_STAGES; q++) if (run->pending >> q & 1u) {
+        unsigned int g = run->pos; while (g % LN_STAGES != (unsigned)q) g++;
+        mbar_wait(&bar[q], (g / LN_STAGES) & 1u);
+    }
     __syncthreads();
 }
 
 // One force evaluation of this CTA's tile range at the coordinates X + lam * XB (all in *run).
+// tm: the pair-term constants, handed over by value from the KERNEL PARAMETER (constant bank -> uniform registers: they do not
+// occupy vector registers of the pair loop)
 template <bool WANT_E, bool LOW_SOFT>
-__device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* smem) {
+__device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* smem, const LnTerms tm) {
 #ifdef CHR3D_DEV
     const int dbg = run->dbg;
 #else
@@ -262,7 +284,6 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
     float4* cbuf = (float4*)(smem + LN_CBUF_OFF);       // [stage][a|b][128]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = run->n;
-    const LnTerms tm = run->terms;
     const float lam = run->lam;
     // column coordinates of tile column Jn -> cbuf[stg] with cp.async (L2 latency hidden behind the previous tile's pairs)
     auto prefetch_cols = [&](int Jn, int stg) {
@@ -275,18 +296,26 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    uint32_t phases = run->phases;                           // bit q: parity to wait for on bar[q]
-    int stage = run->stage, cstage = run->cstage;            // tile ring / column-coordinate double buffer
-    int I = run->I0, J = run->J0;
-    if (n > 0) prefetch_cols(J, cstage);
+    // tile k of this evaluation = position pos + k of the periodic sequence: stage (pos + k) % LN_STAGES, whose mbarrier
+    // completes its ((pos + k) / LN_STAGES)-th phase when the tile has landed; the "colp free" barrier completes one phase per
+    // tile (consumed by the next tile, the last one at the end of the evaluation)
+    auto make_step = [&](int k, int I, int J, int seg, int newrow) {         // thread 0
+        LnTileRun::Step st;
+        const unsigned int g = run->pos + (unsigned)k;
+        st.I = I; st.J = J; st.stage = (int)(g % LN_STAGES); st.tpar = (int)((g / LN_STAGES) & 1u); st.cpar = (int)((g + 1u) & 1u);
+        int Jn = J + 1; if (Jn == run->nT) Jn = I + 1;
+        st.Jn = Jn; st.near = (J <= I + 1 || (J + 1) * LN_TB > run->N) ? 1 : 0; st.newrow = newrow; st.seg = seg; st.last = (J + 1 == run->nT || k + 1 == n) ? 1 : 0;
+        run->step[k & 1] = st;
+    };
+    if (tid == 0 && n > 0) make_step(0, run->I0, run->J0, 0, 1);
+    __syncthreads();
+    if (n > 0) prefetch_cols(LN_RUN(step[0].J), (int)(LN_RUN(pos) & 1u));
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    int seg = -1;
-    bool newrow = true;
     float2 xi[4], yi[4], zi[4], fix[4], fiy[4], fiz[4];          // row pairs (8w + 2rp, 8w + 2rp + 1)
     float2 en = bc(0.f), ev = bc(0.f);
 
-    auto flush_rows = [&]() {
+    auto flush_rows = [&](int seg) {
         // reduce the 8 row accumulators over the 32 lanes (columns) of this warp
         float4* rp_out = LN_RUN(rowpart) + (size_t)seg * LN_TB + warp * 8;
 #pragma unroll
@@ -299,9 +328,10 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
     };
 
     for (int k = 0; k < n; k++) {
-        if (newrow) {
-            newrow = false; seg++;
-            const float4* X = LN_RUN(X); const float4* XB = LN_RUN(XB); const int N = LN_RUN(N);
+        const volatile LnTileRun::Step* sp = &((volatile LnTileRun*)run)->step[k & 1];
+        const int cstage = (int)((LN_RUN(pos) + (unsigned)k) & 1u);
+        if (sp->newrow) {
+            const float4* X = LN_RUN(X); const float4* XB = LN_RUN(XB); const int N = LN_RUN(N), I = sp->I;
 #pragma unroll
             for (int rp = 0; rp < 4; rp++) {
                 int i0 = I * LN_TB + warp * 8 + 2 * rp, i1 = i0 + 1;
@@ -312,15 +342,26 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
                 zi[rp] = f2(fmaf(lam, q0.z, p0.z), fmaf(lam, q1.z, p1.z)); fix[rp] = fiy[rp] = fiz[rp] = bc(0.f);
             }
         }
-        const int nT = LN_RUN(nT);
-        if (k + 1 < n) { int Jn = J + 1; if (Jn == nT) Jn = I + 1; prefetch_cols(Jn, cstage ^ 1); }
-        if (dbg != 2) { mbar_wait(&bar[stage], (phases >> stage) & 1u); phases ^= 1u << stage; }
+        if (k + 1 < n) {
+            prefetch_cols(sp->Jn, cstage ^ 1);
+            if (tid == 0) {           // the next tile's bookkeeping, one tile ahead
+                int I = sp->I, J = sp->J + 1, nr = 0, seg = sp->seg;
+                if (J == LN_RUN(nT)) { I++; J = I; nr = 1; seg++; }
+                make_step(k + 1, I, J, seg, nr);
+            }
+        }
+        const int stage = sp->stage;
+        if (dbg != 2) mbar_wait(&bar[stage], (uint32_t)sp->tpar);
         const float4* D4 = reinterpret_cast<const float4*>(dbuf + (size_t)stage * LN_TILE_FLOATS) + (warp * 8) * 32 + lane;   // see ln_tile_cell
         // padding beads (index >= N) exist only in the last tile row / column; their cells are -2 like the diagonal band's
-        const bool near = J <= I + 1 || (J + 1) * LN_TB > LN_RUN(N);
+        const bool near = sp->near != 0;
         // the lane's four columns in two halves (columns 32*(2ch) + lane and 32*(2ch+1) + lane): only two columns' coordinates
         // and force accumulators are live at a time, which is what keeps the pair loop inside the register budget
+#ifdef LN_UNROLL_CH
 #pragma unroll
+#else
+#pragma unroll 1          // (unrolled, the two halves overlap a little better, but in the persistent kernel ptxas then spills accumulators)
+#endif
         for (int ch = 0; ch < 2; ch++) {
             float xj[2], yj[2], zj[2];
             float2 gjx[2], gjy[2], gjz[2];
@@ -348,13 +389,14 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
             }
             // column partials: [comp][warp][128], this lane's 4 consecutive positions; the single buffer is free once the reducer
             // warps of the previous tile have drained it (they arrived long ago: this wait does not block in practice)
-            if (ch == 0 && k > 0) { mbar_wait(&bar[LN_STAGES], (phases >> LN_STAGES) & 1u); phases ^= 1u << LN_STAGES; }
+            if (ch == 0 && k > 0) mbar_wait(&bar[LN_STAGES], (uint32_t)sp->cpar);
             *reinterpret_cast<float2*>(colp + (0 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjx[0].x + gjx[0].y), -(gjx[1].x + gjx[1].y));
             *reinterpret_cast<float2*>(colp + (1 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjy[0].x + gjy[0].y), -(gjy[1].x + gjy[1].y));
             *reinterpret_cast<float2*>(colp + (2 * 16 + warp) * LN_TB + lane * 4 + 2 * ch) = make_float2(-(gjz[0].x + gjz[0].y), -(gjz[1].x + gjz[1].y));
         }
+        if (sp->last) flush_rows(sp->seg);          // (before the barrier: behind it thread 0 may already rewrite this bookkeeping slot)
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                 // tile buffer `stage` is free, column partials are complete, next column coordinates have landed
+        __syncthreads();                 // tile buffer `stage` is free, column partials are complete, next column coordinates and bookkeeping are in place
         if (tid == 0 && dbg != 2) {      // next position of the periodic tile sequence that wants this stage
             LN_RUN(pending) = LN_RUN(pending) & ~(1u << stage);
             const int nx = k + LN_STAGES;
@@ -370,13 +412,9 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar[LN_STAGES])) : "memory");
         }
-        stage = stage + 1 == LN_STAGES ? 0 : stage + 1; cstage ^= 1;
-        J++;
-        if (J == nT) { I++; J = I; newrow = true; }
-        if (newrow || k + 1 == n) flush_rows();
     }
     // the last tile's reducer arrivals complete a phase nobody waited for: consume it, so that the next evaluation starts clean
-    if (n > 0) { mbar_wait(&bar[LN_STAGES], (phases >> LN_STAGES) & 1u); phases ^= 1u << LN_STAGES; }
+    if (n > 0) mbar_wait(&bar[LN_STAGES], (LN_RUN(pos) + (unsigned)n - 1u) & 1u);
     // block energy (the column-partial buffer is free now)
     if (WANT_E) {
         double den = (double)(en.x + en.y), dev = (double)(ev.x + ev.y);
@@ -392,7 +430,7 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
         }
     }
     __syncthreads();
-    if (tid == 0) { run->phases = phases; run->stage = stage; run->cstage = cstage; }
+    if (tid == 0) run->pos = run->pos + (unsigned)n;
     __syncthreads();
 }
 
@@ -419,7 +457,7 @@ __global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs
     }
     __syncthreads();
     ln_ring_init(&run, smem, false);
-    ln_tile_phase<WANT_E, LOW_SOFT>(&run, smem);
+    ln_tile_phase<WANT_E, LOW_SOFT>(&run, smem, a.terms);
 }
 
 // ------------------------------------------------------------------------------------------------

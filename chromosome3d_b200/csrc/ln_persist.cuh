@@ -481,9 +481,22 @@ __device__ __forceinline__ void ln_barrier(const LnCtx& c, volatile LnLoop* L, i
     __syncthreads();
 }
 
-// What follows a tile phase, out of line and fed from shared memory (the kernel body keeps nothing in registers across the
-// inlined tile phase): first barrier, step phase, second barrier with the decisions, loop state.
-__device__ __noinline__ void ln_md_rest(const LnCtx& c, const LnOp& op, LnScratch* sc, volatile LnLoop* L, int* s_flag, bool timing) {
+// The state of a persistent launch, in shared memory at file scope: the out-of-line phases below take NO arguments, so the
+// kernel body keeps nothing alive in registers across the inlined tile phase (which needs all of them).
+__shared__ LnCtx lnp_c;
+__shared__ LnOp lnp_op;
+__shared__ LnTileRun lnp_run;
+__shared__ LnLoop lnp_L;
+__shared__ int lnp_flag;
+extern __shared__ __align__(128) unsigned char lnp_smem[];
+#define LNP_SC (reinterpret_cast<LnScratch*>(lnp_smem + LN_COLP_OFF))
+#define LNP_TIMING (blockIdx.x == (unsigned)lnp_c.cta0 && threadIdx.x == 0)
+
+// What follows a tile phase: first barrier, step phase, second barrier with the decisions, loop state.
+__device__ __noinline__ void ln_md_rest() {
+    const LnCtx& c = lnp_c; const LnOp& op = lnp_op; LnScratch* sc = LNP_SC; volatile LnLoop* L = &lnp_L; int* s_flag = &lnp_flag;
+    const bool timing = LNP_TIMING;
+    if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
     const int step = L->step, par = L->par;
     const int first = step < 0, want_e = !first && step == op.nstep - 1;
     ln_tprof(L, 0, timing);
@@ -501,7 +514,10 @@ __device__ __noinline__ void ln_md_rest(const LnCtx& c, const LnOp& op, LnScratc
     __syncthreads();
     ln_tprof(L, 3, timing);
 }
-__device__ __noinline__ void ln_min_rest(const LnCtx& c, const LnOp& op, LnScratch* sc, volatile LnLoop* L, int* s_flag, bool timing) {
+__device__ __noinline__ void ln_min_rest() {
+    const LnCtx& c = lnp_c; const LnOp& op = lnp_op; LnScratch* sc = LNP_SC; volatile LnLoop* L = &lnp_L; int* s_flag = &lnp_flag;
+    const bool timing = LNP_TIMING;
+    if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
     const int step = L->step, init = step < 0;
     ln_tprof(L, 0, timing);
     const unsigned int epoch = L->epoch + 1u;
@@ -517,7 +533,10 @@ __device__ __noinline__ void ln_min_rest(const LnCtx& c, const LnOp& op, LnScrat
     __syncthreads();
     ln_tprof(L, 4, timing);
 }
-__device__ __noinline__ void ln_eval_rest(const LnCtx& c, const LnOp& op, LnScratch* sc, volatile LnLoop* L, int* s_flag, bool timing) {
+__device__ __noinline__ void ln_eval_rest() {
+    const LnCtx& c = lnp_c; const LnOp& op = lnp_op; LnScratch* sc = LNP_SC; volatile LnLoop* L = &lnp_L; int* s_flag = &lnp_flag;
+    const bool timing = LNP_TIMING;
+    if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
     ln_tprof(L, 0, timing);
     const unsigned int epoch = L->epoch + 1u;
     ln_barrier(c, L, s_flag, [&]() { ln_energy_publish(c, sc, epoch); });
@@ -529,85 +548,82 @@ __device__ __noinline__ void ln_eval_rest(const LnCtx& c, const LnOp& op, LnScra
     __syncthreads();
     ln_tprof(L, 3, timing);
 }
-// coordinates of the next MD evaluation -> run (one thread)
-__device__ __forceinline__ void ln_md_setup(const LnCtx& c, const LnOp& op, volatile LnLoop* L, LnTileRun* run) {
-    const int step = L->step, par = L->par, first = step < 0;
-    run->X = first ? c.v.x : c.va[par]; run->XB = first ? c.v.x : c.vb[par];
-    run->lam = first ? 0.f : __ldcg(&c.st->lamf); run->more = step + 1 < op.nstep;
+// coordinates of the next evaluation -> lnp_run, start of the tile clock (all threads call)
+__device__ __noinline__ void ln_md_setup() {
+    if (threadIdx.x == 0) {
+        const LnCtx& c = lnp_c; volatile LnLoop* L = &lnp_L; LnTileRun* run = &lnp_run;
+        const int step = L->step, par = L->par, first = step < 0;
+        run->X = first ? c.v.x : c.va[par]; run->XB = first ? c.v.x : c.vb[par];
+        run->lam = first ? 0.f : __ldcg(&c.st->lamf); run->more = step + 1 < lnp_op.nstep;
+        L->t0tile = ln_globaltimer();
+    }
+    __syncthreads();
+}
+__device__ __noinline__ void ln_min_setup() {
+    if (threadIdx.x == 0) {
+        const LnCtx& c = lnp_c; LnTileRun* run = &lnp_run;
+        const int init = lnp_L.step < 0;
+        run->X = init ? c.v.x : c.v.xb; run->XB = init ? c.v.x : c.v.p;
+        run->lam = init ? 0.f : __ldcg(&c.st->tstepf); run->more = 1;
+        lnp_L.t0tile = ln_globaltimer();
+    }
+    __syncthreads();
+}
+__device__ __noinline__ void ln_launch_setup(const LnCtx* __restrict__ ctxs, int nvr, const LnOp* op) {
+    {   // which (virtual) rank does this CTA belong to
+        int vr = 0;
+        while (vr + 1 < nvr && (int)blockIdx.x >= ctxs[vr + 1].cta0) vr++;
+        const int* src = reinterpret_cast<const int*>(ctxs + vr); int* dst = reinterpret_cast<int*>(&lnp_c);
+        for (int k = threadIdx.x; k < (int)(sizeof(LnCtx) / 4); k += LN_P_THREADS) dst[k] = src[k];
+        const int* so = reinterpret_cast<const int*>(op); int* sd = reinterpret_cast<int*>(&lnp_op);
+        for (int k = threadIdx.x; k < (int)(sizeof(LnOp) / 4); k += LN_P_THREADS) sd[k] = so[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const LnCtx& c = lnp_c;
+        ln_run_setup(&lnp_run, c.Dt, c.t0, c.cstart, c.nT, c.N, c.colpart, c.rowpart, c.epart, c.maxseg, blockIdx.x - c.cta0);
+        lnp_run.terms = lnp_op.terms; lnp_run.dbg = lnp_op.dbg; lnp_run.stream_l2 = c.stream_l2;
+        lnp_L.step = -1; lnp_L.par = 0; lnp_L.stop = 0;
+        lnp_L.gen = ld_acquire_gpu(c.bar + 32);             // stable between launches
+        lnp_L.epoch = c.st->epoch;
+        for (int q = 0; q < 8; q++) lnp_L.tacc[q] = 0;
+        lnp_L.tlast = ln_globaltimer(); lnp_L.ttile = 0;
+    }
+    __syncthreads();
+    ln_ring_init(&lnp_run, lnp_smem, true);
+}
+__device__ __noinline__ void ln_launch_finish() {
+    ln_ring_drain(&lnp_run, lnp_smem);
+    if (threadIdx.x == 0) lnp_c.cta_ns[blockIdx.x - lnp_c.cta0] += lnp_L.ttile;
+    if (LNP_TIMING) { lnp_c.st->epoch = lnp_L.epoch; for (int q = 0; q < 8; q++) lnp_c.st->tprof[q] += lnp_L.tacc[q]; }
 }
 
 template <bool LOW_SOFT>
 __global__ void __launch_bounds__(LN_P_THREADS, 1) ln_persist_kernel(const LnCtx* __restrict__ ctxs, int nvr, const __grid_constant__ LnOp op) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ LnCtx c;
-    __shared__ LnOp sop;                     // the op for the out-of-line phases
-    __shared__ LnTileRun run;
-    __shared__ LnLoop Ls;
-    __shared__ int s_flag;
-    volatile LnLoop* L = &Ls;
-    {   // which (virtual) rank does this CTA belong to
-        int vr = 0;
-        while (vr + 1 < nvr && (int)blockIdx.x >= ctxs[vr + 1].cta0) vr++;
-        const int* src = reinterpret_cast<const int*>(ctxs + vr); int* dst = reinterpret_cast<int*>(&c);
-        for (int k = threadIdx.x; k < (int)(sizeof(LnCtx) / 4); k += LN_P_THREADS) dst[k] = src[k];
-        const int* so = reinterpret_cast<const int*>(&op); int* sd = reinterpret_cast<int*>(&sop);
-        for (int k = threadIdx.x; k < (int)(sizeof(LnOp) / 4); k += LN_P_THREADS) sd[k] = so[k];
-    }
-    __syncthreads();
-    LnScratch* sc = reinterpret_cast<LnScratch*>(smem + LN_COLP_OFF);
-    const bool timing = blockIdx.x == c.cta0 && threadIdx.x == 0;
-    if (threadIdx.x == 0) {
-        ln_run_setup(&run, c.Dt, c.t0, c.cstart, c.nT, c.N, c.colpart, c.rowpart, c.epart, c.maxseg, blockIdx.x - c.cta0);
-        run.terms = op.terms; run.dbg = op.dbg; run.stream_l2 = c.stream_l2;
-        Ls.step = -1; Ls.par = 0; Ls.stop = 0;
-        Ls.gen = ld_acquire_gpu(c.bar + 32);             // stable between launches
-        Ls.epoch = c.st->epoch;
-        for (int q = 0; q < 8; q++) Ls.tacc[q] = 0;
-        Ls.tlast = ln_globaltimer(); Ls.ttile = 0;
-    }
-    __syncthreads();
-    ln_ring_init(&run, smem, true);
-
+    ln_launch_setup(ctxs, nvr, &op);
     if (op.kind == LN_OP_MD) {
         // every evaluation but the last one without energies
-        while (L->step < 0 || L->step < sop.nstep - 1) {
-            if (threadIdx.x == 0) ln_md_setup(c, sop, L, &run);
-            if (threadIdx.x == 0) L->t0tile = ln_globaltimer();
-            __syncthreads();
-            ln_tile_phase<false, LOW_SOFT>(&run, smem);
-            if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
-            ln_md_rest(c, sop, sc, L, &s_flag, timing);
+        while (((volatile LnLoop*)&lnp_L)->step < 0 || ((volatile LnLoop*)&lnp_L)->step < op.nstep - 1) {
+            ln_md_setup();
+            ln_tile_phase<false, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
+            ln_md_rest();
         }
-        if (sop.nstep > 0) {
-            if (threadIdx.x == 0) ln_md_setup(c, sop, L, &run);
-            if (threadIdx.x == 0) L->t0tile = ln_globaltimer();
-            __syncthreads();
-            ln_tile_phase<true, LOW_SOFT>(&run, smem);
-            if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
-            ln_md_rest(c, sop, sc, L, &s_flag, timing);
+        if (op.nstep > 0) {
+            ln_md_setup();
+            ln_tile_phase<true, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
+            ln_md_rest();
         }
     } else if (op.kind == LN_OP_MIN) {
-        while (!L->stop) {
-            if (threadIdx.x == 0) {
-                const int init = L->step < 0;
-                run.X = init ? c.v.x : c.v.xb; run.XB = init ? c.v.x : c.v.p;
-                run.lam = init ? 0.f : __ldcg(&c.st->tstepf); run.more = 1;
-            }
-            if (threadIdx.x == 0) L->t0tile = ln_globaltimer();
-            __syncthreads();
-            ln_tile_phase<true, LOW_SOFT>(&run, smem);
-            if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
-            ln_min_rest(c, sop, sc, L, &s_flag, timing);
+        while (!((volatile LnLoop*)&lnp_L)->stop) {
+            ln_min_setup();
+            ln_tile_phase<true, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
+            ln_min_rest();
         }
     } else {
-        if (threadIdx.x == 0) { run.X = c.v.x; run.XB = c.v.x; run.lam = 0.f; run.more = 0; }
-        if (threadIdx.x == 0) L->t0tile = ln_globaltimer();
+        if (threadIdx.x == 0) { lnp_run.X = lnp_c.v.x; lnp_run.XB = lnp_c.v.x; lnp_run.lam = 0.f; lnp_run.more = 0; lnp_L.t0tile = ln_globaltimer(); }
         __syncthreads();
-        ln_tile_phase<true, LOW_SOFT>(&run, smem);
-        if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
-        ln_eval_rest(c, sop, sc, L, &s_flag, timing);
+        ln_tile_phase<true, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
+        ln_eval_rest();
     }
-    ln_ring_drain(&run, smem);
-    if (threadIdx.x == 0) c.cta_ns[blockIdx.x - c.cta0] += L->ttile;
-    if (timing) { c.st->epoch = L->epoch; for (int q = 0; q < 8; q++) c.st->tprof[q] += L->tacc[q]; }
+    ln_launch_finish();
 }

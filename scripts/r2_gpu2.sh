@@ -1,10 +1,10 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_persist.py tests/test_gpu_large_n.py tests/test_gpu_parity2.py -m gpu -q --timeout 600 > gpurun_out/pytest_persist.log 2>&1; echo "persist rc=$?"; tail -3 gpurun_out/pytest_persist.log
-timeout 600 python scripts/ln_cta_fit.py > gpurun_out/r02_cta_fit.log 2>&1; echo "fit rc=$?"; cat gpurun_out/r02_cta_fit.log
-timeout 600 python bench.py --workload synth_10kb_single --steps 2 --warmup 1 > gpurun_out/r02_bench_10kb.json 2> gpurun_out/r02_bench_10kb.err; echo "10kb rc=$?"
-timeout 600 python bench.py --workload synth_50kb_single --steps 3 --warmup 2 > gpurun_out/r02_bench_50kb.json 2> gpurun_out/r02_bench_50kb.err; echo "50kb rc=$?"
+timeout 300 python -m pytest tests/test_gpu_persist.py tests/test_gpu_large_n.py tests/test_gpu_parity2.py -m gpu -q --timeout 120 > gpurun_out/pytest_persist.log 2>&1; echo "persist rc=$?"; tail -3 gpurun_out/pytest_persist.log
+timeout 150 python scripts/ln_cta_fit.py > gpurun_out/r02_cta_fit.log 2>&1; echo "fit rc=$?"; cat gpurun_out/r02_cta_fit.log
+timeout 200 python bench.py --workload synth_10kb_single --steps 2 --warmup 1 > gpurun_out/r02_bench_10kb.json 2> gpurun_out/r02_bench_10kb.err; echo "10kb rc=$?"
+timeout 200 python bench.py --workload synth_50kb_single --steps 3 --warmup 2 > gpurun_out/r02_bench_50kb.json 2> gpurun_out/r02_bench_50kb.err; echo "50kb rc=$?"
 python - <<'PY'
 import json
 for f in ["r02_bench_10kb.json","r02_bench_50kb.json"]:

@@ -7,9 +7,9 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/r02_mg${N}_gpus.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-CHR3D_TEST_P2P=1 timeout 600 $TR --master-port 29511 scripts/mg_worker.py > gpurun_out/r02_mg${N}_equality.log 2>&1; echo "equality rc=$?"; grep RESULT gpurun_out/r02_mg${N}_equality.log | cut -c1-1200
-timeout 900 $TR --master-port 29512 bench.py --gpus $N --workload synth_10kb_single --steps 2 --warmup 1 > gpurun_out/r02_scale_10kb_n${N}.json 2> gpurun_out/r02_scale_10kb_n${N}.err; echo "10kb rc=$?"
-timeout 900 $TR --master-port 29513 bench.py --gpus $N --workload synth_50kb_single --steps 3 --warmup 2 > gpurun_out/r02_scale_50kb_n${N}.json 2> gpurun_out/r02_scale_50kb_n${N}.err; echo "50kb rc=$?"
+CHR3D_TEST_P2P=1 timeout 200 $TR --master-port 29511 scripts/mg_worker.py > gpurun_out/r02_mg${N}_equality.log 2>&1; echo "equality rc=$?"; grep RESULT gpurun_out/r02_mg${N}_equality.log | cut -c1-1200
+timeout 200 $TR --master-port 29512 bench.py --gpus $N --workload synth_10kb_single --steps 2 --warmup 1 > gpurun_out/r02_scale_10kb_n${N}.json 2> gpurun_out/r02_scale_10kb_n${N}.err; echo "10kb rc=$?"
+timeout 200 $TR --master-port 29513 bench.py --gpus $N --workload synth_50kb_single --steps 3 --warmup 2 > gpurun_out/r02_scale_50kb_n${N}.json 2> gpurun_out/r02_scale_50kb_n${N}.err; echo "50kb rc=$?"
 if [ "$N" = "2" ] && [ -z "$QUICK" ]; then
   timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 800 > gpurun_out/r02_mg2_pytest.log 2>&1; echo "pytest multi rc=$?"; tail -3 gpurun_out/r02_mg2_pytest.log
   CHR3D_NO_P2P=1 timeout 900 $TR --master-port 29514 bench.py --gpus $N --workload synth_10kb_single --steps 1 --warmup 1 > gpurun_out/r02_scale_10kb_nccl_n${N}.json 2> gpurun_out/r02_scale_10kb_nccl_n${N}.err; echo "10kb nccl rc=$?"
