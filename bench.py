@@ -257,15 +257,20 @@ def single_structure(args, torch, dist, api, rank, world, local, workload, steps
                    "ms_per_step": ms[-1]}
         except Exception as ex:
             e2e = {"value": None, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)}
-    t = torch.tensor([step_ms, tile_ms, eval_ms] + [prof[k] / max(steps, 1) for k in ("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms", "gather_push_ms", "peer_wait_ms")],
+    t = torch.tensor([step_ms, tile_ms, eval_ms] + [prof[k] / max(steps, 1) for k in ("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms", "gather_push_ms", "peer_wait_ms", "gather_ms")],
                      dtype=torch.float64, device="cuda")
     w = torch.tensor([rows_rank], dtype=torch.float64, device="cuda")
     wmax = w.clone()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
         dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
-    step_ms_max, tile_ms_max, eval_ms_max, ph_tile, ph_b1, ph_step, ph_b2, ph_upd, ph_push, ph_wait = t.tolist()
+    by_rank = None
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        by_rank = [[round(v, 3) for v in a.tolist()] for a in allt]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms_max, tile_ms_max, eval_ms_max, ph_tile, ph_b1, ph_step, ph_b2, ph_upd, ph_push, ph_wait, ph_gather = t.tolist()
     rows_all, rows_max = w.item(), wmax.item()
     single.close()
     del flush
@@ -283,8 +288,9 @@ def single_structure(args, torch, dist, api, rank, world, local, workload, steps
             "steps": steps, "warmup": warmup, "ms_per_step": step_ms_max, "sa_models_per_sec": 1.0 / (step_ms_max * 1e-3),
             "value": evals * rows_all / (step_ms_max * 1e-3), "unit": "pair-evals/s", "force_evals_per_model": evals,
             "force_eval_ms": eval_ms_max, "tile_kernel_ms": tile_ms_max,
-            "phases_ms_per_step": {"tile": ph_tile, "barrier1": ph_b1, "gather_push": ph_push, "peer_wait": ph_wait, "sum_integrate": ph_step, "barrier2_decide": ph_b2, "lbfgs_update": ph_upd,
-                                   "note": "phase clock of the persistent kernel (CTA 0 of each rank, max over ranks), per step; with one rank gather and integration are both in sum_integrate"},
+            "phases_ms_per_step": {"tile": ph_tile, "barrier1": ph_b1, "gather": ph_gather, "push": ph_push, "peer_wait": ph_wait, "sum_integrate": ph_step, "barrier2_decide": ph_b2, "lbfgs_update": ph_upd,
+                                   "note": "phase clock of the persistent kernel (CTA 0 of each rank, max over ranks), per step; with one rank gather and integration are both in sum_integrate",
+                                   "by_rank": by_rank, "by_rank_columns": ["step_ms", "tile_kernel_ms", "eval_ms", "tile", "barrier1", "sum_integrate", "barrier2_decide", "lbfgs_update", "push", "peer_wait", "gather"]},
             "tiles": info["n_tiles"], "tiles_rank0": info["tiles_this_rank"], "target_bytes_rank0": info["target_bytes"], "launches_per_step": int(res["launches"]),
             "l2": "flushed between steps (512 MB write); targets exceed L2 at this size" if N > 8000 else "flushed between steps (512 MB write); the 51 MB of targets are re-read from L2 inside a step",
             "parallelism": ("tile-range shards over %d ranks; force exchange per evaluation: %s" % (world, exchange)) if world > 1 else "single GPU",

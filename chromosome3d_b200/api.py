@@ -484,7 +484,7 @@ class Single:
         """Phase clock of the persistent kernel since the last call (ms, CTA 0 of this rank): tile, barrier1, step, barrier2, update."""
         a = (C.c_double * 8)()
         _check(lib().chr3d_single_profile(self._h, a))
-        return dict(zip(("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms", "gather_push_ms", "peer_wait_ms"), [float(v) for v in a[:7]]))
+        return dict(zip(("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms", "gather_push_ms", "peer_wait_ms", "gather_ms"), [float(v) for v in a[:8]]))
 
     def profile_ctas(self):
         """Per-CTA tile counts (all, near, rows started) and tile-phase milliseconds of the persistent kernel since the last call."""

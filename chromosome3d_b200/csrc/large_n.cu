@@ -268,6 +268,18 @@ __device__ __forceinline__ void ln_ring_drain(LnTileRun* run, unsigned char* sme
     __syncthreads();
 }
 
+// The first LN_STAGES tiles of the NEXT evaluation (one thread).  The persistent kernel calls this from the step phase, once the
+// partial forces are on their way to the peers: issued at the end of the tile phase instead, these 28 MB (chip-wide) of bulk
+// copies would sit in front of the latency-critical loads of the gather.
+__device__ __forceinline__ void ln_ring_prefetch(LnTileRun* run, unsigned char* smem) {
+    const int n = run->n;
+    if (n <= 0 || run->dbg == 2) return;
+    for (int q = 0; q < LN_STAGES; q++) {
+        const unsigned int g = run->pos + (unsigned)q;
+        if (!(run->pending >> (g % LN_STAGES) & 1u)) ln_ring_issue(run, smem, q % n, (int)(g % LN_STAGES));
+    }
+}
+
 // One force evaluation of this CTA's tile range at the coordinates X + lam * XB (all in *run).
 // tm: the pair-term constants, handed over by value from the KERNEL PARAMETER (constant bank -> uniform registers: they do not
 // occupy vector registers of the pair loop)
@@ -515,6 +527,7 @@ __device__ __forceinline__ void ln_bonded(LD ld, const float4* a, const float4* 
                                           float& fx, float& fy, float& fz, float& eb) {
     const float4 pi = ld(a + i), qi = ld(b + i);
     const float xi = fmaf(lam, qi.x, pi.x), yi = fmaf(lam, qi.y, pi.y), zi = fmaf(lam, qi.z, pi.z);
+#pragma unroll 1
     for (int s = -1; s <= 1; s += 2) {
         const int nb = i + s; if (nb < 0 || nb >= N) continue;
         const float4 pn = ld(a + nb), qn = ld(b + nb);
@@ -524,7 +537,9 @@ __device__ __forceinline__ void ln_bonded(LD ld, const float4* a, const float4* 
         fx -= g * dx; fy -= g * dy; fz -= g * dz;
         if (s == 1) eb = bd.w_bond * u * u;
     }
-    if (bd.w_ang > 0.f) for (int s = -2; s <= 2; s += 4) {
+    if (bd.w_ang > 0.f)
+#pragma unroll 1
+    for (int s = -2; s <= 2; s += 4) {
         const int nb = i + s; if (nb < 0 || nb >= N) continue;
         const float4 pn = ld(a + nb), qn = ld(b + nb);
         const float dx = xi - fmaf(lam, qn.x, pn.x), dy = yi - fmaf(lam, qn.y, pn.y), dz = zi - fmaf(lam, qn.z, pn.z);
@@ -1359,6 +1374,8 @@ static int ln_launch_persist(LnGroup& g, LnOp& op, cudaStream_t stream) {
 static void ln_op_common(LnEngine& e, const chr3d_stage& s, LnOp& op) {
     memset(&op, 0, sizeof op);
     ln_terms(e.prm, s, op.terms); op.bd = ln_bonded_terms(e.prm, s); op.count_eval = 1;
+    op.defer_ring = (e.p2p && e.world > 1) ? 1 : 0;
+    if (dev_getenv("CHR3D_LN_DEFER_RING")) op.defer_ring = atoi(dev_getenv("CHR3D_LN_DEFER_RING"));
 }
 static void ln_md_cfg(LnEngine& e, const chr3d_stage& s, LnMdCfg& c) {
     c.dt_akma = (float)(s.dt / CHR3D_TIMFAC); c.h = (float)(0.5 * (s.dt / CHR3D_TIMFAC) / e.prm.mass); c.dt_ps = s.dt; c.temp = s.temp;
@@ -1854,8 +1871,8 @@ CHR3D_API int chr3d_single_fetch(chr3d_single* h, double* xyz, double* energies4
 
 // Phase clock of the persistent kernel since the last call (milliseconds, as seen by CTA 0 of this rank), 8 entries: [0] tile
 // phases, [1] first grid barrier (+ energy publication), [2] step phases (one rank: gather + integration; several ranks: summation
-// + integration), [3] second barrier (+ decisions), [4] L-BFGS update + third barrier, [5] gather + push to the peers, [6] wait for
-// the peers' partial forces, [7] unused.  Reading resets the clock.
+// + integration), [3] second barrier (+ decisions), [4] L-BFGS update + third barrier, [5] push to the peers, [6] wait for
+// the peers' partial forces, [7] gather of this rank's partials (several ranks).  Reading resets the clock.
 CHR3D_API int chr3d_single_profile(chr3d_single* h, double* ms8) {
     double* ms5 = ms8;
     if (!h || !ms5) { set_error("chr3d_single_profile: bad arguments"); return CHR3D_ERR_ARG; }

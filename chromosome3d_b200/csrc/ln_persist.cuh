@@ -39,6 +39,9 @@ struct LnCtx {                              // one (virtual) rank
 };
 struct LnOp {
     int kind, nstep, count_eval, dbg;
+    int defer_ring;         // 1: the tile ring stops at the end of an evaluation and is restarted from the step phase, behind the push
+                            // to the peers (several ranks: the copies would otherwise queue in front of the latency-critical gather);
+                            // 0: the ring keeps running across the evaluation boundary (one rank: there is no idle time to hide it in)
     LnTerms terms; LnBonded bd;
     LnMdCfg md; LnMinCfg min; long long max_trials;
 };
@@ -113,7 +116,7 @@ __device__ __forceinline__ void ln_bar_release(const LnCtx& c, unsigned int gen)
 // tacc: phase clock of CTA 0 of a rank (ns, accumulated into LnState::tprof): 0 tile phase, 1 first barrier (+ energy
 // publication), 2 step phase (one rank: gather + integration; several ranks: summation + integration only), 3 second barrier
 // (+ decisions), 4 L-BFGS update + third barrier, 5 gather + push to the peers, 6 wait for the peers' partial forces
-struct LnLoop { int step, par, stop; unsigned int gen, epoch; unsigned long long tlast, tacc[8], t0tile, ttile; };
+struct LnLoop { int step, par, stop, prefetch; unsigned int gen, epoch; unsigned long long tlast, tacc[8], t0tile, ttile; };
 __device__ __forceinline__ void ln_tprof(volatile LnLoop* L, int slot, bool timing) {
     if (timing) { const unsigned long long t = ln_globaltimer(); L->tacc[slot] += t - L->tlast; L->tlast = t; }
 }
@@ -129,111 +132,171 @@ struct LnScratch {
 static_assert(sizeof(LnScratch) <= LN_SCRATCH_BYTES, "scratch must fit the column-partial + column-coordinate buffers");
 static_assert(6 * CHR3D_LBFGS_MAX_M + 6 <= LN_KMAX && 2 * LN_P_THREADS * 8 <= (6 * CHR3D_LBFGS_MAX_M + 6) * LN_TB * 4, "serial-section scratch");
 
-// this rank's partial force on bead (B*128 + tid), valid in threads tid < 128; all threads call.  Fixed summation order.
-__device__ __forceinline__ void ln_gather4(const LnCtx& c, int B, LnScratch* sc, float& fx, float& fy, float& fz) {
-    const int tid = threadIdx.x;
-    int lo = (B >= c.gJ0) ? c.gI0 : c.gI0 + 1, hi = (B < c.gJ1) ? c.gI1 + 1 : c.gI1;
+// The bead blocks of this CTA and the row partials that belong to them, copied into shared memory once per launch: the step
+// phase is a chain of dependent memory accesses, and every index it would otherwise fetch from global memory costs a round
+// trip to L2 per evaluation.
+#define LNP_MAXB 8
+#define LNP_MAXRS 6
+struct LnBlkPlan { int nb, cached; int B[LNP_MAXB], lo[LNP_MAXB], hi[LNP_MAXB], rs_cnt[LNP_MAXB], rs[LNP_MAXB][LNP_MAXRS]; };
+__device__ __forceinline__ void ln_blk_bounds(const LnCtx& c, int B, int& lo, int& hi) {      // owned tiles of column B: rows [lo, hi)
+    lo = (B >= c.gJ0) ? c.gI0 : c.gI0 + 1; hi = (B < c.gJ1) ? c.gI1 + 1 : c.gI1;
     if (hi > B + 1) hi = B + 1;
-    if (tid < LN_P_GGRP * 96) {
-        const int q = tid % 96, grp = tid / 96;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+}
+__device__ void ln_blk_plan_load(const LnCtx& c, LnBlkPlan* bp) {          // one thread
+    const int cta = blockIdx.x - c.cta0;
+    const int b0 = c.blk_off[cta], nb = c.blk_off[cta + 1] - b0;
+    bp->nb = nb; bp->cached = nb <= LNP_MAXB ? 1 : 0;
+    for (int k = 0; k < nb && k < LNP_MAXB; k++) {
+        const int B = c.blk_idx[b0 + k];
+        bp->B[k] = B; ln_blk_bounds(c, B, bp->lo[k], bp->hi[k]);
+        const int r0 = c.rs_off[B], nr = c.rs_off[B + 1] - r0;
+        bp->rs_cnt[k] = nr;
+        if (nr > LNP_MAXRS) bp->cached = 0;
+        for (int q = 0; q < nr && q < LNP_MAXRS; q++) bp->rs[k][q] = c.rs_idx[r0 + q];
+    }
+}
+__shared__ LnBlkPlan lnp_bp;
+__shared__ LnTileRun lnp_run;
+extern __shared__ __align__(128) unsigned char lnp_smem[];
+
+// This rank's partial force on the beads of bead block B.  The CTA works on `nslots` blocks at a time (1 or 2): slot s is
+// the thread range [s*512/nslots, (s+1)*512/nslots), inside it groups of 96 threads each sum every G-th partial of the column
+// (16-byte loads, sixteen in flight per thread: the gather is bound by dependent round trips to L2), the first 128
+// threads of the slot ("lead" threads, lt = 0..127) then add the groups and the row partials in a fixed order.
+// k = index of the block in the CTA's cached plan (-1: not cached, look the row partials up in global memory).
+// All threads call; the result is valid in the lead threads of the slot.
+// (Deliberately compact code — one rolled loop, 32-bit index arithmetic: the step phases run once per evaluation, straight
+// out of a cold instruction cache, so their cost is largely the instruction fetch.)
+__device__ __noinline__ void ln_gather4(const LnCtx& c, int B, int k, int slot, int nslots, LnScratch* sc, float& fx, float& fy, float& fz) {
+    const int per = LN_P_THREADS / nslots, ts = threadIdx.x - slot * per, G = per / 96;
+    int lo, hi;
+    if (k >= 0) { lo = lnp_bp.lo[k]; hi = lnp_bp.hi[k]; } else ln_blk_bounds(c, B, lo, hi);
+    if (B >= 0 && ts < G * 96) {
+        const int q = ts % 96, grp = ts / 96, nT = (int)c.nT, t0 = (int)c.t0;
+        float4 acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // tile (I, B) sits at I*nT - I(I-1)/2 + B - I in the tile list; the rank's partials start at tile t0 (96 float4 each)
         const float4* base = reinterpret_cast<const float4*>(c.colpart) + q;
-        int I = lo + grp;
-#define LN_GLD(u, k) const float4 u = __ldcg(base + (size_t)(tile_index(I + (k) * LN_P_GGRP, B, c.nT) - c.t0) * 96)
-#define LN_GADD(a, u) a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w
-        for (; I + 15 * LN_P_GGRP < hi; I += 16 * LN_P_GGRP) {     // sixteen independent 16-byte loads in flight per thread: the gather is
-            LN_GLD(u0, 0); LN_GLD(u1, 1); LN_GLD(u2, 2); LN_GLD(u3, 3); LN_GLD(u4, 4); LN_GLD(u5, 5); LN_GLD(u6, 6); LN_GLD(u7, 7);     // bound by dependent round trips to L2
-            LN_GLD(u8, 8); LN_GLD(u9, 9); LN_GLD(u10, 10); LN_GLD(u11, 11); LN_GLD(u12, 12); LN_GLD(u13, 13); LN_GLD(u14, 14); LN_GLD(u15, 15);
-            LN_GADD(a0, u0); LN_GADD(a1, u1); LN_GADD(a2, u2); LN_GADD(a3, u3); LN_GADD(a0, u4); LN_GADD(a1, u5); LN_GADD(a2, u6); LN_GADD(a3, u7);
-            LN_GADD(a0, u8); LN_GADD(a1, u9); LN_GADD(a2, u10); LN_GADD(a3, u11); LN_GADD(a0, u12); LN_GADD(a1, u13); LN_GADD(a2, u14); LN_GADD(a3, u15);
+#pragma unroll 1
+        for (int I = lo + grp; I < hi; I += 16 * G) {
+            float4 u[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int Ij = I + j * G;
+                const int Ic = Ij < hi ? Ij : lo;                                   // (a valid address; its value is discarded)
+                u[j] = __ldcg(base + (size_t)(unsigned)((Ic * nT - ((Ic * (Ic - 1)) >> 1) + B - Ic - t0) * 96));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const float m = (I + j * G < hi) ? 1.f : 0.f;
+                acc[j & 3].x = fmaf(m, u[j].x, acc[j & 3].x); acc[j & 3].y = fmaf(m, u[j].y, acc[j & 3].y);
+                acc[j & 3].z = fmaf(m, u[j].z, acc[j & 3].z); acc[j & 3].w = fmaf(m, u[j].w, acc[j & 3].w);
+            }
         }
-        for (; I + 7 * LN_P_GGRP < hi; I += 8 * LN_P_GGRP) {
-            LN_GLD(u0, 0); LN_GLD(u1, 1); LN_GLD(u2, 2); LN_GLD(u3, 3); LN_GLD(u4, 4); LN_GLD(u5, 5); LN_GLD(u6, 6); LN_GLD(u7, 7);
-            LN_GADD(a0, u0); LN_GADD(a1, u1); LN_GADD(a2, u2); LN_GADD(a3, u3); LN_GADD(a0, u4); LN_GADD(a1, u5); LN_GADD(a2, u6); LN_GADD(a3, u7);
+        float4 a0;
+        a0.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x); a0.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+        a0.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z); a0.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
+        *reinterpret_cast<float4*>(&sc->gred[slot * G + grp][q * 4]) = a0;
+    }
+    // the row partials of this block (the lead threads; issued behind the column partials, before anybody waits)
+    float rx = 0.f, ry = 0.f, rz = 0.f;
+    if (B >= 0 && ts < LN_TB) {
+        const int r0 = k >= 0 ? 0 : c.rs_off[B], r1 = k >= 0 ? lnp_bp.rs_cnt[k] : c.rs_off[B + 1];
+#pragma unroll 1
+        for (int r = r0; r < r1; r++) {
+            const int idx = k >= 0 ? lnp_bp.rs[k][r] : c.rs_idx[r];
+            const float4 v = __ldcg(c.rowpart + (size_t)idx * LN_TB + ts);
+            rx += v.x; ry += v.y; rz += v.z;
         }
-        for (; I + 3 * LN_P_GGRP < hi; I += 4 * LN_P_GGRP) {
-            LN_GLD(u0, 0); LN_GLD(u1, 1); LN_GLD(u2, 2); LN_GLD(u3, 3);
-            LN_GADD(a0, u0); LN_GADD(a1, u1); LN_GADD(a2, u2); LN_GADD(a3, u3);
-        }
-        for (; I < hi; I += LN_P_GGRP) { LN_GLD(u0, 0); LN_GADD(a0, u0); }
-#undef LN_GLD
-#undef LN_GADD
-        a0.x = (a0.x + a1.x) + (a2.x + a3.x); a0.y = (a0.y + a1.y) + (a2.y + a3.y); a0.z = (a0.z + a1.z) + (a2.z + a3.z); a0.w = (a0.w + a1.w) + (a2.w + a3.w);
-        *reinterpret_cast<float4*>(&sc->gred[grp][q * 4]) = a0;
     }
     __syncthreads();
     fx = fy = fz = 0.f;
-    if (tid < LN_TB) {
-        const int pos = 4 * (tid & 31) + (tid >> 5);            // column -> position inside a partial (ln_tile_phase)
-#pragma unroll
-        for (int g = 0; g < LN_P_GGRP; g++) { fx += sc->gred[g][pos]; fy += sc->gred[g][LN_TB + pos]; fz += sc->gred[g][2 * LN_TB + pos]; }
-        for (int k = c.rs_off[B]; k < c.rs_off[B + 1]; k++) {
-            const float4 v = __ldcg(c.rowpart + (size_t)c.rs_idx[k] * LN_TB + tid);
-            fx += v.x; fy += v.y; fz += v.z;
-        }
+    if (B >= 0 && ts < LN_TB) {
+        const int pos = 4 * (ts & 31) + (ts >> 5);              // column -> position inside a partial (ln_tile_phase)
+#pragma unroll 1
+        for (int g = 0; g < G; g++) { fx += sc->gred[slot * G + g][pos]; fy += sc->gred[slot * G + g][LN_TB + pos]; fz += sc->gred[slot * G + g][2 * LN_TB + pos]; }
+        fx += rx; fy += ry; fz += rz;
     }
     __syncthreads();                                           // gred may be overwritten by the next block
 }
 
-// total force on the beads of this CTA's blocks: gather, exchange over the ranks.  `emit(B, i, fx, fy, fz)` is called by the
-// 128 lead threads of every block (i = bead index, may be >= N) with all threads of the CTA participating (block-wide
-// reductions inside emit are allowed).
-template <typename Emit>
-__device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch* sc, unsigned int epoch, volatile LnLoop* L, bool timing, Emit emit) {
+// Total force on the beads of this CTA's blocks: gather, exchange over the ranks.
+// emit(active, B, i, lt, slot, fx, fy, fz) is called by ALL threads of the CTA for every round of blocks (block-wide reductions
+// inside are allowed); a thread is a "lead" thread of bead i when lt >= 0 (lt = 0..127 = bead inside the block) and active.
+// PAIR: with several ranks and more than one block, the CTA works on two blocks at a time (two halves of the CTA): every block
+// is a chain of dependent memory latencies (partials, peers' slots, vectors), so two of them side by side take the time of one.
+// Several ranks: pass 0 gathers and pushes every block (slot `rank` of every rank's receive buffer, the epoch in .w), pass 1
+// polls the slots of the contributors of each block until they carry this epoch and adds them in rank order.  One rank: a
+// single pass, the gathered force goes straight to emit.  (One call site each for the gather and for emit: compact code.)
+// preload(active, i, lt) -> whatever emit needs from memory that does not depend on the forces (coordinates of the bead and of its
+// chain neighbours, velocity, previous force ...): issued BEFORE the gather (one rank) or before the poll of the peers' slots
+// (several ranks), so that those round trips to L2 overlap instead of queueing up behind one another.
+struct LnNoPre {};
+template <bool PAIR, typename Preload, typename Emit>
+__device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch* sc, unsigned int epoch, volatile LnLoop* L, bool timing, Preload preload, Emit emit) {
     const int tid = threadIdx.x, cta = blockIdx.x - c.cta0;
     const LnXchg& x = c.xc;
-    if (x.world <= 1) {
-        for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
-            float fx, fy, fz;
-            ln_gather4(c, B, sc, fx, fy, fz);
-            emit(B, B * LN_TB + tid, fx, fy, fz);
-        }
-        return;
-    }
+    const int nb = lnp_bp.nb, cached = lnp_bp.cached;
+    const bool multi = x.world > 1;
     const int parity = (int)(epoch & 1u);
-    const size_t slot = ((size_t)parity * x.world + x.rank) * x.n4;
-    // push: this rank's partial of every block it contributes to -> slot `rank` of every rank (self included), the epoch in .w
-    for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
-        if (B < c.bmin[x.rank]) continue;
-        float fx, fy, fz;
-        ln_gather4(c, B, sc, fx, fy, fz);
-        const int i = B * LN_TB + tid;
-        if (tid < LN_TB && i < c.N) {
-            const float4 v = make_float4(fx, fy, fz, __uint_as_float(epoch));
-            for (int g = 0; g < x.world; g++) st_v4_sys(x.recv[g] + slot + i, v);
-        }
-    }
-    ln_tprof(L, 5, timing);
-    // poll the slots of the contributors of each block until they carry this epoch, add them in rank order
-    for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
-        const int i = B * LN_TB + tid;
-        float fx = 0.f, fy = 0.f, fz = 0.f;
-        if (tid < LN_TB && i < c.N) {
-            const float4* R = x.recv[x.rank] + (size_t)parity * x.world * x.n4 + i;
-            for (int g = 0; g < x.world; g++) if (B >= c.bmin[g]) {
-                float4 v = ld_v4_sys(R + (size_t)g * x.n4);
-                if (__float_as_uint(v.w) != epoch) {
-                    const long long t0 = clock64();
-                    do { v = ld_v4_sys(R + (size_t)g * x.n4); if (clock64() - t0 > LN_WAIT_LIMIT) ln_fail(x.err, 1); } while (__float_as_uint(v.w) != epoch);
+    const size_t myslot = ((size_t)parity * x.world + x.rank) * x.n4;
+    const int nslots = (PAIR && multi && nb > 1) ? 2 : 1, per = LN_P_THREADS / nslots, slot = tid / per, ts = tid - slot * per, lt = ts < LN_TB ? ts : -1;
+#pragma unroll 1
+    for (int pass = 0; pass < (multi ? 2 : 1); pass++) {
+        // the partial forces are out (several ranks): now the first tiles of the next evaluation may start to stream in
+        if (pass == 1 && tid == 0 && L->prefetch) ln_ring_prefetch(&lnp_run, lnp_smem);
+#pragma unroll 1
+        for (int k0 = 0; k0 < nb; k0 += nslots) {
+            const int k = k0 + slot;
+            const int B = k < nb ? (cached ? lnp_bp.B[k] : c.blk_idx[c.blk_off[cta] + k]) : -1;
+            const int i = B * LN_TB + lt;
+            float fx = 0.f, fy = 0.f, fz = 0.f;
+            decltype(preload(false, 0, 0)) pre = decltype(preload(false, 0, 0))();
+            if (pass == (multi ? 1 : 0)) pre = preload(B >= 0 && lt >= 0 && i < c.N, i, lt);
+            if (pass == 0) {
+                const int Bg = (B >= 0 && multi && B < c.bmin[x.rank]) ? -1 : B;          // nothing of this block in this rank's tiles
+                ln_gather4(c, Bg, (cached && Bg >= 0) ? k : -1, slot, nslots, sc, fx, fy, fz);
+                if (multi) {
+                    ln_tprof(L, 7, timing);
+                    if (Bg >= 0 && lt >= 0 && i < c.N) {
+                        const float4 v = make_float4(fx, fy, fz, __uint_as_float(epoch));
+#pragma unroll 1
+                        for (int g = 0; g < x.world; g++) st_v4_sys(x.recv[g] + myslot + i, v);
+                    }
+                    if (k0 + nslots >= nb) ln_tprof(L, 5, timing);
+                    continue;
                 }
-                fx += v.x; fy += v.y; fz += v.z;
+            } else {
+                if (B >= 0 && lt >= 0 && i < c.N) {
+                    const float4* R = x.recv[x.rank] + (size_t)parity * x.world * x.n4 + i;
+#pragma unroll 1
+                    for (int g = 0; g < x.world; g++) if (B >= c.bmin[g]) {
+                        float4 v = ld_v4_sys(R + (size_t)g * x.n4);
+                        if (__float_as_uint(v.w) != epoch) {
+                            const long long t0 = clock64();
+                            do { v = ld_v4_sys(R + (size_t)g * x.n4); if (clock64() - t0 > LN_WAIT_LIMIT) ln_fail(x.err, 1); } while (__float_as_uint(v.w) != epoch);
+                        }
+                        fx += v.x; fy += v.y; fz += v.z;
+                    }
+                }
+                if (k0 + nslots >= nb) ln_tprof(L, 6, timing);
             }
+            emit(B >= 0, B, i, lt, slot, fx, fy, fz, pre);
         }
-        if (bk + 1 == c.blk_off[cta + 1]) ln_tprof(L, 6, timing);
-        emit(B, i, fx, fy, fz);
     }
+    if (!multi && tid == 0 && L->prefetch) ln_ring_prefetch(&lnp_run, lnp_smem);
 }
 
-// sum of `v` over the 128 lead threads (4 warps), result in every thread; all threads call; fixed order
-__device__ __forceinline__ double ln_lead_sum(double v, double* sh4) {
-    const int tid = threadIdx.x;
-    if (tid < LN_TB) {
+// sum of `v` over the 128 lead threads (4 warps) of each slot, result in every thread of the slot; all threads call; fixed order
+__device__ __forceinline__ double ln_lead_sum(double v, double* sh8, int lt, int slot) {
+    if (lt >= 0) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0) sh4[tid >> 5] = v;
+        if ((lt & 31) == 0) sh8[slot * 4 + (lt >> 5)] = v;
     }
     __syncthreads();
-    const double s = (sh4[0] + sh4[1]) + (sh4[2] + sh4[3]);
+    const double s = (sh8[slot * 4] + sh8[slot * 4 + 1]) + (sh8[slot * 4 + 2] + sh8[slot * 4 + 3]);
     __syncthreads();
     return s;
 }
@@ -295,14 +358,38 @@ __device__ __noinline__ void ln_step_md(const LnCtx& c, const LnOp& op, LnScratc
                                         float4* a_next, float4* b_next, unsigned int epoch, volatile LnLoop* L, bool timing) {
     const int tid = threadIdx.x;
     const float h = op.md.h, dt = op.md.dt_akma, dth = dt * h;
-    ln_forces_of_my_blocks(c, sc, epoch, L, timing, [&](int B, int i, float fx, float fy, float fz) {
+    struct MdPre { float4 p0, q0, pm, qm, pp, qp, v, f; };
+    const bool fast_bond = !(op.bd.w_ang > 0.f);
+    ln_forces_of_my_blocks<true>(c, sc, epoch, L, timing,
+        [&](bool live, int i, int lt) {
+            MdPre r;
+            r.p0 = r.q0 = r.pm = r.qm = r.pp = r.qp = r.v = r.f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                r.p0 = __ldcg(A + i); r.q0 = __ldcg(Bv + i); r.v = __ldcg(c.v.v + i); r.f = __ldcg(c.v.f + i);
+                if (i > 0) { r.pm = __ldcg(A + i - 1); r.qm = __ldcg(Bv + i - 1); }
+                if (i + 1 < c.N) { r.pp = __ldcg(A + i + 1); r.qp = __ldcg(Bv + i + 1); }
+            }
+            return r;
+        },
+        [&](bool active, int B, int i, int lt, int slot, float fx, float fy, float fz, const MdPre& r) {
         float eb = 0.f, k2 = 0.f;
-        if (tid < LN_TB && i < c.N) {
-            ln_bond_cg(A, Bv, lam, i, c.N, op.bd, fx, fy, fz, eb);
-            const float4 xi = ln_ldx_cg(A, Bv, lam, i);
-            float4 vv = c.v.v[i];
+        if (active && lt >= 0 && i < c.N) {
+            const float4 xi = make_float4(fmaf(lam, r.q0.x, r.p0.x), fmaf(lam, r.q0.y, r.p0.y), fmaf(lam, r.q0.z, r.p0.z), 0.f);
+            if (fast_bond) {           // the bonds (i-1, i) and (i, i+1) from the preloaded neighbours: same arithmetic as ln_bonded
+#pragma unroll
+                for (int s = -1; s <= 1; s += 2) {
+                    const int nb = i + s; if (nb < 0 || nb >= c.N) continue;
+                    const float4 pn = s < 0 ? r.pm : r.pp, qn = s < 0 ? r.qm : r.qp;
+                    const float dx = xi.x - fmaf(lam, qn.x, pn.x), dy = xi.y - fmaf(lam, qn.y, pn.y), dz = xi.z - fmaf(lam, qn.z, pn.z);
+                    const float r2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-12f), rinv = ln_rsqrt(r2), rr = r2 * rinv, u = rr - op.bd.r0;
+                    const float g = 2.f * op.bd.w_bond * u * rinv;
+                    fx -= g * dx; fy -= g * dy; fz -= g * dz;
+                    if (s == 1) eb = op.bd.w_bond * u * u;
+                }
+            } else ln_bond_cg(A, Bv, lam, i, c.N, op.bd, fx, fy, fz, eb);
+            float4 vv = r.v;
             if (!first) {
-                const float4 fo = c.v.f[i];
+                const float4 fo = r.f;
                 vv.x = fmaf(h, fo.x, lam * vv.x); vv.y = fmaf(h, fo.y, lam * vv.y); vv.z = fmaf(h, fo.z, lam * vv.z);   // v1
                 vv.x = fmaf(h, fx, vv.x); vv.y = fmaf(h, fy, vv.y); vv.z = fmaf(h, fz, vv.z);                          // v2
             }
@@ -311,22 +398,21 @@ __device__ __noinline__ void ln_step_md(const LnCtx& c, const LnOp& op, LnScratc
             a_next[i] = make_float4(fmaf(dth, fx, xi.x), fmaf(dth, fy, xi.y), fmaf(dth, fz, xi.z), 0.f);
             b_next[i] = make_float4(dt * vv.x, dt * vv.y, dt * vv.z, 0.f);
         }
-        const double kb = ln_lead_sum((double)k2, sc->dsum), ebb = ln_lead_sum((double)eb, sc->dsum);
-        if (tid == 0) { c.blockpart[(size_t)B * LN_KMAX] = kb; c.blockpart[(size_t)B * LN_KMAX + 1] = ebb; }
+        const double kb = ln_lead_sum((double)k2, sc->dsum, lt, slot), ebb = ln_lead_sum((double)eb, sc->dsum, lt, slot);
+        if (active && lt == 0) { c.blockpart[(size_t)B * LN_KMAX] = kb; c.blockpart[(size_t)B * LN_KMAX + 1] = ebb; }
     });
 }
 // serial section after ln_step_md (all threads of the last arriver)
 __device__ __noinline__ void ln_decide_md(const LnCtx& c, const LnOp& op, LnScratch* sc, int want_e, unsigned int epoch) {
     const int tid = threadIdx.x;
+    if (tid >= 32) return;                  // one warp: lane-strided partial sums, then the butterfly (fixed order, no block barrier)
     double a0 = 0, a1 = 0;
-    for (int q = tid; q < c.nblk; q += LN_P_THREADS) { a0 += __ldcg(c.blockpart + (size_t)q * LN_KMAX); a1 += __ldcg(c.blockpart + (size_t)q * LN_KMAX + 1); }
-    double* red = reinterpret_cast<double*>(sc->prod);
-    red[tid] = a0; red[LN_P_THREADS + tid] = a1;
-    __syncthreads();
-    for (int o = LN_P_THREADS / 2; o > 0; o >>= 1) { if (tid < o) { red[tid] += red[tid + o]; red[LN_P_THREADS + tid] += red[LN_P_THREADS + tid + o]; } __syncthreads(); }
+    for (int q = tid; q < c.nblk; q += 32) { a0 += __ldcg(c.blockpart + (size_t)q * LN_KMAX); a1 += __ldcg(c.blockpart + (size_t)q * LN_KMAX + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
     if (tid == 0) {
         LnState* st = c.st;
-        const double ke = 0.5 * op.md.mass * red[0], ndof = 3.0 * c.N - 3.0;
+        const double ke = 0.5 * op.md.mass * a0, ndof = 3.0 * c.N - 3.0;
         const double T = 2.0 * ke / (op.md.kboltz * ndof);
         double l2 = 1.0;
         if (T > 0.0) {
@@ -336,7 +422,7 @@ __device__ __noinline__ void ln_decide_md(const LnCtx& c, const LnOp& op, LnScra
         st->ke = ke; st->lam = l2; st->lamf = (float)l2; st->nevals += op.count_eval;
         if (want_e) {
             double e0, e1; ln_energy_collect(c, epoch, e0, e1);
-            st->Enoe = e0; st->Evdw = e1; st->Ebond = red[LN_P_THREADS]; st->E = e0 + e1 + red[LN_P_THREADS];
+            st->Enoe = e0; st->Evdw = e1; st->Ebond = a1; st->E = e0 + e1 + a1;
         }
     }
 }
@@ -348,11 +434,12 @@ __device__ __noinline__ void ln_step_min(const LnCtx& c, const LnOp& op, LnScrat
     const int m = v.m, K = 6 * m + 6, N = v.N;
     const int head = __ldcg(&c.st->head);
     const float4* A = init ? v.x : v.xb;
-    ln_forces_of_my_blocks(c, sc, epoch, L, timing, [&](int B, int i, float fx, float fy, float fz) {
+    ln_forces_of_my_blocks<false>(c, sc, epoch, L, timing, [&](bool, int, int) { return LnNoPre(); },
+                                  [&](bool active, int B, int i, int lt, int slot, float fx, float fy, float fz, const LnNoPre&) {
         float eb = 0.f;
         if (tid < LN_TB) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f), y = s, gn = s;
-            const bool live = i < N;
+            const bool live = active && i < N;
             if (live) {
                 ln_bond_cg(A, v.p, lam, i, N, op.bd, fx, fy, fz, eb);
                 const float4 x = ln_ldx_cg(A, v.p, lam, i), xb = v.xb[i], g = v.g[i];
@@ -373,7 +460,7 @@ __device__ __noinline__ void ln_step_min(const LnCtx& c, const LnOp& op, LnScrat
             sc->prod[LDOT_X(m, 0)][tid] = dot3(s, s); sc->prod[LDOT_X(m, 1)][tid] = dot3(s, y); sc->prod[LDOT_X(m, 2)][tid] = dot3(s, gn);
             sc->prod[LDOT_X(m, 3)][tid] = dot3(y, y); sc->prod[LDOT_X(m, 4)][tid] = dot3(y, gn); sc->prod[LDOT_X(m, 5)][tid] = dot3(gn, gn);
         }
-        const double ebb = ln_lead_sum((double)eb, sc->dsum);       // (its barriers also publish prod)
+        const double ebb = ln_lead_sum((double)eb, sc->dsum, lt, slot);       // (its barriers also publish prod)
         for (int k = warp; k < K; k += LN_P_THREADS / 32) {           // a warp per inner product, fixed order
             double s = ((double)sc->prod[k][lane] + (double)sc->prod[k][lane + 32]) + ((double)sc->prod[k][lane + 64] + (double)sc->prod[k][lane + 96]);
 #pragma unroll
@@ -416,7 +503,8 @@ __device__ __noinline__ void ln_update_min(const LnCtx& c) {
     float dl[2 * CHR3D_LBFGS_MAX_M + 1];
 #pragma unroll
     for (int l = 0; l < 2 * CHR3D_LBFGS_MAX_M + 1; l++) dl[l] = l < 2 * m + 1 ? (float)__ldcg(&st->delta[l]) : 0.f;
-    for (int bk = c.blk_off[cta], B = 0; bk < c.blk_off[cta + 1] && ((B = c.blk_idx[bk]), true); bk++) {
+    for (int k = 0; k < lnp_bp.nb; k++) {
+        const int B = lnp_bp.cached ? lnp_bp.B[k] : c.blk_idx[c.blk_off[cta] + k];
         const int i = B * LN_TB + tid;
         if (i >= v.N) continue;
         if (acc == 4) { v.x[i] = v.xb[i]; continue; }
@@ -445,14 +533,15 @@ __device__ __noinline__ void ln_update_min(const LnCtx& c) {
 // energies + forces at explicit coordinates (SAVE / PICK / ENERGY ops)
 __device__ __noinline__ void ln_step_eval(const LnCtx& c, const LnOp& op, LnScratch* sc, unsigned int epoch, volatile LnLoop* L, bool timing) {
     const int tid = threadIdx.x;
-    ln_forces_of_my_blocks(c, sc, epoch, L, timing, [&](int B, int i, float fx, float fy, float fz) {
+    ln_forces_of_my_blocks<true>(c, sc, epoch, L, timing, [&](bool, int, int) { return LnNoPre(); },
+                                 [&](bool active, int B, int i, int lt, int slot, float fx, float fy, float fz, const LnNoPre&) {
         float eb = 0.f;
-        if (tid < LN_TB && i < c.N) {
+        if (active && lt >= 0 && i < c.N) {
             ln_bond_cg(c.v.x, c.v.x, 0.f, i, c.N, op.bd, fx, fy, fz, eb);
             c.v.f[i] = make_float4(fx, fy, fz, 0.f);
         }
-        const double ebb = ln_lead_sum((double)eb, sc->dsum);
-        if (tid == 0) c.blockpart[(size_t)B * LN_KMAX] = ebb;
+        const double ebb = ln_lead_sum((double)eb, sc->dsum, lt, slot);
+        if (active && lt == 0) c.blockpart[(size_t)B * LN_KMAX] = ebb;
     });
 }
 __device__ __noinline__ void ln_decide_eval(const LnCtx& c, const LnOp& op, LnScratch* sc, unsigned int epoch) {
@@ -485,10 +574,8 @@ __device__ __forceinline__ void ln_barrier(const LnCtx& c, volatile LnLoop* L, i
 // kernel body keeps nothing alive in registers across the inlined tile phase (which needs all of them).
 __shared__ LnCtx lnp_c;
 __shared__ LnOp lnp_op;
-__shared__ LnTileRun lnp_run;
 __shared__ LnLoop lnp_L;
 __shared__ int lnp_flag;
-extern __shared__ __align__(128) unsigned char lnp_smem[];
 #define LNP_SC (reinterpret_cast<LnScratch*>(lnp_smem + LN_COLP_OFF))
 #define LNP_TIMING (blockIdx.x == (unsigned)lnp_c.cta0 && threadIdx.x == 0)
 
@@ -554,7 +641,9 @@ __device__ __noinline__ void ln_md_setup() {
         const LnCtx& c = lnp_c; volatile LnLoop* L = &lnp_L; LnTileRun* run = &lnp_run;
         const int step = L->step, par = L->par, first = step < 0;
         run->X = first ? c.v.x : c.va[par]; run->XB = first ? c.v.x : c.vb[par];
-        run->lam = first ? 0.f : __ldcg(&c.st->lamf); run->more = step + 1 < lnp_op.nstep;
+        const int more = step + 1 < lnp_op.nstep ? 1 : 0;
+        run->lam = first ? 0.f : __ldcg(&c.st->lamf);
+        run->more = lnp_op.defer_ring ? 0 : more; L->prefetch = lnp_op.defer_ring ? more : 0;
         L->t0tile = ln_globaltimer();
     }
     __syncthreads();
@@ -564,7 +653,8 @@ __device__ __noinline__ void ln_min_setup() {
         const LnCtx& c = lnp_c; LnTileRun* run = &lnp_run;
         const int init = lnp_L.step < 0;
         run->X = init ? c.v.x : c.v.xb; run->XB = init ? c.v.x : c.v.p;
-        run->lam = init ? 0.f : __ldcg(&c.st->tstepf); run->more = 1;
+        run->lam = init ? 0.f : __ldcg(&c.st->tstepf);
+        run->more = lnp_op.defer_ring ? 0 : 1; lnp_L.prefetch = lnp_op.defer_ring ? 1 : 0;
         lnp_L.t0tile = ln_globaltimer();
     }
     __syncthreads();
@@ -589,6 +679,7 @@ __device__ __noinline__ void ln_launch_setup(const LnCtx* __restrict__ ctxs, int
         for (int q = 0; q < 8; q++) lnp_L.tacc[q] = 0;
         lnp_L.tlast = ln_globaltimer(); lnp_L.ttile = 0;
     }
+    if (threadIdx.x == 32) ln_blk_plan_load(lnp_c, &lnp_bp);
     __syncthreads();
     ln_ring_init(&lnp_run, lnp_smem, true);
 }
@@ -620,7 +711,7 @@ __global__ void __launch_bounds__(LN_P_THREADS, 1) ln_persist_kernel(const LnCtx
             ln_min_rest();
         }
     } else {
-        if (threadIdx.x == 0) { lnp_run.X = lnp_c.v.x; lnp_run.XB = lnp_c.v.x; lnp_run.lam = 0.f; lnp_run.more = 0; lnp_L.t0tile = ln_globaltimer(); }
+        if (threadIdx.x == 0) { lnp_run.X = lnp_c.v.x; lnp_run.XB = lnp_c.v.x; lnp_run.lam = 0.f; lnp_run.more = 0; lnp_L.prefetch = 0; lnp_L.t0tile = ln_globaltimer(); }
         __syncthreads();
         ln_tile_phase<true, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
         ln_eval_rest();

@@ -238,7 +238,8 @@ int chr3d_single_info(const chr3d_single* h, int64_t* n_tiles, int64_t* tiles_th
 /* Phase clock of the persistent kernel since the last call, milliseconds as seen by CTA 0 of this rank, 8 entries:
  * [0] tile phases, [1] first grid barrier (+ energy publication), [2] step phases (one rank: gather + integration;
  * several ranks: summation + integration), [3] second barrier (+ decisions), [4] L-BFGS update + third barrier,
- * [5] gather + push to the peers, [6] wait for the peers' partial forces, [7] unused.  Reading resets it. */
+ * [5] push to the peers, [6] wait for the peers' partial forces, [7] gather of this rank's partials (several
+ * ranks).  Reading resets it. */
 int chr3d_single_profile(chr3d_single* h, double* ms8);
 /* Per-CTA view of the tile walk (arrays of `cap` entries, *n = CTAs of this rank): tiles, tiles on the slow "near" path, tile
  * rows started, and the milliseconds every CTA spent in tile phases of the persistent kernel since the last call (reset by
