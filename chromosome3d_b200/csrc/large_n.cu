@@ -212,6 +212,7 @@ struct LnTileRun {
     const float4* X; const float4* XB; float lam;      // coordinates X + lam * XB
     int n, I0, J0, nT, N;     // tiles, tile coordinates of the first one
     int more, dbg;            // more: another evaluation follows in this launch (keep the ring running across the boundary)
+    int ring_tail;            // tiles of the next evaluation requested before this tile phase ends (the others at its start)
     int stream_l2;            // 1: the targets of this rank exceed what L2 can keep between evaluations -> the TMA copies carry an
                               // evict-first L2 policy, so that the stream does not push the partial forces and the vectors out of L2
     LnTerms terms;
@@ -319,7 +320,13 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
         st.Jn = Jn; st.near = (J <= I + 1 || (J + 1) * LN_TB > run->N) ? 1 : 0; st.newrow = newrow; st.seg = seg; st.last = (J + 1 == run->nT || k + 1 == n) ? 1 : 0;
         run->step[k & 1] = st;
     };
-    if (tid == 0 && n > 0) make_step(0, run->I0, run->J0, 0, 1);
+    if (tid == 0 && n > 0) {
+        make_step(0, run->I0, run->J0, 0, 1);
+        if (dbg != 2) for (int q = 0; q < LN_STAGES && q < n; q++) {      // top the ring up (tiles a shortened tail left out, or a deferred ring)
+            const unsigned int g = run->pos + (unsigned)q;
+            if (!(run->pending >> (g % LN_STAGES) & 1u)) ln_ring_issue(run, smem, q, (int)(g % LN_STAGES));
+        }
+    }
     __syncthreads();
     if (n > 0) prefetch_cols(LN_RUN(step[0].J), (int)(LN_RUN(pos) & 1u));
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -413,7 +420,7 @@ __device__ __forceinline__ void ln_tile_phase(LnTileRun* run, unsigned char* sme
             LN_RUN(pending) = LN_RUN(pending) & ~(1u << stage);
             const int nx = k + LN_STAGES;
             if (nx < n) ln_ring_issue(run, smem, nx, stage);
-            else if (LN_RUN(more)) ln_ring_issue(run, smem, nx % n, stage);
+            else if (LN_RUN(more) && nx - n < LN_RUN(ring_tail)) ln_ring_issue(run, smem, nx % n, stage);
         }
         if (tid < 3 * LN_TB) {
             const int comp = tid / LN_TB, col = tid % LN_TB;
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(LN_BOUND_THREADS, 1) ln_tile_kernel(LnTileArgs
     if (a.done && *a.done) return;
     if (threadIdx.x == 0) {
         ln_run_setup(&run, a.Dt, a.t0, a.cstart, a.nT, a.N, a.colpart, a.rowpart, a.epart, a.maxseg, blockIdx.x);
-        run.X = a.x; run.XB = a.xb2 ? a.xb2 : a.x; run.lam = a.xb2 ? *a.lam : 0.f; run.more = 0; run.dbg = LN_DBG(a); run.terms = a.terms; run.stream_l2 = a.stream_l2;
+        run.X = a.x; run.XB = a.xb2 ? a.xb2 : a.x; run.lam = a.xb2 ? *a.lam : 0.f; run.more = 0; run.dbg = LN_DBG(a); run.terms = a.terms; run.stream_l2 = a.stream_l2; run.ring_tail = LN_STAGES;
     }
     __syncthreads();
     ln_ring_init(&run, smem, false);
@@ -600,6 +607,7 @@ struct LnState {
     int cnt, head, it, ls, done, accepted, keep, have_E, hand, cur_image, nsteps, fresh;
     long long nevals;
     float lamf, tstepf, zerof, pad_;      // device scalars read by the tile kernel: x = a + lamf*b (MD), x = xb + tstepf*p (L-BFGS)
+    unsigned int revals, pad3_;           // evaluations since the tile plan was made (targets of the per-block completion counters)
     unsigned int counter, epoch;          // "last block done" counter of the legacy step kernels; evaluation counter of the peer exchange
     double eloc[2];                       // pair energies of this rank (persistent kernel)
     unsigned long long tprof[8];          // phase clock of the persistent kernel (ns, CTA 0): tile, barrier 1, step, barrier 2, update
@@ -1160,8 +1168,8 @@ struct LnEngine {
     int N = 0, nT = 0, rank = 0, world = 1, m = 5, ncta = 0, maxseg = 0, nblk = 0, nparts = 0, sms = 148, stream_l2 = 0;
     long long n_tiles = 0, t0 = 0, t1 = 0, pairs_total = 0; std::vector<long long> rank_cut;
     DevBuf<float> Dt, colpart, x0; DevBuf<float4> rowpart, vx, vxb, vg, vp, vv, vf, vS, vY, sx, sv, va[2], vb[2], vfr;
-    DevBuf<int> rs_off, rs_idx, blk_off, blk_idx; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st; DevBuf<unsigned int> bar;
-    DevBuf<long long> cstart; DevBuf<unsigned long long> cta_ns; std::vector<long long> h_cstart;
+    DevBuf<int> rs_off, rs_idx, blk_off, blk_idx, tb_off, tb_idx, need; DevBuf<unsigned int> ready; DevBuf<double2> kslot; DevBuf<double> epart, escal, part, blockpart; DevBuf<LnState> st; DevBuf<unsigned int> bar;
+    DevBuf<long long> cstart; DevBuf<unsigned long long> cta_ns, trace; std::vector<long long> h_cstart;
     chr3d_sa_params prm; unsigned long long seed = 0; int model = 0;     // model: Philox stream of the coil / Maxwell draws
     cudaStream_t stream = nullptr;
     long long n_launches = 0;
@@ -1171,6 +1179,7 @@ struct LnEngine {
     // peer-memory exchange (world > 1): this rank's buffer, the mapped peer buffers
     void* xbuf = nullptr; size_t xbytes = 0; void* peer[LN_MAXWORLD] = {nullptr}; bool p2p = false, peers_local = false;
     int* xerr = nullptr;                       // pinned host word the kernel writes before it traps on a wait that cannot complete
+    bool l2_window_set = false;
     bool legacy = false;                       // multi-launch evaluation (NCCL all-reduce between ranks): the baseline path
     LnGroup self; LnGroup* group = nullptr;    // group: the launch group this engine currently belongs to (&self unless virtual ranks)
     static size_t up16(size_t v) { return (v + 15) / 16 * 16; }
@@ -1264,6 +1273,23 @@ static int ln_plan(LnEngine& e, int ncta) {
         CHR3D_CUDA(cudaMemcpy(e.blk_off.p, boff.data(), sizeof(int) * boff.size(), cudaMemcpyHostToDevice));
         if (!bidx.empty()) CHR3D_CUDA(cudaMemcpy(e.blk_idx.p, bidx.data(), sizeof(int) * bidx.size(), cudaMemcpyHostToDevice));
     }
+    {   // bead blocks every CTA's tiles feed (rows and columns), and how many CTAs feed each block: the completion counters
+        // of the barrier-free evaluations count per CTA, from zero at this plan
+        std::vector<int> toff(e.ncta + 1, 0), tidx, need(e.nblk, 0);
+        for (int c = 0; c < e.ncta; c++) {
+            std::vector<char> seen(e.nblk, 0);
+            for (long long t = e.h_cstart[c]; t < e.h_cstart[c + 1]; t++) { int I, J; tile_coords(t, e.nT, I, J); seen[I] = 1; seen[J] = 1; }
+            for (int B = 0; B < e.nblk; B++) if (seen[B]) { tidx.push_back(B); need[B]++; }
+            toff[c + 1] = (int)tidx.size();
+        }
+        CHR3D_CUDA(e.tb_off.alloc(toff.size())); CHR3D_CUDA(e.tb_idx.alloc(std::max<size_t>(tidx.size(), 1))); CHR3D_CUDA(e.need.alloc(e.nblk));
+        CHR3D_CUDA(cudaMemcpy(e.tb_off.p, toff.data(), sizeof(int) * toff.size(), cudaMemcpyHostToDevice));
+        if (!tidx.empty()) CHR3D_CUDA(cudaMemcpy(e.tb_idx.p, tidx.data(), sizeof(int) * tidx.size(), cudaMemcpyHostToDevice));
+        CHR3D_CUDA(cudaMemcpy(e.need.p, need.data(), sizeof(int) * e.nblk, cudaMemcpyHostToDevice));
+        CHR3D_CUDA(e.ready.alloc(e.nblk)); CHR3D_CUDA(cudaMemset(e.ready.p, 0, sizeof(unsigned int) * e.nblk));
+        CHR3D_CUDA(e.kslot.alloc((size_t)4 * e.nblk)); CHR3D_CUDA(cudaMemset(e.kslot.p, 0, sizeof(double2) * 4 * e.nblk));
+        if (e.st.p) CHR3D_CUDA(cudaMemset(&e.st.p->revals, 0, sizeof(unsigned int)));
+    }
     if (e.group) e.group->dirty = true;
     return 0;
 }
@@ -1286,11 +1312,11 @@ static int ln_alloc(LnEngine& e) {
     e.self.es.assign(1, &e); e.group = &e.self;
     CHR3D_CUDA(e.Dt.alloc((size_t)std::max<long long>(ntl, 1) * LN_TILE_FLOATS));
     CHR3D_CUDA(e.colpart.alloc((size_t)std::max<long long>(ntl, 1) * 3 * LN_TB));
+    CHR3D_CUDA(e.st.alloc(1));
+    CHR3D_CUDA(cudaMemset(e.st.p, 0, sizeof(LnState)));
     if (int rc = ln_plan(e, e.sms)) return rc;
     CHR3D_CUDA(e.escal.alloc((size_t)3 + e.nblk));
     CHR3D_CUDA(e.part.alloc((size_t)e.nparts * LN_KMAX));
-    CHR3D_CUDA(e.st.alloc(1));
-    CHR3D_CUDA(cudaMemset(e.st.p, 0, sizeof(LnState)));
     CHR3D_CUDA(e.bar.alloc(64));
     CHR3D_CUDA(cudaMemset(e.bar.p, 0, sizeof(unsigned int) * 64));
     const size_t n4 = (size_t)N + 1;
@@ -1303,6 +1329,9 @@ static int ln_alloc(LnEngine& e) {
     CHR3D_CUDA(cudaMemset(e.vf.p, 0, sizeof(float4) * n4));
     CHR3D_CUDA(cudaMemset(e.vp.p, 0, sizeof(float4) * n4));
     CHR3D_CUDA(cudaMallocHost((void**)&e.xerr, sizeof(int))); *e.xerr = 0;
+#ifdef CHR3D_DEV
+    CHR3D_CUDA(e.trace.alloc(2 * 512 * 2)); CHR3D_CUDA(cudaMemset(e.trace.p, 0, sizeof(unsigned long long) * 2 * 512 * 2));
+#endif
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
     CHR3D_CUDA(cudaFuncSetAttribute(ln_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
@@ -1333,6 +1362,8 @@ static void ln_fill_ctx(LnEngine& e, int cta0, LnCtx& c) {
     memset(&c, 0, sizeof c);
     c.Dt = e.Dt.p; c.t0 = e.t0; c.t1 = e.t1; c.nT = e.nT; c.N = e.N; c.nblk = e.nblk; c.maxseg = e.maxseg; c.cta0 = cta0; c.ncta = e.ncta;
     c.colpart = e.colpart.p; c.rowpart = e.rowpart.p; c.epart = e.epart.p; c.rs_off = e.rs_off.p; c.rs_idx = e.rs_idx.p;
+    c.trace = e.trace.p;
+    c.tb_off = e.tb_off.p; c.tb_idx = e.tb_idx.p; c.need = e.need.p; c.ready = e.ready.p; c.kslot = e.kslot.p;
     c.stream_l2 = e.stream_l2; c.cstart = e.cstart.p; c.blk_off = e.blk_off.p; c.blk_idx = e.blk_idx.p; c.cta_ns = e.cta_ns.p;
     tile_coords(e.t0, e.nT, c.gI0, c.gJ0);
     if (e.t1 >= e.n_tiles) { c.gI1 = e.nT; c.gJ1 = e.nT; } else tile_coords(e.t1, e.nT, c.gI1, c.gJ1);
@@ -1362,6 +1393,18 @@ static int ln_group_sync(LnGroup& g) {        // (re)build the device copy of th
 static int ln_launch_persist(LnGroup& g, LnOp& op, cudaStream_t stream) {
     if (int rc = ln_group_sync(g)) return rc;
     LnEngine& e0 = *g.es[0];
+    if (dev_getenv("CHR3D_LN_L2_PERSIST") && !e0.l2_window_set) {      // development: pin the column partials in L2 (access policy window)
+        int dev = 0, maxp = 0, maxw = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev); cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t bytes = std::min<size_t>(std::min<size_t>((size_t)maxw, (size_t)maxp), sizeof(float) * (size_t)std::max<long long>(e0.t1 - e0.t0, 1) * 3 * LN_TB);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+        cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.base_ptr = e0.colpart.p; av.accessPolicyWindow.num_bytes = bytes; av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+        e0.l2_window_set = true;
+    }
     op.dbg = ln_dbg();
     const LnCtx* ctxs = g.ctxs.p; int nvr = (int)g.es.size();
     void* args[3] = {(void*)&ctxs, (void*)&nvr, (void*)&op};
@@ -1374,7 +1417,11 @@ static int ln_launch_persist(LnGroup& g, LnOp& op, cudaStream_t stream) {
 static void ln_op_common(LnEngine& e, const chr3d_stage& s, LnOp& op) {
     memset(&op, 0, sizeof op);
     ln_terms(e.prm, s, op.terms); op.bd = ln_bonded_terms(e.prm, s); op.count_eval = 1;
-    op.defer_ring = (e.p2p && e.world > 1) ? 1 : 0;
+    op.flow = 1;
+    if (dev_getenv("CHR3D_LN_FLOW")) op.flow = atoi(dev_getenv("CHR3D_LN_FLOW"));
+    op.ring_tail = LN_STAGES;
+    if (dev_getenv("CHR3D_LN_RING_TAIL")) op.ring_tail = atoi(dev_getenv("CHR3D_LN_RING_TAIL"));
+    op.defer_ring = 0;
     if (dev_getenv("CHR3D_LN_DEFER_RING")) op.defer_ring = atoi(dev_getenv("CHR3D_LN_DEFER_RING"));
 }
 static void ln_md_cfg(LnEngine& e, const chr3d_stage& s, LnMdCfg& c) {
@@ -1904,6 +1951,14 @@ CHR3D_API int chr3d_single_profile_ctas(chr3d_single* h, int32_t cap, int32_t* n
         }
         if (tiles) tiles[c] = nt; if (near_tiles) near_tiles[c] = nn; if (rows) rows[c] = nr; if (tile_ms) tile_ms[c] = 1e-6 * (double)ns[c];
     }
+    return 0;
+}
+
+// development (-DCHR3D_DEV builds): raw event trace of two CTAs of the last persistent launch, 2 x 512 x (event, ns)
+CHR3D_API int chr3d_single_trace(chr3d_single* h, unsigned long long* out2048) {
+    if (!h || !out2048 || !h->e.trace.p) { set_error("chr3d_single_trace: not a development build"); return CHR3D_ERR_ARG; }
+    CHR3D_CUDA(cudaStreamSynchronize(h->e.stream));
+    CHR3D_CUDA(cudaMemcpy(out2048, h->e.trace.p, sizeof(unsigned long long) * 2048, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -31,6 +31,13 @@ struct LnCtx {                              // one (virtual) rank
     const long long* cstart;                // [ncta + 1] first tile of every CTA (cost-balanced, ln_plan)
     const int* blk_off; const int* blk_idx; // bead blocks of every CTA (balanced by gather length)
     unsigned long long* cta_ns;             // [ncta] time spent in tile phases (ns)
+    // barrier-free evaluations (the bulk of an MD op): which bead blocks this CTA's tiles feed, how many CTAs feed each block,
+    // the per-block completion counters and the per-block {sum of v.v, epoch} / {bond energy, epoch} slots
+    const int* tb_off; const int* tb_idx;   // blocks touched by every CTA (rows and columns of its tiles)
+    const int* need;                        // [nblk] CTAs that touch block B
+    unsigned int* ready;                    // [nblk] contributions finished, monotonic: evaluation E of this plan is complete at E * need[B]
+    double2* kslot;                         // [2 parities][nblk][2]
+    unsigned long long* trace;              // development trace buffer (or nullptr)
     int gI0, gJ0, gI1, gJ1;                 // tile coordinates of t0 and t1: the owned tiles of a column are a contiguous row range
     LnVec v; float4* va[2]; float4* vb[2];
     LnState* st; double* blockpart;
@@ -39,6 +46,9 @@ struct LnCtx {                              // one (virtual) rank
 };
 struct LnOp {
     int kind, nstep, count_eval, dbg;
+    int flow;               // 1: the evaluations in the middle of an MD op run without grid barriers (see "barrier-free evaluations")
+    int ring_tail;          // how many tiles of the next evaluation are requested before the current tile phase ends (0 .. LN_STAGES);
+                            // the rest is requested when the next tile phase starts
     int defer_ring;         // 1: the tile ring stops at the end of an evaluation and is restarted from the step phase, behind the push
                             // to the peers (several ranks: the copies would otherwise queue in front of the latency-critical gather);
                             // 0: the ring keeps running across the evaluation boundary (one rank: there is no idle time to hide it in)
@@ -116,7 +126,21 @@ __device__ __forceinline__ void ln_bar_release(const LnCtx& c, unsigned int gen)
 // tacc: phase clock of CTA 0 of a rank (ns, accumulated into LnState::tprof): 0 tile phase, 1 first barrier (+ energy
 // publication), 2 step phase (one rank: gather + integration; several ranks: summation + integration only), 3 second barrier
 // (+ decisions), 4 L-BFGS update + third barrier, 5 gather + push to the peers, 6 wait for the peers' partial forces
-struct LnLoop { int step, par, stop, prefetch; unsigned int gen, epoch; unsigned long long tlast, tacc[8], t0tile, ttile; };
+struct LnLoop { int step, par, stop, prefetch; unsigned int gen, epoch, revals; float lam; unsigned long long tlast, tacc[8], t0tile, ttile; };
+__shared__ LnCtx lnp_c;
+__shared__ LnOp lnp_op;
+__shared__ LnLoop lnp_L;
+__shared__ int lnp_flag;
+// Development trace (-DCHR3D_DEV): raw (event, globaltimer) pairs of two CTAs of a rank, first LN_TRACE_MAX events of a launch
+#ifdef CHR3D_DEV
+#define LN_TRACE_MAX 512
+#define LN_TRACE(ev) do { const int w_ = ((int)blockIdx.x - lnp_c.cta0 == 0) ? 0 : (((int)blockIdx.x - lnp_c.cta0 == lnp_c.ncta / 2) ? 1 : -1); \
+    if (w_ >= 0 && threadIdx.x == 0 && lnp_c.trace) { const unsigned int n_ = lnp_trace_n; if (n_ < LN_TRACE_MAX) { \
+        lnp_c.trace[((size_t)w_ * LN_TRACE_MAX + n_) * 2] = (unsigned long long)(ev); lnp_c.trace[((size_t)w_ * LN_TRACE_MAX + n_) * 2 + 1] = ln_globaltimer(); lnp_trace_n = n_ + 1; } } } while (0)
+__shared__ unsigned int lnp_trace_n;
+#else
+#define LN_TRACE(ev) do { } while (0)
+#endif
 __device__ __forceinline__ void ln_tprof(volatile LnLoop* L, int slot, bool timing) {
     if (timing) { const unsigned long long t = ln_globaltimer(); L->tacc[slot] += t - L->tlast; L->tlast = t; }
 }
@@ -132,11 +156,74 @@ struct LnScratch {
 static_assert(sizeof(LnScratch) <= LN_SCRATCH_BYTES, "scratch must fit the column-partial + column-coordinate buffers");
 static_assert(6 * CHR3D_LBFGS_MAX_M + 6 <= LN_KMAX && 2 * LN_P_THREADS * 8 <= (6 * CHR3D_LBFGS_MAX_M + 6) * LN_TB * 4, "serial-section scratch");
 
+// ---- barrier-free evaluations -------------------------------------------------------------------------------------------------
+// Inside an MD op only the first evaluation (nothing to integrate yet) and the last one (energies) need the whole grid in step.
+// The evaluations in between run as a dataflow:
+//   * a CTA that has finished its tile phase adds 1 (release) to the counter of every bead block its tiles feed;
+//   * the CTA that gathers block B waits until the counter shows that all feeders are through (acquire): no grid barrier
+//     between tile phase and gather;
+//   * after integrating block B its CTA publishes {sum of v.v over the block, epoch} (and the bond energy) in a 16-byte slot;
+//   * before its next tile phase every CTA waits for the slots of ALL blocks and adds them up itself, in the fixed order the
+//     barrier path uses (lane-strided sums of one warp, then the butterfly): every CTA gets the same thermostat factor with no
+//     second grid barrier, and because that factor needs every block, no CTA can run ahead far enough to overwrite anything
+//     that is still being read (partials, coordinate buffers, slots of the other parity).
+__device__ __forceinline__ void red_release_gpu(unsigned int* p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
+__device__ __forceinline__ void ln_signal_tiles_done(const LnCtx& c) {           // all threads, after the tile phase
+    __syncthreads();
+    const int cta = blockIdx.x - c.cta0;
+    for (int k = c.tb_off[cta] + (int)threadIdx.x; k < c.tb_off[cta + 1]; k += LN_P_THREADS) red_release_gpu(c.ready + c.tb_idx[k]);
+}
+__device__ __forceinline__ void ln_wait_ready(const LnCtx& c, int B, unsigned int revals) {     // one thread
+    const unsigned int target = revals * (unsigned)c.need[B];
+    if ((int)(ld_acquire_gpu(c.ready + B) - target) >= 0) return;
+    const long long t0 = clock64();
+    while ((int)(ld_relaxed_gpu(c.ready + B) - target) < 0) if (clock64() - t0 > LN_WAIT_LIMIT) ln_fail(c.xc.err, 3);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+// one thread, after the block's vectors have been written (and a CTA barrier): publish the block's scalars of evaluation `epoch`
+__device__ __forceinline__ void ln_publish_block(const LnCtx& c, int B, unsigned int epoch, double k2, double eb) {
+    __threadfence();
+    double2* s = c.kslot + ((size_t)(epoch & 1u) * c.nblk + B) * 2;
+    const double ep = __longlong_as_double((long long)epoch);
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(s), "d"(k2), "d"(ep) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(s + 1), "d"(eb), "d"(ep) : "memory");
+}
+// warp 0 of every CTA: wait for the slots of all blocks of evaluation `epoch`, thermostat factor from their sum (as ln_decide_md)
+__device__ __forceinline__ float ln_lambda_from_slots(const LnCtx& c, const LnOp& op, unsigned int epoch, double* ke_out) {
+    const int lane = threadIdx.x & 31;
+    double a0 = 0;
+    for (int q = lane; q < c.nblk; q += 32) {
+        const double2* s = c.kslot + ((size_t)(epoch & 1u) * c.nblk + q) * 2;
+        double2 v;
+        asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(s) : "memory");
+        if (__double_as_longlong(v.y) != (long long)epoch) {
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(s) : "memory");
+                if (clock64() - t0 > LN_WAIT_LIMIT) ln_fail(c.xc.err, 4);
+            } while (__double_as_longlong(v.y) != (long long)epoch);
+        }
+        a0 += v.x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");              // the coordinates the integrators wrote before their slots
+    const double ke = 0.5 * op.md.mass * a0, ndof = 3.0 * c.N - 3.0;
+    const double T = 2.0 * ke / (op.md.kboltz * ndof);
+    double l2 = 1.0;
+    if (T > 0.0) {
+        if (op.md.flag == CHR3D_COUPLE_TCOUP) l2 = sqrt(fmax(0.0, 1.0 + 2.0 * op.md.fbeta * op.md.dt_ps * (op.md.temp / T - 1.0)));
+        else if (op.md.flag == CHR3D_COUPLE_VSCALE) l2 = sqrt(op.md.temp / T);
+    }
+    if (ke_out) *ke_out = ke;
+    return (float)l2;
+}
+
 // The bead blocks of this CTA and the row partials that belong to them, copied into shared memory once per launch: the step
 // phase is a chain of dependent memory accesses, and every index it would otherwise fetch from global memory costs a round
 // trip to L2 per evaluation.
 #define LNP_MAXB 8
-#define LNP_MAXRS 6
+#define LNP_MAXRS 16
 struct LnBlkPlan { int nb, cached; int B[LNP_MAXB], lo[LNP_MAXB], hi[LNP_MAXB], rs_cnt[LNP_MAXB], rs[LNP_MAXB][LNP_MAXRS]; };
 __device__ __forceinline__ void ln_blk_bounds(const LnCtx& c, int B, int& lo, int& hi) {      // owned tiles of column B: rows [lo, hi)
     lo = (B >= c.gJ0) ? c.gI0 : c.gI0 + 1; hi = (B < c.gJ1) ? c.gI1 + 1 : c.gI1;
@@ -184,33 +271,37 @@ __device__ __noinline__ void ln_gather4(const LnCtx& c, int B, int k, int slot, 
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const int Ij = I + j * G;
-                const int Ic = Ij < hi ? Ij : lo;                                   // (a valid address; its value is discarded)
-                u[j] = __ldcg(base + (size_t)(unsigned)((Ic * nT - ((Ic * (Ic - 1)) >> 1) + B - Ic - t0) * 96));
+                u[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (Ij < hi) u[j] = __ldcg(base + (size_t)(unsigned)((Ij * nT - ((Ij * (Ij - 1)) >> 1) + B - Ij - t0) * 96));
             }
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const float m = (I + j * G < hi) ? 1.f : 0.f;
-                acc[j & 3].x = fmaf(m, u[j].x, acc[j & 3].x); acc[j & 3].y = fmaf(m, u[j].y, acc[j & 3].y);
-                acc[j & 3].z = fmaf(m, u[j].z, acc[j & 3].z); acc[j & 3].w = fmaf(m, u[j].w, acc[j & 3].w);
-            }
+            for (int j = 0; j < 16; j++) { acc[j & 3].x += u[j].x; acc[j & 3].y += u[j].y; acc[j & 3].z += u[j].z; acc[j & 3].w += u[j].w; }
         }
         float4 a0;
         a0.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x); a0.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
         a0.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z); a0.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
         *reinterpret_cast<float4*>(&sc->gred[slot * G + grp][q * 4]) = a0;
     }
+    LN_TRACE(25);
     // the row partials of this block (the lead threads; issued behind the column partials, before anybody waits)
     float rx = 0.f, ry = 0.f, rz = 0.f;
     if (B >= 0 && ts < LN_TB) {
         const int r0 = k >= 0 ? 0 : c.rs_off[B], r1 = k >= 0 ? lnp_bp.rs_cnt[k] : c.rs_off[B + 1];
 #pragma unroll 1
-        for (int r = r0; r < r1; r++) {
-            const int idx = k >= 0 ? lnp_bp.rs[k][r] : c.rs_idx[r];
-            const float4 v = __ldcg(c.rowpart + (size_t)idx * LN_TB + ts);
-            rx += v.x; ry += v.y; rz += v.z;
+        for (int r = r0; r < r1; r += 8) {                       // eight independent loads in flight (a long tile row is cut into a dozen segments)
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r + j < r1) v[j] = __ldcg(c.rowpart + (size_t)(k >= 0 ? lnp_bp.rs[k][r + j] : c.rs_idx[r + j]) * LN_TB + ts);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { rx += v[j].x; ry += v[j].y; rz += v[j].z; }
         }
     }
+    LN_TRACE(26);
     __syncthreads();
+    LN_TRACE(27);
     fx = fy = fz = 0.f;
     if (B >= 0 && ts < LN_TB) {
         const int pos = 4 * (ts & 31) + (ts >> 5);              // column -> position inside a partial (ln_tile_phase)
@@ -234,7 +325,8 @@ __device__ __noinline__ void ln_gather4(const LnCtx& c, int B, int k, int slot, 
 // (several ranks), so that those round trips to L2 overlap instead of queueing up behind one another.
 struct LnNoPre {};
 template <bool PAIR, typename Preload, typename Emit>
-__device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch* sc, unsigned int epoch, volatile LnLoop* L, bool timing, Preload preload, Emit emit) {
+__device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch* sc, unsigned int epoch, volatile LnLoop* L, bool timing, Preload preload, Emit emit,
+                                                       unsigned int flow_revals = 0u /* != 0: barrier-free evaluation number of this plan: wait for the feeders of each block */) {
     const int tid = threadIdx.x, cta = blockIdx.x - c.cta0;
     const LnXchg& x = c.xc;
     const int nb = lnp_bp.nb, cached = lnp_bp.cached;
@@ -256,7 +348,11 @@ __device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch
             if (pass == (multi ? 1 : 0)) pre = preload(B >= 0 && lt >= 0 && i < c.N, i, lt);
             if (pass == 0) {
                 const int Bg = (B >= 0 && multi && B < c.bmin[x.rank]) ? -1 : B;          // nothing of this block in this rank's tiles
+                LN_TRACE(10 + k0);
+                if (flow_revals) { if (Bg >= 0 && ts == 0) ln_wait_ready(c, Bg, flow_revals); __syncthreads(); }
+                LN_TRACE(20 + k0);
                 ln_gather4(c, Bg, (cached && Bg >= 0) ? k : -1, slot, nslots, sc, fx, fy, fz);
+                LN_TRACE(30 + k0);
                 if (multi) {
                     ln_tprof(L, 7, timing);
                     if (Bg >= 0 && lt >= 0 && i < c.N) {
@@ -264,6 +360,7 @@ __device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch
 #pragma unroll 1
                         for (int g = 0; g < x.world; g++) st_v4_sys(x.recv[g] + myslot + i, v);
                     }
+                    LN_TRACE(40 + k0);
                     if (k0 + nslots >= nb) ln_tprof(L, 5, timing);
                     continue;
                 }
@@ -280,9 +377,12 @@ __device__ __forceinline__ void ln_forces_of_my_blocks(const LnCtx& c, LnScratch
                         fx += v.x; fy += v.y; fz += v.z;
                     }
                 }
+                __syncthreads();
+                LN_TRACE(50 + k0);
                 if (k0 + nslots >= nb) ln_tprof(L, 6, timing);
             }
             emit(B >= 0, B, i, lt, slot, fx, fy, fz, pre);
+            LN_TRACE(60 + k0);
         }
     }
     if (!multi && tid == 0 && L->prefetch) ln_ring_prefetch(&lnp_run, lnp_smem);
@@ -355,7 +455,7 @@ __device__ __forceinline__ void ln_energy_collect(const LnCtx& c, unsigned int e
 // ---- the step phases ----------------------------------------------------------------------------------------------------
 // Verlet step (definition of the oracle's sim_dynamics, see ln_md_step_kernel)
 __device__ __noinline__ void ln_step_md(const LnCtx& c, const LnOp& op, LnScratch* sc, const float4* A, const float4* Bv, float lam, int first,
-                                        float4* a_next, float4* b_next, unsigned int epoch, volatile LnLoop* L, bool timing) {
+                                        float4* a_next, float4* b_next, unsigned int epoch, volatile LnLoop* L, bool timing, unsigned int flow_revals) {
     const int tid = threadIdx.x;
     const float h = op.md.h, dt = op.md.dt_akma, dth = dt * h;
     struct MdPre { float4 p0, q0, pm, qm, pp, qp, v, f; };
@@ -399,8 +499,8 @@ __device__ __noinline__ void ln_step_md(const LnCtx& c, const LnOp& op, LnScratc
             b_next[i] = make_float4(dt * vv.x, dt * vv.y, dt * vv.z, 0.f);
         }
         const double kb = ln_lead_sum((double)k2, sc->dsum, lt, slot), ebb = ln_lead_sum((double)eb, sc->dsum, lt, slot);
-        if (active && lt == 0) { c.blockpart[(size_t)B * LN_KMAX] = kb; c.blockpart[(size_t)B * LN_KMAX + 1] = ebb; }
-    });
+        if (active && lt == 0) { c.blockpart[(size_t)B * LN_KMAX] = kb; c.blockpart[(size_t)B * LN_KMAX + 1] = ebb; ln_publish_block(c, B, epoch, kb, ebb); }
+    }, flow_revals);
 }
 // serial section after ln_step_md (all threads of the last arriver)
 __device__ __noinline__ void ln_decide_md(const LnCtx& c, const LnOp& op, LnScratch* sc, int want_e, unsigned int epoch) {
@@ -572,10 +672,6 @@ __device__ __forceinline__ void ln_barrier(const LnCtx& c, volatile LnLoop* L, i
 
 // The state of a persistent launch, in shared memory at file scope: the out-of-line phases below take NO arguments, so the
 // kernel body keeps nothing alive in registers across the inlined tile phase (which needs all of them).
-__shared__ LnCtx lnp_c;
-__shared__ LnOp lnp_op;
-__shared__ LnLoop lnp_L;
-__shared__ int lnp_flag;
 #define LNP_SC (reinterpret_cast<LnScratch*>(lnp_smem + LN_COLP_OFF))
 #define LNP_TIMING (blockIdx.x == (unsigned)lnp_c.cta0 && threadIdx.x == 0)
 
@@ -592,14 +688,28 @@ __device__ __noinline__ void ln_md_rest() {
     ln_tprof(L, 1, timing);
     {
         const float4* A = first ? c.v.x : c.va[par]; const float4* Bv = first ? c.v.x : c.vb[par];
-        const float lam = first ? 0.f : __ldcg(&c.st->lamf);
-        ln_step_md(c, op, sc, A, Bv, lam, first, first ? c.va[0] : c.va[par ^ 1], first ? c.vb[0] : c.vb[par ^ 1], epoch, L, timing);
+        const float lam = first ? 0.f : L->lam;
+        ln_step_md(c, op, sc, A, Bv, lam, first, first ? c.va[0] : c.va[par ^ 1], first ? c.vb[0] : c.vb[par ^ 1], epoch, L, timing, 0u);
     }
     ln_tprof(L, 2, timing);
     ln_barrier(c, L, s_flag, [&]() { ln_decide_md(c, op, sc, want_e, epoch); });
     if (threadIdx.x == 0) { L->epoch = epoch; L->step = step + 1; if (!first) L->par = par ^ 1; }
     __syncthreads();
     ln_tprof(L, 3, timing);
+}
+// the same for an evaluation in the middle of an MD op: no grid barrier (see "barrier-free evaluations")
+__device__ __noinline__ void ln_md_rest_flow() {
+    const LnCtx& c = lnp_c; const LnOp& op = lnp_op; LnScratch* sc = LNP_SC; volatile LnLoop* L = &lnp_L;
+    const bool timing = LNP_TIMING;
+    if (threadIdx.x == 0) L->ttile += ln_globaltimer() - L->t0tile;
+    LN_TRACE(3);
+    const int step = L->step, par = L->par;
+    ln_tprof(L, 0, timing);
+    const unsigned int epoch = L->epoch + 1u;
+    ln_step_md(c, op, sc, c.va[par], c.vb[par], L->lam, 0, c.va[par ^ 1], c.vb[par ^ 1], epoch, L, timing, L->revals);
+    if (threadIdx.x == 0) { L->epoch = epoch; L->step = step + 1; L->par = par ^ 1; if (timing) c.st->nevals += op.count_eval; }
+    __syncthreads();
+    ln_tprof(L, 2, timing);
 }
 __device__ __noinline__ void ln_min_rest() {
     const LnCtx& c = lnp_c; const LnOp& op = lnp_op; LnScratch* sc = LNP_SC; volatile LnLoop* L = &lnp_L; int* s_flag = &lnp_flag;
@@ -637,14 +747,25 @@ __device__ __noinline__ void ln_eval_rest() {
 }
 // coordinates of the next evaluation -> lnp_run, start of the tile clock (all threads call)
 __device__ __noinline__ void ln_md_setup() {
-    if (threadIdx.x == 0) {
-        const LnCtx& c = lnp_c; volatile LnLoop* L = &lnp_L; LnTileRun* run = &lnp_run;
-        const int step = L->step, par = L->par, first = step < 0;
-        run->X = first ? c.v.x : c.va[par]; run->XB = first ? c.v.x : c.vb[par];
-        const int more = step + 1 < lnp_op.nstep ? 1 : 0;
-        run->lam = first ? 0.f : __ldcg(&c.st->lamf);
-        run->more = lnp_op.defer_ring ? 0 : more; L->prefetch = lnp_op.defer_ring ? more : 0;
-        L->t0tile = ln_globaltimer();
+    const LnCtx& c = lnp_c; volatile LnLoop* L = &lnp_L; LnTileRun* run = &lnp_run;
+    const int step = L->step, first = step < 0;
+    if (threadIdx.x < 32) {
+        // every evaluation but the first continues from an integration: wait for the scalars of all bead blocks of that evaluation
+        // (every CTA adds them up in the same order, so every CTA gets the same factor; no grid barrier needed for it)
+        float lam = 0.f; double ke = 0.0;
+        LN_TRACE(1);
+        if (!first) lam = ln_lambda_from_slots(c, lnp_op, L->epoch, &ke);
+        LN_TRACE(2);
+        if (threadIdx.x == 0) {
+            const int par = L->par;
+            const int more = step + 1 < lnp_op.nstep ? 1 : 0;
+            run->X = first ? c.v.x : c.va[par]; run->XB = first ? c.v.x : c.vb[par];
+            run->lam = lam; L->lam = lam;
+            run->more = lnp_op.defer_ring ? 0 : more; L->prefetch = lnp_op.defer_ring ? more : 0;
+            L->revals = L->revals + 1u;
+            if (!first && LNP_TIMING) { c.st->ke = ke; c.st->lam = (double)lam; c.st->lamf = lam; }
+            L->t0tile = ln_globaltimer();
+        }
     }
     __syncthreads();
 }
@@ -655,6 +776,7 @@ __device__ __noinline__ void ln_min_setup() {
         run->X = init ? c.v.x : c.v.xb; run->XB = init ? c.v.x : c.v.p;
         run->lam = init ? 0.f : __ldcg(&c.st->tstepf);
         run->more = lnp_op.defer_ring ? 0 : 1; lnp_L.prefetch = lnp_op.defer_ring ? 1 : 0;
+        lnp_L.revals = lnp_L.revals + 1u;
         lnp_L.t0tile = ln_globaltimer();
     }
     __syncthreads();
@@ -672,13 +794,16 @@ __device__ __noinline__ void ln_launch_setup(const LnCtx* __restrict__ ctxs, int
     if (threadIdx.x == 0) {
         const LnCtx& c = lnp_c;
         ln_run_setup(&lnp_run, c.Dt, c.t0, c.cstart, c.nT, c.N, c.colpart, c.rowpart, c.epart, c.maxseg, blockIdx.x - c.cta0);
-        lnp_run.terms = lnp_op.terms; lnp_run.dbg = lnp_op.dbg; lnp_run.stream_l2 = c.stream_l2;
+        lnp_run.terms = lnp_op.terms; lnp_run.dbg = lnp_op.dbg; lnp_run.stream_l2 = c.stream_l2; lnp_run.ring_tail = lnp_op.ring_tail;
         lnp_L.step = -1; lnp_L.par = 0; lnp_L.stop = 0;
         lnp_L.gen = ld_acquire_gpu(c.bar + 32);             // stable between launches
-        lnp_L.epoch = c.st->epoch;
+        lnp_L.epoch = c.st->epoch; lnp_L.revals = c.st->revals; lnp_L.lam = 0.f;
         for (int q = 0; q < 8; q++) lnp_L.tacc[q] = 0;
         lnp_L.tlast = ln_globaltimer(); lnp_L.ttile = 0;
     }
+#ifdef CHR3D_DEV
+    if (threadIdx.x == 0) lnp_trace_n = 0;
+#endif
     if (threadIdx.x == 32) ln_blk_plan_load(lnp_c, &lnp_bp);
     __syncthreads();
     ln_ring_init(&lnp_run, lnp_smem, true);
@@ -686,34 +811,44 @@ __device__ __noinline__ void ln_launch_setup(const LnCtx* __restrict__ ctxs, int
 __device__ __noinline__ void ln_launch_finish() {
     ln_ring_drain(&lnp_run, lnp_smem);
     if (threadIdx.x == 0) lnp_c.cta_ns[blockIdx.x - lnp_c.cta0] += lnp_L.ttile;
-    if (LNP_TIMING) { lnp_c.st->epoch = lnp_L.epoch; for (int q = 0; q < 8; q++) lnp_c.st->tprof[q] += lnp_L.tacc[q]; }
+    if (LNP_TIMING) { lnp_c.st->epoch = lnp_L.epoch; lnp_c.st->revals = lnp_L.revals; for (int q = 0; q < 8; q++) lnp_c.st->tprof[q] += lnp_L.tacc[q]; }
 }
 
 template <bool LOW_SOFT>
 __global__ void __launch_bounds__(LN_P_THREADS, 1) ln_persist_kernel(const LnCtx* __restrict__ ctxs, int nvr, const __grid_constant__ LnOp op) {
     ln_launch_setup(ctxs, nvr, &op);
     if (op.kind == LN_OP_MD) {
-        // every evaluation but the last one without energies
-        while (((volatile LnLoop*)&lnp_L)->step < 0 || ((volatile LnLoop*)&lnp_L)->step < op.nstep - 1) {
+        // the first evaluation (nothing to integrate yet) with the grid barriers ...
+        ln_md_setup();
+        ln_tile_phase<false, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
+        ln_signal_tiles_done(lnp_c);
+        ln_md_rest();
+        // ... the evaluations in the middle as a dataflow, no grid barrier ...
+        while (((volatile LnLoop*)&lnp_L)->step < op.nstep - 1) {
             ln_md_setup();
             ln_tile_phase<false, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
-            ln_md_rest();
+            ln_signal_tiles_done(lnp_c);
+            if (op.flow) ln_md_rest_flow(); else ln_md_rest();
         }
+        // ... the last one with energies and the barriers again
         if (op.nstep > 0) {
             ln_md_setup();
             ln_tile_phase<true, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
+            ln_signal_tiles_done(lnp_c);
             ln_md_rest();
         }
     } else if (op.kind == LN_OP_MIN) {
         while (!((volatile LnLoop*)&lnp_L)->stop) {
             ln_min_setup();
             ln_tile_phase<true, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
+            ln_signal_tiles_done(lnp_c);
             ln_min_rest();
         }
     } else {
-        if (threadIdx.x == 0) { lnp_run.X = lnp_c.v.x; lnp_run.XB = lnp_c.v.x; lnp_run.lam = 0.f; lnp_run.more = 0; lnp_L.prefetch = 0; lnp_L.t0tile = ln_globaltimer(); }
+        if (threadIdx.x == 0) { lnp_run.X = lnp_c.v.x; lnp_run.XB = lnp_c.v.x; lnp_run.lam = 0.f; lnp_run.more = 0; lnp_L.prefetch = 0; lnp_L.revals = lnp_L.revals + 1u; lnp_L.t0tile = ln_globaltimer(); }
         __syncthreads();
         ln_tile_phase<true, LOW_SOFT>(&lnp_run, lnp_smem, op.terms);
+        ln_signal_tiles_done(lnp_c);
         ln_eval_rest();
     }
     ln_launch_finish();

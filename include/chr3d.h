@@ -246,6 +246,8 @@ int chr3d_single_profile(chr3d_single* h, double* ms8);
  * reading).  This is the data the cost model of the tile partition is fitted to.                                        */
 int chr3d_single_profile_ctas(chr3d_single* h, int32_t cap, int32_t* n, int32_t* tiles, int32_t* near_tiles, int32_t* rows,
                               double* tile_ms);
+/* Development builds (-DCHR3D_DEV) only: raw (event, ns) trace of two CTAs of the last persistent launch, 2 x 512 pairs. */
+int chr3d_single_trace(chr3d_single* h, unsigned long long* out2048);
 /* Test aid: this rank's targets as a dense row-major N*N fp32 matrix (cells of other ranks' tiles and the
  * diagonal: NaN; sentinels as stored: -1 no restraint, -2 no restraint and no repel).                  */
 int chr3d_single_targets(chr3d_single* h, float* out);

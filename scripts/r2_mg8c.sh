@@ -12,8 +12,11 @@ print("$tag: ms/step", round(d["ms_per_step"],2), "evals", d["config"]["force_ev
 ph=d["phases_ms_per_step"]; ev=d["config"]["force_evals_per_model"]
 print(ph["by_rank_columns"][3:])
 for r in ph["by_rank"]:
-    print([round(1e3*v/ev,2) for v in r[3:]])
+    print([round(1e3*v/ev,1) for v in r[3:]])
 PY
 }
-run defer X=1
-run ring CHR3D_LIBRARY=$PWD/chromosome3d_b200/libchr3d_dev.so CHR3D_LN_DEFER_RING=0
+DEV=CHR3D_LIBRARY=$PWD/chromosome3d_b200/libchr3d_dev.so
+run base X=1
+run tail1 $DEV CHR3D_LN_RING_TAIL=1
+run persist $DEV CHR3D_LN_L2_PERSIST=1
+run noflow $DEV CHR3D_LN_FLOW=0
