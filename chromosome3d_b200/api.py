@@ -428,13 +428,20 @@ class Single:
     (tile-range) partition over the GPUs of a node.  Same dgsa.inp protocol (C3D:1573-1829)."""
 
     def __init__(self, IF=None, N=None, alpha=0.5, K=11.0, min_sep=5, synth_seed=0, x0=None, seed=0, p=None, program=None,
-                 rank=0, world=1, nccl_id=None):
+                 rank=0, world=1, nccl_id=None, restraints=None):
         self.IF = None if IF is None else np.ascontiguousarray(IF, dtype=np.float64)
         self.N = int(self.IF.shape[0] if self.IF is not None else N)
         self.p = p or default_params()
         self.program = program if program is not None else build_program(self.p)
         self.x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).reshape(self.N, 3)
         self._h = C.c_void_p()
+        if restraints is not None:          # sparse restraint table: CSR rows + cell-list repel (chr3d_single_create_sparse)
+            ri, rj, rd = restraints
+            self._r = (np.ascontiguousarray(ri, dtype=np.int32), np.ascontiguousarray(rj, dtype=np.int32), np.ascontiguousarray(rd, dtype=np.float64))
+            _check(lib().chr3d_single_create_sparse(self.N, _i(self._r[0]), _i(self._r[1]), _d(self._r[2]), C.c_int64(len(self._r[0])),
+                                                    _d(self.x0) if self.x0 is not None else None, C.c_uint64(seed), C.byref(self.p),
+                                                    self.program, len(self.program), C.byref(self._h)))
+            return
         idbuf = None
         if nccl_id is not None:
             idbuf = (C.c_ubyte * 128).from_buffer_copy(bytes(nccl_id))
@@ -485,6 +492,11 @@ class Single:
         a = (C.c_double * 8)()
         _check(lib().chr3d_single_profile(self._h, a))
         return dict(zip(("tile_ms", "barrier1_ms", "step_ms", "barrier2_ms", "update_ms", "gather_push_ms", "peer_wait_ms", "gather_ms"), [float(v) for v in a[:8]]))
+
+    def sparse_info(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        _check(lib().chr3d_single_sparse_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(rebuilds=a.value, csr_entries=b.value, noe_bytes_per_eval=c.value)
 
     def profile_ctas(self):
         """Per-CTA tile counts (all, near, rows started) and tile-phase milliseconds of the persistent kernel since the last call."""

@@ -987,6 +987,7 @@ __global__ void __launch_bounds__(LN_STEP_THREADS) ln_min_step_kernel(LnMinStepA
 }
 
 #include "ln_persist.cuh"
+#include "ln_sparse.cuh"
 
 // sums of a float4 array (COM velocity / geometric centre): partials then subtraction
 __global__ void __launch_bounds__(256) ln_sum3_kernel(const float4* a, int N, double* part) {
@@ -1180,13 +1181,17 @@ struct LnEngine {
     void* xbuf = nullptr; size_t xbytes = 0; void* peer[LN_MAXWORLD] = {nullptr}; bool p2p = false, peers_local = false;
     int* xerr = nullptr;                       // pinned host word the kernel writes before it traps on a wait that cannot complete
     bool l2_window_set = false;
+    // sparse force provider (ln_sparse.cuh): symmetric CSR of the restraint table, hashed cell grid for the repel term
+    bool sparse = false; long long sp_nnz = 0; int sp_hbits = 0, sp_blocks = 0; float sp_inv_cs = 0.f;
+    DevBuf<long long> sp_row_ptr, sp_nreb; DevBuf<int> sp_col, sp_cell_start, sp_cell_count, sp_cell_fill, sp_order, sp_rebuild; DevBuf<float> sp_dist;
+    DevBuf<float4> sp_xs, sp_xref, sp_fnoe; DevBuf<double> sp_erow, sp_epart; DevBuf<unsigned int> sp_done;
     bool legacy = false;                       // multi-launch evaluation (NCCL all-reduce between ranks): the baseline path
     LnGroup self; LnGroup* group = nullptr;    // group: the launch group this engine currently belongs to (&self unless virtual ranks)
     static size_t up16(size_t v) { return (v + 15) / 16 * 16; }
     size_t x_off_es() const { return sizeof(float4) * 2 * (size_t)world * (N + 1); }
     size_t x_total() const { return x_off_es() + sizeof(double2) * 2 * 2 * (size_t)world; }
     LnVec vec() { LnVec v; v.x = vx.p; v.xb = vxb.p; v.g = vg.p; v.p = vp.p; v.v = vv.p; v.f = vf.p; v.S = vS.p; v.Y = vY.p; v.N = N; v.m = m; return v; }
-    bool persistent() const { return !legacy && (world == 1 || p2p); }
+    bool persistent() const { return !sparse && !legacy && (world == 1 || p2p); }
 };
 
 // Cost model of the tile walk, in units of one far tile: a tile that touches the diagonal band or the padded last column takes
@@ -1294,31 +1299,17 @@ static int ln_plan(LnEngine& e, int ncta) {
     return 0;
 }
 
-static int ln_alloc(LnEngine& e) {
+// state, vectors and scratch every force provider needs
+static int ln_alloc_vectors(LnEngine& e) {
     const int N = e.N;
     e.nT = (N + LN_TB - 1) / LN_TB; e.nblk = e.nT;
-    e.n_tiles = (long long)e.nT * (e.nT + 1) / 2;
-    {   // rank boundaries: contiguous tile ranges of equal modelled cost (every rank derives the same cuts)
-        std::vector<long long> cut = ln_cost_split(0, e.n_tiles, e.world, e.nT, e.N);
-        e.t0 = cut[e.rank]; e.t1 = cut[e.rank + 1]; e.rank_cut = cut;
-    }
-    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&e.sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long ntl = e.t1 - e.t0;
-    {   // targets that cannot stay in L2 from one evaluation to the next are streamed with an evict-first policy
-        int l2 = 0; cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
-        e.stream_l2 = (double)ntl * LN_TILE_FLOATS * 4 > 0.6 * (double)l2 ? 1 : 0;
-    }
     e.nparts = std::min(64, std::max(1, (N + 255) / 256));
     e.self.es.assign(1, &e); e.group = &e.self;
-    CHR3D_CUDA(e.Dt.alloc((size_t)std::max<long long>(ntl, 1) * LN_TILE_FLOATS));
-    CHR3D_CUDA(e.colpart.alloc((size_t)std::max<long long>(ntl, 1) * 3 * LN_TB));
+    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&e.sms, cudaDevAttrMultiProcessorCount, dev);
     CHR3D_CUDA(e.st.alloc(1));
     CHR3D_CUDA(cudaMemset(e.st.p, 0, sizeof(LnState)));
-    if (int rc = ln_plan(e, e.sms)) return rc;
     CHR3D_CUDA(e.escal.alloc((size_t)3 + e.nblk));
     CHR3D_CUDA(e.part.alloc((size_t)e.nparts * LN_KMAX));
-    CHR3D_CUDA(e.bar.alloc(64));
-    CHR3D_CUDA(cudaMemset(e.bar.p, 0, sizeof(unsigned int) * 64));
     const size_t n4 = (size_t)N + 1;
     CHR3D_CUDA(e.vx.alloc(n4)); CHR3D_CUDA(e.vxb.alloc(n4)); CHR3D_CUDA(e.vg.alloc(n4)); CHR3D_CUDA(e.vp.alloc(n4));
     CHR3D_CUDA(e.vv.alloc(n4)); CHR3D_CUDA(e.vf.alloc(n4)); CHR3D_CUDA(e.sx.alloc(n4)); CHR3D_CUDA(e.sv.alloc(n4));
@@ -1329,6 +1320,27 @@ static int ln_alloc(LnEngine& e) {
     CHR3D_CUDA(cudaMemset(e.vf.p, 0, sizeof(float4) * n4));
     CHR3D_CUDA(cudaMemset(e.vp.p, 0, sizeof(float4) * n4));
     CHR3D_CUDA(cudaMallocHost((void**)&e.xerr, sizeof(int))); *e.xerr = 0;
+    return 0;
+}
+static int ln_alloc(LnEngine& e) {
+    const int N = e.N;
+    if (int rc = ln_alloc_vectors(e)) return rc;
+    e.n_tiles = (long long)e.nT * (e.nT + 1) / 2;
+    {   // rank boundaries: contiguous tile ranges of equal modelled cost (every rank derives the same cuts)
+        std::vector<long long> cut = ln_cost_split(0, e.n_tiles, e.world, e.nT, e.N);
+        e.t0 = cut[e.rank]; e.t1 = cut[e.rank + 1]; e.rank_cut = cut;
+    }
+    int dev = 0; cudaGetDevice(&dev);
+    const long long ntl = e.t1 - e.t0;
+    {   // targets that cannot stay in L2 from one evaluation to the next are streamed with an evict-first policy
+        int l2 = 0; cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+        e.stream_l2 = (double)ntl * LN_TILE_FLOATS * 4 > 0.6 * (double)l2 ? 1 : 0;
+    }
+    CHR3D_CUDA(e.Dt.alloc((size_t)std::max<long long>(ntl, 1) * LN_TILE_FLOATS));
+    CHR3D_CUDA(e.colpart.alloc((size_t)std::max<long long>(ntl, 1) * 3 * LN_TB));
+    if (int rc = ln_plan(e, e.sms)) return rc;
+    CHR3D_CUDA(e.bar.alloc(64));
+    CHR3D_CUDA(cudaMemset(e.bar.p, 0, sizeof(unsigned int) * 64));
 #ifdef CHR3D_DEV
     CHR3D_CUDA(e.trace.alloc(2 * 512 * 2)); CHR3D_CUDA(cudaMemset(e.trace.p, 0, sizeof(unsigned long long) * 2 * 512 * 2));
 #endif
@@ -1471,6 +1483,34 @@ static void ln_tiles(LnEngine& e, const chr3d_stage& s, const float4* x, const f
     ln_launch_tiles(e, a, want_e);
     e.n_launches++;
 }
+// ---- sparse force provider: total forces into e.vfr, energies into e.escal[0..2] (ln_sparse.cuh) ------------------------------
+static SpGrid sp_grid(LnEngine& e) {
+    SpGrid g; g.inv_cs = e.sp_inv_cs; g.hbits = e.sp_hbits; g.cell_start = e.sp_cell_start.p; g.cell_count = e.sp_cell_count.p; g.cell_fill = e.sp_cell_fill.p;
+    g.order = e.sp_order.p; g.xref = e.sp_xref.p; g.rebuild = e.sp_rebuild.p; g.n_rebuilds = e.sp_nreb.p;
+    return g;
+}
+static int sp_eval(LnEngine& e, const chr3d_stage& s, const float4* a, const float4* b, const float* lam, bool force_rebuild) {
+    const int N = e.N, nb = (N + SP_THREADS - 1) / SP_THREADS;
+    SpGrid g = sp_grid(e);
+    LnTerms t; ln_terms(e.prm, s, t);
+    sp_coords_kernel<<<std::min(nb, 2 * e.sms), SP_THREADS, 0, e.stream>>>(a, b, lam, N, e.sp_xs.p, g, force_rebuild ? 1 : 0);
+    // the bins: every kernel returns at once unless a bead has moved more than skin / 2 since the last build (device-side decision)
+    sp_grid_clear_kernel<<<std::min(((1 << e.sp_hbits) + 255) / 256, 2 * e.sms), 256, 0, e.stream>>>(g);
+    sp_grid_count_kernel<<<std::min(nb, 2 * e.sms), SP_THREADS, 0, e.stream>>>(e.sp_xs.p, N, g);
+    sp_grid_scan_kernel<<<1, 1024, 0, e.stream>>>(g);
+    sp_grid_place_kernel<<<std::min(nb, 2 * e.sms), SP_THREADS, 0, e.stream>>>(e.sp_xs.p, N, g);
+    sp_grid_sort_kernel<<<std::min(((1 << e.sp_hbits) + 255) / 256, 2 * e.sms), 256, 0, e.stream>>>(g, e.sp_done.p);
+    SpCsr m; m.row_ptr = e.sp_row_ptr.p; m.col = e.sp_col.p; m.dist = e.sp_dist.p;
+    const int noe_blocks = std::min((N * 32 + SP_THREADS - 1) / SP_THREADS, 8 * e.sms);
+    if (e.prm.noe_low_soft) sp_noe_kernel<true><<<noe_blocks, SP_THREADS, 0, e.stream>>>(m, e.sp_xs.p, N, t, e.sp_fnoe.p, e.sp_erow.p);
+    else sp_noe_kernel<false><<<noe_blocks, SP_THREADS, 0, e.stream>>>(m, e.sp_xs.p, N, t, e.sp_fnoe.p, e.sp_erow.p);
+    sp_repel_combine_kernel<<<nb, SP_THREADS, 0, e.stream>>>(e.sp_xs.p, N, g, t, ln_bonded_terms(e.prm, s), e.prm.vdw_min_sep, e.sp_fnoe.p, e.sp_erow.p, e.vfr.p, e.sp_epart.p);
+    sp_energy_kernel<<<1, 32, 0, e.stream>>>(e.sp_epart.p, nb, e.escal.p);
+    e.n_launches += 9;
+    CHR3D_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---- legacy multi-launch path (the NCCL baseline between ranks) ---------------------------------------------------------
 // several ranks: reduce this rank's partial forces (+ bond on rank 0) into vfr, sum vfr and the three energies over the
 // ranks with NCCL; afterwards every rank holds the total force in vfr and the totals in escal[0..2]
@@ -1494,6 +1534,11 @@ static int ln_exchange(LnEngine& e, const chr3d_stage& s, const float4* x, const
 }
 // one energy + force evaluation at explicit coordinates e.vx, forces into e.vf, totals in escal[0..2]
 static int ln_eval_legacy(LnEngine& e, const chr3d_stage& s, bool want_e = true) {
+    if (e.sparse) {
+        if (int rc = sp_eval(e, s, e.vx.p, nullptr, nullptr, true)) return rc;
+        CHR3D_CUDA(cudaMemcpyAsync(e.vf.p, e.vfr.p, sizeof(float4) * (size_t)e.N, cudaMemcpyDeviceToDevice, e.stream));
+        return 0;
+    }
     ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, want_e);
     LnReduceArgs r; r.g = ln_gather_args(e); r.epart = e.epart.p; r.N = e.N; r.ncta = e.ncta; r.add_bond = e.rank == 0 ? 1 : 0;
     r.x = e.vx.p; r.xb2 = nullptr; r.lam = nullptr; r.f = e.vf.p; r.escal = e.escal.p; r.bd = ln_bonded_terms(e.prm, s);
@@ -1525,13 +1570,16 @@ static int ln_poll_done(LnEngine& e, int* done) {
 static int ln_minimize_legacy(LnEngine& e, const chr3d_stage& s) {
     const int vb = std::min(296, (e.N + 255) / 256);
     LnVec v = e.vec();
-    const bool multi = e.world > 1;
+    const bool multi = e.world > 1 || e.sparse;          // forces arrive complete in vfr, energies in escal
     LnMinCfg c; ln_min_cfg(e, s, c);
     LnMinStepArgs m; m.g = ln_gather_args(e); m.fsum = multi ? e.vfr.p : nullptr; m.v = v; m.lam = &e.st.p->tstepf; m.init = 1;
     m.es.epart = e.epart.p; m.es.ncta = e.ncta; m.es.escal = multi ? e.escal.p : nullptr; m.st = e.st.p; m.blockpart = e.blockpart.p; m.nblk = e.nblk;
     m.bd = ln_bonded_terms(e.prm, s); m.cfg = c;
-    ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, true);
-    if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
+    if (e.sparse) { if (int rc = sp_eval(e, s, e.vx.p, nullptr, nullptr, true)) return rc; }
+    else {
+        ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, true);
+        if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
+    }
     ln_min_step_kernel<<<e.nblk, LN_STEP_THREADS, 0, e.stream>>>(m);
     ln_min_update_kernel<<<vb, 256, 0, e.stream>>>(v, e.st.p);
     e.n_launches += 2;
@@ -1540,8 +1588,11 @@ static int ln_minimize_legacy(LnEngine& e, const chr3d_stage& s) {
     const int poll_every = 32;
     for (long long trial = 0; trial < max_trials;) {
         for (int k = 0; k < poll_every; k++, trial++) {
-            ln_tiles(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf, &e.st.p->done, true);
-            if (multi) if (int rc = ln_exchange(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf)) return rc;
+            if (e.sparse) { if (int rc = sp_eval(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf, false)) return rc; }
+            else {
+                ln_tiles(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf, &e.st.p->done, true);
+                if (multi) if (int rc = ln_exchange(e, s, e.vxb.p, e.vp.p, &e.st.p->tstepf)) return rc;
+            }
             ln_launch_pdl(ln_min_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, m);
             ln_launch_pdl2(ln_min_update_kernel, vb, 256, e.stream, v, (const LnState*)e.st.p);
             e.n_launches += 2;
@@ -1555,22 +1606,28 @@ static int ln_minimize_legacy(LnEngine& e, const chr3d_stage& s) {
 }
 // Verlet MD, legacy: per step two launches (tiles at a + lam*b, ln_md_step_kernel); (a, b) double-buffered by parity
 static int ln_dynamics_legacy(LnEngine& e, const chr3d_stage& s) {
-    const bool multi = e.world > 1;
+    const bool multi = e.world > 1 || e.sparse;
     LnMdCfg c; ln_md_cfg(e, s, c);
     LnMdStepArgs p; p.g = ln_gather_args(e); p.fsum = multi ? e.vfr.p : nullptr; p.x = e.vx.p; p.v = e.vv.p; p.f = e.vf.p;
     p.es.epart = e.epart.p; p.es.ncta = e.ncta; p.es.escal = multi ? e.escal.p : nullptr; p.st = e.st.p; p.blockpart = e.blockpart.p; p.nblk = e.nblk; p.N = e.N;
     p.bd = ln_bonded_terms(e.prm, s); p.h = c.h; p.dt_akma = c.dt_akma; p.md = c;
     // evaluation at the starting point: explicit x, nothing pending
-    ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, false);
-    if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
+    if (e.sparse) { if (int rc = sp_eval(e, s, e.vx.p, nullptr, nullptr, true)) return rc; }
+    else {
+        ln_tiles(e, s, e.vx.p, nullptr, nullptr, nullptr, false);
+        if (multi) if (int rc = ln_exchange(e, s, e.vx.p, nullptr, nullptr)) return rc;
+    }
     p.a = e.vx.p; p.b = e.vx.p; p.lam = &e.st.p->zerof; p.a_next = e.va[0].p; p.b_next = e.vb[0].p; p.first = 1; p.want_e = 0;
     ln_launch_pdl(ln_md_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, p);
     e.n_launches++;
     int par = 0;
     for (int step = 0; step < s.nstep; step++) {
         const bool want_e = step == s.nstep - 1;                               // energies only matter after the last step
-        ln_tiles(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf, nullptr, want_e);
-        if (multi) if (int rc = ln_exchange(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf)) return rc;
+        if (e.sparse) { if (int rc = sp_eval(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf, false)) return rc; }
+        else {
+            ln_tiles(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf, nullptr, want_e);
+            if (multi) if (int rc = ln_exchange(e, s, e.va[par].p, e.vb[par].p, &e.st.p->lamf)) return rc;
+        }
         p.a = e.va[par].p; p.b = e.vb[par].p; p.lam = &e.st.p->lamf; p.a_next = e.va[par ^ 1].p; p.b_next = e.vb[par ^ 1].p; p.first = 0; p.want_e = want_e ? 1 : 0;
         ln_launch_pdl(ln_md_step_kernel, e.nblk, LN_STEP_THREADS, 0, e.stream, p);
         e.n_launches++;
@@ -1795,6 +1852,85 @@ int chr3d_single_run_model(chr3d_single* h, int model, const float* d_x0, void* 
     return 0;
 }
 
+// One structure from an explicit (sparse) restraint table: rows (ri < rj, 0-based, distance rd) as chr3d_if_to_restraints or a
+// contact.tbl give them.  Forces come from the sparse provider (CSR restraint rows + cell-list repel, ln_sparse.cuh): memory
+// traffic per evaluation is proportional to the number of rows, not to N^2.  One GPU.
+CHR3D_API int chr3d_single_create_sparse(int32_t N, const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr, const double* x0, uint64_t seed,
+                                         const chr3d_sa_params* p, const chr3d_stage* program, int32_t nstages, chr3d_single** out) {
+    if (N < 2 || nr < 0 || (nr > 0 && (!ri || !rj || !rd)) || !p || !program || nstages < 1 || !out) { set_error("chr3d_single_create_sparse: bad arguments"); return CHR3D_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    std::unique_ptr<chr3d_single> h(new chr3d_single());
+    LnEngine& e = h->e;
+    e.N = N; e.rank = 0; e.world = 1; e.prm = *p; e.seed = seed ? seed : p->seed; e.sparse = true;
+    e.m = std::max(1, std::min((int)p->lbfgs_m, CHR3D_LBFGS_MAX_M));
+    h->prog.assign(program, program + nstages);
+    if (int rc = ln_alloc_vectors(e)) return rc;
+    {   // symmetric CSR, columns ascending; rows are validated (0 <= i < j < N) and must not repeat
+        std::vector<long long> ptr((size_t)N + 1, 0);
+        for (int64_t k = 0; k < nr; k++) {
+            if (ri[k] < 0 || rj[k] <= ri[k] || rj[k] >= N || !(rd[k] > 0)) { set_error("chr3d_single_create_sparse: row %lld is not 0 <= i < j < N with d > 0", (long long)k); return CHR3D_ERR_ARG; }
+            ptr[ri[k] + 1]++; ptr[rj[k] + 1]++;
+        }
+        for (int i = 0; i < N; i++) ptr[i + 1] += ptr[i];
+        const size_t nnz = (size_t)ptr[N];
+        std::vector<std::pair<int, float>> ent(nnz);
+        std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
+        for (int64_t k = 0; k < nr; k++) { ent[fill[ri[k]]++] = std::make_pair((int)rj[k], (float)rd[k]); ent[fill[rj[k]]++] = std::make_pair((int)ri[k], (float)rd[k]); }
+        std::vector<int> col(std::max<size_t>(nnz, 1)); std::vector<float> dist(std::max<size_t>(nnz, 1));
+        for (int i = 0; i < N; i++) {
+            std::sort(ent.begin() + ptr[i], ent.begin() + ptr[i + 1]);
+            for (long long q = ptr[i]; q < ptr[i + 1]; q++) {
+                if (q > ptr[i] && ent[q].first == ent[q - 1].first) { set_error("chr3d_single_create_sparse: the pair (%d, %d) is listed twice", i, ent[q].first); return CHR3D_ERR_ARG; }
+                col[q] = ent[q].first; dist[q] = ent[q].second;
+            }
+        }
+        e.sp_nnz = (long long)nnz;
+        CHR3D_CUDA(e.sp_row_ptr.alloc(ptr.size())); CHR3D_CUDA(e.sp_col.alloc(col.size())); CHR3D_CUDA(e.sp_dist.alloc(dist.size()));
+        CHR3D_CUDA(cudaMemcpy(e.sp_row_ptr.p, ptr.data(), sizeof(long long) * ptr.size(), cudaMemcpyHostToDevice));
+        CHR3D_CUDA(cudaMemcpy(e.sp_col.p, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice));
+        CHR3D_CUDA(cudaMemcpy(e.sp_dist.p, dist.data(), sizeof(float) * dist.size(), cudaMemcpyHostToDevice));
+    }
+    {   // cell grid: edge = largest repel radius of the program + skin, 2N buckets (hashed: no bounding box)
+        double rmax = 0.0;
+        for (const chr3d_stage& s : h->prog) rmax = std::max(rmax, s.repel * p->vdw_rmin);
+        if (!(rmax > 0.0)) rmax = p->vdw_rmin;
+        e.sp_inv_cs = (float)(1.0 / (rmax + (double)SP_SKIN));
+        e.sp_hbits = 4; while ((1 << e.sp_hbits) < 2 * N && e.sp_hbits < 17) e.sp_hbits++;
+        const size_t H = (size_t)1 << e.sp_hbits;
+        e.sp_blocks = (N + SP_THREADS - 1) / SP_THREADS;
+        CHR3D_CUDA(e.sp_cell_start.alloc(H + 1)); CHR3D_CUDA(e.sp_cell_count.alloc(H)); CHR3D_CUDA(e.sp_cell_fill.alloc(H)); CHR3D_CUDA(e.sp_order.alloc(N));
+        CHR3D_CUDA(e.sp_rebuild.alloc(1)); CHR3D_CUDA(e.sp_nreb.alloc(1)); CHR3D_CUDA(e.sp_done.alloc(1));
+        CHR3D_CUDA(cudaMemset(e.sp_rebuild.p, 0, sizeof(int))); CHR3D_CUDA(cudaMemset(e.sp_nreb.p, 0, sizeof(long long))); CHR3D_CUDA(cudaMemset(e.sp_done.p, 0, sizeof(unsigned int)));
+        CHR3D_CUDA(cudaMemset(e.sp_cell_start.p, 0, sizeof(int) * (H + 1)));
+        CHR3D_CUDA(e.sp_xs.alloc(N)); CHR3D_CUDA(e.sp_xref.alloc(N)); CHR3D_CUDA(e.sp_fnoe.alloc(N)); CHR3D_CUDA(e.sp_erow.alloc(N)); CHR3D_CUDA(e.sp_epart.alloc((size_t)e.sp_blocks * 3));
+        CHR3D_CUDA(cudaMemset(e.sp_xref.p, 0, sizeof(float4) * N));
+    }
+    e.pairs_total = nr;
+    if (x0) {
+        std::vector<float> hx((size_t)N * 3);
+        for (size_t k = 0; k < hx.size(); k++) hx[k] = (float)x0[k];
+        CHR3D_CUDA(cudaMemcpy(e.x0.p, hx.data(), sizeof(float) * hx.size(), cudaMemcpyHostToDevice));
+    } else {
+        if (int rc = dev_random_coil(e.x0.p, N, 1, 0, p->bond_r0, e.seed, 0)) return rc;
+    }
+    CHR3D_CUDA(cudaEventCreate(&h->ev0)); CHR3D_CUDA(cudaEventCreate(&h->ev1));
+    CHR3D_CUDA(cudaDeviceSynchronize());
+    *out = h.release();
+    return 0;
+}
+// sparse provider: bin rebuilds so far, entries of the symmetric CSR, bytes the NOE term reads per evaluation
+CHR3D_API int chr3d_single_sparse_info(chr3d_single* h, int64_t* n_rebuilds, int64_t* csr_entries, int64_t* noe_bytes_per_eval) {
+    if (!h || !h->e.sparse) { set_error("chr3d_single_sparse_info: not a sparse structure"); return CHR3D_ERR_ARG; }
+    LnEngine& e = h->e;
+    CHR3D_CUDA(cudaStreamSynchronize(e.stream));
+    long long nb = 0;
+    CHR3D_CUDA(cudaMemcpy(&nb, e.sp_nreb.p, sizeof nb, cudaMemcpyDeviceToHost));
+    if (n_rebuilds) *n_rebuilds = nb;
+    if (csr_entries) *csr_entries = e.sp_nnz;
+    if (noe_bytes_per_eval) *noe_bytes_per_eval = e.sp_nnz * 8 + (long long)(e.N + 1) * 8;
+    return 0;
+}
+
 static bool ln_integrates(const std::vector<chr3d_stage>& prog) {
     for (const chr3d_stage& s : prog) if (s.op == CHR3D_OP_MINIMIZE || s.op == CHR3D_OP_DYNAMICS) return true;
     return false;
@@ -1811,7 +1947,7 @@ CHR3D_API int chr3d_single_run(chr3d_single* h, void* stream) {
     if (!connected && ln_integrates(h->prog)) {
         set_error("chr3d_single_run: a sharded structure without a communicator or a peer connection can only evaluate (INIT/ENERGY)"); return CHR3D_ERR_ARG;
     }
-    e.legacy = e.world > 1 && !e.p2p;
+    e.legacy = (e.world > 1 && !e.p2p) || e.sparse;
     if (dev_getenv("CHR3D_LN_LEGACY")) e.legacy = true;
     if (e.legacy && e.world > 1 && !connected) {     // partial sums of a shard on one GPU (tests of the partition)
         e.legacy = true;
@@ -1856,7 +1992,7 @@ CHR3D_API int chr3d_single_group_run(chr3d_single** hs, int32_t n, void* stream)
 CHR3D_API int chr3d_single_eval_bench(chr3d_single* h, void* stream, int32_t reps, int32_t want_energy, double* tile_ms, double* eval_ms) {
     if (!h || reps < 1) { set_error("chr3d_single_eval_bench: bad arguments"); return CHR3D_ERR_ARG; }
     LnEngine& e = h->e; e.stream = (cudaStream_t)stream;
-    if (e.group != &e.self) { set_error("chr3d_single_eval_bench: not available for virtual ranks"); return CHR3D_ERR_ARG; }
+    if (e.group != &e.self || e.sparse) { set_error("chr3d_single_eval_bench: not available for virtual ranks / sparse structures"); return CHR3D_ERR_ARG; }
     e.legacy = e.world > 1 && !e.p2p;
     if (dev_getenv("CHR3D_LN_LEGACY")) e.legacy = true;
     LnVec v = e.vec();

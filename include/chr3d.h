@@ -265,6 +265,15 @@ int chr3d_single_comm_error(chr3d_single* h, int32_t* err);
  * are plain device pointers.  The multi-rank protocol on a single GPU (used by the parity tests).               */
 int chr3d_single_group_connect(chr3d_single** hs, int32_t n);
 int chr3d_single_group_run(chr3d_single** hs, int32_t n, void* stream);
+/* Sparse restraint tables (real high-resolution Hi-C: most bin pairs have IF = 0 and no restraint, C3D:148-152, 196): one
+ * structure from explicit rows (0 <= ri < rj < N, rd > 0, no pair twice — the rows of contact.tbl / chr3d_if_to_restraints).  The
+ * NOE term walks a CSR of the rows (8 B per entry and evaluation instead of 4 B for every one of the N^2/2 pairs), the repel
+ * term uses a cell list that is rebuilt on the device when a bead has moved more than half the skin (CNS: nbonds cutnb /
+ * tolerance, C3D:1395-1404, 1729-1738); run / fetch / destroy are the chr3d_single_* calls.  One GPU.                      */
+int chr3d_single_create_sparse(int32_t N, const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr,
+                               const double* x0, uint64_t seed, const chr3d_sa_params* p, const chr3d_stage* program,
+                               int32_t nstages, chr3d_single** out);
+int chr3d_single_sparse_info(chr3d_single* h, int64_t* n_rebuilds, int64_t* csr_entries, int64_t* noe_bytes_per_eval);
 /* Synthetic IF matrix of SURVEY 8(d) (N*N doubles, generated on the device, copied back).     */
 int chr3d_synthetic_if(int32_t N, uint64_t seed, double* out);
 
