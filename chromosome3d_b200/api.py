@@ -89,6 +89,20 @@ def default_params():
     return p
 
 
+CNS_PIN = dict(angle_d2=6.0, angle_k=100.0, vdw_rmin=5.5)
+
+
+def cns_pin_params():
+    """default_params() plus the bead-model stand-ins for what CNS's full-atom poly-GLY chain adds (default off): a soft
+    CA(i)-CA(i+2) lower bound (the angle / improper terms keep a real chain from folding back on itself) and a larger repel
+    radius (backbone atoms around each CA).  Fitted on the 45 shipped CNS models with the fp64 oracle (scripts/fit_cns_pin.py,
+    profiles/r02_cns_pin.md): median IF-Spearman within 0.02 of the shipped model for 42 of 45 (35 without)."""
+    p = default_params()
+    for k, v in CNS_PIN.items():
+        setattr(p, k, v)
+    return p
+
+
 def build_program(p):
     """The dgsa.inp protocol body as a stage program (C3D:1573-1829)."""
     n = lib().chr3d_build_program(C.byref(p), None, 0)
@@ -385,6 +399,22 @@ def dg_embed(ri, rj, rd, N, n_models=1, seed=0, p=None):
     bad = C.c_int64(0)
     _check(lib().chr3d_dg_embed(_i(ri), _i(rj), _d(rd), C.c_int64(len(ri)), N, C.byref(p), n_models, C.c_uint64(seed), _d(xyz), _d(eig), C.byref(bad)))
     return xyz, eig, bad.value
+
+
+def dg_starts(ri, rj, rd, N, n_models=1, seed=0, p=None, dg_scale=100.0, nstep=200, drop=1.0):
+    """The whole DG stage (C3D:1470-1526): embedding, `x *= $dgscale`, then md.dg.step = 200 L-BFGS iterations (drop = 1.) on the
+    bounds-violation energy alone.  Returns (xyz (n_models, N, 3), eig3, stats rows {dgscale, e_scaled, e_final, iterations,
+    evaluations, rms_gradient}, inconsistent pairs); pass xyz as Job(x0=...)."""
+    ri, rj, rd = _list(ri, rj, rd)
+    p = p or default_params()
+    xyz = np.zeros((n_models, N, 3))
+    eig = np.zeros((n_models, 3))
+    st = np.zeros((n_models, 6))
+    bad = C.c_int64(0)
+    _check(lib().chr3d_dg_starts(_i(ri), _i(rj), _d(rd), C.c_int64(len(ri)), N, C.byref(p), n_models, C.c_uint64(seed), C.c_double(dg_scale), nstep,
+                                 C.c_double(drop), _d(xyz), _d(eig), _d(st), C.byref(bad)))
+    keys = ("dgscale", "e_scaled", "e_final", "iterations", "evaluations", "rms_gradient")
+    return xyz, eig, [dict(zip(keys, row)) for row in st.tolist()], bad.value
 
 
 def alpha_sweep(IF, alphas, n_models=20, K=11.0, seed=0, rng=3, p=None):

@@ -263,6 +263,156 @@ int dev_dg_embed(int N, const double* d_U, const double* d_L, unsigned long long
     return 0;
 }
 
+// ---- the rest of the DG stage (C3D:1516-1521): x *= dgscale, then `minimize lbfgs nstep=200 drop=1.` on the bounds-violation
+// energy alone (`flags exclude * include dg`, C3D:1495).  Same definitions and the same operation order as the oracle's
+// orc_dg_refine (bit-identical): E = scale * sum_{i<j} [max(0, d^2 - U^2)^2 + max(0, L^2 - d^2)^2], dgscale = least-squares
+// factor onto the bound midpoints, L-BFGS of the SA minimiser in fp64.  One CTA per model; a warp per row of the bounds
+// matrices (lanes stride the row, so U and L stream coalesced from L2), vectors in global scratch, the scalar logic of the
+// minimiser replicated in every thread from block-uniform inner products.
+struct DgRefineArgs {
+    int N, nstep, m, max_ls;
+    double scale, drop, c1, gtol, ftol;
+    const double* U; const double* L;
+    double* xyz; double* work; double* stats;
+};
+__device__ __forceinline__ double dg_fold32(double p) {      // lane 0 holds the oracle's p[0]
+    for (int o = 16; o > 0; o >>= 1) { const double q = __shfl_down_sync(0xffffffffu, p, o); p = p + q; }
+    return p;
+}
+__device__ __forceinline__ double dg_sum32(const double* a, int n, int lane) {
+    double p = 0.0;
+    for (int i = lane; i < n; i += 32) p = p + a[i];
+    return __shfl_sync(0xffffffffu, dg_fold32(p), 0);
+}
+// block-wide: inner product in the fixed warp order, the value returned to every thread
+__device__ double dg_block_dot(const double* a, const double* b, int n, double* slot) {
+    __syncthreads();
+    if (threadIdx.x < 32) { const double r = dg_dot32(a, 1, b, 1, n, threadIdx.x); if (threadIdx.x == 0) *slot = r; }
+    __syncthreads();
+    return *slot;
+}
+__device__ double dg_block_energy(int N, const double* __restrict__ U, const double* __restrict__ L, double scale, const double* x, double* g, double* er, double* slot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    __syncthreads();
+    for (int i = warp; i < N; i += nwarp) {
+        double pe = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+        const double xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+        for (int j = lane; j < N; j += 32) {
+            const double dx = xi - x[3 * j], dy = yi - x[3 * j + 1], dz = zi - x[3 * j + 2];
+            const double d2 = (dx * dx + dy * dy) + dz * dz;
+            const double u = U[(size_t)i * N + j], lo_b = L[(size_t)i * N + j];
+            double hi = d2 - u * u; if (!(hi > 0.0)) hi = 0.0;
+            double lo = lo_b * lo_b - d2; if (!(lo > 0.0)) lo = 0.0;
+            const double w = hi - lo;
+            pe = pe + (hi * hi + lo * lo);
+            px = px + w * dx; py = py + w * dy; pz = pz + w * dz;
+        }
+        pe = dg_fold32(pe); px = dg_fold32(px); py = dg_fold32(py); pz = dg_fold32(pz);
+        if (lane == 0) { er[i] = pe; g[3 * i] = (4.0 * scale) * px; g[3 * i + 1] = (4.0 * scale) * py; g[3 * i + 2] = (4.0 * scale) * pz; }
+    }
+    __syncthreads();
+    if (warp == 0) { const double r = dg_sum32(er, N, lane); if (lane == 0) *slot = (0.5 * scale) * r; }
+    __syncthreads();
+    return *slot;
+}
+__global__ void __launch_bounds__(DG_THREADS, 1) dg_refine_kernel(const DgRefineArgs a) {
+    const int N = a.N, n = 3 * N, m = a.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = DG_THREADS / 32;
+    double* x = a.xyz + (size_t)blockIdx.x * n;
+    double* w = a.work + (size_t)blockIdx.x * ((size_t)n * (4 + 2 * m) + 3 * (size_t)N);
+    double *g = w, *gt = g + n, *xt = gt + n, *d = xt + n, *S = d + n, *Y = S + (size_t)n * m, *er = Y + (size_t)n * m, *num = er + N, *den = num + N;
+    const double* __restrict__ U = a.U; const double* __restrict__ L = a.L;
+    __shared__ double slot[4];
+    double rho[CHR3D_LBFGS_MAX_M], al[CHR3D_LBFGS_MAX_M];
+    for (int i = warp; i < N; i += nwarp) {                 // dgscale: sum m_ij d_ij / sum d_ij^2 over the pairs with a finite upper bound
+        double pn = 0.0, pd = 0.0;
+        for (int j = lane; j < N; j += 32) {
+            const double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+            const double d2 = (dx * dx + dy * dy) + dz * dz;
+            const double mid = 0.5 * (U[(size_t)i * N + j] + L[(size_t)i * N + j]);
+            if (i != j && mid < 0.5 * DG_BIG) { pn = pn + mid * sqrt(d2); pd = pd + d2; }
+        }
+        pn = dg_fold32(pn); pd = dg_fold32(pd);
+        if (lane == 0) { num[i] = pn; den[i] = pd; }
+    }
+    __syncthreads();
+    if (warp == 0) { const double sn = dg_sum32(num, N, lane), sd = dg_sum32(den, N, lane); if (lane == 0) slot[0] = sd > 0.0 ? sn / sd : 1.0; }
+    __syncthreads();
+    const double dgscale = slot[0];
+    for (int i = tid; i < n; i += DG_THREADS) x[i] = x[i] * dgscale;
+    double e = dg_block_energy(N, U, L, a.scale, x, g, er, &slot[1]), et = e;
+    const double e_start = e;
+    int cnt = 0, head = 0, iters = 0, evals = 1;
+    for (int it = 0; it < a.nstep; it++) {
+        const double gg = dg_block_dot(g, g, n, &slot[2]);
+        if (sqrt(gg / n) < a.gtol) break;
+        double t0;
+        if (cnt == 0) {
+            for (int i = tid; i < n; i += DG_THREADS) d[i] = -g[i];
+            t0 = a.drop > 0 ? fmin(1.0, a.drop / gg) : fmin(1.0, 1.0 / sqrt(gg));
+        } else {
+            for (int i = tid; i < n; i += DG_THREADS) d[i] = g[i];
+            for (int k = 0; k < cnt; k++) {
+                const int idx = ((head - 1 - k) % m + m) % m;
+                al[idx] = rho[idx] * dg_block_dot(S + (size_t)idx * n, d, n, &slot[2]);
+                for (int i = tid; i < n; i += DG_THREADS) d[i] = d[i] - al[idx] * Y[(size_t)idx * n + i];
+            }
+            const int nw = ((head - 1) % m + m) % m;
+            const double sy0 = dg_block_dot(S + (size_t)nw * n, Y + (size_t)nw * n, n, &slot[2]);
+            const double yy0 = dg_block_dot(Y + (size_t)nw * n, Y + (size_t)nw * n, n, &slot[3]);
+            const double gam = sy0 / yy0;
+            for (int i = tid; i < n; i += DG_THREADS) d[i] = d[i] * gam;
+            for (int k = cnt - 1; k >= 0; k--) {
+                const int idx = ((head - 1 - k) % m + m) % m;
+                const double be = rho[idx] * dg_block_dot(Y + (size_t)idx * n, d, n, &slot[2]);
+                const double c = al[idx] - be;
+                for (int i = tid; i < n; i += DG_THREADS) d[i] = d[i] + S[(size_t)idx * n + i] * c;
+            }
+            for (int i = tid; i < n; i += DG_THREADS) d[i] = -d[i];
+            t0 = 1.0;
+        }
+        const double gd = dg_block_dot(g, d, n, &slot[3]);
+        if (!(gd < 0)) { if (cnt == 0) break; cnt = 0; it--; continue; }
+        double tt = t0; int ok = 0; const int cnt_before = cnt;
+        for (int ls = 0; ls <= a.max_ls; ls++) {
+            for (int i = tid; i < n; i += DG_THREADS) xt[i] = x[i] + tt * d[i];
+            et = dg_block_energy(N, U, L, a.scale, xt, gt, er, &slot[1]); evals++;
+            if (et < e && et <= e + a.c1 * tt * gd) { ok = 1; break; }
+            tt = tt * 0.5;
+        }
+        iters++;
+        if (!ok) { if (cnt == 0) break; cnt = 0; continue; }
+        double* sk = S + (size_t)head * n; double* yk = Y + (size_t)head * n;
+        for (int i = tid; i < n; i += DG_THREADS) { sk[i] = tt * d[i]; yk[i] = gt[i] - g[i]; }
+        const double sy = dg_block_dot(sk, yk, n, &slot[2]), ss = dg_block_dot(sk, sk, n, &slot[3]), yy = dg_block_dot(yk, yk, n, &slot[2]);
+        if (sy > 1e-10 * sqrt(ss * yy)) { rho[head] = 1.0 / sy; head = (head + 1) % m; if (cnt < m) cnt++; }
+        const int small = cnt_before > 0 && (e - et) <= a.ftol * fmax(fabs(et), 1.0);
+        __syncthreads();
+        for (int i = tid; i < n; i += DG_THREADS) { x[i] = xt[i]; g[i] = gt[i]; }
+        e = et;
+        if (small) break;
+    }
+    const double g2 = dg_block_dot(g, g, n, &slot[3]);
+    if (tid == 0 && a.stats) {
+        double* st = a.stats + 6 * (size_t)blockIdx.x;
+        st[0] = dgscale; st[1] = e_start; st[2] = e; st[3] = iters; st[4] = evals; st[5] = sqrt(g2 / n);
+    }
+}
+// scale + minimise n_models embedded structures in place (d_xyz: n_models x N x 3); d_stats: 6 per model
+int dev_dg_refine(int N, const double* d_U, const double* d_L, const chr3d_sa_params& p, double scale, int nstep, double drop, int n_models,
+                  double* d_xyz, double* d_stats, cudaStream_t s) {
+    if (p.lbfgs_m < 1 || p.lbfgs_m > CHR3D_LBFGS_MAX_M) { set_error("dg refine: lbfgs_m out of range"); return CHR3D_ERR_ARG; }
+    DevBuf<double> work;
+    const size_t per = (size_t)3 * N * (4 + 2 * p.lbfgs_m) + 3 * (size_t)N;
+    CHR3D_CUDA(work.alloc(per * n_models));
+    DgRefineArgs a;
+    a.N = N; a.nstep = nstep; a.m = p.lbfgs_m; a.max_ls = p.lbfgs_max_ls; a.scale = scale; a.drop = drop; a.c1 = p.lbfgs_c1; a.gtol = p.lbfgs_gtol; a.ftol = p.lbfgs_ftol;
+    a.U = d_U; a.L = d_L; a.xyz = d_xyz; a.work = work.p; a.stats = d_stats;
+    dg_refine_kernel<<<n_models, DG_THREADS, 0, s>>>(a);
+    CHR3D_CUDA(cudaGetLastError());
+    CHR3D_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 }  // namespace chr3d
 
 using namespace chr3d;
@@ -270,9 +420,10 @@ using namespace chr3d;
 // Starting coordinates by distance-geometry embedding for n_models models of one restraint table (0-based ri < rj).
 // xyz_out: n_models*N*3; eig3_out (optional): the three eigenvalues used, per model; n_inconsistent (optional): pairs whose
 // bounds the triangle inequality contradicted.  Pass the result as chr3d_job.x0 to anneal from it instead of a random coil.
-CHR3D_API int chr3d_dg_embed(const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr, int32_t N, const chr3d_sa_params* p,
-                             int32_t n_models, uint64_t seed, double* xyz_out, double* eig3_out, int64_t* n_inconsistent) {
-    if (N < 2 || n_models < 1 || !p || !xyz_out || nr < 0 || (nr > 0 && (!ri || !rj || !rd))) { set_error("chr3d_dg_embed: bad arguments"); return CHR3D_ERR_ARG; }
+static int dg_stage(const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr, int32_t N, const chr3d_sa_params* p,
+                    int32_t n_models, uint64_t seed, double* xyz_out, double* eig3_out, int64_t* n_inconsistent,
+                    bool refine, double dg_scale, int nstep, double drop, double* stats_out) {
+    if (N < 2 || n_models < 1 || !p || !xyz_out || nr < 0 || (nr > 0 && (!ri || !rj || !rd))) { set_error("chr3d_dg_embed / chr3d_dg_starts: bad arguments"); return CHR3D_ERR_ARG; }
     if (int rc = require_device()) return rc;
     for (int64_t k = 0; k < nr; k++) if (ri[k] < 0 || rj[k] < 0 || ri[k] >= N || rj[k] >= N || ri[k] == rj[k]) { set_error("chr3d_dg_embed: restraint %lld out of range", (long long)k); return CHR3D_ERR_ARG; }
     DevBuf<int32_t> di, dj; DevBuf<double> dd, U, L, x, e3;
@@ -290,12 +441,30 @@ CHR3D_API int chr3d_dg_embed(const int32_t* ri, const int32_t* rj, const double*
     // same distance matrix, so one embedding serves all of them (bit-identical to embedding each)
     const int n_embed = slack == 0 ? 1 : n_models;
     if (int rc = dev_dg_embed(N, U.p, L.p, seed ? seed : p->seed, 0, n_embed, x.p, e3.p, 0)) return rc;
+    DevBuf<double> st;
+    CHR3D_CUDA(st.alloc((size_t)n_models * 6));
+    if (refine) { if (int rc = dev_dg_refine(N, U.p, L.p, *p, dg_scale, nstep, drop, n_embed, x.p, st.p, 0)) return rc; }
     for (int m = n_embed; m < n_models; m++) {
         CHR3D_CUDA(cudaMemcpy(x.p + (size_t)m * N * 3, x.p, sizeof(double) * (size_t)N * 3, cudaMemcpyDeviceToDevice));
         CHR3D_CUDA(cudaMemcpy(e3.p + (size_t)m * 3, e3.p, sizeof(double) * 3, cudaMemcpyDeviceToDevice));
+        if (refine) CHR3D_CUDA(cudaMemcpy(st.p + (size_t)m * 6, st.p, sizeof(double) * 6, cudaMemcpyDeviceToDevice));
     }
     CHR3D_CUDA(cudaMemcpy(xyz_out, x.p, sizeof(double) * (size_t)n_models * N * 3, cudaMemcpyDeviceToHost));
     if (eig3_out) CHR3D_CUDA(cudaMemcpy(eig3_out, e3.p, sizeof(double) * (size_t)n_models * 3, cudaMemcpyDeviceToHost));
+    if (refine && stats_out) CHR3D_CUDA(cudaMemcpy(stats_out, st.p, sizeof(double) * (size_t)n_models * 6, cudaMemcpyDeviceToHost));
     if (n_inconsistent) *n_inconsistent = bad;
     return 0;
+}
+CHR3D_API int chr3d_dg_embed(const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr, int32_t N, const chr3d_sa_params* p,
+                             int32_t n_models, uint64_t seed, double* xyz_out, double* eig3_out, int64_t* n_inconsistent) {
+    return dg_stage(ri, rj, rd, nr, N, p, n_models, seed, xyz_out, eig3_out, n_inconsistent, false, 0.0, 0, 0.0, nullptr);
+}
+// The whole DG stage (C3D:1470-1526): bounds, embedding, x *= dgscale, nstep (md.dg.step = 200) L-BFGS iterations with drop (1.)
+// on the bounds-violation energy scaled by dg_scale (md.dg.scale = 100).  stats_out (optional): 6 doubles per model
+// {dgscale, E after scaling, E final, iterations, energy evaluations, rms gradient}.
+CHR3D_API int chr3d_dg_starts(const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr, int32_t N, const chr3d_sa_params* p,
+                              int32_t n_models, uint64_t seed, double dg_scale, int32_t nstep, double drop,
+                              double* xyz_out, double* eig3_out, double* stats_out, int64_t* n_inconsistent) {
+    if (!(dg_scale > 0) || nstep < 0) { set_error("chr3d_dg_starts: dg_scale must be positive and nstep >= 0"); return CHR3D_ERR_ARG; }
+    return dg_stage(ri, rj, rd, nr, N, p, n_models, seed, xyz_out, eig3_out, n_inconsistent, true, dg_scale, nstep, drop, stats_out);
 }

@@ -320,6 +320,16 @@ int chr3d_if_from_coo(const int32_t* bi, const int32_t* bj, const double* v, int
 int chr3d_dg_embed(const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr, int32_t N, const chr3d_sa_params* p,
                    int32_t n_models, uint64_t seed, double* xyz_out, double* eig3_out, int64_t* n_inconsistent);
 
+/* The whole DG stage of dgsa.inp (C3D:1470-1526): the embedding above, then `do (x = x * $dgscale)` (C3D:1516-1518) and
+ * `minimize lbfgs nstep=&md.dg.step drop=1.` (C3D:1519-1521; md.dg.step = 200, C3D:1090) on the bounds-violation energy alone
+ * (`flags exclude * include dg`, C3D:1495) with weight dg_scale (md.dg.scale = 100, exponent 2, C3D:1078-1080).  The template
+ * fit that follows in the script (C3D:1604-1621) is the identity for one-atom residues; the enantiomer loop is
+ * the INIT(+1/-1) ... SAVE / PICK pair of the stage program.  stats_out (optional): 6 doubles per model {dgscale, E after
+ * scaling, E final, iterations, energy evaluations, rms gradient}. */
+int chr3d_dg_starts(const int32_t* ri, const int32_t* rj, const double* rd, int64_t nr, int32_t N, const chr3d_sa_params* p,
+                    int32_t n_models, uint64_t seed, double dg_scale, int32_t nstep, double drop,
+                    double* xyz_out, double* eig3_out, double* stats_out, int64_t* n_inconsistent);
+
 #ifdef __cplusplus
 }
 #endif

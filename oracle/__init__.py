@@ -246,3 +246,14 @@ def dg_embed(N, ri, rj, rd, p, seed, n_models):
     for m in range(n_models):
         lib().orc_dg_embed_model(N, _d(U), _d(L), C.c_uint64(seed), m, _d(xyz[m]), _d(eig[m]))
     return xyz, eig, bad
+
+
+def dg_starts(N, ri, rj, rd, p, seed, n_models, dg_scale=100.0, nstep=200, drop=1.0):
+    """orc_dg_embed_model + orc_dg_refine: the whole DG stage (C3D:1470-1526) per model."""
+    U, L, bad = dg_bounds(N, ri, rj, rd, p)
+    xyz, eig, st = np.zeros((n_models, N, 3)), np.zeros((n_models, 3)), np.zeros((n_models, 6))
+    for m in range(n_models):
+        lib().orc_dg_embed_model(N, _d(U), _d(L), C.c_uint64(seed), m, _d(xyz[m]), _d(eig[m]))
+        lib().orc_dg_refine(N, _d(U), _d(L), C.byref(p), C.c_double(dg_scale), nstep, C.c_double(drop), _d(xyz[m]), _d(st[m]))
+    keys = ("dgscale", "e_scaled", "e_final", "iterations", "evaluations", "rms_gradient")
+    return xyz, eig, [dict(zip(keys, row)) for row in st.tolist()], bad

@@ -187,6 +187,52 @@ def test_gpu_dg_embed_bit_identical_to_oracle(gpu_api):
         assert bad == obad and np.array_equal(eig, oeig) and np.array_equal(xyz, oxyz), name
 
 
+def test_oracle_dg_refine_lowers_the_bounds_energy():
+    """C3D:1516-1521 restated: x *= dgscale, then the 200-step L-BFGS on the bounds-violation energy alone.  A consistent set of
+    bounds is minimised to (numerically) zero; on Hi-C bounds the energy drops and the restrained distances move closer."""
+    X, ri, rj, rd = _exact_case()
+    p = orc.default_params()
+    xyz, eig, st, bad = orc.dg_starts(len(X), ri, rj, rd, p, 7, 1)
+    assert bad == 0 and abs(st[0]["dgscale"] - 1.0) < 1e-6 and st[0]["e_final"] <= st[0]["e_scaled"] and st[0]["e_final"] < 1e-12
+    IF = ds.load_if_matrix(ds.input_path("chr22_1mb"))
+    N = IF.shape[0]
+    ri, rj, rd = orc.if_to_restraints(IF, 0.5)
+    x0, _, _ = orc.dg_embed(N, ri, rj, rd, p, 82364, 1)
+    xyz, eig, st, bad = orc.dg_starts(N, ri, rj, rd, p, 82364, 1)
+    assert 1.0 < st[0]["dgscale"] < 1.5                          # the projection onto three dimensions shrinks the structure
+    assert st[0]["e_final"] < 0.8 * st[0]["e_scaled"] and 1 <= st[0]["iterations"] <= 200 and st[0]["evaluations"] > st[0]["iterations"]
+    dev = lambda x: np.sqrt(np.mean((np.linalg.norm(x[ri] - x[rj], axis=1) ** 2 - rd ** 2) ** 2))
+    assert dev(xyz[0]) < dev(x0[0])
+    z, _, st0, _ = orc.dg_starts(N, ri, rj, rd, p, 82364, 1, nstep=0)
+    assert np.array_equal(z[0], x0[0] * st0[0]["dgscale"]) and st0[0]["iterations"] == 0 and st0[0]["e_scaled"] == st[0]["e_scaled"]
+
+
+@pytest.mark.gpu
+def test_gpu_dg_starts_bit_identical_to_oracle(gpu_api):
+    """chr3d_dg_starts (embedding + dgscale + 200 L-BFGS iterations on the bounds energy, one CTA per model, fp64, fixed
+    summation order) against orc_dg_refine: coordinates and statistics bit for bit."""
+    p = orc.default_params()
+    X, ri, rj, rd = _exact_case()
+    xyz, eig, st, bad = gpu_api.dg_starts(ri, rj, rd, len(X), n_models=2, seed=7)
+    oxyz, oeig, ost, obad = orc.dg_starts(len(X), ri, rj, rd, p, 7, 2)
+    assert bad == obad == 0 and np.array_equal(xyz, oxyz) and st == ost
+    for name, alpha, nstep in (("chr21_500kb", 1.1, 200), ("chr22_1mb", 0.5, 200), ("chr1_1mb", 1.1, 25)):
+        IF = ds.load_if_matrix(ds.input_path(name))
+        ri, rj, rd = orc.if_to_restraints(IF, alpha)
+        xyz, eig, st, bad = gpu_api.dg_starts(ri, rj, rd, IF.shape[0], n_models=2, seed=82364, nstep=nstep)
+        oxyz, oeig, ost, obad = orc.dg_starts(IF.shape[0], ri, rj, rd, p, 82364, 2, nstep=nstep)
+        assert bad == obad and np.array_equal(eig, oeig) and st == ost and np.array_equal(xyz, oxyz), (name, st, ost)
+        assert st[0]["e_final"] < st[0]["e_scaled"]
+    # a sparse table leaves slack between the bounds: the models differ, each one is refined on its own
+    N = 60
+    Xs = orc.random_coil(N, 3.0, 5, 0)
+    k = np.array([(i, j) for i in range(N) for j in range(i + 2, N) if (i * 7 + j * 3) % 5 == 0], dtype=np.int32)
+    dd = np.linalg.norm(Xs[k[:, 0]] - Xs[k[:, 1]], axis=1)
+    xyz, eig, st, bad = gpu_api.dg_starts(k[:, 0], k[:, 1], dd, N, n_models=3, seed=11)
+    oxyz, oeig, ost, obad = orc.dg_starts(N, k[:, 0], k[:, 1], dd, p, 11, 3)
+    assert np.array_equal(xyz, oxyz) and st == ost and not np.array_equal(xyz[0], xyz[1])
+
+
 @pytest.mark.gpu
 def test_gpu_annealing_from_dg_start(gpu_api):
     """The embedded coordinates feed the annealer through Job.x0; the ensemble ends at least as well (IF-Spearman) as from coils."""
