@@ -338,7 +338,21 @@ CHR3D_API int chr3d_write_tbl(const char* path, const int32_t* ri, const int32_t
 }
 
 // ------------------------------ ensemble --------------------------------------------------------
-static int upload_list(JobDev& jd, const int32_t* ri, const int32_t* rj, const double* rd, long long nr, cudaStream_t s) {
+// Rows index beads on the device (coordinates, the dense target table): every row is checked on the host.  `unique`: the
+// dense-table paths also refuse a pair that is listed twice (the scatter would keep whichever row landed last).
+static int upload_list(JobDev& jd, const int32_t* ri, const int32_t* rj, const double* rd, long long nr, cudaStream_t s, int N, bool unique, const char* who) {
+    for (long long k = 0; k < nr; k++)
+        if (ri[k] < 0 || rj[k] < 0 || ri[k] >= N || rj[k] >= N || ri[k] == rj[k] || !(rd[k] > 0.0)) {
+            set_error("%s: restraint row %lld (%d, %d, %g) is not a pair of distinct beads 0 .. %d with a positive distance", who, k, ri[k], rj[k], rd[k], N - 1);
+            return CHR3D_ERR_ARG;
+        }
+    if (unique && nr > 1) {
+        std::vector<unsigned long long> key((size_t)nr);
+        for (long long k = 0; k < nr; k++) { const unsigned a = (unsigned)std::min(ri[k], rj[k]), b = (unsigned)std::max(ri[k], rj[k]); key[(size_t)k] = ((unsigned long long)a << 32) | b; }
+        std::sort(key.begin(), key.end());
+        for (size_t k = 1; k < key.size(); k++)
+            if (key[k] == key[k - 1]) { set_error("%s: the pair (%u, %u) is listed more than once", who, (unsigned)(key[k] >> 32), (unsigned)key[k]); return CHR3D_ERR_ARG; }
+    }
     jd.nr = nr;
     CHR3D_CUDA(jd.ri.alloc((size_t)std::max<long long>(nr, 1))); CHR3D_CUDA(jd.rj.alloc((size_t)std::max<long long>(nr, 1)));
     CHR3D_CUDA(jd.rd.alloc((size_t)std::max<long long>(nr, 1)));
@@ -397,7 +411,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             if (int rc = dev_tenths_to_list(dT.p, N, jb.min_sep, jd->ri.p, jd->rj.p, jd->rd.p, std::max<long long>(n, 1), &n, 0)) return rc;
         } else {
             if (jb.nr > 0 && (!jb.ri || !jb.rj || !jb.rd)) { set_error("job %d: restraint table pointers missing", jn); return CHR3D_ERR_ARG; }
-            if (int rc = upload_list(*jd, jb.ri, jb.rj, jb.rd, jb.nr, 0)) return rc;
+            if (int rc = upload_list(*jd, jb.ri, jb.rj, jb.rd, jb.nr, 0, N, true, "chr3d_build_models")) return rc;
             if (int rc = dev_list_to_targets(jd->ri.p, jd->rj.p, jd->rd.p, jb.nr, N, p->vdw_min_sep, jd->T.p, 0)) return rc;
         }
         CHR3D_CUDA(jd->Tt.alloc(sa_tiles_floats(N)));
@@ -633,7 +647,7 @@ CHR3D_API int chr3d_assess(const double* xyz, int32_t n_models, int32_t N, const
     if (!xyz || n_models < 1 || N < 1 || !satisfied || !sum_dev || (nr > 0 && (!ri || !rj || !rd))) { set_error("chr3d_assess: bad arguments"); return CHR3D_ERR_ARG; }
     if (int rc = require_device()) return rc;
     JobDev jd;
-    if (int rc = upload_list(jd, ri, rj, rd, nr, 0)) return rc;
+    if (int rc = upload_list(jd, ri, rj, rd, nr, 0, N, false, "chr3d_assess")) return rc;
     const size_t nx = (size_t)n_models * N * 3;
     CHR3D_CUDA(jd.xyz_d.alloc(nx)); CHR3D_CUDA(jd.sat.alloc(n_models)); CHR3D_CUDA(jd.dev.alloc(n_models));
     CHR3D_CUDA(cudaMemcpy(jd.xyz_d.p, xyz, sizeof(double) * nx, cudaMemcpyHostToDevice));
@@ -647,7 +661,7 @@ CHR3D_API int chr3d_assess_rows(const double* xyz, int32_t N, const int32_t* ri,
     if (!xyz || N < 1 || nr < 0 || (nr > 0 && (!ri || !rj || !rd || !flag || !dev || !dist))) { set_error("chr3d_assess_rows: bad arguments"); return CHR3D_ERR_ARG; }
     if (int rc = require_device()) return rc;
     JobDev jd;
-    if (int rc = upload_list(jd, ri, rj, rd, nr, 0)) return rc;
+    if (int rc = upload_list(jd, ri, rj, rd, nr, 0, N, false, "chr3d_assess_rows")) return rc;
     DevBuf<int32_t> df; DevBuf<double> dd, ds;
     const size_t n1 = (size_t)std::max<long long>(nr, 1);
     CHR3D_CUDA(jd.xyz_d.alloc((size_t)N * 3)); CHR3D_CUDA(df.alloc(n1)); CHR3D_CUDA(dd.alloc(n1)); CHR3D_CUDA(ds.alloc(n1));

@@ -93,20 +93,24 @@ __global__ void coil_steps_kernel(double* __restrict__ d, int N, int n_models, i
     }
     for (int q = 0; q < 3; q++) d[3 * k + q] = z[q];
 }
+// prefix sums of the steps and the centring: sequential fp64 sums in index order (the oracle's random_coil), one thread per
+// (model, component) — the three components are independent chains
 __global__ void coil_kernel(float* x0, const double* __restrict__ d, int N, int n_models) {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = t / 3, k = t - 3 * m;
     if (m >= n_models) return;
     float* x = x0 + (size_t)m * N * 3;
     const double* dm = d + (size_t)m * N * 3;
-    double p[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+    double p = 0, c = 0;
     for (int i = 0; i < N; i++) {
-        if (i > 0) for (int k = 0; k < 3; k++) p[k] += dm[3 * i + k];
-        for (int k = 0; k < 3; k++) c[k] += p[k];
+        if (i > 0) p += dm[3 * i + k];
+        c += p;
     }
-    p[0] = p[1] = p[2] = 0;
+    p = 0;
+    const double mean = c / N;
     for (int i = 0; i < N; i++) {
-        if (i > 0) for (int k = 0; k < 3; k++) p[k] += dm[3 * i + k];
-        for (int k = 0; k < 3; k++) x[3 * i + k] = (float)(p[k] - c[k] / N);
+        if (i > 0) p += dm[3 * i + k];
+        x[3 * i + k] = (float)(p - mean);
     }
 }
 int dev_random_coil(float* d_x0, int N, int n_models, int first_model, double step, unsigned long long seed,
@@ -115,7 +119,7 @@ int dev_random_coil(float* d_x0, int N, int n_models, int first_model, double st
     CHR3D_CUDA(d.alloc((size_t)N * n_models * 3));
     const long long n = (long long)N * n_models;
     coil_steps_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d.p, N, n_models, first_model, step, seed);
-    coil_kernel<<<(n_models + 31) / 32, 32, 0, s>>>(d_x0, d.p, N, n_models);
+    coil_kernel<<<(3 * n_models + 31) / 32, 32, 0, s>>>(d_x0, d.p, N, n_models);
     CHR3D_CUDA(cudaGetLastError());
     if (s != (cudaStream_t)0) CHR3D_CUDA(cudaStreamSynchronize(s));     // the scratch buffer is released on the default stream
     return 0;

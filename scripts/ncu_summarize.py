@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
-"""Turns the ncu artefacts of scripts/ncu_round.sh (gpurun_out/<tag>_*) into the tracked summaries under profiles/.
+"""Turns the ncu artefacts of scripts/r2_final.sh (gpurun_out/<tag>_*) into the tracked summaries under profiles/.
 usage: ncu_summarize.py <tag>"""
 import collections, csv, io, json, os, subprocess, sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02e"
 G, P = "gpurun_out", "profiles"
 os.makedirs(P, exist_ok=True)
 WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__cluster_size", "launch__registers_per_thread",
@@ -76,7 +76,7 @@ def launches():
         a[0] += 1; a[1] += ms
     tot = sum(a[1] for a in agg.values())
     out = ["# %s — kernel launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` under ncu" % tag,
-           "", "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv` (times are cold-cache and serialised; the SHARE is what matters).",
+           "", "`ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv` (times are cold-cache and serialised; the SHARE is what matters).",
            "", "| kernel | launches | total ms | share |", "|---|---|---|---|"]
     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append("| %s | %d | %.3f | %.1f %% |" % (k, n, ms, 100.0 * ms / max(tot, 1e-12)))
@@ -90,8 +90,14 @@ sa = kernel_summary(os.path.join(G, "%s_sa_kernel.ncu-rep" % tag), "sa_kernel",
                     "Command: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-large-n` (full dgsa.inp schedule, chr1_500kb alpha=1.1, 20 models); 4th sa_kernel launch captured.")
 ln = kernel_summary(os.path.join(G, "%s_ln_tile_kernel.ncu-rep" % tag), "ln_tile_kernel",
                     "Command: `python scripts/large_n_probe.py 24925` (synthetic 10 kb matrix, N=24,925, 19,110 tiles = 1.25 GB of targets); 4th ln_tile_kernel launch captured.")
-json.dump({"dram_bytes_per_launch": sa["dram_bytes_per_launch"], "ln_tile_dram_bytes_per_launch": ln["dram_bytes_per_launch"], "tag": tag},
-          open(os.path.join(P, "sa_kernel_ncu_summary.json"), "w"), indent=1)
+summary = {"dram_bytes_per_launch": sa["dram_bytes_per_launch"], "ln_tile_dram_bytes_per_launch": ln["dram_bytes_per_launch"], "tag": tag}
+if os.path.exists(os.path.join(G, "%s_ln_persist_kernel.ncu-rep" % tag)):
+    pk = kernel_summary(os.path.join(G, "%s_ln_persist_kernel.ncu-rep" % tag), "ln_persist_kernel",
+                        "Command: `python scripts/persist_probe.py` (N=24,925, one DYNAMICS op of 16 steps = ONE cooperative launch of 17 force evaluations: tile phase, grid barrier / ready counters, gather + Verlet step, per evaluation); 2nd launch captured.")
+    summary["ln_persist_dram_bytes_per_launch"] = pk["dram_bytes_per_launch"]
+    summary["ln_persist_evaluations_per_launch"] = 17
+    print(open(os.path.join(P, "%s_ln_persist_kernel_ncu.md" % tag)).read())
+json.dump(summary, open(os.path.join(P, "sa_kernel_ncu_summary.json"), "w"), indent=1)
 print(open(os.path.join(P, "%s_launches_bench.md" % tag)).read())
 print(open(os.path.join(P, "%s_sa_kernel_ncu.md" % tag)).read())
 print(open(os.path.join(P, "%s_ln_tile_kernel_ncu.md" % tag)).read())

@@ -170,6 +170,21 @@ def test_lbfgs_reaches_the_fp64_minimum(gpu_api, mats, name):
     assert np.abs(r.xyz[0].mean(0)).max() < 1e-3
 
 
+@pytest.mark.parametrize("name", ["chr21_1mb", "chr1_1mb"])
+def test_lbfgs_iterations_track_fp64(gpu_api, mats, name):
+    """The minimiser itself follows the oracle iteration by iteration (same trial counts, energies to 2e-5, coordinates to 2e-3 A
+    over 20 iterations) as soon as the first step is one fp32 coordinates can resolve.  With CNS's drop = 10 on energies of
+    1e6-1e7 the first step is drop / |g|^2 ~ 1e-5 A = two ulps of a coordinate, the curvature pair of that step is rounding
+    noise in any fp32 engine (profiles/r02_lbfgs_tracking.log), and only the converged state is comparable (test above)."""
+    for drop, e_tol, x_tol in ((1.0e4, 2e-5, 2e-3), (1.0e6, 2e-6, 2e-4)):
+        for k in (5, 20):
+            prog = [abi.stage(abi.OP_INIT, flag=1), abi.stage(abi.OP_MINIMIZE, nstep=k, drop=drop), abi.stage(abi.OP_ENERGY)]
+            r, o = _run_both(gpu_api, mats[name], 0.5, prog)
+            assert r.force_evals[0] == o["force_evals"]
+            assert abs(r.energies[0, 0] - o["energies"][0]) <= e_tol * o["energies"][0], (drop, k)
+            assert np.abs(r.xyz[0] - o["xyz"]).max() < x_tol, (drop, k)
+
+
 def test_mirror_image_pick(gpu_api, mats):
     """INIT(+1)...SAVE, INIT(-1)...PICK keeps the lower-energy image (C3D:1711-1727)."""
     w = dict(w_noe=10.0, w_bond=1000.0, w_vdw=0.003, repel=0.9)
@@ -382,3 +397,22 @@ def test_sa_against_all_shipped_cns_models(gpu_api, pin):
     print("pin=%s within 0.02: %d, within 0.05: %d, mean %+.4f, max %.3f" % (pin, (abs(d_rho) <= 0.02).sum(), (abs(d_rho) <= 0.05).sum(), d_rho.mean(), abs(d_rho).max()))
     assert abs(d_rho.mean()) < 0.03 and (abs(d_rho) <= 0.02).sum() >= (39 if pin else 30) and (abs(d_rho) <= 0.055).sum() >= 42 and abs(d_rho).max() < 0.08
     assert abs(d_rg.mean()) < 0.08 and abs(d_rg).max() < 0.25
+
+
+def test_restraint_rows_are_validated(gpu_api):
+    """Caller-supplied rows index device arrays: out-of-range beads, i == j, non-positive distances are refused everywhere; the
+    dense-table paths (annealing, energy / forces) also refuse a pair listed twice."""
+    from chromosome3d_b200.api import Chr3dError
+    x = orc.random_coil(30, 3.8, 1, 0)
+    ok = (np.array([0, 3], dtype=np.int32), np.array([5, 9], dtype=np.int32), np.array([4.0, 6.0]))
+    gpu_api.count_satisfied_and_sum_dev(x[None], *ok)
+    for bad in ((np.array([0, 3]), np.array([5, 30]), np.array([4.0, 6.0])), (np.array([-1]), np.array([5]), np.array([4.0])),
+                (np.array([4]), np.array([4]), np.array([4.0])), (np.array([1]), np.array([5]), np.array([0.0]))):
+        with pytest.raises(Chr3dError):
+            gpu_api.count_satisfied_and_sum_dev(x[None], *bad)
+        with pytest.raises(Chr3dError):
+            gpu_api.build_models([gpu_api.Job(restraints=bad, N=30, n_models=1)])
+    dup = (np.array([0, 5, 2]), np.array([5, 0, 9]), np.array([4.0, 4.5, 6.0]))
+    gpu_api.count_satisfied_and_sum_dev(x[None], *dup)                              # row-wise scoring counts every row, like assess_dgsa (C3D:769-880)
+    with pytest.raises(Chr3dError):
+        gpu_api.build_models([gpu_api.Job(restraints=dup, N=30, n_models=1)])
