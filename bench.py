@@ -478,7 +478,8 @@ def main():
                        "parallelism": "ensemble shards, no collectives"},
             "sa_models_per_sec": models_all / (kernel_ms_max * 1e-3),
             "e2e": {"value": e2e_pe_all / (e2e_ms_max * 1e-3), "unit": "pair-evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms_max, "sa_models_per_sec": models_all / (e2e_ms_max * 1e-3)},
+                    "ms_per_step": e2e_ms_max, "sa_models_per_sec": models_all / (e2e_ms_max * 1e-3),
+                    "ms_samples_rank0": [round(v, 3) for v in e2e_ms]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
                          "traffic": (prof.get("dram_bytes_per_launch") or 0) * max(int(info["launches"]), 1) or None,

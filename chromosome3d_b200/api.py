@@ -89,6 +89,11 @@ def default_params():
     return p
 
 
+def set_option(name, value=None):
+    """chr3d_set_option: launch-shape options of the ensemble kernel ("sa_cluster", "sa_warps", "sa_min_smem", "sa_split"); None clears."""
+    _check(lib().chr3d_set_option(name.encode(), None if value is None else str(value).encode()))
+
+
 CNS_PIN = dict(angle_d2=6.0, angle_k=100.0, vdw_rmin=5.5)
 
 

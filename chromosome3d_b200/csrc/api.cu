@@ -8,9 +8,20 @@
 #include <map>
 #include <memory>
 #include <vector>
+#include <mutex>
 #include "common.h"
 
 namespace chr3d {
+
+// ---- options (chr3d_set_option): a small process-wide table, consulted by dev_getenv before the environment ----------------
+static std::mutex g_opt_mu;
+static std::map<std::string, std::string>& opt_table() { static std::map<std::string, std::string> t; return t; }
+const char* option_lookup(const char* name) {
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    auto& t = opt_table();
+    auto it = t.find(name);
+    return it == t.end() ? nullptr : it->second.c_str();
+}
 
 static thread_local std::string g_err;
 void set_error(const char* fmt, ...) {
@@ -721,4 +732,30 @@ CHR3D_API int chr3d_spearman(const double* IF, int32_t L, const double* xyz, int
     CHR3D_CUDA(cudaMemcpy(dIF.p, IF, sizeof(double) * (size_t)L * L, cudaMemcpyHostToDevice));
     CHR3D_CUDA(cudaMemcpy(dx.p, xyz, sizeof(double) * (size_t)n_models * L * 3, cudaMemcpyHostToDevice));
     return dev_spearman(dIF.p, L, dx.p, n_models, range, rho, 0);
+}
+
+// Launch-shape options of the ensemble kernel (process-wide; unset = chosen by the cost model of sa_choose_config):
+//   "sa_cluster" CTAs per trajectory (1..8), "sa_warps" warps per CTA (4..12), "sa_min_smem" bytes of shared memory a CTA asks
+//   for at least (0 lets several CTAs share an SM), "sa_split" = "0": never run the two hot-MD images as trajectories of their own.
+// value NULL or "" clears the option.  Options are read when an ensemble is created.
+CHR3D_API int chr3d_set_option(const char* name, const char* value) {
+    static const char* const known[][2] = {{"sa_cluster", "CHR3D_SA_CLUSTER"}, {"sa_warps", "CHR3D_SA_WARPS"}, {"sa_min_smem", "CHR3D_SA_MIN_SMEM"}, {"sa_split", "CHR3D_NO_SPLIT"}};
+    if (!name) { set_error("chr3d_set_option: null name"); return CHR3D_ERR_ARG; }
+    for (auto& k : known) {
+        if (strcmp(name, k[0]) != 0) continue;
+        std::lock_guard<std::mutex> lk(chr3d::g_opt_mu);
+        auto& t = chr3d::opt_table();
+        const bool clear = !value || !*value;
+        if (strcmp(k[0], "sa_split") == 0) {          // stored under the name of the switch it replaces: present = no split
+            if (clear || strcmp(value, "0") != 0) t.erase(k[1]); else t[k[1]] = "1";
+        } else if (clear) t.erase(k[1]);
+        else {
+            char* end = nullptr; const long v = strtol(value, &end, 10);
+            if (!end || *end || v < 0) { set_error("chr3d_set_option: %s wants a non-negative integer, got '%s'", name, value); return CHR3D_ERR_ARG; }
+            t[k[1]] = value;
+        }
+        return 0;
+    }
+    set_error("chr3d_set_option: unknown option '%s' (sa_cluster, sa_warps, sa_min_smem, sa_split)", name);
+    return CHR3D_ERR_ARG;
 }

@@ -16,13 +16,19 @@
 
 namespace chr3d {
 
-// Development switches (launch shapes, probes, traces) are read from the environment only in a -DCHR3D_DEV build
-// (`make DEV=1`); the release library ignores them, so a stray variable cannot change what a benchmark measures.
+// Tuning options set through chr3d_set_option (launch shape of the ensemble kernel; see include/chr3d.h) are looked up first.
+// Development switches (probes, traces, debug variants of the large-N kernels) are read from the environment only in a
+// -DCHR3D_DEV build (`make DEV=1`); the release library ignores the environment, so a stray variable cannot change what a
+// benchmark measures.
+const char* option_lookup(const char* name);       // api.cu; nullptr when the option is not set
+static inline const char* dev_getenv(const char* name) {
+    if (const char* v = option_lookup(name)) return v;
 #ifdef CHR3D_DEV
-static inline const char* dev_getenv(const char* name) { return getenv(name); }
+    return getenv(name);
 #else
-static inline const char* dev_getenv(const char*) { return nullptr; }
+    return nullptr;
 #endif
+}
 
 void set_error(const char* fmt, ...);
 int  require_device();                 // 0 or CHR3D_ERR_NO_DEVICE, sets the error text

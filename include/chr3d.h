@@ -330,6 +330,14 @@ int chr3d_dg_starts(const int32_t* ri, const int32_t* rj, const double* rd, int6
                     int32_t n_models, uint64_t seed, double dg_scale, int32_t nstep, double drop,
                     double* xyz_out, double* eig3_out, double* stats_out, int64_t* n_inconsistent);
 
+/* Launch-shape options of the ensemble kernel, process-wide, read when an ensemble is created (unset = the cost model of the
+ * library decides): "sa_cluster" = CTAs per trajectory (1..8), "sa_warps" = warps per CTA (4..12), "sa_min_smem" = least shared
+ * memory a CTA asks for in bytes (0 lets several CTAs share an SM), "sa_split" = "0" never runs the two hot-MD images of a model
+ * (C3D:1605-1708) as trajectories of their own.  value NULL or "" clears the option.  (The reference has no counterpart: its
+ * parallelism is one cns_solve process per run, test.sh.)  Everything else that used to be an environment switch is compiled in
+ * only with -DCHR3D_DEV. */
+int chr3d_set_option(const char* name, const char* value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,14 @@ def test_no_cpu_fallback_without_device():
         api.spearman_IF_pdb(IF, np.zeros((8, 3)))
     with pytest.raises(api.Chr3dError):
         api.build_models([api.Job(IF=IF, n_models=1)])
+
+
+def test_set_option_accepts_only_the_launch_shape_options():
+    """chr3d_set_option is host-only bookkeeping: the four launch-shape options of the ensemble kernel, integers, clearable."""
+    for k in ("sa_cluster", "sa_warps", "sa_min_smem", "sa_split"):
+        api.set_option(k, 2)
+        api.set_option(k, None)
+    with pytest.raises(api.Chr3dError):
+        api.set_option("sa_cluster", "two")
+    with pytest.raises(api.Chr3dError):
+        api.set_option("CHR3D_LN_DEBUG", 1)          # development switches are not options (compiled in only with -DCHR3D_DEV)

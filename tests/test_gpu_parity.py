@@ -331,19 +331,22 @@ def test_seeded_random_coil_start_equals_oracle(gpu_api):
             assert np.array_equal(r.xyz[k], ref), (N, k)
 
 
-def test_images_side_by_side_equal_the_sequential_run(gpu_api, mats, monkeypatch):
+def test_images_side_by_side_equal_the_sequential_run(gpu_api, mats):
     """The host may run the two hot-MD images of a model as trajectories of their own and resume at PICK (api.cu,
     ensemble_create).  With the launch shape pinned, that run must be bit-identical to the one-launch run: same Philox
     streams, same reduction orders, same stage program."""
     IF = mats["chr21_500kb"]
-    monkeypatch.setenv("CHR3D_SA_CLUSTER", "2")
-    monkeypatch.setenv("CHR3D_SA_WARPS", "8")
     job = lambda: [gpu_api.Job(IF=IF, alpha=0.5, n_models=3, seed=11)]
-    e = gpu_api.Ensemble(job()); split_launches = e.info()["launches"]; e.close()
-    a = gpu_api.build_models(job())[0]
-    monkeypatch.setenv("CHR3D_NO_SPLIT", "1")
-    e = gpu_api.Ensemble(job()); one_launch = e.info()["launches"]; e.close()
-    b = gpu_api.build_models(job())[0]
+    try:
+        gpu_api.set_option("sa_cluster", 2); gpu_api.set_option("sa_warps", 8)
+        e = gpu_api.Ensemble(job()); split_launches = e.info()["launches"]; e.close()
+        a = gpu_api.build_models(job())[0]
+        gpu_api.set_option("sa_split", 0)
+        e = gpu_api.Ensemble(job()); one_launch = e.info()["launches"]; e.close()
+        b = gpu_api.build_models(job())[0]
+    finally:
+        for k in ("sa_cluster", "sa_warps", "sa_split"):
+            gpu_api.set_option(k, None)
     assert split_launches == 2 and one_launch == 1
     assert np.array_equal(a.xyz, b.xyz) and np.array_equal(a.energies, b.energies)
     assert np.array_equal(a.force_evals, b.force_evals) and np.array_equal(a.hand, b.hand)
@@ -360,11 +363,12 @@ def test_co_resident_clusters_complete(gpu_api):
     code = ("import sys; sys.path.insert(0, %r)\n"
             "from chromosome3d_b200 import api, datasets as ds\n"
             "api.init(0)\n"
+            "for k, v in (('sa_min_smem', 0), ('sa_split', 0), ('sa_cluster', 4), ('sa_warps', 4)): api.set_option(k, v)\n"
             "IF = ds.load_if_matrix(ds.input_path('chr9_1mb'))\n"
             "p = api.default_params(); p.hot_step = p.cool_step = 60; p.pow_step = 20; p.premin_step = 5\n"
             "r = api.build_models([api.Job(IF=IF, alpha=1.1, n_models=120, seed=82364)], p)[0]\n"
             "print('ok', int(r.force_evals.min()))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CHR3D_SA_MIN_SMEM="0", CHR3D_NO_SPLIT="1", CHR3D_SA_CLUSTER="4", CHR3D_SA_WARPS="4")
+    env = dict(os.environ)
     for _ in range(4):
         r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
         assert r.returncode == 0 and r.stdout.startswith("ok"), r.stderr[-400:]
