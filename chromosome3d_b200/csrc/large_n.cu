@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <memory>
 #include <vector>
+#include <cooperative_groups.h>
 #include "common.h"
 #ifdef CHR3D_WITH_NCCL
 #include <dlfcn.h>
@@ -1184,7 +1185,7 @@ struct LnEngine {
     // sparse force provider (ln_sparse.cuh): symmetric CSR of the restraint table, hashed cell grid for the repel term
     bool sparse = false; long long sp_nnz = 0; int sp_hbits = 0, sp_blocks = 0; float sp_inv_cs = 0.f;
     DevBuf<long long> sp_row_ptr, sp_nreb; DevBuf<int> sp_col, sp_cell_start, sp_cell_count, sp_cell_fill, sp_order, sp_rebuild; DevBuf<float> sp_dist;
-    DevBuf<float4> sp_xs, sp_xref, sp_fnoe; DevBuf<double> sp_erow, sp_epart; DevBuf<unsigned int> sp_done;
+    DevBuf<float4> sp_xs, sp_xref; DevBuf<double> sp_epart; DevBuf<unsigned int> sp_done; DevBuf<int> sp_bsum; DevBuf<int4> sp_ent;
     bool legacy = false;                       // multi-launch evaluation (NCCL all-reduce between ranks): the baseline path
     LnGroup self; LnGroup* group = nullptr;    // group: the launch group this engine currently belongs to (&self unless virtual ranks)
     static size_t up16(size_t v) { return (v + 15) / 16 * 16; }
@@ -1486,28 +1487,19 @@ static void ln_tiles(LnEngine& e, const chr3d_stage& s, const float4* x, const f
 // ---- sparse force provider: total forces into e.vfr, energies into e.escal[0..2] (ln_sparse.cuh) ------------------------------
 static SpGrid sp_grid(LnEngine& e) {
     SpGrid g; g.inv_cs = e.sp_inv_cs; g.hbits = e.sp_hbits; g.cell_start = e.sp_cell_start.p; g.cell_count = e.sp_cell_count.p; g.cell_fill = e.sp_cell_fill.p;
-    g.order = e.sp_order.p; g.xref = e.sp_xref.p; g.rebuild = e.sp_rebuild.p; g.n_rebuilds = e.sp_nreb.p;
+    g.order = e.sp_order.p; g.bsum = e.sp_bsum.p; g.ent = e.sp_ent.p; g.xref = e.sp_xref.p; g.rebuild = e.sp_rebuild.p; g.n_rebuilds = e.sp_nreb.p;
     return g;
 }
 static int sp_eval(LnEngine& e, const chr3d_stage& s, const float4* a, const float4* b, const float* lam, bool force_rebuild) {
-    const int N = e.N, nb = (N + SP_THREADS - 1) / SP_THREADS;
-    SpGrid g = sp_grid(e);
-    LnTerms t; ln_terms(e.prm, s, t);
-    sp_coords_kernel<<<std::min(nb, 2 * e.sms), SP_THREADS, 0, e.stream>>>(a, b, lam, N, e.sp_xs.p, g, force_rebuild ? 1 : 0);
-    // the bins: every kernel returns at once unless a bead has moved more than skin / 2 since the last build (device-side decision)
-    sp_grid_clear_kernel<<<std::min(((1 << e.sp_hbits) + 255) / 256, 2 * e.sms), 256, 0, e.stream>>>(g);
-    sp_grid_count_kernel<<<std::min(nb, 2 * e.sms), SP_THREADS, 0, e.stream>>>(e.sp_xs.p, N, g);
-    sp_grid_scan_kernel<<<1, 1024, 0, e.stream>>>(g);
-    sp_grid_place_kernel<<<std::min(nb, 2 * e.sms), SP_THREADS, 0, e.stream>>>(e.sp_xs.p, N, g);
-    sp_grid_sort_kernel<<<std::min(((1 << e.sp_hbits) + 255) / 256, 2 * e.sms), 256, 0, e.stream>>>(g, e.sp_done.p);
-    SpCsr m; m.row_ptr = e.sp_row_ptr.p; m.col = e.sp_col.p; m.dist = e.sp_dist.p;
-    const int noe_blocks = std::min((N * 32 + SP_THREADS - 1) / SP_THREADS, 8 * e.sms);
-    if (e.prm.noe_low_soft) sp_noe_kernel<true><<<noe_blocks, SP_THREADS, 0, e.stream>>>(m, e.sp_xs.p, N, t, e.sp_fnoe.p, e.sp_erow.p);
-    else sp_noe_kernel<false><<<noe_blocks, SP_THREADS, 0, e.stream>>>(m, e.sp_xs.p, N, t, e.sp_fnoe.p, e.sp_erow.p);
-    sp_repel_combine_kernel<<<nb, SP_THREADS, 0, e.stream>>>(e.sp_xs.p, N, g, t, ln_bonded_terms(e.prm, s), e.prm.vdw_min_sep, e.sp_fnoe.p, e.sp_erow.p, e.vfr.p, e.sp_epart.p);
-    sp_energy_kernel<<<1, 32, 0, e.stream>>>(e.sp_epart.p, nb, e.escal.p);
-    e.n_launches += 9;
-    CHR3D_CUDA(cudaGetLastError());
+    SpEvalArgs A;
+    A.a = a; A.b = b; A.lam = lam; A.N = e.N; A.force_rebuild = force_rebuild ? 1 : 0; A.xs = e.sp_xs.p; A.g = sp_grid(e);
+    A.m.row_ptr = e.sp_row_ptr.p; A.m.col = e.sp_col.p; A.m.dist = e.sp_dist.p;
+    ln_terms(e.prm, s, A.t); A.bd = ln_bonded_terms(e.prm, s); A.vdw_min_sep = e.prm.vdw_min_sep;
+    A.fsum = e.vfr.p; A.epart = e.sp_epart.p; A.escal = e.escal.p; A.ticket = e.sp_done.p;
+    void* args[] = {&A};
+    const void* fn = e.prm.noe_low_soft ? (const void*)sp_eval_kernel<true> : (const void*)sp_eval_kernel<false>;
+    CHR3D_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)e.sp_blocks), dim3(SP_THREADS), args, 0, e.stream));      // one launch per evaluation
+    e.n_launches += 1;
     return 0;
 }
 
@@ -1897,12 +1889,19 @@ CHR3D_API int chr3d_single_create_sparse(int32_t N, const int32_t* ri, const int
         e.sp_inv_cs = (float)(1.0 / (rmax + (double)SP_SKIN));
         e.sp_hbits = 4; while ((1 << e.sp_hbits) < 2 * N && e.sp_hbits < 17) e.sp_hbits++;
         const size_t H = (size_t)1 << e.sp_hbits;
-        e.sp_blocks = (N + SP_THREADS - 1) / SP_THREADS;
+        {   // one cooperative launch per evaluation: as many CTAs as are co-resident (at most eight per SM), no more than a warp per bead needs
+            int bps = 0;
+            CHR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sp_eval_kernel<false>, SP_THREADS, 0));
+            int bps1 = 0;
+            CHR3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps1, sp_eval_kernel<true>, SP_THREADS, 0));
+            bps = std::max(1, std::min(std::min(bps, bps1), 8));
+            e.sp_blocks = std::max(1, std::min(bps * e.sms, (N * 32 + SP_THREADS - 1) / SP_THREADS));
+        }
         CHR3D_CUDA(e.sp_cell_start.alloc(H + 1)); CHR3D_CUDA(e.sp_cell_count.alloc(H)); CHR3D_CUDA(e.sp_cell_fill.alloc(H)); CHR3D_CUDA(e.sp_order.alloc(N));
         CHR3D_CUDA(e.sp_rebuild.alloc(1)); CHR3D_CUDA(e.sp_nreb.alloc(1)); CHR3D_CUDA(e.sp_done.alloc(1));
         CHR3D_CUDA(cudaMemset(e.sp_rebuild.p, 0, sizeof(int))); CHR3D_CUDA(cudaMemset(e.sp_nreb.p, 0, sizeof(long long))); CHR3D_CUDA(cudaMemset(e.sp_done.p, 0, sizeof(unsigned int)));
-        CHR3D_CUDA(cudaMemset(e.sp_cell_start.p, 0, sizeof(int) * (H + 1)));
-        CHR3D_CUDA(e.sp_xs.alloc(N)); CHR3D_CUDA(e.sp_xref.alloc(N)); CHR3D_CUDA(e.sp_fnoe.alloc(N)); CHR3D_CUDA(e.sp_erow.alloc(N)); CHR3D_CUDA(e.sp_epart.alloc((size_t)e.sp_blocks * 3));
+        CHR3D_CUDA(cudaMemset(e.sp_cell_start.p, 0, sizeof(int) * (H + 1))); CHR3D_CUDA(cudaMemset(e.sp_cell_count.p, 0, sizeof(int) * H)); CHR3D_CUDA(cudaMemset(e.sp_cell_fill.p, 0, sizeof(int) * H));
+        CHR3D_CUDA(e.sp_xs.alloc(N)); CHR3D_CUDA(e.sp_xref.alloc(N)); CHR3D_CUDA(e.sp_epart.alloc((size_t)e.sp_blocks * 3)); CHR3D_CUDA(e.sp_bsum.alloc((size_t)e.sp_blocks)); CHR3D_CUDA(e.sp_ent.alloc(N));
         CHR3D_CUDA(cudaMemset(e.sp_xref.p, 0, sizeof(float4) * N));
     }
     e.pairs_total = nr;
