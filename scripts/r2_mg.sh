@@ -12,7 +12,7 @@ timeout 200 $TR --master-port 29512 bench.py --gpus $N --workload synth_10kb_sin
 timeout 200 $TR --master-port 29513 bench.py --gpus $N --workload synth_50kb_single --steps 3 --warmup 2 > gpurun_out/r02_scale_50kb_n${N}.json 2> gpurun_out/r02_scale_50kb_n${N}.err; echo "50kb rc=$?"
 if [ "$N" = "2" ] && [ -z "$QUICK" ]; then
   timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 800 > gpurun_out/r02_mg2_pytest.log 2>&1; echo "pytest multi rc=$?"; tail -3 gpurun_out/r02_mg2_pytest.log
-  CHR3D_NO_P2P=1 timeout 900 $TR --master-port 29514 bench.py --gpus $N --workload synth_10kb_single --steps 1 --warmup 1 > gpurun_out/r02_scale_10kb_nccl_n${N}.json 2> gpurun_out/r02_scale_10kb_nccl_n${N}.err; echo "10kb nccl rc=$?"
+  [ -n "$WITH_NCCL" ] && { CHR3D_NO_P2P=1 timeout 900 $TR --master-port 29514 bench.py --gpus $N --workload synth_10kb_single --steps 1 --warmup 1 > gpurun_out/r02_scale_10kb_nccl_n${N}.json 2> gpurun_out/r02_scale_10kb_nccl_n${N}.err; echo "10kb nccl rc=$?"; }
 fi
 [ -z "$QUICK" ] && timeout 1200 $TR --master-port 29515 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r02_scale_default_n${N}.json 2> gpurun_out/r02_scale_default_n${N}.err; echo "default rc=$?"
 python - <<PY
