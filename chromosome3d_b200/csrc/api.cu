@@ -351,10 +351,17 @@ CHR3D_API int chr3d_write_tbl(const char* path, const int32_t* ri, const int32_t
 // ------------------------------ ensemble --------------------------------------------------------
 // Rows index beads on the device (coordinates, the dense target table): every row is checked on the host.  `unique`: the
 // dense-table paths also refuse a pair that is listed twice (the scatter would keep whichever row landed last).
-static int upload_list(JobDev& jd, const int32_t* ri, const int32_t* rj, const double* rd, long long nr, cudaStream_t s, int N, bool unique, const char* who) {
+static int upload_list(JobDev& jd, const int32_t* ri, const int32_t* rj, const double* rd, long long nr, cudaStream_t s, int N, bool unique, const char* who, int vdw_min_sep = 0) {
     for (long long k = 0; k < nr; k++)
         if (ri[k] < 0 || rj[k] < 0 || ri[k] >= N || rj[k] >= N || ri[k] == rj[k] || !(rd[k] > 0.0)) {
             set_error("%s: restraint row %lld (%d, %d, %g) is not a pair of distinct beads 0 .. %d with a positive distance", who, k, ri[k], rj[k], rd[k], N - 1);
+            return CHR3D_ERR_ARG;
+        }
+    // the dense table encodes "restraint" as "restraint + repel": a row between beads closer than vdw_min_sep (bonded neighbours, which
+    // the reference's 1-2 exclusion and the oracle keep free of repel) cannot be represented there
+    for (long long k = 0; k < nr && vdw_min_sep > 0; k++)
+        if (abs(ri[k] - rj[k]) < vdw_min_sep) {
+            set_error("%s: restraint row %lld joins beads %d and %d, closer than vdw_min_sep = %d (the dense table would add the repel term to it; the sparse engine, chr3d_single_create_sparse, takes such rows)", who, k, ri[k], rj[k], vdw_min_sep);
             return CHR3D_ERR_ARG;
         }
     if (unique && nr > 1) {
@@ -422,7 +429,7 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             if (int rc = dev_tenths_to_list(dT.p, N, jb.min_sep, jd->ri.p, jd->rj.p, jd->rd.p, std::max<long long>(n, 1), &n, 0)) return rc;
         } else {
             if (jb.nr > 0 && (!jb.ri || !jb.rj || !jb.rd)) { set_error("job %d: restraint table pointers missing", jn); return CHR3D_ERR_ARG; }
-            if (int rc = upload_list(*jd, jb.ri, jb.rj, jb.rd, jb.nr, 0, N, true, "chr3d_build_models")) return rc;
+            if (int rc = upload_list(*jd, jb.ri, jb.rj, jb.rd, jb.nr, 0, N, true, "chr3d_build_models", p->vdw_min_sep)) return rc;
             if (int rc = dev_list_to_targets(jd->ri.p, jd->rj.p, jd->rd.p, jb.nr, N, p->vdw_min_sep, jd->T.p, 0)) return rc;
         }
         CHR3D_CUDA(jd->Tt.alloc(sa_tiles_floats(N)));

@@ -1917,6 +1917,30 @@ CHR3D_API int chr3d_single_create_sparse(int32_t N, const int32_t* ri, const int
     *out = h.release();
     return 0;
 }
+// Host-only (no device needed): the tile-range split the engine uses for a structure of N beads on `world` ranks with
+// `ctas` CTAs per rank.  rank_cut[world + 1]: tile t of the row-major upper-triangle list belongs to rank g when
+// rank_cut[g] <= t < rank_cut[g + 1]; cta_cut[world * (ctas + 1)] (optional): the same per rank for its CTAs; cost[world]
+// (optional): modelled cost of every rank's range (a far tile = 1).
+CHR3D_API int chr3d_single_tile_split(int32_t N, int32_t world, int32_t ctas, int64_t* rank_cut, int64_t* cta_cut, double* cost) {
+    if (N < 2 || world < 1 || ctas < 1 || !rank_cut) { set_error("chr3d_single_tile_split: bad arguments"); return CHR3D_ERR_ARG; }
+    const int nT = (N + LN_TB - 1) / LN_TB;
+    const long long n_tiles = (long long)nT * (nT + 1) / 2;
+    const std::vector<long long> cut = ln_cost_split(0, n_tiles, world, nT, N);
+    for (int g = 0; g <= world; g++) rank_cut[g] = cut[g];
+    for (int g = 0; g < world; g++) {
+        if (cta_cut) {
+            const int nc = (int)std::max<long long>(1, std::min<long long>(ctas, std::max<long long>(cut[g + 1] - cut[g], 1)));
+            const std::vector<long long> cc = ln_cost_split(cut[g], cut[g + 1], nc, nT, N);
+            for (int c = 0; c <= ctas; c++) cta_cut[(size_t)g * (ctas + 1) + c] = c <= nc ? cc[c] : cut[g + 1];
+        }
+        if (cost) {
+            double a = 0.0;
+            if (cut[g + 1] > cut[g]) { int I, J; tile_coords(cut[g], nT, I, J); for (long long t = cut[g]; t < cut[g + 1]; t++) { a += ln_tile_cost(I, J, nT, N); if (++J == nT) { I++; J = I; } } }
+            cost[g] = a;
+        }
+    }
+    return 0;
+}
 // sparse provider: bin rebuilds so far, entries of the symmetric CSR, bytes the NOE term reads per evaluation
 CHR3D_API int chr3d_single_sparse_info(chr3d_single* h, int64_t* n_rebuilds, int64_t* csr_entries, int64_t* noe_bytes_per_eval) {
     if (!h || !h->e.sparse) { set_error("chr3d_single_sparse_info: not a sparse structure"); return CHR3D_ERR_ARG; }

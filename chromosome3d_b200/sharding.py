@@ -33,10 +33,25 @@ def n_tiles(n_beads):
     return nt * (nt + 1) // 2
 
 
+def tile_split(n_beads, world, ctas=148):
+    """The engine's own split (chr3d_single_tile_split, host-only): rank cuts [world + 1], per-rank CTA cuts [world][ctas + 1]
+    and the modelled cost of every rank's range."""
+    import ctypes as C
+    import numpy as np
+    from . import api
+    cut = np.zeros(world + 1, dtype=np.int64)
+    cta = np.zeros((world, ctas + 1), dtype=np.int64)
+    cost = np.zeros(world)
+    api._check(api.lib().chr3d_single_tile_split(n_beads, world, ctas, cut.ctypes.data_as(C.POINTER(C.c_int64)), cta.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 cost.ctypes.data_as(C.POINTER(C.c_double))))
+    return cut, cta, cost
+
+
 def tile_range(n_beads, rank, world):
-    """[t0, t1) of the row-major upper-triangle tile list owned by `rank` (balanced by pair count)."""
-    n = n_tiles(n_beads)
-    return n * rank // world, n * (rank + 1) // world
+    """[t0, t1) of the row-major upper-triangle tile list owned by `rank`: contiguous ranges of equal modelled cost, the split
+    chr3d_single_create makes (every rank derives the same cuts)."""
+    cut, _, _ = tile_split(n_beads, world, 1)
+    return int(cut[rank]), int(cut[rank + 1])
 
 
 def tile_coords(t, n_beads):

@@ -330,6 +330,11 @@ int chr3d_dg_starts(const int32_t* ri, const int32_t* rj, const double* rd, int6
                     int32_t n_models, uint64_t seed, double dg_scale, int32_t nstep, double drop,
                     double* xyz_out, double* eig3_out, double* stats_out, int64_t* n_inconsistent);
 
+/* Host-only (no device): the cost-balanced tile-range split chr3d_single_create uses for N beads on `world` ranks (SURVEY 8(e):
+ * upper-triangle layout, contiguous ranges; a diagonal tile and the start of a tile row cost more than a far tile).
+ * rank_cut[world + 1]; cta_cut[world * (ctas + 1)] and cost[world] are optional. */
+int chr3d_single_tile_split(int32_t N, int32_t world, int32_t ctas, int64_t* rank_cut, int64_t* cta_cut, double* cost);
+
 /* Launch-shape options of the ensemble kernel, process-wide, read when an ensemble is created (unset = the cost model of the
  * library decides): "sa_cluster" = CTAs per trajectory (1..8), "sa_warps" = warps per CTA (4..12), "sa_min_smem" = least shared
  * memory a CTA asks for in bytes (0 lets several CTAs share an SM), "sa_split" = "0" never runs the two hot-MD images of a model

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-2 end-state visit of one B200: parity tests, bench lines, sparse provider timing, ncu evidence (launch list + one --set full
 # capture per hot kernel, each after a plain run of the same command that exited 0).  Outputs: gpurun_out/${TAG}_*.
+# LEAN=1: tests, default bench, reference arm and smoke only; NO_NCU=1: skip the profiler passes.
 TAG=${TAG:-r02e}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -8,10 +9,10 @@ O=gpurun_out/${TAG}
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > ${O}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 ${O}_pytest_gpu.log
 timeout 600 python bench.py > ${O}_bench_default.json 2> ${O}_bench_default.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference > ${O}_bench_reference.json 2> ${O}_bench_reference.err; echo "reference rc=$?"
-timeout 300 python bench.py --workload synth_10kb_single --steps 3 --warmup 1 > ${O}_bench_synth_10kb_single.json 2> ${O}_bench_10kb.err; echo "10kb rc=$?"
-timeout 300 python bench.py --workload synth_50kb_single --steps 5 --warmup 2 > ${O}_bench_synth_50kb_single.json 2> ${O}_bench_50kb.err; echo "50kb rc=$?"
+[ -z "$LEAN" ] && timeout 300 python bench.py --workload synth_10kb_single --steps 3 --warmup 1 > ${O}_bench_synth_10kb_single.json 2> ${O}_bench_10kb.err; echo "10kb rc=$?"
+[ -z "$LEAN" ] && timeout 300 python bench.py --workload synth_50kb_single --steps 5 --warmup 2 > ${O}_bench_synth_50kb_single.json 2> ${O}_bench_50kb.err; echo "50kb rc=$?"
 timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > ${O}_smoke.log 2>&1; echo "smoke rc=$?"
-timeout 600 python scripts/sparse_bench.py > ${O}_sparse_bench.jsonl 2> ${O}_sparse_bench.err; echo "sparse rc=$?"; cat ${O}_sparse_bench.jsonl
+[ -z "$LEAN" ] && timeout 600 python scripts/sparse_bench.py > ${O}_sparse_bench.jsonl 2> ${O}_sparse_bench.err; echo "sparse rc=$?"; cat ${O}_sparse_bench.jsonl
 if [ -z "$NO_NCU" ]; then
 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > ${O}_plain_bench.json 2> ${O}_plain_bench.err && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file ${O}_launches_bench.csv \

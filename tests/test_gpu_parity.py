@@ -416,6 +416,8 @@ def test_restraint_rows_are_validated(gpu_api):
             gpu_api.count_satisfied_and_sum_dev(x[None], *bad)
         with pytest.raises(Chr3dError):
             gpu_api.build_models([gpu_api.Job(restraints=bad, N=30, n_models=1)])
+    with pytest.raises(Chr3dError):                            # bonded neighbours: the dense table cannot keep repel off such a row
+        gpu_api.build_models([gpu_api.Job(restraints=(np.array([3]), np.array([4]), np.array([3.8])), N=30, n_models=1)])
     dup = (np.array([0, 5, 2]), np.array([5, 0, 9]), np.array([4.0, 4.5, 6.0]))
     gpu_api.count_satisfied_and_sum_dev(x[None], *dup)                              # row-wise scoring counts every row, like assess_dgsa (C3D:769-880)
     with pytest.raises(Chr3dError):
