@@ -94,17 +94,13 @@ def set_option(name, value=None):
     _check(lib().chr3d_set_option(name.encode(), None if value is None else str(value).encode()))
 
 
-CNS_PIN = dict(angle_d2=6.0, angle_k=100.0, vdw_rmin=5.5)
-
-
 def cns_pin_params():
-    """default_params() plus the bead-model stand-ins for what CNS's full-atom poly-GLY chain adds (default off): a soft
-    CA(i)-CA(i+2) lower bound (the angle / improper terms keep a real chain from folding back on itself) and a larger repel
-    radius (backbone atoms around each CA).  Fitted on the 45 shipped CNS models with the fp64 oracle (scripts/fit_cns_pin.py,
-    profiles/r02_cns_pin.md): median IF-Spearman within 0.02 of the shipped model for 42 of 45 (35 without)."""
-    p = default_params()
-    for k, v in CNS_PIN.items():
-        setattr(p, k, v)
+    """chr3d_cns_pin_params: default_params() plus the bead-model stand-ins for what CNS's full-atom poly-GLY chain adds (default
+    off): a soft CA(i)-CA(i+2) lower bound (the angle / improper terms keep a real chain from folding back on itself) and a
+    larger repel radius (backbone atoms around each CA).  Fitted on the 45 shipped CNS models with the fp64 oracle
+    (scripts/fit_cns_pin.py, profiles/r02_cns_pin.md): median IF-Spearman within 0.02 of the shipped model for 42 of 45 (35 without)."""
+    p = abi.SaParams()
+    lib().chr3d_cns_pin_params(C.byref(p))
     return p
 
 

@@ -741,6 +741,14 @@ CHR3D_API int chr3d_spearman(const double* IF, int32_t L, const double* xyz, int
     return dev_spearman(dIF.p, L, dx.p, n_models, range, rho, 0);
 }
 
+// chr3d_default_params plus the default-off bead-model stand-ins for what CNS's full-atom poly-GLY chain adds, as fitted on the 45
+// shipped CNS models (profiles/r02_cns_pin.md): soft CA(i)-CA(i+2) lower bound, larger repel radius.
+CHR3D_API void chr3d_cns_pin_params(chr3d_sa_params* p) {
+    if (!p) return;
+    chr3d_default_params(p);
+    p->angle_d2 = 6.0; p->angle_k = 100.0; p->vdw_rmin = 5.5;
+}
+
 // Launch-shape options of the ensemble kernel (process-wide; unset = chosen by the cost model of sa_choose_config):
 //   "sa_cluster" CTAs per trajectory (1..8), "sa_warps" warps per CTA (4..12), "sa_min_smem" bytes of shared memory a CTA asks
 //   for at least (0 lets several CTAs share an SM), "sa_split" = "0": never run the two hot-MD images as trajectories of their own.

@@ -154,6 +154,9 @@ int  chr3d_init(int device);          /* bind this host thread/process to a CUDA
 int  chr3d_shutdown(void);
 
 void chr3d_default_params(chr3d_sa_params* p);
+/* the same plus the default-off stand-ins for CNS's poly-GLY chain terms (angle_d2 = 6.0, angle_k = 100, vdw_rmin = 5.5), fitted on the
+ * 45 shipped CNS models: 42 of 45 within 0.02 of the shipped IF-Spearman instead of 35                       */
+void chr3d_cns_pin_params(chr3d_sa_params* p);
 /* sizeof of the ABI structs as this build of the library sees them: a binding checks its own layout against these */
 void chr3d_abi_sizes(int32_t* sa_params, int32_t* stage, int32_t* job, int32_t* result);
 /* Writes the stage program for `p`; returns the number of stages (or <0).  cap==0: size query. */

@@ -23,6 +23,7 @@ my %SIG = (    # name => [ret, args] in FFI::Platypus type names (pointers = opa
     chr3d_init             => ['int',    ['int']],
     chr3d_shutdown         => ['int',    []],
     chr3d_default_params   => ['void',   ['opaque']],
+    chr3d_cns_pin_params   => ['void',   ['opaque']],
     chr3d_build_program    => ['int',    ['opaque', 'opaque', 'int']],
     chr3d_if_to_dist       => ['int',    ['opaque', 'sint32', 'double', 'double', 'opaque', 'opaque']],
     chr3d_if_to_restraints => ['int',    ['opaque', 'sint32', 'double', 'double', 'sint32', 'opaque', 'opaque', 'opaque', 'sint64', 'opaque']],
@@ -90,6 +91,8 @@ sub init         { _load(); _check(_c_chr3d_init($_[0] // 0), "chr3d_init"); }
 use constant PARAMS_BYTES => 240;
 use constant STAGE_BYTES  => 72;
 sub default_params { _load(); my $p = _buf(PARAMS_BYTES); _c_chr3d_default_params(ptr($p)); return $p; }
+# the defaults plus the default-off stand-ins for CNS's poly-GLY chain terms (chr3d_cns_pin_params, DESIGN.md section 2)
+sub cns_pin_params { _load(); my $p = _buf(PARAMS_BYTES); _c_chr3d_cns_pin_params(ptr($p)); return $p; }
 sub build_program {
     my ($p) = @_;
     my $n = _c_chr3d_build_program(ptr($p), 0, 0);

@@ -22,13 +22,13 @@ use FindBin;
 use lib $FindBin::Bin;
 use Chr3D;
 
-my ($help, $dir_out, $KSCALING, $ALPHA, $mcount, $file_if, $seed, $device, $range, $start);
+my ($help, $dir_out, $KSCALING, $ALPHA, $mcount, $file_if, $seed, $device, $range, $start, $pin);
 ($KSCALING, $ALPHA, $mcount) = (11, 0.5, 20);          # C3D:18-21
 my $min_sep  = 5;                                       # $SEPARATION, C3D:20
 my $DISTRELAX = 0.5;                                    # C3D:74
 Getopt::Long::Configure("no_auto_abbrev");
 GetOptions("h" => \$help, "o=s" => \$dir_out, "k=i" => \$KSCALING, "a=s" => \$ALPHA, "m=i" => \$mcount,
-           "i|if=s" => \$file_if, "seed=i" => \$seed, "device=i" => \$device, "start=s" => \$start) or usage("bad option");
+           "i|if=s" => \$file_if, "seed=i" => \$seed, "device=i" => \$device, "start=s" => \$start, "pin" => \$pin) or usage("bad option");
 $start //= "coil";
 usage("--start must be coil or dg") if $start ne "coil" && $start ne "dg";
 usage("") if $help;
@@ -73,7 +73,7 @@ if ($start eq "dg") {
     print "DG start   : embedded $mcount models ($bad pairs with triangle-inconsistent bounds)\n";
 }
 my $res = Chr3D::run_ensemble(IF => $IF, L => $L, alpha => $ALPHA + 0, K => $KSCALING + 0, min_sep => $min_sep,
-                              n_models => $mcount, seed => $seed // 0, x0 => $x0);
+                              n_models => $mcount, seed => $seed // 0, x0 => $x0, params => ($pin ? Chr3D::cns_pin_params() : undef));
 my @energies = unpack("d" . (4 * $mcount), $res->{energies});
 my $xyz_bytes = 8 * 3 * $L;
 my @pdb;
@@ -154,6 +154,7 @@ Usage:  $0 -i <IF matrix> -o <output directory> [options]
   -h   this message
   --seed <n>    annealing seed [82364]     --device <n>   CUDA device [0]
   --start coil|dg   starting coordinates: seeded random coil [default] or distance-geometry embedding (the DG stage of dgsa.inp)
+  --pin         bead-level stand-ins for the angle terms and backbone atoms of CNS's poly-GLY chain (closer to the shipped CNS models)
 EOT
     exit 1;
 }

@@ -51,6 +51,12 @@ chr3d_default_params(p)
   CODE:
     chr3d_default_params(P(chr3d_sa_params*, p));
 
+void
+chr3d_cns_pin_params(p)
+    UV p
+  CODE:
+    chr3d_cns_pin_params(P(chr3d_sa_params*, p));
+
 int
 chr3d_build_program(p, out, cap)
     UV p

@@ -181,3 +181,21 @@ def test_front_end_dg_start(tmp_path):
     IF = ds.load_if_matrix(ds.input_path("chr21_1mb"))
     xyz = ds.read_ca_pdb(str(out / "chr21_1mb_matrix_model1.pdb"))
     assert orc.spearman(IF, xyz, 3)[0] < -0.8
+
+
+@pytest.mark.gpu
+def test_front_end_cns_pin(tmp_path):
+    """--pin: the run anneals with chr3d_cns_pin_params (soft CA(i)-CA(i+2) lower bound, repel radius 5.5 A) and equals the Python
+    mirror's run with the same parameters; no CA(i)-CA(i+2) distance of the best model falls far below the bound."""
+    from chromosome3d_b200 import api
+    out = tmp_path / "pin"
+    r = _perl([os.path.join(PERL, "chromosome3D.pl"), "-i", ds.input_path("chr21_1mb"), "-o", str(out), "-m", "3", "--pin"])
+    assert r.returncode == 0, r.stderr + r.stdout
+    IF = ds.load_if_matrix(ds.input_path("chr21_1mb"))
+    xyz = ds.read_ca_pdb(str(out / "chr21_1mb_matrix_model1.pdb"))
+    api.init(0)
+    res = api.build_models([api.Job(IF=IF, alpha=0.5, n_models=3, seed=82364)], p=api.cns_pin_params())[0]
+    best = int(api.rank_models(res.energies)[0])
+    assert np.abs(np.round(res.xyz[best], 3) - xyz).max() <= 1.5e-3          # the PDB holds three decimals
+    d2 = np.linalg.norm(xyz[2:] - xyz[:-2], axis=1)
+    assert d2.min() > 5.0
