@@ -389,6 +389,20 @@ def if_from_coo(bi, bj, v, L, base=0):
     return out
 
 
+def coo_to_restraints(bi, bj, v, L, alpha, K=11.0, min_sep=5, base=0):
+    """chr3d_coo_to_restraints: sparse (bin_i, bin_j, value) triplets -> restraint rows (ri, rj, rd), i-major, without the L x L matrix;
+    the same distances as if_to_restraints(if_from_coo(...)).  For Single(restraints=...) / Job(restraints=...)."""
+    bi = np.ascontiguousarray(bi, dtype=np.int32)
+    bj = np.ascontiguousarray(bj, dtype=np.int32)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    cap = max(1, len(v))
+    ri, rj, rd = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32), np.zeros(cap)
+    n = C.c_int64(0)
+    _check(lib().chr3d_coo_to_restraints(_i(bi), _i(bj), _d(v), C.c_int64(len(v)), L, base, C.c_double(alpha), C.c_double(K), min_sep,
+                                         _i(ri), _i(rj), _d(rd), C.c_int64(cap), C.byref(n)))
+    return ri[:n.value].copy(), rj[:n.value].copy(), rd[:n.value].copy()
+
+
 def dg_embed(ri, rj, rd, N, n_models=1, seed=0, p=None):
     """DG stage of dgsa.inp (C3D:1470-1526) at bead level: starting coordinates (n_models, N, 3) by metric-matrix
     embedding of the smoothed bounds; also returns the eigenvalues used and the number of triangle-inconsistent pairs.

@@ -130,6 +130,75 @@ int if_to_tenths_certified(const double* IF, int L, double alpha, double K, DevB
     return 0;
 }
 
+// Sparse triplets -> restraint rows without ever forming the L x L matrix (matrix input at scale).  The
+// triplets are symmetrised and ordered on the host (data-format work, like the text parser): every (i, j, v) counts for (i, j)
+// and (j, i), repeated cells add up in input order.  The arithmetic — IF**alpha, the mean in the reference's order, K / (IF**alpha /
+// mean), the certified `%.1f` rounding — runs on the device over the non-zero cells only (dev_cells_to_tenths); flagged cells are
+// re-derived with libm exactly as for a dense matrix.  Rows come out in i-major order (not the string order of `sort keys`,
+// C3D:203: the engines do not care, chr3d_write_rr / _tbl of these rows would differ from the reference's files in row order only).
+CHR3D_API int chr3d_coo_to_restraints(const int32_t* bi, const int32_t* bj, const double* v, int64_t nnz, int32_t L, int32_t base,
+                                      double alpha, double K, int32_t min_sep, int32_t* ri, int32_t* rj, double* rd, int64_t cap, int64_t* n_out) {
+    if (L < 2 || nnz < 0 || (nnz > 0 && (!bi || !bj || !v)) || (base != 0 && base != 1) || !n_out || !(alpha > 0) || (cap > 0 && (!ri || !rj || !rd))) {
+        set_error("chr3d_coo_to_restraints: bad arguments (alpha must be positive: 0**alpha of the absent cells has to be 0)"); return CHR3D_ERR_ARG;
+    }
+    if (int rc = require_device()) return rc;
+    struct Ent { unsigned long long key; double v; };
+    std::vector<Ent> ent; ent.reserve((size_t)nnz * 2);
+    for (int64_t k = 0; k < nnz; k++) {
+        const long long i = (long long)bi[k] - base, j = (long long)bj[k] - base;
+        if (i < 0 || j < 0 || i >= L || j >= L) { set_error("chr3d_coo_to_restraints: bin index outside [%d, %d] in triplet %lld", base, L - 1 + base, (long long)k); return CHR3D_ERR_ARG; }
+        if (!(v[k] >= 0.0)) { set_error("chr3d_coo_to_restraints: triplet %lld has a negative or NaN value", (long long)k); return CHR3D_ERR_ARG; }
+        ent.push_back({(unsigned long long)i * (unsigned long long)L + (unsigned long long)j, v[k]});
+        if (i != j) ent.push_back({(unsigned long long)j * (unsigned long long)L + (unsigned long long)i, v[k]});
+    }
+    std::stable_sort(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) { return a.key < b.key; });
+    std::vector<unsigned long long> key; std::vector<double> val;
+    for (size_t k = 0; k < ent.size(); k++) {
+        if (!key.empty() && key.back() == ent[k].key) val.back() += ent[k].v;
+        else { key.push_back(ent[k].key); val.push_back(ent[k].v); }
+    }
+    {   // cells that are (or sum to) zero are absent cells
+        size_t w = 0;
+        for (size_t k = 0; k < key.size(); k++) if (val[k] != 0.0) { key[w] = key[k]; val[w] = val[k]; w++; }
+        key.resize(w); val.resize(w);
+    }
+    const long long n = (long long)key.size();
+    std::vector<long long> row_ptr((size_t)L + 1, 0);
+    for (long long k = 0; k < n; k++) row_ptr[(size_t)(key[(size_t)k] / (unsigned long long)L) + 1]++;
+    for (int i = 0; i < L; i++) row_ptr[(size_t)i + 1] += row_ptr[(size_t)i];
+    DevBuf<double> dv; DevBuf<long long> dptr, dT;
+    CHR3D_CUDA(dv.alloc((size_t)std::max<long long>(n, 1))); CHR3D_CUDA(dT.alloc((size_t)std::max<long long>(n, 1))); CHR3D_CUDA(dptr.alloc((size_t)L + 1));
+    if (n > 0) CHR3D_CUDA(cudaMemcpy(dv.p, val.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    CHR3D_CUDA(cudaMemcpy(dptr.p, row_ptr.data(), sizeof(long long) * ((size_t)L + 1), cudaMemcpyHostToDevice));
+    long long nu = 0; std::vector<long long> flagged;
+    if (int rc = dev_cells_to_tenths(dv.p, n, dptr.p, L, alpha, K, dT.p, &nu, &flagged, 0)) return rc;
+    std::vector<long long> t((size_t)std::max<long long>(n, 1));
+    if (n > 0) CHR3D_CUDA(cudaMemcpy(t.data(), dT.p, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (nu > 0) {   // decimal-rounding certification failed for these cells: libm, the reference's own arithmetic
+        double sum = 0.0;
+        for (long long k = 0; k < n; k++) sum += pow(val[(size_t)k], alpha);
+        const double mean = sum / ((double)L * (double)L);
+        auto cell = [&](size_t k) -> long long {
+            const double q = pow(val[k], alpha) / mean;
+            if (q == 0) return -10;
+            char buf[512]; snprintf(buf, sizeof buf, "%.1f", K / q);
+            return parse_tenths(buf);
+        };
+        if (nu > CHR3D_MAX_FLAGGED) { for (long long k = 0; k < n; k++) t[(size_t)k] = cell((size_t)k); }
+        else for (long long k : flagged) t[(size_t)k] = cell((size_t)k);
+    }
+    int64_t rows = 0;
+    for (long long k = 0; k < n; k++) {
+        const long long i = (long long)(key[(size_t)k] / (unsigned long long)L), j = (long long)(key[(size_t)k] % (unsigned long long)L);
+        if (j <= i || j - i < min_sep || t[(size_t)k] <= 0) continue;             // C3D:195-196
+        if (rows < cap) { ri[rows] = (int32_t)i; rj[rows] = (int32_t)j; rd[rows] = (double)t[(size_t)k] / 10.0; }
+        rows++;
+    }
+    *n_out = rows;
+    if (cap > 0 && rows > cap) { set_error("chr3d_coo_to_restraints: %lld rows, capacity %lld", (long long)rows, (long long)cap); return CHR3D_ERR_SIZE; }
+    return 0;
+}
+
 static const char* REFSEQ =   // the fake protein sequence CNS is given, one residue per bead (C3D:93)
     "RSEDWQCPRTPYAASRDFDVKYVVPSFSAGGLVQAMVTYEGDRNESAVFVAIRNRLHVLGPDLKSVQSLATGPAGDPGCQTCAACGPGPHGPPGDTDTKVLVLDPALPALVSCGSSLQGRCFLHDLEPQGTAVHLAAPACLFSAHHNRPDDCPDCVASPLGTRVTVVEQGQASYFYVASSLDAAVAGSFSPRSVSIRRLKADASGFAPGFVALSVLPKHLVSYSIEYVHSFHTGAFVYFLTVQPASVTDDPSALHTRLARLSATEPELGDYRELVLDCRFAPKLVPRGSPEGGQPYPVLQVAHSAPVGAQLATELSIAEGQEVLFGVFVTGKDGGPGVGPNSVVCAFPIDLLDTLIDEGVERCCESPVHPGLRRGLDFFQSPSFCPNPPGLEALSPNTSCRHFPLLVSSSFSRVDLFNGLLGPVQVTALYVTRLDNVTVAHMGTMDGRILQVELVRSLNYLLYVSNFSLGDSGQPVQRDVSRLGDHLLFASGDQVFQVPIQGPGCRHFLTCGRCLRAWHFMGCGWCGNMCGQQKECPGSWQQDHCPPKLTEFHPHSGPLRGSTRLTLCGSNFYLHPSGLVPEGTHQVTVGQSPCRPLPKDSSKLRPVPRKDFVEEFECELEPLGTQAVGPTNVSLTVTNMPPGKHFRVDGTSVLRGFSFMETG";
 static const char* aa3(char c) {

@@ -95,6 +95,8 @@ static inline int target_pitch(int N) { return (N + 31) & ~31; }
 #define CHR3D_MAX_FLAGGED 4096
 int dev_if_to_tenths(const double* d_IF, int L, double alpha, double K, long long* d_tenths,
                      long long* n_uncertain_host, std::vector<long long>* flagged_host, cudaStream_t s);
+int dev_cells_to_tenths(const double* d_vals, long long n, const long long* d_row_ptr, int L, double alpha, double K, long long* d_tenths,
+                        long long* n_uncertain_host, std::vector<long long>* flagged_host, cudaStream_t s);
 // Dense fp32 target matrix [N][pitch] from tenths: d>0 restraint, -1 none, -2 none + no repel.
 int dev_tenths_to_targets(const long long* d_tenths, int L, int min_sep, int vdw_min_sep, float* d_T,
                           cudaStream_t s);

@@ -125,6 +125,57 @@ int dev_if_to_tenths(const double* d_IF, int L, double alpha, double K, long lon
     return 0;
 }
 
+// ---- the same derivation for a sparse matrix: only the non-zero cells, in i-major order (a CSR of the symmetric matrix).
+// Zero cells contribute exactly 0 to the reference's sum (C3D:132-137: 0**alpha = 0 for alpha > 0) and get no restraint
+// (C3D:148-150, 196), so summing the non-zero cells in the same order gives the same bits as the dense pass.
+__global__ void row_sum_csr_kernel(const double* __restrict__ P, const long long* __restrict__ row_ptr, int L, double* __restrict__ rows) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    double s = 0.0;
+    for (long long k = row_ptr[i]; k < row_ptr[i + 1]; k++) s += P[k];
+    rows[i] = s;
+}
+// d_vals: n non-zero cell values in i-major order; d_row_ptr: L + 1 offsets.  Tenths per cell as dev_if_to_tenths gives them.
+int dev_cells_to_tenths(const double* d_vals, long long n, const long long* d_row_ptr, int L, double alpha, double K, long long* d_tenths,
+                        long long* n_uncertain_host, std::vector<long long>* flagged_host, cudaStream_t s) {
+    DevBuf<double> P, sum, rows;
+    DevBuf<unsigned long long> nunc;
+    DevBuf<long long> flagged;
+    CHR3D_CUDA(P.alloc((size_t)std::max<long long>(n, 1)));
+    CHR3D_CUDA(sum.alloc(1)); CHR3D_CUDA(nunc.alloc(1)); CHR3D_CUDA(flagged.alloc(MAX_FLAGGED));
+    CHR3D_CUDA(cudaMemsetAsync(nunc.p, 0, sizeof(unsigned long long), s));
+    CHR3D_CUDA(cudaMemsetAsync(sum.p, 0, sizeof(double), s));
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 16));
+    if (n > 0) pow_kernel<<<blocks, 256, 0, s>>>(d_vals, P.p, n, alpha);
+    if (L <= SEQ_SUM_MAX_L) {
+        if (n > 0) seq_sum_staged_kernel<<<1, 256, 0, s>>>(P.p, n, sum.p);
+    } else {
+        CHR3D_CUDA(rows.alloc((size_t)L));
+        row_sum_csr_kernel<<<(L + 127) / 128, 128, 0, s>>>(P.p, d_row_ptr, L, rows.p);
+        seq_sum_staged_kernel<<<1, 256, 0, s>>>(rows.p, L, sum.p);
+    }
+    CHR3D_CUDA(cudaGetLastError());
+    double total = 0.0;
+    CHR3D_CUDA(cudaMemcpyAsync(&total, sum.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CHR3D_CUDA(cudaStreamSynchronize(s));
+    const double mean = total / ((double)L * (double)L);            // C3D:139
+    if (n > 0) tenths_kernel<<<blocks, 256, 0, s>>>(P.p, n, mean, K, d_tenths, nunc.p, flagged.p);
+    CHR3D_CUDA(cudaGetLastError());
+    unsigned long long nu = 0;
+    CHR3D_CUDA(cudaMemcpyAsync(&nu, nunc.p, sizeof(nu), cudaMemcpyDeviceToHost, s));
+    CHR3D_CUDA(cudaStreamSynchronize(s));
+    if (n_uncertain_host) *n_uncertain_host = (long long)nu;
+    if (flagged_host) {
+        flagged_host->clear();
+        if (nu > 0 && nu <= MAX_FLAGGED) {
+            flagged_host->resize((size_t)nu);
+            CHR3D_CUDA(cudaMemcpyAsync(flagged_host->data(), flagged.p, sizeof(long long) * (size_t)nu, cudaMemcpyDeviceToHost, s));
+            CHR3D_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    return 0;
+}
+
 __global__ void targets_from_tenths_kernel(const long long* __restrict__ tenths, int L, int pitch, int min_sep,
                                            int vdw_min_sep, float* __restrict__ T) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;

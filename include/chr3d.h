@@ -317,6 +317,13 @@ int chr3d_read_if_binary(const char* path, double* out, int64_t cap, int32_t* L)
 /* sparse (bin_i, bin_j, value) triplets, base 0 or 1, -> dense symmetric L*L matrix (device scatter; repeats add up)        */
 int chr3d_if_from_coo(const int32_t* bi, const int32_t* bj, const double* v, int64_t nnz, int32_t L, int32_t base, double* out);
 
+/* sparse triplets -> restraint rows (IF2dist_new + dist2rr, C3D:110-206) without forming the L x L matrix: the arithmetic runs on
+ * the device over the non-zero cells only and gives the rows of chr3d_if_to_restraints on the dense matrix chr3d_if_from_coo would
+ * build (same distances, bit for bit), in i-major row order instead of the reference's string order.  alpha > 0.  ri/rj/rd: capacity
+ * `cap` rows (nnz is always enough); cap = 0 only counts.  Feed the rows to chr3d_single_create_sparse or chr3d_job.ri/rj/rd.        */
+int chr3d_coo_to_restraints(const int32_t* bi, const int32_t* bj, const double* v, int64_t nnz, int32_t L, int32_t base,
+                            double alpha, double K, int32_t min_sep, int32_t* ri, int32_t* rj, double* rd, int64_t cap, int64_t* n_out);
+
 /* DG stage of dgsa.inp (C3D:1470-1526) at bead level: bounds from the restraint table (0-based ri < rj), triangle smoothing,
  * per-model trial distances, metric-matrix embedding (three largest positive eigenpairs).  xyz_out: n_models*N*3 starting
  * coordinates — pass them as chr3d_job.x0; eig3_out (n_models*3) and n_inconsistent are optional diagnostics.  N <= 1600.   */

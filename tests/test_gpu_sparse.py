@@ -100,3 +100,49 @@ def test_sparse_rows_are_validated(gpu_api):
     for bad in (([0, 5], [3, 50], [4.0, 5.0]), ([2], [2], [4.0]), ([0, 0], [3, 3], [4.0, 4.1]), ([0], [3], [0.0])):
         with pytest.raises(Chr3dError):
             gpu_api.Single(N=40, restraints=bad, p=p, program=prog)
+
+
+@pytest.mark.parametrize("L,keep", [(300, 0.08), (2600, 0.01), (9000, 0.002)])
+def test_coo_to_restraints_equals_the_dense_derivation(gpu_api, L, keep):
+    """Sparse triplets -> rows without the L x L matrix (device arithmetic over the non-zero cells only): the same rows and the same
+    distances, bit for bit, as IF2dist_new + dist2rr on the dense matrix (C3D:110-206) — the oracle for the small case, the dense
+    CUDA path for the larger ones (9,000 bins: beyond the single-thread sum, the mean is summed row by row in both)."""
+    rng = np.random.default_rng(L)
+    n = int(keep * L * L / 2)
+    bi = rng.integers(0, L, n).astype(np.int32)
+    bj = rng.integers(0, L, n).astype(np.int32)
+    lo, hi = np.minimum(bi, bj), np.maximum(bi, bj)
+    v = np.round(rng.gamma(0.7, 40.0, n) / (1.0 + (hi - lo)) ** 0.8 + 0.01, 4)
+    diag = np.arange(L, dtype=np.int32)                       # a full diagonal and first off-diagonal, plus repeats that must add up
+    bi = np.concatenate([lo, diag, diag[:-1], lo[:50]]); bj = np.concatenate([hi, diag, diag[:-1] + 1, hi[:50]])
+    v = np.concatenate([v, rng.uniform(100, 900, L), rng.uniform(50, 300, L - 1), v[:50]])
+    alpha = 0.7
+    ri, rj, rd = gpu_api.coo_to_restraints(bi, bj, v, L, alpha)
+    assert np.all(rj - ri >= 5) and np.all(rd > 0) and np.all(np.diff(ri.astype(np.int64) * L + rj) > 0)          # i-major, unique
+    dense = np.zeros((L, L))
+    np.add.at(dense, (bi, bj), v)
+    dense = dense + np.triu(dense, 1).T                       # all triplets are upper-triangle here: (i, j) and (j, i) both receive them
+    if L <= 300:
+        oi, oj, od = orc.if_to_restraints(dense, alpha)
+    else:
+        oi, oj, od = gpu_api.if_to_restraints(dense, alpha)
+    order = np.argsort(oi.astype(np.int64) * L + oj, kind="stable")
+    assert len(ri) == len(oi) and np.array_equal(ri, oi[order]) and np.array_equal(rj, oj[order]) and np.array_equal(rd, od[order])
+    # one-based indices, and the rows feed the sparse engine
+    r1 = gpu_api.coo_to_restraints(bi + 1, bj + 1, v, L, alpha, base=1)
+    assert np.array_equal(r1[0], ri) and np.array_equal(r1[2], rd)
+    if L == 2600:
+        prog = abi.stage_array([abi.stage(abi.OP_INIT, flag=1), abi.stage(abi.OP_ENERGY, w_noe=10, w_bond=1000, w_vdw=4.0, repel=0.85)])
+        x = orc.random_coil(L, 3.8, 2, 0).astype(np.float32).astype(np.float64)
+        s = gpu_api.Single(N=L, restraints=(ri, rj, rd), x0=x, p=gpu_api.default_params(), program=prog)
+        s.run()
+        r = s.fetch()
+        s.close()
+        eo, fo = orc.energy_forces(x, ri, rj, rd, gpu_api.default_params(), abi.stage(abi.OP_ENERGY, w_noe=10, w_bond=1000, w_vdw=4.0, repel=0.85))
+        assert np.allclose(r["energies"], eo[0], rtol=1e-5, atol=1e-5 * abs(eo[0, 0]))
+    from chromosome3d_b200.api import Chr3dError
+    with pytest.raises(Chr3dError):
+        gpu_api.coo_to_restraints([0], [L], [1.0], L, alpha)
+    with pytest.raises(Chr3dError):
+        gpu_api.coo_to_restraints([0], [9], [1.0], L, 0.0)
+    assert len(gpu_api.coo_to_restraints([], [], [], 12, alpha)[0]) == 0
