@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(SP_THREADS) sp_eval_kernel(const SpEvalArgs A)
         const float4 xi = xs[i];
         float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f, ev = 0.f;
         const long long r0 = A.m.row_ptr[i], r1 = A.m.row_ptr[i + 1];
-        for (long long k = r0 + lane; k < r1; k += 32) {
+#pragma unroll 4
+        for (long long k = r0 + lane; k < r1; k += 32) {      // (unrolled: four column -> coordinate load chains in flight per lane)
             const float4 xj = xs[__ldg(A.m.col + k)];
             const float d = __ldg(A.m.dist + k);
             const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
