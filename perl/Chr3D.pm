@@ -37,6 +37,7 @@ my %SIG = (    # name => [ret, args] in FFI::Platypus type names (pointers = opa
     chr3d_write_pdb        => ['int',    ['string', 'opaque', 'sint32', 'opaque', 'opaque', 'sint32']],
     chr3d_spearman         => ['int',    ['opaque', 'sint32', 'opaque', 'sint32', 'sint32', 'opaque']],
     chr3d_dg_embed         => ['int',    ['opaque', 'opaque', 'opaque', 'sint64', 'sint32', 'opaque', 'sint32', 'uint64', 'opaque', 'opaque', 'opaque']],
+    chr3d_dg_starts        => ['int',    ['opaque', 'opaque', 'opaque', 'sint64', 'sint32', 'opaque', 'sint32', 'uint64', 'double', 'sint32', 'double', 'opaque', 'opaque', 'opaque', 'opaque']],
     chr3d_reduce_model     => ['int',    ['opaque', 'sint32', 'opaque']],
     chr3d_write_reduced_pdb => ['int',   ['string', 'opaque', 'sint32']],
     chr3d_model_similarity => ['int',    ['opaque', 'sint32', 'opaque', 'sint32', 'opaque', 'opaque']],
@@ -203,6 +204,16 @@ sub dg_embed {
     my ($xyz, $eig, $bad) = (_buf(8 * 3 * $N * $m), _buf(8 * 3 * $m), _buf(8));
     _check(_c_chr3d_dg_embed(ptr($ri), ptr($rj), ptr($rd), $nr, $N, ptr($p), $m, $seed // 0, ptr($xyz), ptr($eig), ptr($bad)), "chr3d_dg_embed");
     return ($xyz, unpack("q", $bad));
+}
+# The whole DG stage (C3D:1470-1526): embedding, x *= $dgscale, md.dg.step = 200 L-BFGS iterations (drop = 1.) on the bounds energy with
+# md.dg.scale = 100.  Returns (packed xyz, inconsistent pairs, [dgscale, E scaled, E final, iterations, evaluations, rms gradient] of model 1)
+sub dg_starts {
+    my ($ri, $rj, $rd, $nr, $N, $m, $seed, $params) = @_;
+    _load();
+    my $p = $params // default_params();
+    my ($xyz, $eig, $st, $bad) = (_buf(8 * 3 * $N * $m), _buf(8 * 3 * $m), _buf(8 * 6 * $m), _buf(8));
+    _check(_c_chr3d_dg_starts(ptr($ri), ptr($rj), ptr($rd), $nr, $N, ptr($p), $m, $seed // 0, 100.0, 200, 1.0, ptr($xyz), ptr($eig), ptr($st), ptr($bad)), "chr3d_dg_starts");
+    return ($xyz, unpack("q", $bad), [unpack("d6", $st)]);
 }
 sub reduce_model {      # (packed xyz, N) -> (packed xyz of ceil(N/2) beads, n)
     my ($xyz, $N) = @_;

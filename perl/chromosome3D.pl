@@ -67,10 +67,11 @@ die "no restraints: nothing to fold\n" if $nr < 1;
 
 # ---- the DGSA run (replaces build_extended/build_models, C3D:234-289) --------------------------
 print "\n(B) Build models using libchr3d dgsa (" . Chr3D::version() . ", binding: " . Chr3D::backend() . ")..\n";
-my $x0;      # --start dg: the DG stage of dgsa.inp (C3D:1470-1526), metric-matrix embedding of the smoothed bounds
+my $x0;      # --start dg: the DG stage of dgsa.inp (C3D:1470-1526): embedding of the smoothed bounds, dgscale, 200-step bounds-only minimisation
 if ($start eq "dg") {
-    ($x0, my $bad) = Chr3D::dg_embed($ri, $rj, $rd, $nr, $L, $mcount, $seed // 0);
+    ($x0, my $bad, my $st) = Chr3D::dg_starts($ri, $rj, $rd, $nr, $L, $mcount, $seed // 0);
     print "DG start   : embedded $mcount models ($bad pairs with triangle-inconsistent bounds)\n";
+    printf "DG start   : dgscale %.3f, %d iterations of the bounds-only minimisation (md.dg.step 200), E_dg %.4g -> %.4g\n", $st->[0], $st->[3], $st->[1], $st->[2];
 }
 my $res = Chr3D::run_ensemble(IF => $IF, L => $L, alpha => $ALPHA + 0, K => $KSCALING + 0, min_sep => $min_sep,
                               n_models => $mcount, seed => $seed // 0, x0 => $x0, params => ($pin ? Chr3D::cns_pin_params() : undef));

@@ -300,3 +300,27 @@ chr3d_dg_embed(ri, rj, rd, nr, N, p, n_models, seed, xyz_out, eig3_out, n_incons
                             n_models, (uint64_t)seed, P(double*, xyz_out), P(double*, eig3_out), P(int64_t*, n_inconsistent));
   OUTPUT:
     RETVAL
+
+int
+chr3d_dg_starts(ri, rj, rd, nr, N, p, n_models, seed, dg_scale, nstep, drop, xyz_out, eig3_out, stats_out, n_inconsistent)
+    UV ri
+    UV rj
+    UV rd
+    IV nr
+    int N
+    UV p
+    int n_models
+    UV seed
+    double dg_scale
+    int nstep
+    double drop
+    UV xyz_out
+    UV eig3_out
+    UV stats_out
+    UV n_inconsistent
+  CODE:
+    RETVAL = chr3d_dg_starts(P(const int32_t*, ri), P(const int32_t*, rj), P(const double*, rd), (int64_t)nr, N, P(const chr3d_sa_params*, p),
+                             n_models, (uint64_t)seed, dg_scale, nstep, drop, P(double*, xyz_out), P(double*, eig3_out), P(double*, stats_out),
+                             P(int64_t*, n_inconsistent));
+  OUTPUT:
+    RETVAL

@@ -177,6 +177,8 @@ def test_front_end_dg_start(tmp_path):
     r = _perl([os.path.join(PERL, "chromosome3D.pl"), "-i", ds.input_path("chr21_1mb"), "-o", str(out), "-m", "3", "--start", "dg"])
     assert r.returncode == 0, r.stderr + r.stdout
     assert re.search(r"DG start\s+: embedded 3 models \(\d+ pairs", r.stdout)
+    m = re.search(r"DG start\s+: dgscale ([0-9.]+), (\d+) iterations .* E_dg ([0-9.e+]+) -> ([0-9.e+]+)", r.stdout)
+    assert m and 1.0 < float(m.group(1)) < 1.5 and 1 <= int(m.group(2)) <= 200 and float(m.group(4)) < float(m.group(3))
     assert all(os.path.exists(out / ("chr21_1mb_matrix_model%d.pdb" % k)) for k in (1, 2, 3))
     IF = ds.load_if_matrix(ds.input_path("chr21_1mb"))
     xyz = ds.read_ca_pdb(str(out / "chr21_1mb_matrix_model1.pdb"))
