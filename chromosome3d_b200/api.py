@@ -90,8 +90,20 @@ def default_params():
 
 
 def set_option(name, value=None):
-    """chr3d_set_option: launch-shape options of the ensemble kernel ("sa_cluster", "sa_warps", "sa_min_smem", "sa_split"); None clears."""
+    """chr3d_set_option: launch-shape options of the ensemble kernel ("sa_cluster", "sa_warps", "sa_min_smem", "sa_split") and
+    "seqsum" = "serial" (the left-to-right sums as a serial chain instead of in parallel; same bits); None clears."""
     _check(lib().chr3d_set_option(name.encode(), None if value is None else str(value).encode()))
+
+
+def seq_sum(a):
+    """chr3d_seq_sum: the left-to-right fp64 sum of every row of `a` (1-D: one sum), with the bits of `for v in row: s += v`
+    (the Perl's `$sum += ...` loops, C3D:132-139, 590-598), evaluated in parallel on the device."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    one = a.ndim == 1
+    a2 = a.reshape(1, -1) if one else a.reshape(a.shape[0], -1)
+    out = np.zeros(a2.shape[0], dtype=np.float64)
+    _check(lib().chr3d_seq_sum(_d(a2), C.c_int64(a2.shape[1]), C.c_int32(a2.shape[0]), _d(out)))
+    return float(out[0]) if one else out
 
 
 def cns_pin_params():

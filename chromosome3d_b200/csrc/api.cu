@@ -823,7 +823,8 @@ CHR3D_API void chr3d_cns_pin_params(chr3d_sa_params* p) {
 //   for at least (0 lets several CTAs share an SM), "sa_split" = "0": never run the two hot-MD images as trajectories of their own.
 // value NULL or "" clears the option.  Options are read when an ensemble is created.
 CHR3D_API int chr3d_set_option(const char* name, const char* value) {
-    static const char* const known[][2] = {{"sa_cluster", "CHR3D_SA_CLUSTER"}, {"sa_warps", "CHR3D_SA_WARPS"}, {"sa_min_smem", "CHR3D_SA_MIN_SMEM"}, {"sa_split", "CHR3D_NO_SPLIT"}};
+    static const char* const known[][2] = {{"sa_cluster", "CHR3D_SA_CLUSTER"}, {"sa_warps", "CHR3D_SA_WARPS"}, {"sa_min_smem", "CHR3D_SA_MIN_SMEM"}, {"sa_split", "CHR3D_NO_SPLIT"},
+                                           {"seqsum", "CHR3D_SEQSUM"}};
     if (!name) { set_error("chr3d_set_option: null name"); return CHR3D_ERR_ARG; }
     for (auto& k : known) {
         if (strcmp(name, k[0]) != 0) continue;
@@ -832,6 +833,10 @@ CHR3D_API int chr3d_set_option(const char* name, const char* value) {
         const bool clear = !value || !*value;
         if (strcmp(k[0], "sa_split") == 0) {          // stored under the name of the switch it replaces: present = no split
             if (clear || strcmp(value, "0") != 0) t.erase(k[1]); else t[k[1]] = "1";
+        } else if (strcmp(k[0], "seqsum") == 0) {     // "serial" or cleared (= the parallel evaluation)
+            if (clear) t.erase(k[1]);
+            else if (strcmp(value, "serial") == 0) t[k[1]] = "serial";
+            else { set_error("chr3d_set_option: seqsum wants \"serial\" or nothing, got '%s'", value); return CHR3D_ERR_ARG; }
         } else if (clear) t.erase(k[1]);
         else {
             char* end = nullptr; const long v = strtol(value, &end, 10);
@@ -840,6 +845,6 @@ CHR3D_API int chr3d_set_option(const char* name, const char* value) {
         }
         return 0;
     }
-    set_error("chr3d_set_option: unknown option '%s' (sa_cluster, sa_warps, sa_min_smem, sa_split)", name);
+    set_error("chr3d_set_option: unknown option '%s' (sa_cluster, sa_warps, sa_min_smem, sa_split, seqsum)", name);
     return CHR3D_ERR_ARG;
 }

@@ -115,7 +115,7 @@ int dev_assess(const double* d_xyz, int n_models, int N, const int32_t* d_ri, co
     dim3 grid((unsigned)((nr + 255) / 256), n_models);
     assess_terms_kernel<<<grid, 256, 0, s>>>(mx.p, n_models, N, d_ri, d_rj, d_rd, nr, d_sat, dense ? terms.p : nullptr, dense ? nullptr : terms.p);
     CHR3D_CUDA(cudaGetLastError());
-    if (dense) seq_sum_staged_kernel<<<n_models, 256, 0, s>>>(terms.p, per_model, d_dev);
+    if (dense) seq_sum_launch(terms.p, per_model, n_models, d_dev, s);
     else block_sum_kernel<<<n_models, 256, 0, s>>>(terms.p, per_model, d_dev);
     CHR3D_CUDA(cudaGetLastError());
     CHR3D_CUDA(cudaStreamSynchronize(s));

@@ -7,9 +7,10 @@
 // The device works in integer tenths of an Angstrom (the exact content of the "%.1f" text).
 //
 // Bit-exactness against the Perl:
-//   * the sum runs in the reference's order on one thread (L <= SEQ_SUM_MAX_L), so the fp64
-//     roundings of C3D:132-139 are reproduced; above that size (beyond the reference's own 663
-//     bead cap, C3D:93-94) a fixed blocked order is used;
+//   * the sum is the reference's left-to-right sum (L <= SEQ_SUM_MAX_L), so the fp64 roundings of
+//     C3D:132-139 are reproduced — evaluated in parallel without changing a bit (seqsum.cuh);
+//     above that size (beyond the reference's own 663 bead cap, C3D:93-94) a fixed blocked order
+//     is used;
 //   * the decimal rounding is decided exactly with an FMA residual (no rint(10*x));
 //   * CUDA's pow() is within 2 ulp of the correctly rounded result, glibc's within 1 ulp, so D may
 //     differ from Perl's by a few ulp.  Every cell whose rounding would change under a relative
@@ -97,11 +98,11 @@ int dev_if_to_tenths(const double* d_IF, int L, double alpha, double K, long lon
     pow_kernel<<<blocks, 256, 0, s>>>(d_IF, P.p, n, alpha);
     CHR3D_CUDA(cudaGetLastError());
     if (L <= SEQ_SUM_MAX_L) {
-        seq_sum_staged_kernel<<<1, 256, 0, s>>>(P.p, n, sum.p);
+        seq_sum_launch(P.p, n, 1, sum.p, s);
     } else {
         CHR3D_CUDA(rows.alloc((size_t)L));
         row_sum_kernel<<<(L + 127) / 128, 128, 0, s>>>(P.p, L, rows.p);
-        seq_sum_staged_kernel<<<1, 256, 0, s>>>(rows.p, L, sum.p);
+        seq_sum_launch(rows.p, L, 1, sum.p, s);
     }
     CHR3D_CUDA(cudaGetLastError());
     double total = 0.0;
@@ -148,11 +149,11 @@ int dev_cells_to_tenths(const double* d_vals, long long n, const long long* d_ro
     const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 16));
     if (n > 0) pow_kernel<<<blocks, 256, 0, s>>>(d_vals, P.p, n, alpha);
     if (L <= SEQ_SUM_MAX_L) {
-        if (n > 0) seq_sum_staged_kernel<<<1, 256, 0, s>>>(P.p, n, sum.p);
+        if (n > 0) seq_sum_launch(P.p, n, 1, sum.p, s);
     } else {
         CHR3D_CUDA(rows.alloc((size_t)L));
         row_sum_csr_kernel<<<(L + 127) / 128, 128, 0, s>>>(P.p, d_row_ptr, L, rows.p);
-        seq_sum_staged_kernel<<<1, 256, 0, s>>>(rows.p, L, sum.p);
+        seq_sum_launch(rows.p, L, 1, sum.p, s);
     }
     CHR3D_CUDA(cudaGetLastError());
     double total = 0.0;
@@ -296,3 +297,19 @@ int dev_tenths_to_list(const long long* d_tenths, int L, int min_sep, int32_t* d
 }
 
 }  // namespace chr3d
+
+// The left-to-right sum as an entry point of its own (include/chr3d.h): host arrays in, the bits of the scalar loop out.
+CHR3D_API int chr3d_seq_sum(const double* a, int64_t n_per, int32_t nseg, double* out) {
+    using namespace chr3d;
+    if (n_per < 0 || nseg < 0 || (nseg > 0 && !out) || (n_per > 0 && nseg > 0 && !a)) { set_error("chr3d_seq_sum: bad arguments"); return CHR3D_ERR_ARG; }
+    if (int rc = require_device()) return rc;
+    if (nseg == 0) return 0;
+    DevBuf<double> d, r;
+    const size_t n = (size_t)n_per * (size_t)nseg;
+    CHR3D_CUDA(d.alloc(n > 0 ? n : 1)); CHR3D_CUDA(r.alloc((size_t)nseg));
+    if (n > 0) CHR3D_CUDA(cudaMemcpy(d.p, a, sizeof(double) * n, cudaMemcpyHostToDevice));
+    seq_sum_launch(d.p, n_per, nseg, r.p, 0);
+    CHR3D_CUDA(cudaGetLastError());
+    CHR3D_CUDA(cudaMemcpy(out, r.p, sizeof(double) * (size_t)nseg, cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -349,9 +349,16 @@ int chr3d_single_tile_split(int32_t N, int32_t world, int32_t ctas, int64_t* ran
  * library decides): "sa_cluster" = CTAs per trajectory (1..8), "sa_warps" = warps per CTA (4..12), "sa_min_smem" = least shared
  * memory a CTA asks for in bytes (0 lets several CTAs share an SM), "sa_split" = "0" never runs the two hot-MD images of a model
  * (C3D:1605-1708) as trajectories of their own.  value NULL or "" clears the option.  (The reference has no counterpart: its
- * parallelism is one cns_solve process per run, test.sh.)  Everything else that used to be an environment switch is compiled in
- * only with -DCHR3D_DEV. */
+ * parallelism is one cns_solve process per run, test.sh.)  "seqsum" = "serial" evaluates the left-to-right fp64 sums (below) as
+ * a serial chain instead of in parallel — same bits, for cross-checks.  Everything else that used to be an environment switch
+ * is compiled in only with -DCHR3D_DEV. */
 int chr3d_set_option(const char* name, const char* value);
+
+/* The left-to-right fp64 sum `for (k) s += a[k]` of each of nseg segments of n_per terms (host arrays), evaluated on the device
+ * with the bits of the scalar loop: what the restraint derivation uses for the mean of IF**alpha (`$sum += ...`, C3D:132-139)
+ * and the assessment for the sum of deviations (C3D:590-598).  Parallel inside a binade of the running sum (integer prefix
+ * scans), one real addition per tie / carry / irregular term; csrc/seqsum_core.h states the argument. */
+int chr3d_seq_sum(const double* a, int64_t n_per, int32_t nseg, double* out);
 
 #ifdef __cplusplus
 }
