@@ -68,7 +68,9 @@ static __global__ void __launch_bounds__(SEQSUM_THREADS) seq_sum_exact_kernel(co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { sh_s = 0.0; sh_pos = 0; sh_run = 1; }
     __syncthreads();
+    long long passes = 0;
     while (true) {
+        if (++passes > n_per + 8) __trap();        // every pass consumes at least one term: more passes than terms is a bug, not a wait
         const long long pos = sh_pos;
         const double s = sh_s;
         const int run = sh_run;
