@@ -490,12 +490,13 @@ static int ensemble_create(const chr3d_job* jobs, int njobs, const chr3d_sa_para
             if (int rc = if_to_tenths_certified(jb.IF, N, jb.alpha, jb.K, dIF, dT, nullptr, 0)) return rc;
             tr.lap("tenths");
             if (int rc = dev_tenths_to_targets(dT.p, N, jb.min_sep, p->vdw_min_sep, jd->T.p, 0)) return rc;
-            long long n = 0;
-            if (int rc = dev_tenths_to_list(dT.p, N, jb.min_sep, nullptr, nullptr, nullptr, 0, &n, 0)) return rc;
+            // rows are at most the cells with j - i >= min_sep: room for all of them, so that counting and filling is one pass
+            long long n = 0, room = 0;
+            for (int i = 0; i < N; i++) room += N - std::min(N, std::max(0, i + jb.min_sep));
+            room = std::max<long long>(room, 1);
+            CHR3D_CUDA(jd->ri.alloc((size_t)room)); CHR3D_CUDA(jd->rj.alloc((size_t)room)); CHR3D_CUDA(jd->rd.alloc((size_t)room));
+            if (int rc = dev_tenths_to_list(dT.p, N, jb.min_sep, jd->ri.p, jd->rj.p, jd->rd.p, room, &n, 0)) return rc;
             jd->nr = n;
-            CHR3D_CUDA(jd->ri.alloc((size_t)std::max<long long>(n, 1))); CHR3D_CUDA(jd->rj.alloc((size_t)std::max<long long>(n, 1)));
-            CHR3D_CUDA(jd->rd.alloc((size_t)std::max<long long>(n, 1)));
-            if (int rc = dev_tenths_to_list(dT.p, N, jb.min_sep, jd->ri.p, jd->rj.p, jd->rd.p, std::max<long long>(n, 1), &n, 0)) return rc;
         } else {
             if (jb.nr > 0 && (!jb.ri || !jb.rj || !jb.rd)) { set_error("job %d: restraint table pointers missing", jn); return CHR3D_ERR_ARG; }
             if (int rc = upload_list(*jd, jb.ri, jb.rj, jb.rd, jb.nr, 0, N, true, "chr3d_build_models", p->vdw_min_sep)) return rc;

@@ -245,11 +245,21 @@ __global__ void list_count_kernel(const long long* __restrict__ tenths, int L, i
     }
     if (lane == 0) counts[a] = cnt;
 }
+// exclusive prefix sum of the per-row counts, one warp (integers: any order gives the same offsets)
 __global__ void list_scan_kernel(unsigned long long* counts, int L, unsigned long long* total) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    unsigned long long s = 0;
-    for (int a = 0; a < L; a++) { unsigned long long c = counts[a]; counts[a] = s; s += c; }
-    *total = s;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    unsigned long long carry = 0;
+    for (int a0 = 0; a0 < L; a0 += 32) {
+        const int a = a0 + lane;
+        const unsigned long long c = a < L ? counts[a] : 0ull;
+        unsigned long long incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (a < L) counts[a] = carry + incl - c;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) *total = carry;
 }
 __global__ void list_fill_kernel(const long long* __restrict__ tenths, int L, int min_sep, const int* __restrict__ perm,
                                  const unsigned long long* __restrict__ offs, long long cap,
