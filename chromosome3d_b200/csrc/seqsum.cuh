@@ -50,8 +50,9 @@ static __global__ void __launch_bounds__(256) seq_sum_staged_kernel(const double
 // denormal / non-finite term, or no valid frame yet) ends the pass: everything before it is added at once, that term with a real
 // fp64 add by the thread that owns it.  Real data (positive, unremarkable) needs one short pass per doubling of the sum and one
 // per full window after that: 34 passes for the 207,025 cells of chr1_500kb.  Inputs that stop all the time (denormal sums,
-// dyadic values that tie at every step) would pay a pass per term, so a pass that got nowhere lengthens the serial run that
-// follows its stop (up to 4,096 terms): such inputs degrade to the serial chain, not below it.
+// dyadic values that tie at every step) would pay a pass per term, so a pass that folded in fewer than 32 terms doubles the
+// serial run that follows its stop (up to 4,096 terms; any longer pass resets it to the one stopping term): such inputs degrade
+// to the serial chain, not below it.
 #define SEQSUM_THREADS 1024
 #define SEQSUM_PER_THREAD 8
 #define SEQSUM_WINDOW (SEQSUM_THREADS * SEQSUM_PER_THREAD)
@@ -76,6 +77,7 @@ static __global__ void __launch_bounds__(SEQSUM_THREADS) seq_sum_exact_kernel(co
         const int run = sh_run;
         if (pos >= n_per) break;
         const SeqSumFrame f = seqsum_frame(s);
+        const SeqSumFpFrame g = seqsum_fp_frame(f);
         const long long end = pos + SEQSUM_WINDOW < n_per ? pos + SEQSUM_WINDOW : n_per;
         const long long k0 = pos + (long long)tid * SEQSUM_PER_THREAD;
         // all loads of the pass first (behind the branches of the classification they would be issued one L2 round trip after the
@@ -86,7 +88,7 @@ static __global__ void __launch_bounds__(SEQSUM_THREADS) seq_sum_exact_kernel(co
         unsigned long long c[SEQSUM_PER_THREAD];
         unsigned stopmask = 0;
 #pragma unroll
-        for (int j = 0; j < SEQSUM_PER_THREAD; j++) { bool st; c[j] = seqsum_contrib(a[j], f.ef, f.ok, st); if (st) stopmask |= 1u << j; }
+        for (int j = 0; j < SEQSUM_PER_THREAD; j++) { bool st; c[j] = seqsum_contrib_fp(a[j], g, f.ok, st); if (st) stopmask |= 1u << j; }
         // thread total, capped at 2^53 (a thread that reaches it holds a carry, and nothing behind a carry is used): the block
         // total stays below 2^63
         unsigned long long loc = 0;
@@ -142,7 +144,7 @@ static __global__ void __launch_bounds__(SEQSUM_THREADS) seq_sum_exact_kernel(co
             sh_s = t;
             sh_pos = kend;
             const long long consumed = km - pos;
-            sh_run = consumed < 256 ? (run * 2 < SEQSUM_MAX_RUN ? run * 2 : SEQSUM_MAX_RUN) : (consumed >= 1024 ? 1 : run);
+            sh_run = consumed < 32 ? (run * 2 < SEQSUM_MAX_RUN ? run * 2 : SEQSUM_MAX_RUN) : 1;
         }
         __syncthreads();
     }

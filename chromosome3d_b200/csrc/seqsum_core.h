@@ -77,4 +77,36 @@ SEQSUM_HD uint64_t seqsum_contrib(double a, int ef, bool frame_ok, bool& stop) {
     return (m >> sh) + (r > half ? 1ull : 0ull);
 }
 
+// The same contribution through three fp64 additions instead of 64-bit integer shifts (what the kernel runs: a fifth of the
+// instructions).  B = 2^e is the bottom of the frame's binade — an even multiple of u — so for 0 < a < B/2
+//     x = B + a        rounds a to a multiple of u exactly as s + a does (ties aside), and stays below 1.5 B,
+//     cu = x - B       is exact (Sterbenz), the contribution times u; its integer value is the low 52 bits of x,
+//     r = a - cu       is exact as well (|r| <= u/2, a multiple of a's own last place): |r| = u/2 is the tie.
+// Terms of B/2 and more (a quarter of the running sum: only the first few terms of a sum) are left to the fp64 add, like
+// negative and non-finite ones; a denormal term adds 0 here (it is below u/2 in every valid frame).
+struct SeqSumFpFrame { double B, halfB, halfu; };
+SEQSUM_HD SeqSumFpFrame seqsum_fp_frame(const SeqSumFrame& f) {
+    SeqSumFpFrame g;
+    const uint64_t ef = (uint64_t)(f.ok ? f.ef : 1023);
+    g.B = seqsum_from_bits(ef << 52); g.halfB = seqsum_from_bits((ef - 1) << 52); g.halfu = seqsum_from_bits((ef - 53) << 52);
+    return g;
+}
+SEQSUM_HD double seqsum_add(double x, double y) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(x, y);         // never re-associated or fused
+#else
+    volatile double t = x + y; return t;
+#endif
+}
+SEQSUM_HD uint64_t seqsum_contrib_fp(double a, const SeqSumFpFrame& g, bool frame_ok, bool& stop) {
+    stop = false;
+    if (a == 0.0) return 0;                                                   // +0 / -0
+    if (!frame_ok || !(a > 0.0) || !(a < g.halfB)) { stop = true; return 0; }  // a NaN fails both comparisons
+    const double x = seqsum_add(g.B, a);
+    const double cu = seqsum_add(x, -g.B);
+    const double r = seqsum_add(a, -cu);
+    if (r == g.halfu || r == -g.halfu) { stop = true; return 0; }
+    return seqsum_bits(x) & (SEQSUM_ONE52 - 1);
+}
+
 }  // namespace chr3d

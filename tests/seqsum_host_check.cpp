@@ -25,13 +25,19 @@ static double windowed_sum(const std::vector<double>& a, long long window, long 
     while (pos < n) {
         it++;
         const SeqSumFrame f = seqsum_frame(s);
+        const SeqSumFpFrame g = seqsum_fp_frame(f);
         const long long end = pos + window < n ? pos + window : n;
         uint64_t P = 0;                 // inclusive prefix of the contributions (saturating at 2^53, as the kernel's thread-local prefix)
         long long kstop = end;
         uint64_t Pexcl = 0;
         for (long long k = pos; k < end; k++) {
             bool stop;
-            const uint64_t c = seqsum_contrib(a[k], f.ef, f.ok, stop);
+            const uint64_t c = seqsum_contrib_fp(a[k], g, f.ok, stop);
+            {   // the integer formulation agrees wherever both fold the term in
+                bool stop_i; const uint64_t ci = seqsum_contrib(a[k], f.ef, f.ok, stop_i);
+                if (!stop && !stop_i && c != ci) { printf("FAIL contribution: a=%a frame ef=%d fp=%llu int=%llu\n", a[k], f.ef, (unsigned long long)c, (unsigned long long)ci); exit(1); }
+                if (!stop && stop_i && !(seqsum_bits(a[k]) >> 52 == 0)) { printf("FAIL: the integer form stops at a=%a (ef=%d), the fp form does not\n", a[k], f.ef); exit(1); }
+            }
             const uint64_t Pn = P + c;
             if (stop || (f.ok && f.S + Pn >= SEQSUM_TOP)) { kstop = k; Pexcl = P; break; }
             P = Pn; Pexcl = P;
@@ -41,7 +47,7 @@ static double windowed_sum(const std::vector<double>& a, long long window, long 
             const long long kend = kstop + run < n ? kstop + run : n, consumed = kstop - pos;
             for (long long k = kstop; k < kend; k++) { volatile double t = s + a[k]; s = t; }
             pos = kend;
-            run = consumed < 256 ? (run * 2 < 4096 ? run * 2 : 4096) : (consumed >= 1024 ? 1 : run);
+            run = consumed < 32 ? (run * 2 < 4096 ? run * 2 : 4096) : 1;
         } else { pos = end; run = 1; }
     }
     if (iterations) *iterations = it;
@@ -64,13 +70,14 @@ static double emulated_block_sum(const std::vector<double>& a, long long* passes
         if (pos >= n_per) break;
         it++;
         const SeqSumFrame f = seqsum_frame(s);
+        const SeqSumFpFrame g = seqsum_fp_frame(f);
         const long long end = pos + WINDOW < n_per ? pos + WINDOW : n_per;
         for (int tid = 0; tid < T; tid++) {
             const long long k0 = pos + (long long)tid * PER;
             stopmask[tid] = 0;
             for (int j = 0; j < PER; j++) {
                 c[(size_t)tid * PER + j] = 0;
-                if (k0 + j < end) { bool st; c[(size_t)tid * PER + j] = seqsum_contrib(a[k0 + j], f.ef, f.ok, st); if (st) stopmask[tid] |= 1u << j; }
+                if (k0 + j < end) { bool st; c[(size_t)tid * PER + j] = seqsum_contrib_fp(a[k0 + j], g, f.ok, st); if (st) stopmask[tid] |= 1u << j; }
             }
             uint64_t l = 0;
             for (int j = 0; j < PER; j++) { l += c[(size_t)tid * PER + j]; if (l > SEQSUM_TOP) l = SEQSUM_TOP; }
@@ -107,7 +114,7 @@ static double emulated_block_sum(const std::vector<double>& a, long long* passes
                 for (long long k = km; k < kend; k++) t = t + a[k];
                 sh_s = t; sh_pos = kend;
                 const long long consumed = km - pos;
-                sh_run = consumed < 256 ? (run * 2 < 4096 ? run * 2 : 4096) : (consumed >= 1024 ? 1 : run);
+                sh_run = consumed < 32 ? (run * 2 < 4096 ? run * 2 : 4096) : 1;
                 writers++;
             }
         }
