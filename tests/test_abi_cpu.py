@@ -98,3 +98,18 @@ def test_set_option_accepts_only_the_launch_shape_options():
         api.set_option("sa_cluster", "two")
     with pytest.raises(api.Chr3dError):
         api.set_option("CHR3D_LN_DEBUG", 1)          # development switches are not options (compiled in only with -DCHR3D_DEV)
+    api.set_option("seqsum", "serial")               # the left-to-right sums as a serial chain (cross-checks); nothing else is a value
+    api.set_option("seqsum", None)
+    with pytest.raises(api.Chr3dError):
+        api.set_option("seqsum", "tree")
+
+
+def test_seq_sum_needs_a_device():
+    """chr3d_seq_sum has no CPU path either: bad arguments are refused, and without a GPU the call fails loudly."""
+    import ctypes as C
+    out = (C.c_double * 1)()
+    assert api.lib().chr3d_seq_sum(None, C.c_int64(5), C.c_int32(1), out) == abi.ERR_ARG
+    if api.device_count() <= 0:
+        with pytest.raises(api.Chr3dError) as ei:
+            api.seq_sum([1.0, 2.0])
+        assert ei.value.code == abi.ERR_NO_DEVICE
