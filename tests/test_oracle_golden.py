@@ -170,3 +170,29 @@ def test_oracle_sa_reproduces_shipped_statistics():
     assert 3.6 < bl.min() and bl.max() < 5.2
     rg = np.sqrt(((x - x.mean(1, keepdims=True)) ** 2).sum(2).mean(1))
     assert abs(rg.mean() - 18.1) < 1.5
+
+
+def test_spearman_against_an_independent_implementation():
+    """The rank-correlation arithmetic of the un-vendored Statistics::RankCorrelation 0.1204 (SP:10-13, 65-69: average ranks for
+    ties, Pearson on the ranks) is restated in the oracle; scipy.stats.spearmanr is an independent implementation of the same
+    published definition.  Same pair selection as the script (all ordered pairs with |i-j| >= range, SP:42-60), distances as the
+    '%.3f' text the script compares: the two must agree to rounding noise, ties (zero IF cells, equal distances) included."""
+    stats = pytest.importorskip("scipy.stats")
+    for name, pdb in (("chr21_1mb", "chr21_1mb_rank07_a11.pdb"), ("chr22_500kb", None), ("chr1_1mb", None)):
+        IF = ds.load_if_matrix(ds.input_path(name))
+        L = IF.shape[0]
+        if pdb:
+            xyz = ds.read_ca_pdb(os.path.join(ds.shipped_models_dir(), pdb))
+        else:
+            xyz = np.round(orc.random_coil(L, 3.8, 11, 0), 3)          # 3-decimal coordinates, as a PDB file holds them
+        for rng in (3, 1):
+            a, b = [], []
+            for i in range(L):
+                for j in range(L):
+                    if abs(i - j) < rng:
+                        continue
+                    a.append(IF[i, j])
+                    b.append(float("%.3f" % np.sqrt(((xyz[i] - xyz[j]) ** 2).sum())))
+            want = stats.spearmanr(a, b).statistic
+            got = orc.spearman(IF, xyz, rng)[0]
+            assert abs(got - want) < 1e-12, (name, rng, got, want)
