@@ -196,3 +196,56 @@ def test_spearman_against_an_independent_implementation():
             want = stats.spearmanr(a, b).statistic
             got = orc.spearman(IF, xyz, rng)[0]
             assert abs(got - want) < 1e-12, (name, rng, got, want)
+
+
+def test_energy_terms_against_a_vectorised_restatement():
+    """A second restatement of the three terms, written from the formulas of SURVEY App. A.2-A.4 as whole-array numpy expressions
+    (the C oracle loops pair by pair): soft-square NOE with the general (a, b, c) tail, harmonic bead bond, quartic repel over
+    all pairs at least vdw_min_sep apart.  Energies must agree to 1e-12 relative, forces (analytic, vectorised) to 1e-10."""
+    from chromosome3d_b200 import abi
+    for name, alpha in (("chr21_1mb", 0.5), ("chr22_500kb", 1.1)):
+        IF = ds.load_if_matrix(ds.input_path(name))
+        N = IF.shape[0]
+        ri, rj, rd = orc.if_to_restraints(IF, alpha)
+        for (w_noe, w_bond, w_vdw, repel, asym, low_soft, scale) in ((10.0, 1000.0, 4.0, 0.85, 2.0, 0, 1.0), (2.0, 100.0, 20.0, 1.5, 0.5, 1, 0.5),
+                                                                     (1.0, 100.0, 0.003, 0.9, 3.0, 0, 2.0)):
+            p = orc.default_params()
+            p.noe_asymptote, p.noe_low_soft = asym, low_soft
+            st = abi.stage(abi.OP_ENERGY, w_noe=w_noe, w_bond=w_bond, w_vdw=w_vdw, repel=repel)
+            x = orc.random_coil(N, 3.8, 5, 0) * scale
+            e, f = orc.energy_forces(x, ri, rj, rd, p, st)
+            C, rsw, c = p.noe_sqconst, p.noe_rswitch, p.noe_asymptote
+            b = (c - 2.0 * C * rsw) * rsw * rsw                       # App. A.2 with e = 2, s = 1
+            a = C * rsw * rsw - b / rsw - c * rsw
+            F = np.zeros_like(x)
+            # NOE
+            d = x[ri] - x[rj]
+            R = np.sqrt((d * d).sum(1))
+            delta = R - rd
+            u = np.abs(delta)
+            tail = (u > rsw) & ((delta > 0) | bool(low_soft))
+            uu = np.where(tail, u, 1.0)
+            e_noe = w_noe * np.where(tail, a + b / uu + c * u, C * u * u).sum()
+            dEdu = np.where(tail, c - b / (uu * uu), 2.0 * C * u)
+            g = (w_noe * dEdu * np.sign(delta) / R)[:, None] * d
+            np.add.at(F, ri, -g)
+            np.add.at(F, rj, g)
+            # bond
+            d = x[:-1] - x[1:]
+            R = np.sqrt((d * d).sum(1))
+            e_bond = w_bond * ((R - p.bond_r0) ** 2).sum()
+            g = (2.0 * w_bond * (R - p.bond_r0) / R)[:, None] * d
+            F[:-1] -= g
+            F[1:] += g
+            # repel
+            i, j = np.triu_indices(N, k=p.vdw_min_sep)
+            d = x[i] - x[j]
+            r2 = (d * d).sum(1)
+            ov = np.maximum(0.0, (repel * p.vdw_rmin) ** 2 - r2)
+            e_vdw = w_vdw * (ov * ov).sum()
+            g = (-4.0 * w_vdw * ov)[:, None] * d
+            np.add.at(F, i, -g)
+            np.add.at(F, j, g)
+            want = np.array([e_noe + e_bond + e_vdw, e_bond, e_vdw, e_noe])
+            assert np.allclose(e[0], want, rtol=1e-12, atol=1e-9), (name, e[0], want)
+            assert np.abs(f[0] - F).max() <= 1e-10 * max(1.0, np.abs(F).max()), np.abs(f[0] - F).max()
