@@ -45,14 +45,16 @@ static __global__ void __launch_bounds__(256) seq_sum_staged_kernel(const double
 
 // ---- the same sum, in parallel ------------------------------------------------------------------------------------------
 // Per pass the block looks at a window of SEQSUM_THREADS x SEQSUM_PER_THREAD terms behind the current position: every thread
-// turns its terms into integer contributions in units of the running sum's last place (seqsum_contrib), a block-wide prefix scan
-// gives the sum after every term, and the first term that cannot be folded in (a tie, a carry out of the binade, a negative /
-// denormal / non-finite term, or no valid frame yet) ends the pass: everything before it is added at once, that term with a real
-// fp64 add by the thread that owns it.  Real data (positive, unremarkable) needs one short pass per doubling of the sum and one
-// per full window after that: 34 passes for the 207,025 cells of chr1_500kb.  Inputs that stop all the time (denormal sums,
-// dyadic values that tie at every step) would pay a pass per term, so a pass that folded in fewer than 32 terms doubles the
-// serial run that follows its stop (up to 4,096 terms; any longer pass resets it to the one stopping term): such inputs degrade
-// to the serial chain, not below it.
+// turns its terms into integer contributions in units of the running sum's last place (seqsum_contrib_fp: three fp64 additions
+// per term; seqsum_contrib states the same thing in integer shifts), a block-wide prefix scan gives the sum after every term,
+// and the first term that cannot be folded in (a tie, a carry out of the binade, a negative / non-finite term, a term of a
+// quarter of the running sum or more, or no valid frame yet) ends the pass: everything before it is added at once, that term
+// with a real fp64 add by the thread that owns it.  Real data (positive, unremarkable) needs one short pass per doubling of the
+// sum and one per full window after that: 36 passes for the 207,025 cells of chr1_500kb at alpha = 1.1 (0.92 ms as a serial
+// chain; 0.24 ms with the integer contributions, less with the three additions: profiles/r02j_launches_e2e.md,
+// r02k_e2e_ab.json).  Inputs that stop all the time (denormal sums, dyadic values that tie at every step) would pay a pass per
+// term, so a pass that folded in fewer than 32 terms doubles the serial run that follows its stop (up to 4,096 terms; any
+// longer pass resets it to the one stopping term): such inputs degrade to the serial chain, not below it.
 #define SEQSUM_THREADS 1024
 #define SEQSUM_PER_THREAD 8
 #define SEQSUM_WINDOW (SEQSUM_THREADS * SEQSUM_PER_THREAD)
